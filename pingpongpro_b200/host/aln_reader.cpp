@@ -1,0 +1,415 @@
+// aln_reader.cpp -- see aln_reader.h.  Own implementation over the system zlib.
+#include "aln_reader.h"
+
+#include <zlib.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+
+namespace ppp {
+
+struct AlnReader::NameMap {
+    std::unordered_map<std::string, int32_t> m;
+};
+
+static const size_t kRawChunk = 4u << 20;
+
+AlnReader::AlnReader() {}
+AlnReader::~AlnReader() { close(); }
+
+void AlnReader::close() {
+    if (fp_) fclose(fp_);
+    fp_ = nullptr;
+    delete nameMap_;
+    nameMap_ = nullptr;
+    good_ = false;
+}
+
+// ---------------------------------------------------------------------------
+// raw / BGZF input
+// ---------------------------------------------------------------------------
+static inline void compact(std::vector<uint8_t>& buf, size_t& cur, size_t& end) {
+    if (cur == 0) return;
+    if (end > cur) memmove(buf.data(), buf.data() + cur, end - cur);
+    end -= cur;
+    cur = 0;
+}
+
+bool AlnReader::readBgzfBlock() {
+    uint8_t hdr[12];
+    size_t got = fread(hdr, 1, 12, fp_);
+    if (got == 0) { eofRaw_ = true; return false; }
+    if (got != 12 || hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) { good_ = false; eofRaw_ = true; return false; }
+    uint32_t xlen = hdr[10] | (hdr[11] << 8);
+    uint8_t extra[65536];
+    if (fread(extra, 1, xlen, fp_) != xlen) { good_ = false; eofRaw_ = true; return false; }
+    int bsize = -1;
+    for (uint32_t i = 0; i + 4 <= xlen;) {
+        uint32_t slen = extra[i + 2] | (extra[i + 3] << 8);
+        if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2) bsize = extra[i + 4] | (extra[i + 5] << 8);
+        i += 4 + slen;
+    }
+    if (bsize < 0) { good_ = false; eofRaw_ = true; return false; }
+    size_t clen = (size_t)bsize + 1 - xlen - 12 - 8;
+    zin_.resize(clen + 8);
+    if (fread(zin_.data(), 1, clen + 8, fp_) != clen + 8) { good_ = false; eofRaw_ = true; return false; }
+    uint32_t isize;
+    memcpy(&isize, zin_.data() + clen + 4, 4);
+    if (isize == 0) return true;  // empty block (e.g. the EOF marker)
+    if (buf_.size() < end_ + isize) buf_.resize(end_ + isize + kRawChunk);
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) { good_ = false; return false; }
+    zs.next_in = zin_.data();
+    zs.avail_in = (uInt)clen;
+    zs.next_out = buf_.data() + end_;
+    zs.avail_out = isize;
+    int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END || zs.avail_out != 0) { good_ = false; eofRaw_ = true; return false; }
+    end_ += isize;
+    return true;
+}
+
+bool AlnReader::fill() {
+    if (eofRaw_) return false;
+    compact(buf_, cur_, end_);
+    if (isBam_) {
+        size_t before = end_;
+        while (!eofRaw_ && end_ == before) readBgzfBlock();
+        return end_ > before;
+    }
+    if (buf_.size() < end_ + kRawChunk) buf_.resize(end_ + kRawChunk);
+    size_t got = fread(buf_.data() + end_, 1, kRawChunk, fp_);
+    if (got == 0) { eofRaw_ = true; return false; }
+    end_ += got;
+    return true;
+}
+
+bool AlnReader::ensure(size_t n) {
+    while (end_ - cur_ < n)
+        if (!fill()) return false;
+    return true;
+}
+
+// Returns one text line without its terminator ('\n' or "\r\n").
+bool AlnReader::getLine(const char*& line, size_t& len) {
+    size_t scanFrom = cur_;
+    for (;;) {
+        const uint8_t* p = (const uint8_t*)memchr(buf_.data() + scanFrom, '\n', end_ - scanFrom);
+        if (p) {
+            line = (const char*)buf_.data() + cur_;
+            len = (size_t)(p - (buf_.data() + cur_));
+            cur_ += len + 1;
+            if (len && line[len - 1] == '\r') --len;
+            return true;
+        }
+        size_t have = end_ - cur_;
+        if (!fill()) {
+            if (have == 0) return false;
+            line = (const char*)buf_.data() + cur_;  // last line without '\n'
+            len = have;
+            cur_ = end_;
+            if (len && line[len - 1] == '\r') --len;
+            return true;
+        }
+        scanFrom = cur_ + have;  // fill() compacted: cur_ == 0
+    }
+}
+
+// ---------------------------------------------------------------------------
+// open / header
+// ---------------------------------------------------------------------------
+bool AlnReader::parseSamHeaderLine(const char* line, size_t len) {
+    if (len < 3 || line[1] != 'S' || line[2] != 'Q') return true;  // only @SQ matters
+    std::string name;
+    uint64_t ln = 0;
+    size_t i = 3;
+    while (i < len) {
+        if (line[i] == '\t') { ++i; continue; }
+        size_t j = i;
+        while (j < len && line[j] != '\t') ++j;
+        if (j - i >= 3 && line[i + 2] == ':') {
+            if (line[i] == 'S' && line[i + 1] == 'N') name.assign(line + i + 3, j - i - 3);
+            else if (line[i] == 'L' && line[i + 1] == 'N') ln = strtoull(std::string(line + i + 3, j - i - 3).c_str(), nullptr, 10);
+        }
+        i = j;
+    }
+    nameMap_->m.emplace(name, (int32_t)names_.size());
+    names_.push_back(name);
+    lengths_.push_back(ln);
+    return true;
+}
+
+bool AlnReader::open(const char* path) {
+    close();
+    fp_ = fopen(path, "rb");
+    if (!fp_) return false;
+    setvbuf(fp_, nullptr, _IOFBF, 1 << 20);
+    nameMap_ = new NameMap;
+    names_.clear();
+    lengths_.clear();
+    cur_ = end_ = 0;
+    eofRaw_ = false;
+    nRecords_ = 0;
+    pendingLine_ = false;
+    good_ = true;
+    int c0 = fgetc(fp_), c1 = fgetc(fp_);
+    isBam_ = (c0 == 31 && c1 == 139);
+    rewind(fp_);
+    if (isBam_) {
+        if (!ensure(12) || memcmp(buf_.data() + cur_, "BAM\1", 4) != 0) { good_ = false; return false; }
+        uint32_t lText;
+        memcpy(&lText, buf_.data() + cur_ + 4, 4);
+        cur_ += 8;
+        if (!ensure((size_t)lText + 4)) { good_ = false; return false; }
+        cur_ += lText;  // the reference table below is authoritative for names and lengths
+        uint32_t nRef;
+        memcpy(&nRef, buf_.data() + cur_, 4);
+        cur_ += 4;
+        for (uint32_t r = 0; r < nRef; ++r) {
+            if (!ensure(4)) { good_ = false; return false; }
+            uint32_t lName;
+            memcpy(&lName, buf_.data() + cur_, 4);
+            cur_ += 4;
+            if (!ensure((size_t)lName + 4)) { good_ = false; return false; }
+            std::string name((const char*)buf_.data() + cur_, lName ? lName - 1 : 0);
+            cur_ += lName;
+            uint32_t lRef;
+            memcpy(&lRef, buf_.data() + cur_, 4);
+            cur_ += 4;
+            names_.push_back(name);
+            lengths_.push_back(lRef);
+        }
+        return good_;
+    }
+    // SAM: consume '@' lines
+    for (;;) {
+        if (end_ == cur_ && !fill()) break;
+        if (buf_[cur_] != '@') break;
+        const char* line;
+        size_t len;
+        if (!getLine(line, len)) break;
+        parseSamHeaderLine(line, len);
+    }
+    return good_;
+}
+
+bool AlnReader::atEnd() {
+    if (!good_ && !fp_) return true;
+    for (;;) {
+        if (!isBam_)  // SAM: blank lines (e.g. a trailing newline) are not records
+            while (cur_ < end_ && (buf_[cur_] == '\n' || buf_[cur_] == '\r')) ++cur_;
+        if (end_ > cur_) return false;
+        if (!fill()) return true;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// SAM record
+// ---------------------------------------------------------------------------
+static inline bool parseU32(const char* s, size_t n, uint32_t& v) {
+    if (n == 0) return false;
+    uint64_t x = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        x = x * 10 + (uint64_t)(s[i] - '0');
+        if (x > 0xffffffffull) return false;
+    }
+    v = (uint32_t)x;
+    return true;
+}
+
+static inline int cigarOpCode(char c) {
+    switch (c) {
+        case 'M': return 0; case 'I': return 1; case 'D': return 2; case 'N': return 3; case 'S': return 4;
+        case 'H': return 5; case 'P': return 6; case '=': return 7; case 'X': return 8; default: return -1;
+    }
+}
+
+int AlnReader::nextSam(AlnView& out) {
+    const char* line;
+    size_t len;
+    if (atEnd() || !getLine(line, len) || len == 0) return 1;
+    // split the 11 mandatory fields
+    const char* f[12];
+    size_t fl[12];
+    int nf = 0;
+    size_t i = 0;
+    while (nf < 11) {
+        size_t j = i;
+        while (j < len && line[j] != '\t') ++j;
+        f[nf] = line + i;
+        fl[nf] = j - i;
+        ++nf;
+        if (j >= len) { i = len; break; }
+        i = j + 1;
+    }
+    if (nf < 11) return 1;
+    uint32_t flag, pos;
+    if (!parseU32(f[1], fl[1], flag) || !parseU32(f[3], fl[3], pos)) return 1;
+    out.flag = flag;
+    out.beginPos = (int32_t)pos - 1;
+    if (fl[2] == 1 && f[2][0] == '*') {
+        out.rID = -1;
+    } else {
+        auto it = nameMap_->m.find(std::string(f[2], fl[2]));
+        if (it == nameMap_->m.end()) {  // contig missing from the header: extend the name store
+            int32_t id = (int32_t)names_.size();
+            nameMap_->m.emplace(std::string(f[2], fl[2]), id);
+            names_.push_back(std::string(f[2], fl[2]));
+            lengths_.push_back(0);
+            out.rID = id;
+        } else {
+            out.rID = it->second;
+        }
+    }
+    // CIGAR
+    cigarScratch_.clear();
+    if (!(fl[5] == 1 && f[5][0] == '*')) {
+        uint64_t cnt = 0;
+        bool haveDigit = false;
+        for (size_t k = 0; k < fl[5]; ++k) {
+            char c = f[5][k];
+            if (c >= '0' && c <= '9') { cnt = cnt * 10 + (uint64_t)(c - '0'); haveDigit = true; if (cnt >= (1ull << 28)) return 1; }
+            else {
+                int op = cigarOpCode(c);
+                if (op < 0 || !haveDigit) return 1;
+                cigarScratch_.push_back((uint32_t)(cnt << 4) | (uint32_t)op);
+                cnt = 0;
+                haveDigit = false;
+            }
+        }
+        if (haveDigit) return 1;
+    }
+    out.cigar = cigarScratch_.data();
+    out.nCigar = (uint32_t)cigarScratch_.size();
+    // SEQ
+    out.seq4 = nullptr;
+    if (fl[9] == 1 && f[9][0] == '*') { out.seqText = f[9]; out.lSeq = 0; }
+    else { out.seqText = f[9]; out.lSeq = (uint32_t)fl[9]; }
+    // optional fields: look for NH:i:<n>
+    out.hasNH = false;
+    out.nh = 1;
+    while (i < len) {
+        size_t j = i;
+        while (j < len && line[j] != '\t') ++j;
+        if (j - i >= 6 && line[i] == 'N' && line[i + 1] == 'H' && line[i + 2] == ':' && line[i + 3] == 'i' && line[i + 4] == ':') {
+            const char* s = line + i + 5;
+            size_t n = j - i - 5;
+            bool neg = (n && s[0] == '-');
+            uint32_t v;
+            if (parseU32(s + (neg ? 1 : 0), n - (neg ? 1 : 0), v)) {
+                out.hasNH = true;
+                out.nh = neg ? (uint32_t)(-(int64_t)v) : v;
+            }
+            break;
+        }
+        i = j + 1;
+    }
+    ++nRecords_;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// BAM record
+// ---------------------------------------------------------------------------
+static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type);
+
+static size_t bamTypeSize(char t) {
+    switch (t) {
+        case 'A': case 'c': case 'C': return 1;
+        case 's': case 'S': return 2;
+        case 'i': case 'I': case 'f': return 4;
+        default: return 0;
+    }
+}
+
+static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type) {
+    size_t sz = bamTypeSize(type);
+    if (sz) { if (n < sz) return false; used = sz; return true; }
+    if (type == 'Z' || type == 'H') {
+        const void* z = memchr(p, 0, n);
+        if (!z) return false;
+        used = (size_t)((const uint8_t*)z - p) + 1;
+        return true;
+    }
+    if (type == 'B') {
+        if (n < 5) return false;
+        size_t es = bamTypeSize((char)p[0]);
+        uint32_t cnt;
+        memcpy(&cnt, p + 1, 4);
+        if (!es || n < 5 + es * (size_t)cnt) return false;
+        used = 5 + es * (size_t)cnt;
+        return true;
+    }
+    return false;
+}
+
+int AlnReader::nextBam(AlnView& out) {
+    if (!ensure(4)) return 1;
+    uint32_t blockSize;
+    memcpy(&blockSize, buf_.data() + cur_, 4);
+    if (blockSize < 32 || !ensure((size_t)blockSize + 4)) return 1;
+    const uint8_t* p = buf_.data() + cur_ + 4;
+    cur_ += (size_t)blockSize + 4;
+    int32_t refID, pos;
+    memcpy(&refID, p, 4);
+    memcpy(&pos, p + 4, 4);
+    uint32_t lReadName = p[8];
+    uint16_t nCigar, flag;
+    memcpy(&nCigar, p + 12, 2);
+    memcpy(&flag, p + 14, 2);
+    uint32_t lSeq;
+    memcpy(&lSeq, p + 16, 4);
+    size_t off = 32 + lReadName;
+    size_t need = off + 4 * (size_t)nCigar + ((size_t)lSeq + 1) / 2 + lSeq;
+    if (need > blockSize) return 1;
+    out.rID = refID;
+    out.beginPos = pos;
+    out.flag = flag;
+    cigarScratch_.resize(nCigar);
+    if (nCigar) memcpy(cigarScratch_.data(), p + off, 4 * (size_t)nCigar);  // unaligned source
+    out.cigar = cigarScratch_.data();
+    out.nCigar = nCigar;
+    off += 4 * (size_t)nCigar;
+    out.seqText = nullptr;
+    out.seq4 = p + off;
+    out.lSeq = lSeq;
+    off += ((size_t)lSeq + 1) / 2 + lSeq;
+    // tags
+    out.hasNH = false;
+    out.nh = 1;
+    const uint8_t* t = p + off;
+    size_t n = blockSize - off;
+    while (n >= 3) {
+        char type = (char)t[2];
+        size_t used = 0;
+        if (!skipBamTag(t + 3, n - 3, used, type)) break;
+        if (t[0] == 'N' && t[1] == 'H') {
+            const uint8_t* v = t + 3;
+            switch (type) {
+                case 'c': out.hasNH = true; out.nh = (uint32_t)(int32_t)(int8_t)v[0]; break;
+                case 'C': out.hasNH = true; out.nh = v[0]; break;
+                case 's': { int16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = (uint32_t)(int32_t)x; break; }
+                case 'S': { uint16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = x; break; }
+                case 'i': { int32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = (uint32_t)x; break; }
+                case 'I': { uint32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = x; break; }
+                default: break;
+            }
+            break;
+        }
+        t += 3 + used;
+        n -= 3 + used;
+    }
+    ++nRecords_;
+    return 0;
+}
+
+int AlnReader::next(AlnView& out) {
+    if (!good_) return 1;
+    return isBam_ ? nextBam(out) : nextSam(out);
+}
+
+}  // namespace ppp

@@ -1,0 +1,102 @@
+// aln_reader.h -- sequential SAM / BGZF-BAM record walker (own code, zlib only).
+//
+// This is the ONE alignment decoder of the project.  It replaces the SeqAn 1.4
+// BamStream the reference uses at pingpongpro.cpp:402-415 and :1482-1520 and is
+// shared by
+//   * the new host front end (pingpongpro_b200/host/*.cpp), and
+//   * the SeqAn compatibility shim that lets the UNMODIFIED reference compile
+//     as the parity oracle (oracle/seqan_shim/seqan/bam_io.h),
+// so a decode difference can never masquerade as a kernel bug.
+//
+// Decode semantics kept: SAM POS -> beginPos = POS-1
+// (POS 0 -> -1 = unmapped); rID = index of RNAME in @SQ order ('*' -> -1);
+// SEQ text kept with its case for SAM, upper-case letters for BAM 4-bit codes;
+// NH is read when its tag type is an integer type (SAM 'i'; BAM c C s S i I).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace ppp {
+
+// One CIGAR element in BAM encoding: (count << 4) | opcode, opcode indexes "MIDNSHP=X".
+static inline char cigar_op_char(uint32_t e) { return "MIDNSHP=X???????"[e & 15u]; }
+static inline uint32_t cigar_op_count(uint32_t e) { return e >> 4; }
+
+// A decoded record.  Pointers stay valid until the next call of AlnReader::next().
+struct AlnView {
+    int32_t rID = -1;
+    int32_t beginPos = -1;       // 0-based; -1 when unmapped (SAM POS 0 / BAM pos -1)
+    uint32_t flag = 0;
+    const uint32_t* cigar = nullptr;  // BAM-encoded elements
+    uint32_t nCigar = 0;
+    uint32_t lSeq = 0;           // number of bases (0 when SEQ is '*')
+    const char* seqText = nullptr;    // SAM: lSeq chars.  nullptr for BAM.
+    const uint8_t* seq4 = nullptr;    // BAM: 4-bit packed.  nullptr for SAM.
+    bool hasNH = false;          // an integer-typed NH tag exists
+    uint32_t nh = 1;             // its value (as unsigned, like extractTagValue(unsigned&))
+
+    inline char base(uint32_t i) const {
+        if (seqText) return seqText[i];
+        return "=ACMGRSVTWYHKDBN"[(seq4[i >> 1] >> ((~i & 1u) << 2)) & 15u];
+    }
+};
+
+class AlnReader {
+public:
+    AlnReader();
+    ~AlnReader();
+    AlnReader(const AlnReader&) = delete;
+    AlnReader& operator=(const AlnReader&) = delete;
+
+    // Opens a file; format is detected by the gzip/BGZF magic (else SAM text).
+    // Reads the header.  Returns false when the file cannot be opened or the
+    // header is malformed.
+    bool open(const char* path);
+    void close();
+    bool good() const { return good_; }
+    bool isBam() const { return isBam_; }
+
+    // Contig names / lengths in @SQ (SAM) or reference-table (BAM) order.
+    const std::vector<std::string>& names() const { return names_; }
+    const std::vector<uint64_t>& lengths() const { return lengths_; }
+
+    // True when no further record exists.
+    bool atEnd();
+    // Decodes the next record.  Returns 0 on success, non-zero on a malformed record
+    // ("Failed to read record", pingpongpro.cpp:411).
+    int next(AlnView& out);
+
+    // Records decoded so far.
+    uint64_t recordCount() const { return nRecords_; }
+
+private:
+    bool fill();                  // refill raw buffer (decompressing BGZF blocks for BAM)
+    bool ensure(size_t n);        // make >= n bytes available at cur_ (BAM)
+    bool readBgzfBlock();
+    bool parseSamHeaderLine(const char* line, size_t len);
+    int nextSam(AlnView& out);
+    int nextBam(AlnView& out);
+    bool getLine(const char*& line, size_t& len);
+
+    FILE* fp_ = nullptr;
+    bool good_ = false;
+    bool isBam_ = false;
+    bool eofRaw_ = false;
+    std::vector<std::string> names_;
+    std::vector<uint64_t> lengths_;
+    // uncompressed byte window [cur_, end_) inside buf_
+    std::vector<uint8_t> buf_;
+    size_t cur_ = 0, end_ = 0;
+    std::vector<uint8_t> zin_;    // compressed block scratch
+    std::vector<uint32_t> cigarScratch_;
+    uint64_t nRecords_ = 0;
+    // name -> rID lookup for SAM
+    struct NameMap;
+    NameMap* nameMap_ = nullptr;
+    bool pendingLine_ = false;    // SAM: first alignment line was consumed while reading the header
+    std::string pending_;
+};
+
+}  // namespace ppp
