@@ -1,0 +1,37 @@
+/* ppp_host.h -- C entry points of the host front end (libppp_host.so, no CUDA):
+ * SAM/BAM decode and per-record feature extraction, i.e. the host half of
+ * countReadsInBamFile (pingpongpro.cpp:402-484) that north_star keeps on the CPU.
+ * Its output (ppp_read records per contig, in file order) is the upload format of
+ * ppp_reads_submit() in ppp_b200.h. */
+#ifndef PPP_HOST_H
+#define PPP_HOST_H
+#include "ppp_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ppp_fe ppp_fe; /* a decoded input file */
+
+/* Decodes a whole SAM/BAM file.  Replaces BamStream + the record loop of pingpongpro.cpp:407-484.
+ * min_len/max_len: -l/-L (:426).  mode: PPP_MULTIHITS_* (reads whose weight is <= 0 are dropped, :458).
+ * Returns 0, or 1 = cannot open ("Failed to open input file", :1485), 2 = malformed record
+ * ("Failed to read record", :411). */
+PPP_API int ppp_fe_decode(const char* path, uint32_t min_len, uint32_t max_len, int mode, ppp_fe** out);
+PPP_API void ppp_fe_free(ppp_fe* fe);
+PPP_API int ppp_fe_n_contigs(const ppp_fe* fe);
+PPP_API const char* ppp_fe_contig_name(const ppp_fe* fe, int contig);
+PPP_API uint64_t ppp_fe_contig_length(const ppp_fe* fe, int contig);
+/* Extracted reads of one contig, in file order. */
+PPP_API size_t ppp_fe_n_reads(const ppp_fe* fe, int contig);
+PPP_API const ppp_read* ppp_fe_reads(const ppp_fe* fe, int contig);
+/* totalReadCount (:488): sum of the read weights in file order, as double. */
+PPP_API double ppp_fe_total_weight(const ppp_fe* fe);
+/* Records seen in the file / records kept after the filters of :415, :426, :458. */
+PPP_API uint64_t ppp_fe_n_records(const ppp_fe* fe);
+PPP_API uint64_t ppp_fe_n_kept(const ppp_fe* fe);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,66 @@
+// frontend.cpp -- whole-file decode into packed per-contig reads + the C API of ppp_host.h.
+#include "frontend.h"
+
+#include "ppp_host.h"
+
+namespace ppp {
+
+int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out) {
+    AlnReader rd;
+    if (!rd.open(path)) return 1;
+    out.names = rd.names();
+    out.lengths = rd.lengths();
+    out.reads.assign(out.names.size(), std::vector<ppp_read>());
+    AlnView v;
+    while (!rd.atEnd()) {
+        if (rd.next(v) != 0) return 2;
+        ++out.nRecords;
+        ppp_read r;
+        int32_t contig;
+        float w;
+        if (!extract_read(v, o, r, contig, w)) continue;
+        if ((size_t)contig >= out.reads.size()) {  // contig that is missing from the header
+            out.names = rd.names();
+            out.lengths = rd.lengths();
+            out.reads.resize(out.names.size());
+            if ((size_t)contig >= out.reads.size()) return 2;
+        }
+        out.reads[contig].push_back(r);
+        out.totalWeight += (double)w;  // :488, file order
+        ++out.nKept;
+    }
+    if (!rd.good()) return 2;
+    return 0;
+}
+
+}  // namespace ppp
+
+struct ppp_fe {
+    ppp::DecodedFile f;
+};
+
+extern "C" {
+
+int ppp_fe_decode(const char* path, uint32_t min_len, uint32_t max_len, int mode, ppp_fe** out) {
+    *out = nullptr;
+    ppp_fe* fe = new ppp_fe;
+    ppp::ExtractOptions o;
+    o.minLen = min_len;
+    o.maxLen = max_len;
+    o.mode = mode;
+    int rc = ppp::decode_file(path, o, fe->f);
+    if (rc != 0) { delete fe; return rc; }
+    *out = fe;
+    return 0;
+}
+void ppp_fe_free(ppp_fe* fe) { delete fe; }
+int ppp_fe_n_contigs(const ppp_fe* fe) { return (int)fe->f.names.size(); }
+const char* ppp_fe_contig_name(const ppp_fe* fe, int c) { return fe->f.names[c].c_str(); }
+uint64_t ppp_fe_contig_length(const ppp_fe* fe, int c) { return fe->f.lengths[c]; }
+size_t ppp_fe_n_reads(const ppp_fe* fe, int c) { return fe->f.reads[c].size(); }
+const ppp_read* ppp_fe_reads(const ppp_fe* fe, int c) { return fe->f.reads[c].data(); }
+double ppp_fe_total_weight(const ppp_fe* fe) { return fe->f.totalWeight; }
+uint64_t ppp_fe_n_records(const ppp_fe* fe) { return fe->f.nRecords; }
+uint64_t ppp_fe_n_kept(const ppp_fe* fe) { return fe->f.nKept; }
+
+}  // extern "C"
