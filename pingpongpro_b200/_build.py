@@ -80,7 +80,7 @@ def build_cuda() -> str:
     out = os.path.join(LIB, "libppp_b200.so")
     src = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
     if _newer(out, src + _headers()):
-        _run([NVCC, *NVCCFLAGS, "-shared", "-o", out, *src, "-cudart", "shared"])
+        _run([NVCC, *NVCCFLAGS, "-shared", "-o", out, *src, "-cudart", "static"])
     return out
 
 

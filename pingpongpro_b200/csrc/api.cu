@@ -1,0 +1,811 @@
+// api.cu -- the C ABI of include/ppp_b200.h: context, memory, stream orchestration and the small pieces of
+// host arithmetic that must use the HOST libm to stay bit-identical to the reference (log10f-based bin
+// thresholds, exp-based Gaussian weights).  No CPU fallback exists anywhere in this file: every entry point
+// that computes launches CUDA kernels and fails with PPP_ERR_CUDA when that is impossible.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ppp_b200.h"
+#include "transposons.cuh"
+
+using namespace pppk;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) return fail(PPP_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr uint32_t kKeySlack = 64;          // keys up to contig length + 63 are accepted (a - key may equal the length, :464)
+constexpr size_t kChunk = (size_t)1 << 23;  // records per upload / sort chunk (64 MB)
+constexpr int kTile = 2048;                 // must match scan.cu
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool used = false;
+};
+
+struct PinnedScalars {
+    uint32_t maxHeight;
+    uint32_t nBins;
+    unsigned long long cursor;
+    unsigned long long maxCount;
+    unsigned long long nLoci;
+    unsigned long long counters[2];
+};
+
+}  // namespace
+
+struct ppp_ctx {
+    int device = 0;
+    int minOv = 3, maxOv = 23, ppOv = 10, W = 21, mode = 0, repr = kReprFloat;
+    std::vector<uint64_t> contigLen;
+    std::vector<Slot> slotOfContig;  // lenMinus == 0: contig not in this context
+    std::vector<Slot> ownedSlots;    // sorted by off
+    uint64_t G = 0, ownedPositions = 0;
+    uint32_t nTiles = 0, haloLo = 0, haloHi = 0;
+
+    cudaStream_t stream = nullptr, copyStream = nullptr;
+    uint32_t* H = nullptr;
+    Slot* dSlots = nullptr;
+    unsigned long long* dCounters = nullptr;  // [0] foreign, [1] range errors
+
+    // upload double buffers
+    ppp_read* dStage[2] = {nullptr, nullptr};
+    ppp_read* hStage[2] = {nullptr, nullptr};
+    cudaEvent_t evCopied[2] = {nullptr, nullptr}, evConsumed[2] = {nullptr, nullptr};
+    bool slotUsed[2] = {false, false};
+    unsigned submitCount = 0;
+    uint64_t readsSubmitted = 0;
+    std::vector<Timer> buildTimers;
+    float buildMs = 0.f;
+    SortScratch sort = {};
+
+    // scan state
+    unsigned long long* dFreqLow = nullptr;
+    uint32_t* dFreqTail = nullptr;
+    float* dLut = nullptr;
+    uint32_t* dMaxHeight = nullptr;
+    unsigned long long* dMaxCount = nullptr;
+    unsigned long long* dCursor = nullptr;
+    unsigned long long* dNLoci = nullptr;
+    uint32_t prevMaxHeight = 0;
+    PairRec *dPairsRaw = nullptr, *dPairs = nullptr;
+    float* dPairFdr = nullptr;
+    LocusOut* dLoci = nullptr;
+    uint64_t pairCapacity = 0, cfgPairCapacity = 0;
+    uint32_t *dTileCnt = nullptr, *dTileBase = nullptr, *dTileDst = nullptr, *dScanScratch = nullptr, *dBlockCnt = nullptr;
+    size_t scanScratchWords = 0, blockCntWords = 0;
+    uint32_t* dGrouped = nullptr;
+    float *dThresholds = nullptr, *hThresholds = nullptr;
+    float *dCells = nullptr, *dFdr = nullptr;
+    uint16_t* dBinMap = nullptr;
+    uint32_t* dNBins = nullptr;
+    double *dXs = nullptr, *dWs = nullptr;
+    int nSteps = 0;
+    PinnedScalars* hs = nullptr;
+    std::vector<uint64_t> hFreq;
+    ppp_locus* hLoci = nullptr;
+    size_t hLociCap = 0;
+    uint64_t nPairs = 0;
+    uint32_t maxHeight = 0;
+    bool finished = false, haveHist = false, haveScan = false, haveScore = false;
+
+    ppp_allreduce_fn allreduce = nullptr;
+    void* allreduceUser = nullptr;
+
+    Timer tScan, tLut, tBin, tScore, tTransposon;
+    int launches = 0;
+};
+
+namespace {
+
+int timerStart(ppp_ctx* c, Timer& t) {
+    if (!t.a) { CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b)); }
+    CK(cudaEventRecord(t.a, c->stream));
+    return PPP_OK;
+}
+int timerStop(ppp_ctx* c, Timer& t) {
+    CK(cudaEventRecord(t.b, c->stream));
+    t.used = true;
+    return PPP_OK;
+}
+float timerMs(Timer& t) {
+    float ms = 0.f;
+    if (t.used && cudaEventElapsedTime(&ms, t.a, t.b) != cudaSuccess) ms = 0.f;
+    return ms;
+}
+
+// ---- host libm pieces ---------------------------------------------------------------------------
+// heightScoreBin of pingpongpro.cpp:591-594 for one float product, evaluated exactly as the reference does
+// (float log10 -> float divide -> float multiply by 999 -> double add 0.5 -> truncate), with the host libm.
+inline int heightScoreBin(float hs, float maxHeightScore) {
+    float t = log10f(hs) / maxHeightScore * (float)(size_t)(PPP_HEIGHT_SCORE_BINS - 1);
+    return (int)(0.5 + t);
+}
+
+// thresholds[b-1] = smallest float hs in [1, maxFreq^2] whose bin is >= b (b = 1..999); +inf when no product
+// reaches bin b.  bin() is a monotone step function of hs, so the device computes it as the
+// number of thresholds <= hs.  Bisection runs on float bit patterns (order-isomorphic for positive floats).
+// Returns false when bin() is found non-monotone around a threshold (never observed with glibc).
+bool computeThresholds(float maxFreq, float* thr) {
+    float maxHs = log10f(maxFreq * maxFreq);  // :551
+    float top = maxFreq * maxFreq;
+    uint32_t loBits, topBits;
+    float one = 1.0f;
+    memcpy(&loBits, &one, 4);
+    memcpy(&topBits, &top, 4);
+    auto binAt = [&](uint32_t bits) {
+        float f;
+        memcpy(&f, &bits, 4);
+        return heightScoreBin(f, maxHs);
+    };
+    bool monotone = true;
+    uint32_t from = loBits;
+    for (int b = 1; b < PPP_HEIGHT_SCORE_BINS; ++b) {
+        if (binAt(topBits) < b) { thr[b - 1] = std::numeric_limits<float>::infinity(); continue; }
+        uint32_t lo = from, hi = topBits;  // invariant: binAt(hi) >= b
+        if (binAt(lo) >= b) hi = lo;
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo) / 2;
+            if (binAt(mid) >= b) hi = mid; else lo = mid + 1;
+        }
+        memcpy(&thr[b - 1], &hi, 4);
+        // local validation: a few patterns either side must respect the step
+        for (uint32_t d = 1; d <= 4; ++d) {
+            if (hi >= loBits + d && binAt(hi - d) >= b) monotone = false;
+            if (hi + d <= topBits && binAt(hi + d) < b) monotone = false;
+        }
+        from = hi;
+    }
+    return monotone;
+}
+
+// x and w(x) of the integral at pingpongpro.cpp:724-734: for (double x = -5; x <= 5; x += 0.01)
+//   w = 0.01 * 1 / sqrt(2 * M_PI) * exp(-0.5 * x * x)
+void gaussianTable(std::vector<double>& xs, std::vector<double>& ws) {
+    const double pi = 3.14159265358979323846;  // :50
+    xs.clear();
+    ws.clear();
+    for (double x = -5.0; x <= +5.0; x += 0.01) {
+        xs.push_back(x);
+        ws.push_back(0.01 * 1 / sqrt(2 * pi) * exp(-0.5 * x * x));
+    }
+}
+
+int buildLayout(ppp_ctx* c, const ppp_config* cfg) {
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < cfg->n_contigs; ++i) total += cfg->contig_lengths[i];
+    uint64_t rb = cfg->range_begin, re = cfg->range_end;
+    if (rb == 0 && re == 0) re = total;
+    if (rb > re) return fail(PPP_ERR_ARG, "range_begin > range_end");
+    if (re > total) re = total;
+    c->slotOfContig.assign(cfg->n_contigs, Slot{0, 0, 0, 0, 0, 0});
+    uint64_t off = 0, cum = 0;
+    c->ownedPositions = 0;
+    c->haloLo = c->haloHi = 0;
+    for (uint32_t i = 0; i < cfg->n_contigs; ++i) {
+        uint64_t L = cfg->contig_lengths[i];
+        uint64_t keySpace = L + kKeySlack;
+        if (keySpace + c->maxOv + 8 >= 0xffffffffull) return fail(PPP_ERR_ARG, "contig %u too long", i);
+        uint64_t lo = rb > cum ? rb - cum : 0;
+        uint64_t hi;
+        bool holdsEnd = re >= cum + L;
+        if (holdsEnd) hi = keySpace; else hi = re > cum ? re - cum : 0;
+        if (L == 0 || lo >= L || hi <= lo) { cum += L; c->slotOfContig[i].keyLimit = (uint32_t)keySpace; c->slotOfContig[i].contig = i; continue; }
+        Slot s;
+        s.off = (uint32_t)off;
+        s.first = (uint32_t)lo;
+        s.lenPlus = (uint32_t)(hi - lo);
+        uint64_t lm = holdsEnd ? hi - lo : std::min<uint64_t>(hi - lo + c->maxOv, keySpace - lo);
+        s.lenMinus = (uint32_t)lm;
+        s.keyLimit = (uint32_t)keySpace;
+        s.contig = i;
+        if (s.lenMinus > s.lenPlus) { c->haloLo = s.off + s.lenPlus; c->haloHi = s.off + s.lenMinus; }
+        uint64_t words = std::max<uint64_t>(s.lenMinus, (uint64_t)s.lenPlus + c->maxOv) + 1;
+        words = (words + 3) & ~3ull;
+        c->slotOfContig[i] = s;
+        c->ownedSlots.push_back(s);
+        c->ownedPositions += std::min<uint64_t>(hi, L) - lo;
+        off += words;
+        if (off >= 0xfffff000ull) return fail(PPP_ERR_ARG, "more than 2^32 positions in one context: shard the genome (range_begin/range_end)");
+        cum += L;
+    }
+    c->G = ((off + kTile - 1) / kTile) * kTile;
+    if (c->G == 0) c->G = kTile;
+    c->nTiles = (uint32_t)(c->G / kTile);
+    return PPP_OK;
+}
+
+int ensurePairCapacity(ppp_ctx* c, uint64_t want) {
+    if (want <= c->pairCapacity && c->dPairsRaw) return PPP_OK;
+    if (want >= 0xfffffff0ull) return fail(PPP_ERR_NOMEM, "signature store would exceed 2^32 records");
+    if (c->dPairsRaw) { cudaFree(c->dPairsRaw); cudaFree(c->dPairs); cudaFree(c->dPairFdr); cudaFree(c->dLoci); cudaFree(c->dBlockCnt); }
+    c->dPairsRaw = c->dPairs = nullptr;
+    c->dPairFdr = nullptr;
+    c->dLoci = nullptr;
+    c->dBlockCnt = nullptr;
+    c->pairCapacity = 0;
+    CK(cudaMalloc(&c->dPairsRaw, want * sizeof(PairRec)));
+    CK(cudaMalloc(&c->dPairs, want * sizeof(PairRec)));
+    CK(cudaMalloc(&c->dPairFdr, want * sizeof(float)));
+    CK(cudaMalloc(&c->dLoci, want * sizeof(LocusOut)));
+    c->blockCntWords = want / 256 + 2;
+    CK(cudaMalloc(&c->dBlockCnt, c->blockCntWords * sizeof(uint32_t)));
+    c->pairCapacity = want;
+    return PPP_OK;
+}
+
+int ensureSortScratch(ppp_ctx* c) {
+    if (c->sort.keysA) return PPP_OK;
+    SortScratch& s = c->sort;
+    s.capacity = kChunk;
+    CK(cudaMalloc(&s.keysA, kChunk * 4));
+    CK(cudaMalloc(&s.keysB, kChunk * 4));
+    CK(cudaMalloc(&s.valsA, kChunk * 4));
+    CK(cudaMalloc(&s.valsB, kChunk * 4));
+    s.blockHistWords = sort_block_hist_words(kChunk);
+    CK(cudaMalloc(&s.blockHist, s.blockHistWords * 4));
+    s.scanScratchWords = exclusive_scan_scratch_words(s.blockHistWords);
+    CK(cudaMalloc(&s.scanScratch, s.scanScratchWords * 4));
+    return PPP_OK;
+}
+
+// Stack-builder kernels for n device-resident records of one contig (n <= kChunk).
+int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n) {
+    Timer t;
+    int rc = timerStart(c, t);
+    if (rc) return rc;
+    if (c->repr == kReprInt) {
+        CK(launch_stack_build_int(dReads, n, c->H, c->G, slot, c->mode, c->dCounters, c->stream, &c->launches));
+    } else {
+        rc = ensureSortScratch(c);
+        if (rc) return rc;
+        CK(launch_stack_build_weighted(dReads, n, c->H, c->G, slot, c->dCounters, c->sort, c->stream, &c->launches));
+    }
+    rc = timerStop(c, t);
+    if (rc) return rc;
+    c->buildTimers.push_back(t);
+    return PPP_OK;
+}
+
+int foldBuildTimers(ppp_ctx* c) {
+    for (Timer& t : c->buildTimers) {
+        c->buildMs += timerMs(t);
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    c->buildTimers.clear();
+    return PPP_OK;
+}
+
+int hookReduce(ppp_ctx* c, void* buf, size_t count, int dtype, int op) {
+    if (!c->allreduce || count == 0) return PPP_OK;
+    int rc = c->allreduce(c->allreduceUser, buf, count, dtype, op, (void*)c->stream);
+    if (rc != 0) return fail(PPP_ERR_CUDA, "all-reduce hook failed with code %d", rc);
+    return PPP_OK;
+}
+
+void invalidateResults(ppp_ctx* c) { c->haveHist = c->haveScan = c->haveScore = false; }
+
+}  // namespace
+
+extern "C" {
+
+const char* ppp_last_error(void) { return g_err.c_str(); }
+
+int ppp_device_count(int* n) {
+    int k = 0;
+    cudaError_t e = cudaGetDeviceCount(&k);
+    if (e != cudaSuccess) { *n = 0; return fail(PPP_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *n = k;
+    return PPP_OK;
+}
+
+int ppp_pinned_alloc(size_t bytes, void** ptr) {
+    CK(cudaMallocHost(ptr, bytes));
+    return PPP_OK;
+}
+int ppp_pinned_free(void* ptr) {
+    CK(cudaFreeHost(ptr));
+    return PPP_OK;
+}
+
+int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
+    if (!cfg || !out) return fail(PPP_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->n_contigs == 0 || !cfg->contig_lengths) return fail(PPP_ERR_ARG, "no contigs");
+    if (cfg->min_overlap < 0 || cfg->max_overlap < cfg->min_overlap || cfg->max_overlap > 32 || cfg->pingpong_overlap < cfg->min_overlap ||
+        cfg->pingpong_overlap > cfg->max_overlap || cfg->max_overlap - cfg->min_overlap + 1 > PPP_MAX_OVERLAPS || cfg->max_overlap - cfg->min_overlap + 1 < 3)
+        return fail(PPP_ERR_ARG, "overlaps must satisfy 0 <= min <= pingpong <= max <= 32 with at least 3 overlaps");
+    if (cfg->multi_hits < 0 || cfg->multi_hits > 2) return fail(PPP_ERR_ARG, "multi_hits must be PPP_MULTIHITS_*");
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess || nDev == 0)
+        return fail(PPP_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= nDev) return fail(PPP_ERR_ARG, "device %d out of range (%d devices)", cfg->device, nDev);
+    CK(cudaSetDevice(cfg->device));
+    ppp_ctx* c = new ppp_ctx;
+    c->device = cfg->device;
+    c->minOv = cfg->min_overlap;
+    c->maxOv = cfg->max_overlap;
+    c->ppOv = cfg->pingpong_overlap;
+    c->W = c->maxOv - c->minOv + 1;
+    c->mode = cfg->multi_hits;
+    c->repr = cfg->multi_hits == PPP_MULTIHITS_WEIGHTED ? kReprFloat : kReprInt;
+    c->cfgPairCapacity = cfg->pair_capacity;
+    c->contigLen.assign(cfg->contig_lengths, cfg->contig_lengths + cfg->n_contigs);
+    int rc = buildLayout(c, cfg);
+    if (rc) { delete c; return rc; }
+#define CKI(expr)                                                                                                     \
+    do {                                                                                                              \
+        cudaError_t e__ = (expr);                                                                                     \
+        if (e__ != cudaSuccess) { int r__ = fail(PPP_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); ppp_destroy(c); return r__; } \
+    } while (0)
+    CKI(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKI(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    size_t hWords = 2 * c->G + 64;
+    CKI(cudaMalloc(&c->H, hWords * sizeof(uint32_t)));
+    CKI(cudaMemsetAsync(c->H, 0, hWords * sizeof(uint32_t), c->stream));
+    if (!c->ownedSlots.empty()) {
+        CKI(cudaMalloc(&c->dSlots, c->ownedSlots.size() * sizeof(Slot)));
+        CKI(cudaMemcpyAsync(c->dSlots, c->ownedSlots.data(), c->ownedSlots.size() * sizeof(Slot), cudaMemcpyHostToDevice, c->stream));
+    }
+    CKI(cudaMalloc(&c->dCounters, 2 * sizeof(unsigned long long)));
+    CKI(cudaMemsetAsync(c->dCounters, 0, 2 * sizeof(unsigned long long), c->stream));
+    for (int k = 0; k < 2; ++k) {
+        CKI(cudaEventCreateWithFlags(&c->evCopied[k], cudaEventDisableTiming));
+        CKI(cudaEventCreateWithFlags(&c->evConsumed[k], cudaEventDisableTiming));
+    }
+    CKI(cudaMalloc(&c->dFreqLow, kLowBins * sizeof(unsigned long long)));
+    CKI(cudaMalloc(&c->dFreqTail, (size_t)kFreqCapacity * sizeof(uint32_t)));
+    CKI(cudaMemsetAsync(c->dFreqTail, 0, (size_t)kFreqCapacity * sizeof(uint32_t), c->stream));
+    CKI(cudaMalloc(&c->dLut, (size_t)kFreqCapacity * sizeof(float)));
+    CKI(cudaMalloc(&c->dMaxHeight, sizeof(uint32_t)));
+    CKI(cudaMalloc(&c->dMaxCount, sizeof(unsigned long long)));
+    CKI(cudaMalloc(&c->dCursor, sizeof(unsigned long long)));
+    CKI(cudaMalloc(&c->dNLoci, sizeof(unsigned long long)));
+    CKI(cudaMalloc(&c->dTileCnt, (size_t)c->nTiles * 4));
+    CKI(cudaMalloc(&c->dTileBase, (size_t)c->nTiles * 4));
+    CKI(cudaMalloc(&c->dTileDst, (size_t)c->nTiles * 4));
+    c->scanScratchWords = exclusive_scan_scratch_words(std::max<size_t>(c->nTiles, (size_t)1 << 24));
+    CKI(cudaMalloc(&c->dScanScratch, c->scanScratchWords * 4));
+    size_t tableWords = (size_t)c->W * kBins * 4;
+    CKI(cudaMalloc(&c->dGrouped, tableWords * 4));
+    CKI(cudaMalloc(&c->dCells, tableWords * 4));
+    CKI(cudaMalloc(&c->dFdr, tableWords * 4));
+    CKI(cudaMalloc(&c->dBinMap, kBins * sizeof(uint16_t)));
+    CKI(cudaMalloc(&c->dNBins, sizeof(uint32_t)));
+    CKI(cudaMalloc(&c->dThresholds, kBins * sizeof(float)));
+    CKI(cudaMallocHost(&c->hThresholds, kBins * sizeof(float)));
+    CKI(cudaMallocHost(&c->hs, sizeof(PinnedScalars)));
+    memset(c->hs, 0, sizeof(PinnedScalars));
+    std::vector<double> xs, ws;
+    gaussianTable(xs, ws);
+    c->nSteps = (int)xs.size();
+    CKI(cudaMalloc(&c->dXs, xs.size() * sizeof(double)));
+    CKI(cudaMalloc(&c->dWs, ws.size() * sizeof(double)));
+    CKI(cudaMemcpyAsync(c->dXs, xs.data(), xs.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CKI(cudaMemcpyAsync(c->dWs, ws.data(), ws.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CKI(cudaStreamSynchronize(c->stream));
+#undef CKI
+    *out = c;
+    return PPP_OK;
+}
+
+void ppp_destroy(ppp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    foldBuildTimers(c);
+    void* dev[] = {c->H, c->dSlots, c->dCounters, c->dStage[0], c->dStage[1], c->sort.keysA, c->sort.keysB, c->sort.valsA, c->sort.valsB, c->sort.blockHist,
+                   c->sort.scanScratch, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
+                   c->dPairFdr, c->dLoci, c->dTileCnt, c->dTileBase, c->dTileDst, c->dScanScratch, c->dBlockCnt, c->dGrouped, c->dThresholds, c->dCells,
+                   c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs};
+    for (void* p : dev)
+        if (p) cudaFree(p);
+    void* pinned[] = {c->hStage[0], c->hStage[1], c->hThresholds, c->hs, c->hLoci};
+    for (void* p : pinned)
+        if (p) cudaFreeHost(p);
+    for (int k = 0; k < 2; ++k) {
+        if (c->evCopied[k]) cudaEventDestroy(c->evCopied[k]);
+        if (c->evConsumed[k]) cudaEventDestroy(c->evConsumed[k]);
+    }
+    for (Timer* t : {&c->tScan, &c->tLut, &c->tBin, &c->tScore, &c->tTransposon})
+        if (t->a) { cudaEventDestroy(t->a); cudaEventDestroy(t->b); }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
+    delete c;
+}
+
+int ppp_reset(ppp_ctx* c) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->copyStream));
+    CK(cudaMemsetAsync(c->H, 0, (2 * c->G + 64) * sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(c->dCounters, 0, 2 * sizeof(unsigned long long), c->stream));
+    c->readsSubmitted = 0;
+    c->finished = false;
+    invalidateResults(c);
+    return PPP_OK;
+}
+
+int ppp_set_allreduce(ppp_ctx* c, ppp_allreduce_fn fn, void* user) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    c->allreduce = fn;
+    c->allreduceUser = user;
+    return PPP_OK;
+}
+
+int ppp_reads_submit_device(ppp_ctx* c, int32_t contig, const ppp_read* dReads, size_t n) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (contig < 0 || (size_t)contig >= c->slotOfContig.size()) return fail(PPP_ERR_ARG, "contig %d out of range", contig);
+    CK(cudaSetDevice(c->device));
+    invalidateResults(c);
+    c->finished = false;
+    const Slot& slot = c->slotOfContig[contig];
+    for (size_t o = 0; o < n; o += kChunk) {
+        size_t k = std::min(kChunk, n - o);
+        int rc = buildChunk(c, slot, dReads + o, k);
+        if (rc) return rc;
+    }
+    c->readsSubmitted += n;
+    return PPP_OK;
+}
+
+int ppp_reads_submit(ppp_ctx* c, int32_t contig, const ppp_read* reads, size_t n, uint64_t /*first_record_index*/) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (contig < 0 || (size_t)contig >= c->slotOfContig.size()) return fail(PPP_ERR_ARG, "contig %d out of range", contig);
+    if (n && !reads) return fail(PPP_ERR_ARG, "null reads");
+    CK(cudaSetDevice(c->device));
+    invalidateResults(c);
+    c->finished = false;
+    const Slot& slot = c->slotOfContig[contig];
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (n && cudaPointerGetAttributes(&attr, reads) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    for (size_t o = 0; o < n; o += kChunk) {
+        size_t k = std::min(kChunk, n - o);
+        int s = (int)(c->submitCount & 1u), prev = s ^ 1;
+        // the double-buffer contract: the copy of the previous submission has left its host buffer
+        if (c->slotUsed[prev]) CK(cudaEventSynchronize(c->evCopied[prev]));
+        if (!c->dStage[s]) CK(cudaMalloc(&c->dStage[s], kChunk * sizeof(ppp_read)));
+        const ppp_read* src = reads + o;
+        if (!pinned) {
+            if (!c->hStage[s]) CK(cudaMallocHost(&c->hStage[s], kChunk * sizeof(ppp_read)));
+            if (c->slotUsed[s]) CK(cudaEventSynchronize(c->evCopied[s]));  // staging buffer free again
+            memcpy(c->hStage[s], src, k * sizeof(ppp_read));
+            src = c->hStage[s];
+        }
+        if (c->slotUsed[s]) CK(cudaStreamWaitEvent(c->copyStream, c->evConsumed[s], 0));  // kernels done with dStage[s]
+        CK(cudaMemcpyAsync(c->dStage[s], src, k * sizeof(ppp_read), cudaMemcpyHostToDevice, c->copyStream));
+        CK(cudaEventRecord(c->evCopied[s], c->copyStream));
+        CK(cudaStreamWaitEvent(c->stream, c->evCopied[s], 0));
+        int rc = buildChunk(c, slot, c->dStage[s], k);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->evConsumed[s], c->stream));
+        c->slotUsed[s] = true;
+        c->submitCount++;
+    }
+    c->readsSubmitted += n;
+    return PPP_OK;
+}
+
+int ppp_stacks_finish(ppp_ctx* c) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->copyStream));
+    CK(cudaMemcpyAsync(c->hs->counters, c->dCounters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    foldBuildTimers(c);
+    c->finished = true;
+    if (c->hs->counters[1]) return fail(PPP_ERR_RANGE, "%llu read(s) lie beyond the end of their contig", c->hs->counters[1]);
+    return PPP_OK;
+}
+
+int ppp_reads_foreign(ppp_ctx* c, uint64_t* n) {
+    if (!c || !n) return fail(PPP_ERR_ARG, "null argument");
+    if (!c->finished) return fail(PPP_ERR_STATE, "call ppp_stacks_finish first");
+    *n = c->hs->counters[0];
+    return PPP_OK;
+}
+
+int ppp_stacks_download(ppp_ctx* c, int32_t contig, int32_t strand, uint64_t begin, uint64_t count, float* reads, uint8_t* a10) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (contig < 0 || (size_t)contig >= c->slotOfContig.size() || strand < 0 || strand > 1) return fail(PPP_ERR_ARG, "bad contig/strand");
+    CK(cudaSetDevice(c->device));
+    const Slot& s = c->slotOfContig[contig];
+    uint64_t len = strand ? s.lenMinus : s.lenPlus;
+    if (begin < s.first || begin - s.first + count > len) return fail(PPP_ERR_ARG, "key range outside this context");
+    std::vector<uint32_t> w(count);
+    const uint32_t* src = c->H + (strand ? c->G : 0) + s.off + (begin - s.first);
+    CK(cudaMemcpyAsync(w.data(), src, count * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (uint64_t i = 0; i < count; ++i) {
+        uint32_t v = w[i] & kValueMask;
+        float f;
+        if (c->repr == kReprInt) f = (float)(v < kSaturate ? v : kSaturate);
+        else memcpy(&f, &v, 4);
+        if (reads) reads[i] = f;
+        if (a10) a10[i] = (uint8_t)(w[i] >> 31);
+    }
+    return PPP_OK;
+}
+
+int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (!c->finished) return fail(PPP_ERR_STATE, "call ppp_stacks_finish before ppp_height_hist");
+    CK(cudaSetDevice(c->device));
+    invalidateResults(c);
+    uint64_t want = c->cfgPairCapacity ? c->cfgPairCapacity : std::max<uint64_t>((uint64_t)1 << 20, c->readsSubmitted);
+    if (want < c->pairCapacity) want = c->pairCapacity;
+    int rc = ensurePairCapacity(c, want);
+    if (rc) return rc;
+    for (int attempt = 0;; ++attempt) {
+        CK(cudaMemsetAsync(c->dFreqLow, 0, kLowBins * sizeof(unsigned long long), c->stream));
+        if (c->prevMaxHeight >= kLowBins)
+            CK(cudaMemsetAsync(c->dFreqTail + kLowBins, 0, ((size_t)c->prevMaxHeight - kLowBins + 1) * sizeof(uint32_t), c->stream));
+        CK(cudaMemsetAsync(c->dMaxHeight, 0, sizeof(uint32_t), c->stream));
+        CK(cudaMemsetAsync(c->dMaxCount, 0, sizeof(unsigned long long), c->stream));
+        CK(cudaMemsetAsync(c->dCursor, 0, sizeof(unsigned long long), c->stream));
+        ScanParams p;
+        p.H = c->H;
+        p.G = c->G;
+        p.nTiles = c->nTiles;
+        p.minOv = c->minOv;
+        p.W = c->W;
+        p.haloLo = c->haloLo;
+        p.haloHi = c->haloHi;
+        p.freqLow = c->dFreqLow;
+        p.freqTail = c->dFreqTail;
+        p.maxHeight = c->dMaxHeight;
+        p.pairsRaw = c->dPairsRaw;
+        p.cursor = c->dCursor;
+        p.capacity = c->pairCapacity;
+        p.tileCnt = c->dTileCnt;
+        p.tileBase = c->dTileBase;
+        if ((rc = timerStart(c, c->tScan))) return rc;
+        CK(launch_scan(p, c->repr, c->stream, &c->launches));
+        if ((rc = timerStop(c, c->tScan))) return rc;
+        if (c->allreduce) {
+            // sizes of the table reductions depend on the global maximum height: one extra round trip
+            if ((rc = hookReduce(c, c->dMaxHeight, 1, 0, 1))) return rc;
+            CK(cudaMemcpyAsync(&c->hs->maxHeight, c->dMaxHeight, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if ((rc = hookReduce(c, c->dFreqLow, kLowBins, 1, 0))) return rc;
+            if (c->hs->maxHeight >= kLowBins && (rc = hookReduce(c, c->dFreqTail + kLowBins, (size_t)c->hs->maxHeight - kLowBins + 1, 0, 0))) return rc;
+        }
+        if ((rc = timerStart(c, c->tLut))) return rc;
+        CK(launch_freq_lut(c->dFreqLow, c->dFreqTail, c->dMaxHeight, c->dLut, c->dMaxCount, c->stream, &c->launches));
+        if ((rc = timerStop(c, c->tLut))) return rc;
+        CK(cudaMemcpyAsync(&c->hs->maxHeight, c->dMaxHeight, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&c->hs->cursor, c->dCursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&c->hs->maxCount, c->dMaxCount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->prevMaxHeight = std::max(c->prevMaxHeight, c->hs->maxHeight);
+        if (c->hs->cursor <= c->pairCapacity) break;
+        if (attempt >= 2) return fail(PPP_ERR_NOMEM, "signature store overflow");
+        if ((rc = ensurePairCapacity(c, c->hs->cursor + c->hs->cursor / 8 + 1024))) return rc;  // rerun with room for every record
+    }
+    c->maxHeight = c->hs->maxHeight;
+    c->nPairs = c->hs->cursor;
+
+    // bin thresholds from the (global) maximum frequency, with the host libm
+    float maxFreq = (float)(c->hs->maxCount < kSaturate ? (uint32_t)c->hs->maxCount : kSaturate);  // :547-550
+    for (int b = 0; b < kBins; ++b) c->hThresholds[b] = std::numeric_limits<float>::infinity();
+    if (maxFreq > 1.0f) {
+        if (!computeThresholds(maxFreq, c->hThresholds)) return fail(PPP_ERR_STATE, "host log10f is not monotone around a bin threshold");
+    } else if (c->nPairs > 0 && !c->allreduce) {
+        return fail(PPP_ERR_DEGENERATE, "every rounded stack height occurs once: the reference's height score is 0/0 (pingpongpro.cpp:551/:593)");
+    }
+    CK(cudaMemcpyAsync(c->dThresholds, c->hThresholds, kBins * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+
+    if (freq) {
+        uint32_t mh = c->maxHeight;
+        c->hFreq.assign((size_t)mh + 1, 0);
+        std::vector<unsigned long long> low(kLowBins);
+        CK(cudaMemcpyAsync(low.data(), c->dFreqLow, kLowBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<uint32_t> tail;
+        if (mh >= kLowBins) {
+            tail.resize((size_t)mh - kLowBins + 1);
+            CK(cudaMemcpyAsync(tail.data(), c->dFreqTail + kLowBins, tail.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        for (uint32_t h = 0; h <= mh; ++h) c->hFreq[h] = h < kLowBins ? low[h] : tail[h - kLowBins];
+        *freq = c->hFreq.data();
+    }
+    if (maxHeight) *maxHeight = c->maxHeight;
+    c->haveHist = true;
+    return PPP_OK;
+}
+
+int ppp_scan(ppp_ctx* c, uint64_t* grouped, uint64_t* nPairs) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (!c->haveHist) return fail(PPP_ERR_STATE, "call ppp_height_hist before ppp_scan");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    size_t tableWords = (size_t)c->W * kBins * 4;
+    if ((rc = timerStart(c, c->tBin))) return rc;
+    CK(cudaMemsetAsync(c->dGrouped, 0, tableWords * 4, c->stream));
+    CK(exclusive_scan_u32(c->dTileCnt, c->dTileDst, c->nTiles, c->dScanScratch, c->scanScratchWords, c->stream, &c->launches));
+    CK(launch_bin_group(c->dPairsRaw, c->dPairs, c->dTileCnt, c->dTileBase, c->dTileDst, c->nTiles, c->dLut, c->dThresholds, c->dGrouped, c->stream,
+                        &c->launches));
+    if ((rc = timerStop(c, c->tBin))) return rc;
+    if ((rc = hookReduce(c, c->dGrouped, tableWords, 0, 0))) return rc;
+    if (grouped) {
+        std::vector<uint32_t> g(tableWords);
+        CK(cudaMemcpyAsync(g.data(), c->dGrouped, tableWords * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < tableWords; ++i) grouped[i] = g[i];
+    }
+    if (nPairs) *nPairs = c->nPairs;
+    c->haveScan = true;
+    return PPP_OK;
+}
+
+int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* binMap, float* cells, float* fdrTable, const ppp_locus** loci, size_t* nLoci) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (!c->haveScan) return fail(PPP_ERR_STATE, "call ppp_scan before ppp_score");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    const int ppIdx = c->ppOv - c->minOv;
+    if ((rc = timerStart(c, c->tScore))) return rc;
+    CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->stream, &c->launches));
+    CK(launch_fdr_table(c->dCells, c->dNBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
+    CK(launch_score_pairs(c->dPairs, c->nPairs, c->dFdr, c->dBinMap, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dPairFdr, c->dLoci,
+                          c->dNLoci, c->dBlockCnt, c->dScanScratch, c->scanScratchWords, c->stream, &c->launches));
+    if ((rc = timerStop(c, c->tScore))) return rc;
+    CK(cudaMemcpyAsync(&c->hs->nLoci, c->dNLoci, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->hs->nBins, c->dNBins, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    size_t n = (size_t)c->hs->nLoci;
+    uint32_t C = c->hs->nBins;
+    if (loci) {
+        if (n > c->hLociCap) {
+            if (c->hLoci) cudaFreeHost(c->hLoci);
+            c->hLoci = nullptr;
+            c->hLociCap = 0;
+            CK(cudaMallocHost(&c->hLoci, (n + n / 4 + 1024) * sizeof(ppp_locus)));
+            c->hLociCap = n + n / 4 + 1024;
+        }
+        static_assert(sizeof(ppp_locus) == sizeof(LocusOut), "locus layout");
+        if (n) CK(cudaMemcpyAsync(c->hLoci, c->dLoci, n * sizeof(ppp_locus), cudaMemcpyDeviceToHost, c->stream));
+    }
+    size_t tableWords = (size_t)c->W * kBins * 4;
+    std::vector<float> tmpCells, tmpFdr;
+    if (cells) { tmpCells.resize(tableWords); CK(cudaMemcpyAsync(tmpCells.data(), c->dCells, tableWords * 4, cudaMemcpyDeviceToHost, c->stream)); }
+    if (fdrTable) { tmpFdr.resize(tableWords); CK(cudaMemcpyAsync(tmpFdr.data(), c->dFdr, tableWords * 4, cudaMemcpyDeviceToHost, c->stream)); }
+    if (binMap) CK(cudaMemcpyAsync(binMap, c->dBinMap, kBins * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    if (loci || cells || fdrTable || binMap) CK(cudaStreamSynchronize(c->stream));
+    // device tables use a fixed bin stride of 1000; the ABI returns them densely as [overlap][C][bias][local]
+    for (int o = 0; o < c->W; ++o)
+        for (uint32_t b = 0; b < C; ++b)
+            for (int k = 0; k < 4; ++k) {
+                if (cells) cells[((size_t)o * C + b) * 4 + k] = tmpCells[((size_t)o * kBins + b) * 4 + k];
+                if (fdrTable) fdrTable[((size_t)o * C + b) * 4 + k] = tmpFdr[((size_t)o * kBins + b) * 4 + k];
+            }
+    if (nBins) *nBins = C;
+    if (loci) *loci = c->hLoci;
+    if (nLoci) *nLoci = n;
+    c->haveScore = true;
+    return PPP_OK;
+}
+
+int ppp_pairs_download(ppp_ctx* c, ppp_pair* out, size_t capacity, size_t* n) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (!c->haveScan) return fail(PPP_ERR_STATE, "call ppp_scan before ppp_pairs_download");
+    CK(cudaSetDevice(c->device));
+    if (n) *n = (size_t)c->nPairs;
+    if (!out) return PPP_OK;
+    if (capacity < c->nPairs) return fail(PPP_ERR_ARG, "capacity %zu < %llu signatures", capacity, (unsigned long long)c->nPairs);
+    std::vector<PairRec> recs((size_t)c->nPairs);
+    std::vector<float> fdr((size_t)c->nPairs, 0.f);
+    std::vector<uint16_t> binMap(kBins, 0);
+    if (c->nPairs) CK(cudaMemcpyAsync(recs.data(), c->dPairs, recs.size() * sizeof(PairRec), cudaMemcpyDeviceToHost, c->stream));
+    if (c->haveScore) {
+        if (c->nPairs) CK(cudaMemcpyAsync(fdr.data(), c->dPairFdr, fdr.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(binMap.data(), c->dBinMap, kBins * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    size_t slot = 0;
+    for (size_t i = 0; i < recs.size(); ++i) {
+        const PairRec& r = recs[i];
+        while (slot + 1 < c->ownedSlots.size() && c->ownedSlots[slot + 1].off <= r.lpos) ++slot;  // records are position-ordered
+        const Slot& s = c->ownedSlots[slot];
+        ppp_pair& p = out[i];
+        p.contig = s.contig;
+        p.position = r.lpos - s.off + s.first;
+        p.overlap = (r.misc & 31u) + (uint32_t)c->minOv;
+        p.height_score_bin = (r.misc >> 7) & 1023u;
+        p.collapsed_bin = c->haveScore ? binMap[p.height_score_bin] : 0;
+        p.local_bin = (r.misc >> 5) & 1u;
+        p.bias_bin = (r.misc >> 6) & 1u;
+        p.reads_plus = r.rp;
+        p.reads_minus = r.rm;
+        p.fdr = fdr[i];
+    }
+    return PPP_OK;
+}
+
+int ppp_transposons(ppp_ctx* c, const ppp_interval* intervals, size_t n, ppp_tp_result* results, uint32_t* order) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (!c->haveScore) return fail(PPP_ERR_STATE, "call ppp_score before ppp_transposons");
+    if (n && (!intervals || !results)) return fail(PPP_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = timerStart(c, c->tTransposon))) return rc;
+    TransposonJob job;
+    job.pairs = c->dPairs;
+    job.pairFdr = c->dPairFdr;
+    job.nPairs = c->nPairs;
+    job.W = c->W;
+    job.ppIdx = c->ppOv - c->minOv;
+    job.slots = &c->slotOfContig;
+    job.stream = c->stream;
+    job.launches = &c->launches;
+    std::string err;
+    cudaError_t e = run_transposons(job, intervals, n, results, order, err);
+    if (e != cudaSuccess) return fail(PPP_ERR_CUDA, "transposons: %s %s", cudaGetErrorString(e), err.c_str());
+    if (!err.empty()) return fail(PPP_ERR_ARG, "%s", err.c_str());
+    if ((rc = timerStop(c, c->tTransposon))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return PPP_OK;
+}
+
+int ppp_timings_get(ppp_ctx* c, ppp_timings* out) {
+    if (!c || !out) return fail(PPP_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    foldBuildTimers(c);
+    memset(out, 0, sizeof *out);
+    out->stack_build_ms = c->buildMs;
+    out->scan_ms = timerMs(c->tScan);
+    out->lut_ms = timerMs(c->tLut);
+    out->bin_ms = timerMs(c->tBin);
+    out->score_ms = timerMs(c->tScore);
+    out->transposon_ms = timerMs(c->tTransposon);
+    out->launches = (uint32_t)c->launches;
+    return PPP_OK;
+}
+
+int ppp_timings_reset(ppp_ctx* c) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    foldBuildTimers(c);
+    c->buildMs = 0.f;
+    c->launches = 0;
+    for (Timer* t : {&c->tScan, &c->tLut, &c->tBin, &c->tScore, &c->tTransposon}) t->used = false;
+    return PPP_OK;
+}
+
+int ppp_layout(ppp_ctx* c, uint64_t* wordsPerStrand, uint64_t* ownedPositions) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (wordsPerStrand) *wordsPerStrand = c->G;
+    if (ownedPositions) *ownedPositions = c->ownedPositions;
+    return PPP_OK;
+}
+
+}  // extern "C"

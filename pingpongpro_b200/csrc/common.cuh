@@ -1,0 +1,110 @@
+// common.cuh -- shared declarations of the sm_100a CUDA layer (libppp_b200.so).
+//
+// Data layout in HBM: one dense 32-bit word per strand per genome position,
+//   H[0 .. G)      plus strand,  H[G .. 2G)  minus strand,   G = padded words per strand.
+// Contigs occupy consecutive "slots" of G; a slot holds the keys this context owns plus a right
+// halo of max_overlap minus-strand keys, and is padded with zero words so that the overlap window of a
+// plus position never reaches the next slot.  A word is 0 when no stack exists, else
+//   integer representation (-m unique / discard): bits 0..30 = number of reads, bit 31 = A10 flag
+//   float   representation (-m weighted)        : bits 0..30 = IEEE-754 bits of the height, bit 31 = A10
+// (heights are > 0, so the sign bit is free).  TReadStack of pingpongpro.cpp:91-99.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ppp_types.h"
+
+namespace pppk {
+
+constexpr uint32_t kA10Bit = 0x80000000u;
+constexpr uint32_t kValueMask = 0x7fffffffu;
+constexpr uint32_t kSaturate = 1u << 24;        // float counters stop at 2^24
+constexpr int kBins = 1000;                     // HEIGHT_SCORE_BINS, pingpongpro.cpp:164
+constexpr uint32_t kLowBins = 2048;             // smem-privatised part of the height histogram
+constexpr uint32_t kFreqCapacity = kSaturate + 1;  // rounded heights never exceed 2^24
+constexpr uint32_t kInvalidPos = 0xffffffffu;
+
+enum Repr { kReprInt = 0, kReprFloat = 1 };
+
+// Per-contig slot of this context (device copy).
+struct Slot {
+    uint32_t off;       // first word of the slot inside a strand array
+    uint32_t first;     // first owned key (contig coordinate)
+    uint32_t lenPlus;   // owned keys
+    uint32_t lenMinus;  // owned keys + halo
+    uint32_t keyLimit;  // keys >= keyLimit are outside the contig altogether (range error)
+    uint32_t contig;    // rID of the contig this slot belongs to
+};
+
+// A signature record while it lives on the device (16 bytes).
+// misc: bits 0..4 overlap index, bit 5 local bin, bit 6 bias bin, bits 7..16 height-score bin.
+struct __align__(16) PairRec {
+    uint32_t lpos;
+    float rp;
+    float rm;
+    uint32_t misc;
+};
+
+struct ScanParams {
+    const uint32_t* H;      // both strands
+    uint64_t G;             // words per strand
+    uint32_t nTiles;
+    int minOv, W;
+    uint32_t haloLo, haloHi;  // minus-strand words in [haloLo, haloHi) are halo copies (not counted)
+    unsigned long long* freqLow;  // [kLowBins]
+    uint32_t* freqTail;           // [kFreqCapacity] (entries >= kLowBins used)
+    uint32_t* maxHeight;
+    PairRec* pairsRaw;
+    unsigned long long* cursor;   // total records produced (may exceed capacity)
+    uint64_t capacity;
+    uint32_t* tileCnt;
+    uint32_t* tileBase;
+};
+
+// ---- device helpers -------------------------------------------------------------------------
+template <int REPR>
+__device__ __forceinline__ float word_height(uint32_t w) {
+    uint32_t v = w & kValueMask;
+    if (REPR == kReprInt) return (float)(v < kSaturate ? v : kSaturate);
+    return __uint_as_float(v);
+}
+// (unsigned)(0.5 + reads): the std::map key conversion of pingpongpro.cpp:508 / :582 / :589.
+__device__ __forceinline__ uint32_t round_height(float h) { return __double2uint_rz(__dadd_rn(0.5, (double)h)); }
+template <int REPR>
+__device__ __forceinline__ uint32_t word_round_height(uint32_t w) {
+    uint32_t v = w & kValueMask;
+    if (REPR == kReprInt) return v < kSaturate ? v : kSaturate;
+    return round_height(__uint_as_float(v));
+}
+
+// ---- host-callable launchers (defined in the .cu files) --------------------------------------
+cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* scratch, size_t scratchWords, cudaStream_t s, int* launches);
+size_t exclusive_scan_scratch_words(size_t n);
+
+cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, Slot slot, int mode, unsigned long long* counters,
+                                   cudaStream_t s, int* launches);
+struct SortScratch {
+    uint32_t *keysA, *keysB, *valsA, *valsB, *blockHist, *scanScratch;
+    size_t capacity, blockHistWords, scanScratchWords;
+};
+size_t sort_block_hist_words(size_t n);
+cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, Slot slot, unsigned long long* counters,
+                                        const SortScratch& scr, cudaStream_t s, int* launches);
+
+cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* launches);
+cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* freqTail, const uint32_t* maxHeight, float* lut,
+                            unsigned long long* maxCount, cudaStream_t s, int* launches);
+cudaError_t launch_bin_group(const PairRec* raw, PairRec* ordered, const uint32_t* tileCnt, const uint32_t* tileBase, const uint32_t* tileDst, uint32_t nTiles,
+                             const float* lut, const float* thresholds, uint32_t* grouped, cudaStream_t s, int* launches);
+cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, cudaStream_t s, int* launches);
+cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, int W, int ppIdx, const double* xs, const double* ws, int nSteps, float* fdr,
+                             cudaStream_t s, int* launches);
+struct LocusOut {
+    uint32_t contig, position;
+    float fdr, rp, rm;
+};
+cudaError_t launch_score_pairs(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int ppIdx, uint32_t minHeight,
+                               const Slot* slots, uint32_t nSlots, float* pairFdr, LocusOut* loci, unsigned long long* nLoci, uint32_t* blockCnt,
+                               uint32_t* scanScratch, size_t scanScratchWords, cudaStream_t s, int* launches);
+
+}  // namespace pppk

@@ -1,0 +1,241 @@
+// stack_build.cu -- K1, the per-strand 5'-end stack builder.
+//
+// Replaces the accumulation of countReadsInBamFile, pingpongpro.cpp:458-488:
+//     stack[strand][contig][key].reads += weight;   .AAtPosition10 |= a10
+// over the dense word arrays described in common.cuh.
+//
+// Integer path (-m unique, -m discard: every weight is 1, so the float sum of :487 is the exact
+// count clipped at 2^24): one warp-aggregated red.add per distinct word per warp (reads of a hot stack
+// that sit in the same warp are merged with match.any before they reach L2) and a red.or for the A10 bit.
+//
+// Weighted path (-m weighted): `reads += 1.0/NH` is a float accumulation in FILE ORDER (:487), which no
+// unordered scatter can reproduce bit-exactly.  Each batch is therefore stably radix-sorted by word index
+// (own LSD sort, 8-bit digits: block histograms -> device scan -> stable scatter) and every run of equal
+// keys is folded sequentially with __fadd_rn, continuing from the word's current value so that
+// successive batches extend the same left-to-right sum.
+//
+// Bound: L2 atomic throughput / 32-byte sector read-modify-write traffic, not streaming bandwidth.
+// Algorithmic bytes: 8 N (records) + 8 N (word read+write) + 8 G (zero fill at init/reset).
+#include "common.cuh"
+
+namespace pppk {
+
+namespace {
+
+constexpr int kBuildThreads = 256;
+
+// counters[0] = foreign reads (another shard's), counters[1] = reads beyond their contig (range error)
+template <bool WEIGHTED>
+__device__ __forceinline__ bool locate(const ppp_read r, const Slot& slot, int mode, uint32_t& pos, unsigned long long* counters) {
+    uint32_t strand = r.meta & PPP_READ_MINUS;
+    uint32_t nh = r.meta >> PPP_READ_NH_SHIFT;
+    if (!WEIGHTED && mode == PPP_MULTIHITS_DISCARD && nh != 1) return false;  // :454 + :458
+    if (r.key >= slot.keyLimit) { atomicAdd(&counters[1], 1ull); return false; }
+    uint32_t rel = r.key - slot.first;  // wraps to a huge value when key < first
+    uint32_t limit = strand ? slot.lenMinus : slot.lenPlus;
+    if (rel >= limit) { atomicAdd(&counters[0], 1ull); return false; }
+    pos = slot.off + rel;
+    return true;
+}
+
+__global__ void __launch_bounds__(kBuildThreads) k_stack_build_int(const ppp_read* __restrict__ reads, size_t n, uint32_t* __restrict__ H, uint64_t G,
+                                                                    Slot slot, int mode, unsigned long long* counters) {
+    const unsigned lane = threadIdx.x & 31;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t nRound = (n + 31) & ~(size_t)31;  // whole warps stay converged for the warp primitives
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+        bool valid = i < n;
+        ppp_read r = {0, 0};
+        if (valid) {
+            uint2 raw = __ldg(reinterpret_cast<const uint2*>(reads) + i);
+            r.key = raw.x;
+            r.meta = raw.y;
+        }
+        uint32_t pos = 0;
+        if (valid) valid = locate<false>(r, slot, mode, pos, counters);
+        unsigned long long widx = (r.meta & PPP_READ_MINUS) ? G + pos : (unsigned long long)pos;
+        unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            unsigned peers = __match_any_sync(active, widx);       // lanes that hit the same word
+            unsigned a10 = __ballot_sync(active, (r.meta & PPP_READ_A10) != 0);
+            if (lane == (unsigned)(__ffs(peers) - 1)) {
+                atomicAdd(&H[widx], (uint32_t)__popc(peers));       // reads += 1 per read (:487)
+                if (a10 & peers) atomicOr(&H[widx], kA10Bit);       // AAtPosition10 = true (:471/:483)
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ weighted path: keys
+__global__ void __launch_bounds__(kBuildThreads) k_sort_keys(const ppp_read* __restrict__ reads, size_t n, Slot slot, uint32_t* __restrict__ keys,
+                                                              uint32_t* __restrict__ vals, unsigned long long* counters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint2 raw = __ldg(reinterpret_cast<const uint2*>(reads) + i);
+    ppp_read r = {raw.x, raw.y};
+    uint32_t pos;
+    bool ok = locate<true>(r, slot, PPP_MULTIHITS_WEIGHTED, pos, counters);
+    keys[i] = ok ? pos : kInvalidPos;  // invalid records sort to the very end
+    vals[i] = r.meta;
+}
+
+// ------------------------------------------------------------------ stable LSD radix sort
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortPerWarp = 512;                      // consecutive keys owned by one warp
+constexpr int kSortTile = kSortWarps * kSortPerWarp;  // 4096 keys per block
+constexpr int kSortRounds = kSortPerWarp / 32;
+
+__global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t* __restrict__ blockHist,
+                                                              uint32_t nBlocks) {
+    __shared__ uint32_t hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    size_t base = (size_t)blockIdx.x * kSortTile;
+    for (int k = threadIdx.x; k < kSortTile; k += kSortThreads) {
+        size_t i = base + k;
+        if (i < n) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    blockHist[(size_t)threadIdx.x * nBlocks + blockIdx.x] = hist[threadIdx.x];  // [digit][block]
+}
+
+// offsets = exclusive scan of blockHist ([digit][block] flattened): the first output slot of (digit, block).
+__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                                                                 uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, size_t n, int shift,
+                                                                 const uint32_t* __restrict__ offsets, uint32_t nBlocks) {
+    __shared__ uint32_t cnt[kSortWarps][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < kSortWarps * 256; k += kSortThreads) (&cnt[0][0])[k] = 0;
+    __syncthreads();
+    size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)warp * kSortPerWarp;
+    uint32_t key[kSortRounds], val[kSortRounds];
+    // phase 1: per-warp digit counts (each warp owns a contiguous run of the tile, so order = warp, round, lane)
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        size_t i = wbase + r * 32 + lane;
+        bool ok = i < n;
+        key[r] = ok ? keysIn[i] : 0xffffffffu;
+        val[r] = ok ? valsIn[i] : 0;
+        unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            uint32_t d = (key[r] >> shift) & 255u;
+            unsigned peers = __match_any_sync(act, d);
+            if (lane == __ffs(peers) - 1) cnt[warp][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // phase 2: first destination of (warp, digit)
+    {
+        uint32_t d = threadIdx.x;
+        uint32_t run = offsets[(size_t)d * nBlocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            uint32_t c = cnt[w][d];
+            cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // phase 3: stable placement
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        size_t i = wbase + r * 32 + lane;
+        bool ok = i < n;
+        unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            uint32_t d = (key[r] >> shift) & 255u;
+            unsigned peers = __match_any_sync(act, d);
+            uint32_t dst = cnt[warp][d] + __popc(peers & ((1u << lane) - 1u));
+            keysOut[dst] = key[r];
+            valsOut[dst] = val[r];
+            __syncwarp(act);
+            if (lane == __ffs(peers) - 1) cnt[warp][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ ordered fold
+// One thread per run of equal keys (the thread at the run's first element).  Within the run the records
+// are in file order (stable sort); plus- and minus-strand records of the same position are folded
+// into their own words.
+__global__ void __launch_bounds__(kBuildThreads) k_fold_runs(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t n,
+                                                              uint32_t* __restrict__ H, uint64_t G) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t pos = keys[i];
+    if (pos == kInvalidPos) return;
+    if (i > 0 && keys[i - 1] == pos) return;  // not a run head
+    uint32_t wp = H[pos], wm = H[G + pos];
+    float hp = __uint_as_float(wp & kValueMask), hm = __uint_as_float(wm & kValueMask);
+    uint32_t ap = wp & kA10Bit, am = wm & kA10Bit;
+    bool anyP = false, anyM = false;
+    for (size_t j = i; j < n && keys[j] == pos; ++j) {
+        uint32_t meta = vals[j];
+        uint32_t nh = meta >> PPP_READ_NH_SHIFT;
+        float w = (float)__ddiv_rn(1.0, (double)nh);  // readWeight = 1.0 / multiHits, narrowed to float (:449)
+        if (!(w > 0.0f)) continue;                     // :458
+        if (meta & PPP_READ_MINUS) {
+            hm = __fadd_rn(hm, w);                     // :487
+            if (meta & PPP_READ_A10) am = kA10Bit;     // :471
+            anyM = true;
+        } else {
+            hp = __fadd_rn(hp, w);
+            if (meta & PPP_READ_A10) ap = kA10Bit;     // :483
+            anyP = true;
+        }
+    }
+    if (anyP) H[pos] = (__float_as_uint(hp) & kValueMask) | ap;
+    if (anyM) H[G + pos] = (__float_as_uint(hm) & kValueMask) | am;
+}
+
+inline unsigned grid_for(size_t n, int threads, unsigned cap) {
+    size_t b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    return (unsigned)(b < cap ? b : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, Slot slot, int mode, unsigned long long* counters,
+                                   cudaStream_t s, int* launches) {
+    if (n == 0) return cudaSuccess;
+    k_stack_build_int<<<grid_for(n, kBuildThreads, 148 * 16), kBuildThreads, 0, s>>>(reads, n, H, G, slot, mode, counters);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+size_t sort_block_hist_words(size_t n) { return ((n + kSortTile - 1) / kSortTile) * 256; }
+
+cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, Slot slot, unsigned long long* counters,
+                                        const SortScratch& scr, cudaStream_t s, int* launches) {
+    if (n == 0) return cudaSuccess;
+    if (n > scr.capacity) return cudaErrorInvalidValue;
+    unsigned blocks = (unsigned)((n + kBuildThreads - 1) / kBuildThreads);
+    k_sort_keys<<<blocks, kBuildThreads, 0, s>>>(reads, n, slot, scr.keysA, scr.valsA, counters);
+    if (launches) *launches += 1;
+    // key bits that can differ: positions < G, plus the all-ones invalid key
+    int bits = 1;
+    while (bits < 32 && (G >> bits) != 0) ++bits;
+    uint32_t nBlocks = (uint32_t)((n + kSortTile - 1) / kSortTile);
+    uint32_t *kin = scr.keysA, *vin = scr.valsA, *kout = scr.keysB, *vout = scr.valsB;
+    for (int shift = 0; shift < 32; shift += 8) {
+        // passes above the highest position bit only matter for the invalid key (all ones): its digits are 255
+        // everywhere, so it stays behind every valid key as long as the top pass is executed.
+        if (shift >= bits && shift + 8 < 32) continue;
+        k_radix_hist<<<nBlocks, kSortThreads, 0, s>>>(kin, n, shift, scr.blockHist, nBlocks);
+        cudaError_t e = exclusive_scan_u32(scr.blockHist, scr.blockHist, (size_t)nBlocks * 256, scr.scanScratch, scr.scanScratchWords, s, launches);
+        if (e != cudaSuccess) return e;
+        k_radix_scatter<<<nBlocks, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, shift, scr.blockHist, nBlocks);
+        if (launches) *launches += 2;
+        uint32_t* t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    k_fold_runs<<<blocks, kBuildThreads, 0, s>>>(kin, vin, n, H, G);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace pppk
