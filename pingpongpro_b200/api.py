@@ -230,7 +230,8 @@ class Context:
         self.n_pairs = n.value
         return g
 
-    def calculate_fdrs(self, min_stack_height=0, want_tables=True, want_loci=True) -> ScoreResult:
+    def calculate_fdrs(self, min_stack_height=0, want_tables=True, want_loci=True, copy_loci=True) -> ScoreResult:
+        """copy_loci=False returns a view of the library's pinned result buffer (valid until the next call)."""
         nb = C.c_uint32(0)
         bin_map = np.empty(BINS, np.uint16) if want_tables else None
         cells = np.empty(self.W * BINS * 4, np.float32) if want_tables else None
@@ -245,7 +246,9 @@ class Context:
         if want_loci:
             if nl.value:
                 buf = (C.c_char * (LOCUS_DTYPE.itemsize * nl.value)).from_address(lp.value)
-                loci = np.frombuffer(buf, dtype=LOCUS_DTYPE).copy()
+                loci = np.frombuffer(buf, dtype=LOCUS_DTYPE)
+                if copy_loci:
+                    loci = loci.copy()
             else:
                 loci = np.empty(0, LOCUS_DTYPE)
         if want_tables:

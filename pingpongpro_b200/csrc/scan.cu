@@ -9,14 +9,18 @@
 // grouped counter :605) is deferred to k_bin_group, which touches only the (few) signature records.
 // Fusing the two passes halves the DRAM traffic of "K2 + K3" from 16 to 8 bytes per position.
 //
-// Tiling: a CTA of 256 threads walks tiles of 2048 positions.  Each thread loads 2 x 16 B of each strand
-// with streaming (L1::no_allocate) vector loads, i.e. one warp-wide load covers 512 contiguous bytes.  The
-// minus words of the tile plus a 32-word right halo are staged in shared memory together with a 1-bit/word
-// occupancy mask (built with warp shuffles), so the window test of a plus stack is one 64-bit funnel shift
-// instead of `W` loads; only real candidates read the window words.  Shared memory is double buffered: two
-// barriers per tile.  Signature records of a tile are written contiguously (block scan + one atomicAdd on a
-// global cursor) in (position, overlap) order and the tile's run is published in tileBase/tileCnt;
-// k_bin_group later copies the runs into global position order.
+// Tiling: a CTA of 256 threads walks tiles of 2048 positions.  Each thread owns 8 consecutive positions and
+// loads them with ONE streaming 256-bit load per strand (LDG.E.256, L1::no_allocate): a warp-wide load covers
+// 1 KB of contiguous memory.  Both strands of the tile plus a 32-word right halo of the minus strand are staged
+// in shared memory together with a 1-bit/word occupancy mask of the minus strand (built with warp shuffles), so
+// the window test of a plus stack is one 64-bit funnel shift instead of `W` loads.
+// The kernel is instruction-issue sensitive (the stack arrays are sparse, but in a 32-wide warp "some lane has a
+// stack" is almost always true), so all per-stack work loops over the SET BITS of the thread's own occupancy
+// mask, and all per-signature work is made dense: candidates write (position, overlap) entries in record
+// order into a shared list (block scan of the counts), then one thread per RECORD evaluates the window.
+// Shared memory is double buffered: two barriers per tile (+1 when the tile has signatures).  The records of a
+// tile are written contiguously (one atomicAdd on a global cursor) in (position, overlap) order and the tile's
+// run is published in tileBase/tileCnt; k_bin_group later copies the runs into global position order.
 // Histogram: bins < 2048 are privatised per CTA in shared memory (height 1, by far the most common, is
 // counted in a register), the rare tall stacks go to a global table with red.add.
 //
@@ -31,11 +35,18 @@ constexpr int kThreads = 256;
 constexpr int kTile = 2048;
 constexpr int kHalo = 32;
 constexpr int kMaskWords = kTile / 32 + 2;
+constexpr int kCandCap = 512;   // candidates staged per round (a tile rarely has more)
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+}
+
+__device__ __forceinline__ void ld_stream256(uint32_t (&r)[8], const uint32_t* p) {  // LDG.E.256, 32-byte aligned
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
 }
 
 __device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
@@ -51,15 +62,16 @@ __device__ __forceinline__ uint32_t nz_nibble(const uint4& v) {
     return (v.x != 0u ? 1u : 0u) | (v.y != 0u ? 2u : 0u) | (v.z != 0u ? 4u : 0u) | (v.w != 0u ? 8u : 0u);
 }
 
-__device__ __forceinline__ uint32_t comp(const uint4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
-
 template <int REPR>
 __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
-    __shared__ __align__(16) uint32_t sM[2][kTile + kHalo];
-    __shared__ uint32_t sMask[2][kMaskWords];
+    __shared__ __align__(32) uint32_t sP[2][kTile];          // plus strand of the tile
+    __shared__ __align__(32) uint32_t sM[2][kTile + kHalo];  // minus strand + right halo
+    __shared__ uint32_t sMask[2][kMaskWords];                // 1 bit per minus word: stack present
     __shared__ uint32_t sHist[kLowBins];
     __shared__ uint32_t sWarpTot[kThreads / 32];
     __shared__ unsigned long long sBase;
+    __shared__ uint32_t sCandBits[kCandCap];                 // per candidate (plus stack with partners): present overlaps
+    __shared__ uint16_t sCandTp[kCandCap], sCandOff[kCandCap];  // its tile position / first record of the tile it writes
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < (int)kLowBins; k += kThreads) sHist[k] = 0;
@@ -69,40 +81,41 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
     const uint32_t ONE = REPR == kReprInt ? 1u : 0x3f800000u;
     const uint32_t wMask = P.W >= 32 ? 0xffffffffu : ((1u << P.W) - 1u);
     const float fW = (float)P.W;
+    const uint32_t myPos = (uint32_t)tid * 8u;  // this thread owns 8 consecutive positions of the tile
     uint32_t ones = 0, localMax = 0;
 
-    auto count_word = [&](uint32_t wv) {
-        uint32_t v = wv & kValueMask;
-        if (v == ONE) { ++ones; return; }
-        uint32_t r = word_round_height<REPR>(wv);
-        if (r < kLowBins) atomicAdd(&sHist[r], 1u);
-        else atomicAdd(&P.freqTail[r], 1u);
-        localMax = max(localMax, r);
+    // software pipeline: the loads of tile t+1 are issued as soon as tile t has been staged, so they are in
+    // flight while tile t is processed
+    uint32_t pw[8], mw[8];
+    uint4 h = make_uint4(0, 0, 0, 0);
+    auto issue_loads = [&](uint32_t t) {
+        const uint32_t tb = t * (uint32_t)kTile;
+        ld_stream256(pw, P.H + tb + myPos);
+        ld_stream256(mw, P.H + P.G + tb + myPos);
+        if (tid < kHalo / 4) h = ld_stream(reinterpret_cast<const uint4*>(P.H + P.G + tb + kTile) + tid);
     };
+    if (blockIdx.x < P.nTiles) issue_loads(blockIdx.x);
 
     int buf = 0;
     for (uint32_t tile = blockIdx.x; tile < P.nTiles; tile += gridDim.x, buf ^= 1) {
         const uint32_t tileBase = tile * (uint32_t)kTile;
-        const uint4* Hp4 = reinterpret_cast<const uint4*>(P.H + tileBase);
-        const uint4* Hm4 = reinterpret_cast<const uint4*>(P.H + P.G + tileBase);
-        uint4 p[2], m[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            p[k] = ld_stream(Hp4 + warp * 64 + k * 32 + lane);
-            m[k] = ld_stream(Hm4 + warp * 64 + k * 32 + lane);
-        }
-        uint4 h = make_uint4(0, 0, 0, 0);
-        if (tid < kHalo / 4) h = ld_stream(Hm4 + kTile / 4 + tid);
 
-        // stage the minus strand + occupancy mask
+        // stage both strands (the rare paths below index them dynamically) + the minus occupancy mask
+        *reinterpret_cast<uint4*>(&sP[buf][myPos]) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        *reinterpret_cast<uint4*>(&sP[buf][myPos + 4]) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+        *reinterpret_cast<uint4*>(&sM[buf][myPos]) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        *reinterpret_cast<uint4*>(&sM[buf][myPos + 4]) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+        uint32_t nzP = 0, nzM = 0;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            *reinterpret_cast<uint4*>(&sM[buf][warp * 256 + k * 128 + lane * 4]) = m[k];
-            uint32_t v = nz_nibble(m[k]) << (4 * (lane & 7));
+        for (int j = 0; j < 8; ++j) {
+            nzP |= (pw[j] != 0u ? 1u : 0u) << j;
+            nzM |= (mw[j] != 0u ? 1u : 0u) << j;
+        }
+        {
+            uint32_t v = nzM << (8 * (lane & 3));
             v |= __shfl_xor_sync(0xffffffffu, v, 1);
             v |= __shfl_xor_sync(0xffffffffu, v, 2);
-            v |= __shfl_xor_sync(0xffffffffu, v, 4);
-            if ((lane & 7) == 0) sMask[buf][warp * 8 + k * 4 + (lane >> 3)] = v;
+            if ((lane & 3) == 0) sMask[buf][warp * 8 + (lane >> 2)] = v;
         }
         if (warp == 0) {
             if (lane < kHalo / 4) *reinterpret_cast<uint4*>(&sM[buf][kTile + lane * 4]) = h;
@@ -112,99 +125,113 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
             v |= __shfl_xor_sync(0xffffffffu, v, 4);
             if (lane == 0) sMask[buf][kTile / 32] = v;
         }
+        if (tile + gridDim.x < P.nTiles) issue_loads(tile + gridDim.x);  // prefetch (pw / mw / h are dead from here on)
 
-        // K2: height histogram of the words this thread loaded (halo copies of a neighbouring shard excluded)
-        const bool haloTile = tileBase < P.haloHi && tileBase + kTile > P.haloLo;
+        // K2: height histogram.  Loop over the set bits of this thread's own occupancy mask (iterations = the
+        // busiest lane's stack count, not 16), re-reading the word it staged itself.
+        {
+            uint32_t nz = nzP | (nzM << 8);
+            if (tileBase < P.haloHi && tileBase + kTile > P.haloLo) {  // halo copies of a neighbouring shard are not counted
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint32_t wp = comp(p[k], j), wm = comp(m[k], j);
-                if (wp) count_word(wp);
-                if (wm) {
-                    if (haloTile) {
-                        uint32_t lp = tileBase + warp * 256 + k * 128 + lane * 4 + j;
-                        if (lp >= P.haloLo && lp < P.haloHi) continue;
-                    }
-                    count_word(wm);
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t lp = tileBase + myPos + j;
+                    if (lp >= P.haloLo && lp < P.haloHi) nz &= ~(256u << j);
                 }
             }
-        }
-        __syncthreads();  // (A) minus tile + mask of this buffer are complete
-
-        // K3: candidates = plus stacks with at least one minus stack at overlaps min..max
-        uint32_t cnt[2] = {0, 0};
-        uint32_t cand = 0;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (comp(p[k], j) == 0u) continue;
-                uint32_t bit = warp * 256 + k * 128 + lane * 4 + j + P.minOv;
-                uint32_t lo = sMask[buf][bit >> 5], hi = sMask[buf][(bit >> 5) + 1];
-                uint32_t bits = __funnelshift_r(lo, hi, bit & 31) & wMask;
-                if (bits) { cnt[k] += __popc(bits); cand |= 1u << (k * 4 + j); }
+            while (nz) {
+                int b = __ffs(nz) - 1;
+                nz &= nz - 1;
+                uint32_t wv = (b & 8) ? sM[buf][myPos + (b & 7)] : sP[buf][myPos + b];
+                if ((wv & kValueMask) == ONE) { ++ones; continue; }
+                uint32_t r = word_round_height<REPR>(wv);
+                if (r < kLowBins) atomicAdd(&sHist[r], 1u);
+                else atomicAdd(&P.freqTail[r], 1u);
+                localMax = max(localMax, r);
             }
         }
-        // records are ordered (warp, k, lane, j, overlap) == (position, overlap): scan both halves at once
-        uint32_t packed = cnt[0] | (cnt[1] << 16);
-        uint32_t inc = warp_inclusive(packed, lane);
-        uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane == 31) sWarpTot[warp] = (wtot & 0xffffu) + (wtot >> 16);
+        __syncthreads();  // (A) both strands + mask of this buffer are complete
+
+        // K3: candidates = plus stacks with at least one minus stack at overlaps min..max
+        uint32_t cnt = 0, ncand = 0, cand = 0;
+        {
+            uint32_t nz = nzP;
+            while (nz) {
+                int b = __ffs(nz) - 1;
+                nz &= nz - 1;
+                uint32_t bit = myPos + b + P.minOv;
+                uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
+                if (bits) { cnt += __popc(bits); ++ncand; cand |= 1u << b; }
+            }
+        }
+        // records and candidates are ordered (thread, position[, overlap]) == (position[, overlap]);
+        // one warp scan carries both counters (records < 2^14 per warp in the low half, candidates above)
+        const uint32_t packed = cnt | (ncand << 16);
+        const uint32_t inc = warp_inclusive(packed, lane);
+        if (lane == 31) sWarpTot[warp] = inc;
         __syncthreads();  // (B)
-        uint32_t before = 0, total = 0;
+        uint32_t beforeP = 0, totalP = 0;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) {
             uint32_t t = sWarpTot[w];
-            if (w < warp) before += t;
-            total += t;
+            if (w < warp) beforeP += t;
+            totalP += t;
         }
+        const uint32_t total = totalP & 0xffffu, candTotal = totalP >> 16;
         if (tid == 0) {
             unsigned long long base = total ? atomicAdd(P.cursor, (unsigned long long)total) : 0ull;
             sBase = base;
             P.tileCnt[tile] = total;
             P.tileBase[tile] = (uint32_t)base;
         }
-        if (total) {  // block-uniform
-            __syncthreads();  // (C)
-            if (cand) {
-                uint32_t ex = inc - packed;
-                uint64_t off[2];
-                off[0] = sBase + before + (ex & 0xffffu);
-                off[1] = sBase + before + (wtot & 0xffffu) + (ex >> 16);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (!(cand & (1u << (k * 4 + j)))) continue;
-                        const uint32_t wp = comp(p[k], j);
-                        const uint32_t tp = warp * 256 + k * 128 + lane * 4 + j;
-                        const uint32_t* win = &sM[buf][tp + P.minOv];
-                        float sum = 0.0f, mx = 0.0f;
-                        for (int o = 0; o < P.W; ++o) {                      // :564-577 (absent stacks add +0)
-                            float mo = word_height<REPR>(win[o]);
-                            sum = __fadd_rn(sum, mo);
-                            mx = fmaxf(mx, mo);
+        if (total) {  // block-uniform: the rare path, processed densely (one thread per candidate)
+            const uint32_t mine = beforeP + inc - packed;
+            const uint32_t firstRec = mine & 0xffffu, firstCand = mine >> 16;  // tile-relative ranks of this thread's first record / candidate
+            for (uint32_t cbase = 0; cbase < candTotal; cbase += kCandCap) {
+                if (cbase) __syncthreads();  // the previous round's list is no longer read
+                uint32_t off = firstRec, rank = firstCand, cm = cand;
+                while (cm) {
+                    int b = __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    uint32_t tp = myPos + b, bit = tp + P.minOv;
+                    uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
+                    uint32_t slot = rank - cbase;  // wraps to a huge value for earlier rounds
+                    if (slot < (uint32_t)kCandCap) { sCandTp[slot] = (uint16_t)tp; sCandBits[slot] = bits; sCandOff[slot] = (uint16_t)off; }
+                    off += __popc(bits);
+                    ++rank;
+                }
+                __syncthreads();  // (C)
+                const uint32_t nIn = min((uint32_t)kCandCap, candTotal - cbase);
+                for (uint32_t c = tid; c < nIn; c += kThreads) {
+                    const uint32_t tp = sCandTp[c];
+                    uint32_t bits = sCandBits[c];
+                    const uint32_t wp = sP[buf][tp];
+                    const uint32_t* win = &sM[buf][tp + P.minOv];
+                    float sum = 0.0f, mx = 0.0f;
+                    for (int q = 0; q < P.W; ++q) {                          // :564-577 (absent stacks add +0)
+                        float mq = word_height<REPR>(win[q]);
+                        sum = __fadd_rn(sum, mq);
+                        mx = fmaxf(mx, mq);
+                    }
+                    const float mean = __fdiv_rn(sum, fW);                    // :578
+                    const float hp = word_height<REPR>(wp);
+                    unsigned long long idx = sBase + sCandOff[c];
+                    while (bits) {                                            // :584-586
+                        const int o = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const uint32_t wm = win[o];
+                        const float mo = word_height<REPR>(wm);
+                        const float local = __fdiv_rn(__fsub_rn(mo, __fsub_rn(mean, __fdiv_rn(mo, fW))), mx);  // :597
+                        const uint32_t lbin = ((double)local < 0.2) ? 1u : 0u;     // :599
+                        const uint32_t bbin = ((wp | wm) & kA10Bit) ? 0u : 1u;     // :602
+                        if (idx < P.capacity) {
+                            PairRec r;
+                            r.lpos = tileBase + tp;
+                            r.rp = hp;
+                            r.rm = mo;
+                            r.misc = (uint32_t)o | (lbin << 5) | (bbin << 6);
+                            *reinterpret_cast<uint4*>(&P.pairsRaw[idx]) = *reinterpret_cast<uint4*>(&r);
                         }
-                        const float mean = __fdiv_rn(sum, fW);                // :578
-                        const float hp = word_height<REPR>(wp);
-                        for (int o = 0; o < P.W; ++o) {
-                            uint32_t wm = win[o];
-                            if (wm == 0u) continue;                           // :586
-                            float mo = word_height<REPR>(wm);
-                            float local = __fdiv_rn(__fsub_rn(mo, __fsub_rn(mean, __fdiv_rn(mo, fW))), mx);  // :597
-                            uint32_t lbin = ((double)local < 0.2) ? 1u : 0u;   // :599
-                            uint32_t bbin = ((wp | wm) & kA10Bit) ? 0u : 1u;   // :602
-                            uint64_t idx = off[k]++;
-                            if (idx < P.capacity) {
-                                PairRec r;
-                                r.lpos = tileBase + tp;
-                                r.rp = hp;
-                                r.rm = mo;
-                                r.misc = (uint32_t)o | (lbin << 5) | (bbin << 6);
-                                *reinterpret_cast<uint4*>(&P.pairsRaw[idx]) = *reinterpret_cast<uint4*>(&r);
-                            }
-                        }
+                        ++idx;
                     }
                 }
             }

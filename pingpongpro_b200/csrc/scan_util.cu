@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* total,
     return r;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ blockSums) {
+__global__ void __launch_bounds__(kScanThreads) k_prefix_reduce(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ blockSums) {
     __shared__ uint32_t sh[33];
     size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
     uint32_t s = 0;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const uint32_t* __
 }
 
 // In-place exclusive scan of a short array by one block (loops with a carry).
-__global__ void __launch_bounds__(kScanThreads) k_scan_single(uint32_t* data, size_t n) {
+__global__ void __launch_bounds__(kScanThreads) k_prefix_single(uint32_t* data, size_t n) {
     __shared__ uint32_t sh[33];
     uint32_t carry = 0;
     for (size_t base = 0; base < n; base += kScanThreads) {
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_single(uint32_t* data, si
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const uint32_t* in, uint32_t* out, size_t n, const uint32_t* __restrict__ blockSums) {
+__global__ void __launch_bounds__(kScanThreads) k_prefix_apply(const uint32_t* in, uint32_t* out, size_t n, const uint32_t* __restrict__ blockSums) {
     __shared__ uint32_t sh[33];
     size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
@@ -91,9 +91,9 @@ cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint
     if (n == 0) return cudaSuccess;
     size_t nBlocks = (n + kScanTile - 1) / kScanTile;
     if (scratchWords < nBlocks) return cudaErrorInvalidValue;
-    k_scan_reduce<<<(unsigned)nBlocks, kScanThreads, 0, s>>>(in, n, scratch);
-    k_scan_single<<<1, kScanThreads, 0, s>>>(scratch, nBlocks);
-    k_scan_apply<<<(unsigned)nBlocks, kScanThreads, 0, s>>>(in, out, n, scratch);
+    k_prefix_reduce<<<(unsigned)nBlocks, kScanThreads, 0, s>>>(in, n, scratch);
+    k_prefix_single<<<1, kScanThreads, 0, s>>>(scratch, nBlocks);
+    k_prefix_apply<<<(unsigned)nBlocks, kScanThreads, 0, s>>>(in, out, n, scratch);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }

@@ -80,7 +80,7 @@ def check_against(res, ref_sigs, ref_freq_dense, ref_grouped_pre, ref_grouped_po
 
 
 def check_transposons(tp, order, ref, W):
-    assert np.array_equal(bits(tp["histogram"][:, :W]), bits(ref["hist"]))
+    assert np.array_equal(bits(tp["histogram"][:, :W]), bits(ref["hist"][:, :W]))
     assert np.array_equal(bits(tp["reads_plus"]), bits(ref["reads_plus"]))
     assert np.array_equal(bits(tp["reads_minus"]), bits(ref["reads_minus"]))
     # p: float value may differ by one ulp when the fp64 sums straddle a rounding boundary; fp64 agreement 1e-9
@@ -263,7 +263,7 @@ def test_key_at_contig_end_and_ragged_contigs():
         reads[c] = r
     o, sigs = oracle_reference(lengths, reads, "unique")
     res = run_gpu(lengths, reads, "unique")
-    assert len(sigs) == 5
+    assert len(sigs) == 4
     check_against(res, sigs, o.freq(), o.grouped_pre(), o.grouped_post(), 21, 7, 3)
 
 
