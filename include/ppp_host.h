@@ -31,6 +31,25 @@ PPP_API double ppp_fe_total_weight(const ppp_fe* fe);
 PPP_API uint64_t ppp_fe_n_records(const ppp_fe* fe);
 PPP_API uint64_t ppp_fe_n_kept(const ppp_fe* fe);
 
+/* Transposon annotation input, replaces readTransposonsFromFile (pingpongpro.cpp:993-1175) incl. the format
+ * detection of main() (:1543-1554).  Files are read in order; contig names that `contig_names` lacks are
+ * appended to the name store (:1101-1106).  Intervals come back in the reference's order: contig id, then
+ * (start, end), ties in file order.  Returns 0, or 1 = a file cannot be opened (:1539). */
+typedef struct ppp_annot ppp_annot;
+typedef struct ppp_annot_interval {
+    uint32_t contig;
+    uint32_t strand;
+    uint32_t start;
+    uint32_t end;
+} ppp_annot_interval;
+PPP_API int ppp_annot_read(const char* const* paths, int n_paths, const char* const* contig_names, int n_names, ppp_annot** out);
+PPP_API void ppp_annot_free(ppp_annot* a);
+PPP_API size_t ppp_annot_count(const ppp_annot* a);
+PPP_API void ppp_annot_intervals(const ppp_annot* a, ppp_annot_interval* out);
+PPP_API const char* ppp_annot_identifier(const ppp_annot* a, size_t i);
+PPP_API int ppp_annot_n_names(const ppp_annot* a);
+PPP_API const char* ppp_annot_name(const ppp_annot* a, int i);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,7 +55,7 @@ def _headers() -> list[str]:
 def build_host() -> str:
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, "libppp_host.so")
-    src = [os.path.join(HOST, "aln_reader.cpp"), os.path.join(HOST, "frontend.cpp")]
+    src = [os.path.join(HOST, "aln_reader.cpp"), os.path.join(HOST, "frontend.cpp"), os.path.join(HOST, "annotation.cpp")]
     if _newer(out, src + _headers()):
         _run([CXX, *CXXFLAGS, "-shared", "-o", out, *src, "-lz", "-lpthread"])
     return out

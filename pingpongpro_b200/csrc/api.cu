@@ -38,7 +38,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr uint32_t kKeySlack = 64;          // keys up to contig length + 63 are accepted (a - key may equal the length, :464)
 constexpr size_t kChunk = (size_t)1 << 23;  // records per upload / sort chunk (64 MB)
-constexpr int kTile = 2048;                 // must match scan.cu
+constexpr int kTile = kScanTile;
 
 struct Timer {
     cudaEvent_t a = nullptr, b = nullptr;
@@ -100,7 +100,10 @@ struct ppp_ctx {
     float *dThresholds = nullptr, *hThresholds = nullptr;
     float *dCells = nullptr, *dFdr = nullptr;
     uint16_t* dBinMap = nullptr;
+    uint16_t* dGroupStart = nullptr;
+    unsigned long long* dCellSums = nullptr;
     uint32_t* dNBins = nullptr;
+    uint32_t* dTileCursor = nullptr;
     double *dXs = nullptr, *dWs = nullptr;
     int nSteps = 0;
     PinnedScalars* hs = nullptr;
@@ -109,6 +112,7 @@ struct ppp_ctx {
     size_t hLociCap = 0;
     uint64_t nPairs = 0;
     uint32_t maxHeight = 0;
+    float binScale = 0.f;  // 999 / maxHeightScore: only seeds the device's bin proposal
     bool finished = false, haveHist = false, haveScan = false, haveScore = false;
 
     ppp_allreduce_fn allreduce = nullptr;
@@ -162,17 +166,42 @@ bool computeThresholds(float maxFreq, float* thr) {
     };
     bool monotone = true;
     uint32_t from = loBits;
+    const int topBin = binAt(topBits);
     for (int b = 1; b < PPP_HEIGHT_SCORE_BINS; ++b) {
-        if (binAt(topBits) < b) { thr[b - 1] = std::numeric_limits<float>::infinity(); continue; }
-        uint32_t lo = from, hi = topBits;  // invariant: binAt(hi) >= b
-        if (binAt(lo) >= b) hi = lo;
+        if (topBin < b) { thr[b - 1] = std::numeric_limits<float>::infinity(); continue; }
+        // analytic estimate of the step (bin >= b  <=>  log10(hs) / maxHs * 999 >= b - 0.5), then gallop + bisect around it
+        float guessF = (float)pow(10.0, ((double)b - 0.5) / 999.0 * (double)maxHs);
+        uint32_t g;
+        memcpy(&g, &guessF, 4);
+        if (!(guessF >= 1.0f) || g < from) g = from;
+        if (g > topBits) g = topBits;
+        uint32_t lo, hi;  // invariant: bin(lo - 1) < b (or lo == from), bin(hi) >= b
+        if (binAt(g) >= b) {
+            hi = g;
+            uint32_t step = 1;
+            lo = from;
+            while (hi - from >= step) {
+                if (binAt(hi - step) >= b) { hi -= step; step <<= 1; }
+                else { lo = hi - step + 1; break; }
+            }
+        } else {
+            lo = g + 1;
+            uint32_t step = 1;
+            hi = topBits;
+            while (topBits - (lo - 1) > step) {
+                uint32_t probe = lo - 1 + step;
+                if (binAt(probe) >= b) { hi = probe; break; }
+                lo = probe + 1;
+                step <<= 1;
+            }
+        }
         while (lo < hi) {
             uint32_t mid = lo + (hi - lo) / 2;
             if (binAt(mid) >= b) hi = mid; else lo = mid + 1;
         }
         memcpy(&thr[b - 1], &hi, 4);
         // local validation: a few patterns either side must respect the step
-        for (uint32_t d = 1; d <= 4; ++d) {
+        for (uint32_t d = 1; d <= 3; ++d) {
             if (hi >= loBits + d && binAt(hi - d) >= b) monotone = false;
             if (hi + d <= topBits && binAt(hi + d) < b) monotone = false;
         }
@@ -377,7 +406,7 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
         CKI(cudaEventCreateWithFlags(&c->evCopied[k], cudaEventDisableTiming));
         CKI(cudaEventCreateWithFlags(&c->evConsumed[k], cudaEventDisableTiming));
     }
-    CKI(cudaMalloc(&c->dFreqLow, kLowBins * sizeof(unsigned long long)));
+    CKI(cudaMalloc(&c->dFreqLow, kScanLowBins * sizeof(unsigned long long)));
     CKI(cudaMalloc(&c->dFreqTail, (size_t)kFreqCapacity * sizeof(uint32_t)));
     CKI(cudaMemsetAsync(c->dFreqTail, 0, (size_t)kFreqCapacity * sizeof(uint32_t), c->stream));
     CKI(cudaMalloc(&c->dLut, (size_t)kFreqCapacity * sizeof(float)));
@@ -395,7 +424,10 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     CKI(cudaMalloc(&c->dCells, tableWords * 4));
     CKI(cudaMalloc(&c->dFdr, tableWords * 4));
     CKI(cudaMalloc(&c->dBinMap, kBins * sizeof(uint16_t)));
+    CKI(cudaMalloc(&c->dGroupStart, (kBins + 1) * sizeof(uint16_t)));
+    CKI(cudaMalloc(&c->dCellSums, tableWords * sizeof(unsigned long long)));
     CKI(cudaMalloc(&c->dNBins, sizeof(uint32_t)));
+    CKI(cudaMalloc(&c->dTileCursor, sizeof(uint32_t)));
     CKI(cudaMalloc(&c->dThresholds, kBins * sizeof(float)));
     CKI(cudaMallocHost(&c->hThresholds, kBins * sizeof(float)));
     CKI(cudaMallocHost(&c->hs, sizeof(PinnedScalars)));
@@ -422,7 +454,7 @@ void ppp_destroy(ppp_ctx* c) {
     void* dev[] = {c->H, c->dSlots, c->dCounters, c->dStage[0], c->dStage[1], c->sort.keysA, c->sort.keysB, c->sort.valsA, c->sort.valsB, c->sort.blockHist,
                    c->sort.scanScratch, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
                    c->dPairFdr, c->dLoci, c->dTileCnt, c->dTileBase, c->dTileDst, c->dScanScratch, c->dBlockCnt, c->dGrouped, c->dThresholds, c->dCells,
-                   c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs};
+                   c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dTileCursor};
     for (void* p : dev)
         if (p) cudaFree(p);
     void* pinned[] = {c->hStage[0], c->hStage[1], c->hThresholds, c->hs, c->hLoci};
@@ -564,9 +596,9 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
     int rc = ensurePairCapacity(c, want);
     if (rc) return rc;
     for (int attempt = 0;; ++attempt) {
-        CK(cudaMemsetAsync(c->dFreqLow, 0, kLowBins * sizeof(unsigned long long), c->stream));
-        if (c->prevMaxHeight >= kLowBins)
-            CK(cudaMemsetAsync(c->dFreqTail + kLowBins, 0, ((size_t)c->prevMaxHeight - kLowBins + 1) * sizeof(uint32_t), c->stream));
+        CK(cudaMemsetAsync(c->dFreqLow, 0, kScanLowBins * sizeof(unsigned long long), c->stream));
+        if (c->prevMaxHeight >= kScanLowBins)
+            CK(cudaMemsetAsync(c->dFreqTail + kScanLowBins, 0, ((size_t)c->prevMaxHeight - kScanLowBins + 1) * sizeof(uint32_t), c->stream));
         CK(cudaMemsetAsync(c->dMaxHeight, 0, sizeof(uint32_t), c->stream));
         CK(cudaMemsetAsync(c->dMaxCount, 0, sizeof(unsigned long long), c->stream));
         CK(cudaMemsetAsync(c->dCursor, 0, sizeof(unsigned long long), c->stream));
@@ -594,8 +626,8 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
             if ((rc = hookReduce(c, c->dMaxHeight, 1, 0, 1))) return rc;
             CK(cudaMemcpyAsync(&c->hs->maxHeight, c->dMaxHeight, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
-            if ((rc = hookReduce(c, c->dFreqLow, kLowBins, 1, 0))) return rc;
-            if (c->hs->maxHeight >= kLowBins && (rc = hookReduce(c, c->dFreqTail + kLowBins, (size_t)c->hs->maxHeight - kLowBins + 1, 0, 0))) return rc;
+            if ((rc = hookReduce(c, c->dFreqLow, kScanLowBins, 1, 0))) return rc;
+            if (c->hs->maxHeight >= kScanLowBins && (rc = hookReduce(c, c->dFreqTail + kScanLowBins, (size_t)c->hs->maxHeight - kScanLowBins + 1, 0, 0))) return rc;
         }
         if ((rc = timerStart(c, c->tLut))) return rc;
         CK(launch_freq_lut(c->dFreqLow, c->dFreqTail, c->dMaxHeight, c->dLut, c->dMaxCount, c->stream, &c->launches));
@@ -615,6 +647,7 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
     // bin thresholds from the (global) maximum frequency, with the host libm
     float maxFreq = (float)(c->hs->maxCount < kSaturate ? (uint32_t)c->hs->maxCount : kSaturate);  // :547-550
     for (int b = 0; b < kBins; ++b) c->hThresholds[b] = std::numeric_limits<float>::infinity();
+    c->binScale = maxFreq > 1.0f ? 999.0f / log10f(maxFreq * maxFreq) : 0.0f;
     if (maxFreq > 1.0f) {
         if (!computeThresholds(maxFreq, c->hThresholds)) return fail(PPP_ERR_STATE, "host log10f is not monotone around a bin threshold");
     } else if (c->nPairs > 0 && !c->allreduce) {
@@ -625,15 +658,15 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
     if (freq) {
         uint32_t mh = c->maxHeight;
         c->hFreq.assign((size_t)mh + 1, 0);
-        std::vector<unsigned long long> low(kLowBins);
-        CK(cudaMemcpyAsync(low.data(), c->dFreqLow, kLowBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<unsigned long long> low(kScanLowBins);
+        CK(cudaMemcpyAsync(low.data(), c->dFreqLow, kScanLowBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         std::vector<uint32_t> tail;
-        if (mh >= kLowBins) {
-            tail.resize((size_t)mh - kLowBins + 1);
-            CK(cudaMemcpyAsync(tail.data(), c->dFreqTail + kLowBins, tail.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (mh >= kScanLowBins) {
+            tail.resize((size_t)mh - kScanLowBins + 1);
+            CK(cudaMemcpyAsync(tail.data(), c->dFreqTail + kScanLowBins, tail.size() * 4, cudaMemcpyDeviceToHost, c->stream));
         }
         CK(cudaStreamSynchronize(c->stream));
-        for (uint32_t h = 0; h <= mh; ++h) c->hFreq[h] = h < kLowBins ? low[h] : tail[h - kLowBins];
+        for (uint32_t h = 0; h <= mh; ++h) c->hFreq[h] = h < kScanLowBins ? low[h] : tail[h - kScanLowBins];
         *freq = c->hFreq.data();
     }
     if (maxHeight) *maxHeight = c->maxHeight;
@@ -650,7 +683,7 @@ int ppp_scan(ppp_ctx* c, uint64_t* grouped, uint64_t* nPairs) {
     if ((rc = timerStart(c, c->tBin))) return rc;
     CK(cudaMemsetAsync(c->dGrouped, 0, tableWords * 4, c->stream));
     CK(exclusive_scan_u32(c->dTileCnt, c->dTileDst, c->nTiles, c->dScanScratch, c->scanScratchWords, c->stream, &c->launches));
-    CK(launch_bin_group(c->dPairsRaw, c->dPairs, c->dTileCnt, c->dTileBase, c->dTileDst, c->nTiles, c->dLut, c->dThresholds, c->dGrouped, c->stream,
+    CK(launch_bin_group(c->dPairsRaw, c->dPairs, c->dTileCnt, c->dTileBase, c->dTileDst, c->nTiles, c->dLut, c->dThresholds, c->binScale, c->W, c->dGrouped, c->dTileCursor, c->stream,
                         &c->launches));
     if ((rc = timerStop(c, c->tBin))) return rc;
     if ((rc = hookReduce(c, c->dGrouped, tableWords, 0, 0))) return rc;
@@ -658,7 +691,9 @@ int ppp_scan(ppp_ctx* c, uint64_t* grouped, uint64_t* nPairs) {
         std::vector<uint32_t> g(tableWords);
         CK(cudaMemcpyAsync(g.data(), c->dGrouped, tableWords * 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        for (size_t i = 0; i < tableWords; ++i) grouped[i] = g[i];
+        for (int o = 0; o < c->W; ++o)  // device tables are bin-major, the ABI is [overlap][bin][bias][local]
+            for (int b = 0; b < kBins; ++b)
+                for (int k = 0; k < 4; ++k) grouped[((size_t)o * kBins + b) * 4 + k] = g[((size_t)b * c->W + o) * 4 + k];
     }
     if (nPairs) *nPairs = c->nPairs;
     c->haveScan = true;
@@ -672,9 +707,9 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     int rc;
     const int ppIdx = c->ppOv - c->minOv;
     if ((rc = timerStart(c, c->tScore))) return rc;
-    CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->stream, &c->launches));
-    CK(launch_fdr_table(c->dCells, c->dNBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
-    CK(launch_score_pairs(c->dPairs, c->nPairs, c->dFdr, c->dBinMap, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dPairFdr, c->dLoci,
+    CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dCellSums, c->stream, &c->launches));
+    CK(launch_fdr_table(c->dCells, c->dNBins, kBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
+    CK(launch_score_pairs(c->dPairs, c->nPairs, c->dFdr, c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dPairFdr, c->dLoci,
                           c->dNLoci, c->dBlockCnt, c->dScanScratch, c->scanScratchWords, c->stream, &c->launches));
     if ((rc = timerStop(c, c->tScore))) return rc;
     CK(cudaMemcpyAsync(&c->hs->nLoci, c->dNLoci, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -699,12 +734,12 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     if (fdrTable) { tmpFdr.resize(tableWords); CK(cudaMemcpyAsync(tmpFdr.data(), c->dFdr, tableWords * 4, cudaMemcpyDeviceToHost, c->stream)); }
     if (binMap) CK(cudaMemcpyAsync(binMap, c->dBinMap, kBins * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
     if (loci || cells || fdrTable || binMap) CK(cudaStreamSynchronize(c->stream));
-    // device tables use a fixed bin stride of 1000; the ABI returns them densely as [overlap][C][bias][local]
+    // device tables are bin-major; the ABI returns them as [overlap][C][bias][local]
     for (int o = 0; o < c->W; ++o)
         for (uint32_t b = 0; b < C; ++b)
             for (int k = 0; k < 4; ++k) {
-                if (cells) cells[((size_t)o * C + b) * 4 + k] = tmpCells[((size_t)o * kBins + b) * 4 + k];
-                if (fdrTable) fdrTable[((size_t)o * C + b) * 4 + k] = tmpFdr[((size_t)o * kBins + b) * 4 + k];
+                if (cells) cells[((size_t)o * C + b) * 4 + k] = tmpCells[((size_t)b * c->W + o) * 4 + k];
+                if (fdrTable) fdrTable[((size_t)o * C + b) * 4 + k] = tmpFdr[((size_t)b * c->W + o) * 4 + k];
             }
     if (nBins) *nBins = C;
     if (loci) *loci = c->hLoci;

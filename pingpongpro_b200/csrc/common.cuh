@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ppp_b200.h"
 #include "ppp_types.h"
 
 namespace pppk {
@@ -20,7 +21,8 @@ constexpr uint32_t kA10Bit = 0x80000000u;
 constexpr uint32_t kValueMask = 0x7fffffffu;
 constexpr uint32_t kSaturate = 1u << 24;        // float counters stop at 2^24
 constexpr int kBins = 1000;                     // HEIGHT_SCORE_BINS, pingpongpro.cpp:164
-constexpr uint32_t kLowBins = 2048;             // smem-privatised part of the height histogram
+constexpr uint32_t kScanLowBins = 512;          // smem-privatised part of the height histogram
+constexpr int kScanTile = 4096;                 // positions per CTA iteration of the fused scan (G is a multiple)
 constexpr uint32_t kFreqCapacity = kSaturate + 1;  // rounded heights never exceed 2^24
 constexpr uint32_t kInvalidPos = 0xffffffffu;
 
@@ -51,8 +53,8 @@ struct ScanParams {
     uint32_t nTiles;
     int minOv, W;
     uint32_t haloLo, haloHi;  // minus-strand words in [haloLo, haloHi) are halo copies (not counted)
-    unsigned long long* freqLow;  // [kLowBins]
-    uint32_t* freqTail;           // [kFreqCapacity] (entries >= kLowBins used)
+    unsigned long long* freqLow;  // [kScanLowBins]
+    uint32_t* freqTail;           // [kFreqCapacity] (entries >= kScanLowBins used)
     uint32_t* maxHeight;
     PairRec* pairsRaw;
     unsigned long long* cursor;   // total records produced (may exceed capacity)
@@ -95,15 +97,17 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
 cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* freqTail, const uint32_t* maxHeight, float* lut,
                             unsigned long long* maxCount, cudaStream_t s, int* launches);
 cudaError_t launch_bin_group(const PairRec* raw, PairRec* ordered, const uint32_t* tileCnt, const uint32_t* tileBase, const uint32_t* tileDst, uint32_t nTiles,
-                             const float* lut, const float* thresholds, uint32_t* grouped, cudaStream_t s, int* launches);
-cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, cudaStream_t s, int* launches);
-cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, int W, int ppIdx, const double* xs, const double* ws, int nSteps, float* fdr,
-                             cudaStream_t s, int* launches);
+                             const float* lut, const float* thresholds, float binScale, int W, uint32_t* grouped, uint32_t* tileCursor, cudaStream_t s,
+                             int* launches);
+cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, uint16_t* groupStart, unsigned long long* sums,
+                            cudaStream_t s, int* launches);
+cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, uint32_t maxBins, int W, int ppIdx, const double* xs, const double* ws, int nSteps,
+                             float* fdr, cudaStream_t s, int* launches);
 struct LocusOut {
     uint32_t contig, position;
     float fdr, rp, rm;
 };
-cudaError_t launch_score_pairs(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int ppIdx, uint32_t minHeight,
+cudaError_t launch_score_pairs(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
                                const Slot* slots, uint32_t nSlots, float* pairFdr, LocusOut* loci, unsigned long long* nLoci, uint32_t* blockCnt,
                                uint32_t* scanScratch, size_t scanScratchWords, cudaStream_t s, int* launches);
 

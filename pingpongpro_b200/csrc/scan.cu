@@ -9,19 +9,19 @@
 // grouped counter :605) is deferred to k_bin_group, which touches only the (few) signature records.
 // Fusing the two passes halves the DRAM traffic of "K2 + K3" from 16 to 8 bytes per position.
 //
-// Tiling: a CTA of 256 threads walks tiles of 2048 positions.  Each thread owns 8 consecutive positions and
-// loads them with ONE streaming 256-bit load per strand (LDG.E.256, L1::no_allocate): a warp-wide load covers
-// 1 KB of contiguous memory.  Both strands of the tile plus a 32-word right halo of the minus strand are staged
-// in shared memory together with a 1-bit/word occupancy mask of the minus strand (built with warp shuffles), so
-// the window test of a plus stack is one 64-bit funnel shift instead of `W` loads.
-// The kernel is instruction-issue sensitive (the stack arrays are sparse, but in a 32-wide warp "some lane has a
-// stack" is almost always true), so all per-stack work loops over the SET BITS of the thread's own occupancy
-// mask, and all per-signature work is made dense: candidates write (position, overlap) entries in record
-// order into a shared list (block scan of the counts), then one thread per RECORD evaluates the window.
-// Shared memory is double buffered: two barriers per tile (+1 when the tile has signatures).  The records of a
-// tile are written contiguously (one atomicAdd on a global cursor) in (position, overlap) order and the tile's
-// run is published in tileBase/tileCnt; k_bin_group later copies the runs into global position order.
-// Histogram: bins < 2048 are privatised per CTA in shared memory (height 1, by far the most common, is
+// Tiling: a CTA of 128 threads walks tiles of 4096 positions; each thread owns 32 CONSECUTIVE positions, i.e.
+// exactly one 32-bit occupancy word per strand.  They are fetched as four 256-bit streaming loads per strand
+// (LDG.E.256, L1::no_allocate, one full 32-byte sector each) through a two-deep register pipeline that also
+// prefetches the next tile, and staged in shared memory with the 1-bit/word occupancy mask of the minus strand;
+// the window test of a plus stack is then one 64-bit funnel shift over two mask words instead of `W` loads.
+// The stack arrays are sparse, but in a 32-wide warp "some lane has a stack here" is almost always true, so
+// per-position branches buy nothing.  Instead all per-stack work loops over the SET BITS of the thread's own
+// occupancy words (trip count = the busiest lane's stack count; 32 positions per thread amortise it), and all
+// per-signature work is made dense: candidates are ranked with a block scan, listed in shared memory, and one
+// thread per CANDIDATE evaluates the window and writes its records.  The records of a tile are written
+// contiguously (one atomicAdd on a global cursor) in (position, overlap) order and the tile's run is published in
+// tileBase/tileCnt; k_bin_group later copies the runs into global position order.
+// Histogram: bins < 512 are privatised per CTA in shared memory (height 1, by far the most common, is
 // counted in a register), the rare tall stacks go to a global table with red.add.
 //
 // Bound: HBM bandwidth.  Algorithmic bytes per launch: 8 * G + 16 * P  (G padded positions, P signatures).
@@ -31,17 +31,13 @@ namespace pppk {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kTile = 2048;
+constexpr int kThreads = 128;
+constexpr int kPerThread = 32;                 // consecutive positions owned by one thread = one occupancy word
+constexpr int kTile = kScanTile;               // 4096 positions per CTA iteration
 constexpr int kHalo = 32;
 constexpr int kMaskWords = kTile / 32 + 2;
-constexpr int kCandCap = 512;   // candidates staged per round (a tile rarely has more)
-
-__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
+constexpr int kCandCap = 224;                  // candidates staged per round
+static_assert(kTile == kThreads * kPerThread, "tile geometry");
 
 __device__ __forceinline__ void ld_stream256(uint32_t (&r)[8], const uint32_t* p) {  // LDG.E.256, 32-byte aligned
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -58,98 +54,112 @@ __device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
     return v;
 }
 
-__device__ __forceinline__ uint32_t nz_nibble(const uint4& v) {
-    return (v.x != 0u ? 1u : 0u) | (v.y != 0u ? 2u : 0u) | (v.z != 0u ? 4u : 0u) | (v.w != 0u ? 8u : 0u);
+// Shared-memory index of tile position p.  A thread owns one 32-word row; without a swizzle every 128-bit store of a
+// warp would hit the same 4 banks (32-way conflict).  The 4-word groups of a row are XOR-permuted with the row
+// number, so 8 consecutive rows cover all 32 banks; positions stay addressable one by one (the window reads cross rows).
+__device__ __forceinline__ uint32_t sw(uint32_t p) { return p ^ (((p >> 5) & 7u) << 2); }
+
+__device__ __forceinline__ uint32_t nz_byte(const uint32_t (&w)[8]) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m |= (w[j] != 0u ? 1u : 0u) << j;
+    return m;
 }
 
 template <int REPR>
-__global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
-    __shared__ __align__(32) uint32_t sP[2][kTile];          // plus strand of the tile
-    __shared__ __align__(32) uint32_t sM[2][kTile + kHalo];  // minus strand + right halo
-    __shared__ uint32_t sMask[2][kMaskWords];                // 1 bit per minus word: stack present
-    __shared__ uint32_t sHist[kLowBins];
+__global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
+    __shared__ __align__(32) uint32_t sP[kTile];          // plus strand of the tile
+    __shared__ __align__(32) uint32_t sM[kTile + kHalo];  // minus strand + right halo
+    __shared__ uint32_t sMask[kMaskWords];                // 1 bit per minus word: stack present
+    __shared__ uint32_t sHist[kScanLowBins];
     __shared__ uint32_t sWarpTot[kThreads / 32];
     __shared__ unsigned long long sBase;
-    __shared__ uint32_t sCandBits[kCandCap];                 // per candidate (plus stack with partners): present overlaps
-    __shared__ uint16_t sCandTp[kCandCap], sCandOff[kCandCap];  // its tile position / first record of the tile it writes
+    __shared__ uint32_t sCandBits[kCandCap], sCandOff[kCandCap];  // per candidate: present overlaps / first record (tile-relative)
+    __shared__ uint16_t sCandTp[kCandCap];                        // its tile position
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < (int)kLowBins; k += kThreads) sHist[k] = 0;
-    if (tid < 2) sMask[tid][kMaskWords - 1] = 0;
+    for (int k = tid; k < (int)kScanLowBins; k += kThreads) sHist[k] = 0;
+    if (tid == 0) sMask[kMaskWords - 1] = 0;
     __syncthreads();
 
     const uint32_t ONE = REPR == kReprInt ? 1u : 0x3f800000u;
     const uint32_t wMask = P.W >= 32 ? 0xffffffffu : ((1u << P.W) - 1u);
     const float fW = (float)P.W;
-    const uint32_t myPos = (uint32_t)tid * 8u;  // this thread owns 8 consecutive positions of the tile
+    const uint32_t myPos = (uint32_t)tid * kPerThread;  // this thread owns 32 consecutive positions of the tile
+    const uint32_t rowSw = (uint32_t)tid & 7u;          // group permutation of this thread's row (see sw())
     uint32_t ones = 0, localMax = 0;
 
-    // software pipeline: the loads of tile t+1 are issued as soon as tile t has been staged, so they are in
-    // flight while tile t is processed
-    uint32_t pw[8], mw[8];
-    uint4 h = make_uint4(0, 0, 0, 0);
-    auto issue_loads = [&](uint32_t t) {
-        const uint32_t tb = t * (uint32_t)kTile;
-        ld_stream256(pw, P.H + tb + myPos);
-        ld_stream256(mw, P.H + P.G + tb + myPos);
-        if (tid < kHalo / 4) h = ld_stream(reinterpret_cast<const uint4*>(P.H + P.G + tb + kTile) + tid);
+    // register pipeline: the 32 positions are fetched as 4 sub-steps of 8 words per strand (LDG.E.256); the loads
+    // of sub-step s+1 (or of the next tile's sub-step 0) are in flight while sub-step s is staged.
+    uint32_t pa[8], ma[8], pb[8], mb[8], hw[8];
+    auto issue = [&](uint32_t (&p)[8], uint32_t (&m)[8], uint32_t t, int sub) {
+        const uint32_t* src = P.H + (size_t)t * kTile + myPos + sub * 8;
+        ld_stream256(p, src);
+        ld_stream256(m, src + P.G);
     };
-    if (blockIdx.x < P.nTiles) issue_loads(blockIdx.x);
+    if (blockIdx.x < P.nTiles) issue(pa, ma, blockIdx.x, 0);
 
-    int buf = 0;
-    for (uint32_t tile = blockIdx.x; tile < P.nTiles; tile += gridDim.x, buf ^= 1) {
+    for (uint32_t tile = blockIdx.x; tile < P.nTiles; tile += gridDim.x) {
         const uint32_t tileBase = tile * (uint32_t)kTile;
-
-        // stage both strands (the rare paths below index them dynamically) + the minus occupancy mask
-        *reinterpret_cast<uint4*>(&sP[buf][myPos]) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-        *reinterpret_cast<uint4*>(&sP[buf][myPos + 4]) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
-        *reinterpret_cast<uint4*>(&sM[buf][myPos]) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-        *reinterpret_cast<uint4*>(&sM[buf][myPos + 4]) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+        if (tid < kHalo / 8) ld_stream256(hw, P.H + P.G + tileBase + kTile + tid * 8);
         uint32_t nzP = 0, nzM = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            nzP |= (pw[j] != 0u ? 1u : 0u) << j;
-            nzM |= (mw[j] != 0u ? 1u : 0u) << j;
-        }
-        {
-            uint32_t v = nzM << (8 * (lane & 3));
-            v |= __shfl_xor_sync(0xffffffffu, v, 1);
-            v |= __shfl_xor_sync(0xffffffffu, v, 2);
-            if ((lane & 3) == 0) sMask[buf][warp * 8 + (lane >> 2)] = v;
-        }
+        auto stage = [&](const uint32_t (&p)[8], const uint32_t (&m)[8], int sub) {
+            const uint32_t g0 = myPos + (((uint32_t)(sub * 2) ^ rowSw) << 2), g1 = myPos + (((uint32_t)(sub * 2 + 1) ^ rowSw) << 2);
+            *reinterpret_cast<uint4*>(&sP[g0]) = make_uint4(p[0], p[1], p[2], p[3]);
+            *reinterpret_cast<uint4*>(&sP[g1]) = make_uint4(p[4], p[5], p[6], p[7]);
+            *reinterpret_cast<uint4*>(&sM[g0]) = make_uint4(m[0], m[1], m[2], m[3]);
+            *reinterpret_cast<uint4*>(&sM[g1]) = make_uint4(m[4], m[5], m[6], m[7]);
+            nzP |= nz_byte(p) << (sub * 8);
+            nzM |= nz_byte(m) << (sub * 8);
+        };
+        issue(pb, mb, tile, 1);
+        stage(pa, ma, 0);
+        issue(pa, ma, tile, 2);
+        stage(pb, mb, 1);
+        issue(pb, mb, tile, 3);
+        stage(pa, ma, 2);
+        if (tile + gridDim.x < P.nTiles) issue(pa, ma, tile + gridDim.x, 0);  // next tile, in flight during the phases below
+        stage(pb, mb, 3);
+        sMask[tid] = nzM;
         if (warp == 0) {
-            if (lane < kHalo / 4) *reinterpret_cast<uint4*>(&sM[buf][kTile + lane * 4]) = h;
-            uint32_t v = lane < kHalo / 4 ? nz_nibble(h) << (4 * lane) : 0u;
+            uint32_t v = 0;
+            if (lane < kHalo / 8) {
+                *reinterpret_cast<uint4*>(&sM[kTile + lane * 8]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(&sM[kTile + lane * 8 + 4]) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                v = nz_byte(hw) << (8 * lane);
+            }
             v |= __shfl_xor_sync(0xffffffffu, v, 1);
             v |= __shfl_xor_sync(0xffffffffu, v, 2);
-            v |= __shfl_xor_sync(0xffffffffu, v, 4);
-            if (lane == 0) sMask[buf][kTile / 32] = v;
+            if (lane == 0) sMask[kTile / 32] = v;
         }
-        if (tile + gridDim.x < P.nTiles) issue_loads(tile + gridDim.x);  // prefetch (pw / mw / h are dead from here on)
 
-        // K2: height histogram.  Loop over the set bits of this thread's own occupancy mask (iterations = the
-        // busiest lane's stack count, not 16), re-reading the word it staged itself.
+        // K2: height histogram.  Loop over the set bits of this thread's own occupancy words (iterations = the
+        // busiest lane's stack count, not 64), re-reading the word it staged itself.
         {
-            uint32_t nz = nzP | (nzM << 8);
+            uint32_t mm = nzM;
             if (tileBase < P.haloHi && tileBase + kTile > P.haloLo) {  // halo copies of a neighbouring shard are not counted
+                uint32_t first = tileBase + myPos;
+                uint32_t lo = P.haloLo > first ? P.haloLo - first : 0u, hi = P.haloHi > first ? P.haloHi - first : 0u;
+                uint32_t below = lo >= 32 ? 0xffffffffu : ((1u << lo) - 1u), upto = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+                mm &= below | ~upto;
+            }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint32_t lp = tileBase + myPos + j;
-                    if (lp >= P.haloLo && lp < P.haloHi) nz &= ~(256u << j);
+            for (int strand = 0; strand < 2; ++strand) {
+                uint32_t nz = strand ? mm : nzP;
+                const uint32_t* src = strand ? sM : sP;
+                while (nz) {
+                    int b = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    uint32_t wv = src[myPos + ((uint32_t)b ^ (rowSw << 2))];
+                    if ((wv & kValueMask) == ONE) { ++ones; continue; }
+                    uint32_t r = word_round_height<REPR>(wv);
+                    if (r < kScanLowBins) atomicAdd(&sHist[r], 1u);
+                    else atomicAdd(&P.freqTail[r], 1u);
+                    localMax = max(localMax, r);
                 }
             }
-            while (nz) {
-                int b = __ffs(nz) - 1;
-                nz &= nz - 1;
-                uint32_t wv = (b & 8) ? sM[buf][myPos + (b & 7)] : sP[buf][myPos + b];
-                if ((wv & kValueMask) == ONE) { ++ones; continue; }
-                uint32_t r = word_round_height<REPR>(wv);
-                if (r < kLowBins) atomicAdd(&sHist[r], 1u);
-                else atomicAdd(&P.freqTail[r], 1u);
-                localMax = max(localMax, r);
-            }
         }
-        __syncthreads();  // (A) both strands + mask of this buffer are complete
+        __syncthreads();  // (A) both strands + mask are complete
 
         // K3: candidates = plus stacks with at least one minus stack at overlaps min..max
         uint32_t cnt = 0, ncand = 0, cand = 0;
@@ -159,13 +169,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
                 int b = __ffs(nz) - 1;
                 nz &= nz - 1;
                 uint32_t bit = myPos + b + P.minOv;
-                uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
+                uint32_t bits = __funnelshift_r(sMask[bit >> 5], sMask[(bit >> 5) + 1], bit & 31) & wMask;
                 if (bits) { cnt += __popc(bits); ++ncand; cand |= 1u << b; }
             }
         }
         // records and candidates are ordered (thread, position[, overlap]) == (position[, overlap]);
-        // one warp scan carries both counters (records < 2^14 per warp in the low half, candidates above)
-        const uint32_t packed = cnt | (ncand << 16);
+        // one warp scan carries both counters (records in the low 20 bits, candidates above)
+        const uint32_t packed = cnt | (ncand << 20);
         const uint32_t inc = warp_inclusive(packed, lane);
         if (lane == 31) sWarpTot[warp] = inc;
         __syncthreads();  // (B)
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
             if (w < warp) beforeP += t;
             totalP += t;
         }
-        const uint32_t total = totalP & 0xffffu, candTotal = totalP >> 16;
+        const uint32_t total = totalP & 0xfffffu, candTotal = totalP >> 20;
         if (tid == 0) {
             unsigned long long base = total ? atomicAdd(P.cursor, (unsigned long long)total) : 0ull;
             sBase = base;
@@ -185,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
         }
         if (total) {  // block-uniform: the rare path, processed densely (one thread per candidate)
             const uint32_t mine = beforeP + inc - packed;
-            const uint32_t firstRec = mine & 0xffffu, firstCand = mine >> 16;  // tile-relative ranks of this thread's first record / candidate
+            const uint32_t firstRec = mine & 0xfffffu, firstCand = mine >> 20;  // tile-relative ranks of this thread's first record / candidate
             for (uint32_t cbase = 0; cbase < candTotal; cbase += kCandCap) {
                 if (cbase) __syncthreads();  // the previous round's list is no longer read
                 uint32_t off = firstRec, rank = firstCand, cm = cand;
@@ -193,9 +203,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
                     int b = __ffs(cm) - 1;
                     cm &= cm - 1;
                     uint32_t tp = myPos + b, bit = tp + P.minOv;
-                    uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
+                    uint32_t bits = __funnelshift_r(sMask[bit >> 5], sMask[(bit >> 5) + 1], bit & 31) & wMask;
                     uint32_t slot = rank - cbase;  // wraps to a huge value for earlier rounds
-                    if (slot < (uint32_t)kCandCap) { sCandTp[slot] = (uint16_t)tp; sCandBits[slot] = bits; sCandOff[slot] = (uint16_t)off; }
+                    if (slot < (uint32_t)kCandCap) { sCandTp[slot] = (uint16_t)tp; sCandBits[slot] = bits; sCandOff[slot] = off; }
                     off += __popc(bits);
                     ++rank;
                 }
@@ -204,11 +214,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
                 for (uint32_t c = tid; c < nIn; c += kThreads) {
                     const uint32_t tp = sCandTp[c];
                     uint32_t bits = sCandBits[c];
-                    const uint32_t wp = sP[buf][tp];
-                    const uint32_t* win = &sM[buf][tp + P.minOv];
+                    const uint32_t wp = sP[sw(tp)];
+                    const uint32_t w0 = tp + P.minOv;  // first window position (tile-relative)
                     float sum = 0.0f, mx = 0.0f;
                     for (int q = 0; q < P.W; ++q) {                          // :564-577 (absent stacks add +0)
-                        float mq = word_height<REPR>(win[q]);
+                        float mq = word_height<REPR>(sM[sw(w0 + q)]);
                         sum = __fadd_rn(sum, mq);
                         mx = fmaxf(mx, mq);
                     }
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
                     while (bits) {                                            // :584-586
                         const int o = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        const uint32_t wm = win[o];
+                        const uint32_t wm = sM[sw(w0 + o)];
                         const float mo = word_height<REPR>(wm);
                         const float local = __fdiv_rn(__fsub_rn(mo, __fsub_rn(mean, __fdiv_rn(mo, fW))), mx);  // :597
                         const uint32_t lbin = ((double)local < 0.2) ? 1u : 0u;     // :599
@@ -236,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
                 }
             }
         }
+        __syncthreads();  // (E) the staged tile is no longer read
     }
 
     // flush the privatised histogram
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
     for (int d = 16; d > 0; d >>= 1) localMax = max(localMax, __shfl_xor_sync(0xffffffffu, localMax, d));
     if (lane == 0 && localMax) atomicMax(P.maxHeight, localMax);
     __syncthreads();
-    for (int k = tid; k < (int)kLowBins; k += kThreads) {
+    for (int k = tid; k < (int)kScanLowBins; k += kThreads) {
         uint32_t c = sHist[k];
         if (c) atomicAdd(&P.freqLow[k], (unsigned long long)c);
     }
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(256) k_freq_lut(const unsigned long long* __re
     const uint32_t maxH = *maxHeight;
     unsigned long long best = 0;
     for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= maxH; h += (uint64_t)gridDim.x * blockDim.x) {
-        unsigned long long c = h < kLowBins ? freqLow[h] : (unsigned long long)freqTail[h];
+        unsigned long long c = h < kScanLowBins ? freqLow[h] : (unsigned long long)freqTail[h];
         lut[h] = (float)(c < kSaturate ? (uint32_t)c : kSaturate);
         best = c > best ? c : best;
     }
@@ -270,66 +281,86 @@ __global__ void __launch_bounds__(256) k_freq_lut(const unsigned long long* __re
 }
 
 // K3 part 2: height-score bin (:589-594) + grouped counter (:605) of every signature, and the copy of the
-// per-tile runs into global (position, overlap) order.  A block handles 256 consecutive tiles.
-constexpr int kBgThreads = 256;
+// per-tile runs into global (position, overlap) order.  Persistent blocks; each WARP takes whole tiles, so a
+// record's tile (and with it its ordered destination) is known without a search.
+// The bin of a height-score product is the number of host-built thresholds <= hs (see api.cu).  A device log10
+// approximation proposes the bin, two short loops against the exact thresholds correct it, so the result is the
+// exact step function whatever the approximation error.
+// The grouped counters are concentrated on a few hundred hot cells (singleton x singleton pairs all land in the
+// top bin), so updates are merged per warp (match.any), then per block in a shared-memory hash table that lives
+// for the whole kernel; only the table's entries reach the global (L2) counters.
+constexpr int kBgThreads = 512;
+constexpr int kBgWarps = kBgThreads / 32;
+constexpr int kBgHash = 4096;
+constexpr uint32_t kBgEmpty = 0xffffffffu;
 __global__ void __launch_bounds__(kBgThreads) k_bin_group(const PairRec* __restrict__ raw, PairRec* __restrict__ ordered, const uint32_t* __restrict__ tileCnt,
                                                           const uint32_t* __restrict__ tileBase, const uint32_t* __restrict__ tileDst, uint32_t nTiles,
-                                                          const float* __restrict__ lut, const float* __restrict__ thresholds, uint32_t* __restrict__ grouped) {
+                                                          const float* __restrict__ lut, const float* __restrict__ thresholds, float binScale, int W,
+                                                          uint32_t* __restrict__ grouped, uint32_t* __restrict__ tileCursor) {
     __shared__ float sThr[kBins];
-    __shared__ uint32_t sStart[kBgThreads + 1];  // exclusive prefix of the block's tile counts
-    __shared__ uint32_t sSrc[kBgThreads];
-    __shared__ uint32_t sWarp[kBgThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ uint32_t sKey[kBgHash], sVal[kBgHash];
+    const int tid = threadIdx.x, lane = tid & 31;
     for (int k = tid; k < kBins - 1; k += kBgThreads) sThr[k] = thresholds[k];
-    uint32_t tile = blockIdx.x * kBgThreads + tid;
-    uint32_t c = tile < nTiles ? tileCnt[tile] : 0u;
-    sSrc[tid] = tile < nTiles ? tileBase[tile] : 0u;
-    uint32_t inc = warp_inclusive(c, lane);
-    if (lane == 31) sWarp[warp] = inc;
+    for (int k = tid; k < kBgHash; k += kBgThreads) { sKey[k] = kBgEmpty; sVal[k] = 0; }
     __syncthreads();
-    uint32_t before = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kBgThreads / 32; ++w) {
-        uint32_t t = sWarp[w];
-        if (w < warp) before += t;
-        total += t;
+    auto bin_of = [&](float hs) {
+        int b = (int)(__log10f(hs) * binScale + 0.5f);             // proposal only
+        b = min(max(b, 0), kBins - 1);
+        while (b > 0 && sThr[b - 1] > hs) --b;                    // exact: bin = #thresholds <= hs
+        while (b < kBins - 1 && sThr[b] <= hs) ++b;
+        return b;
+    };
+    auto count_cell = [&](bool ok, uint32_t cell) {                // :605, one update per distinct cell per warp
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (!ok) return;
+        const unsigned peers = __match_any_sync(act, cell);
+        if (lane != __ffs(peers) - 1) return;
+        const uint32_t n = (uint32_t)__popc(peers);
+        uint32_t h = (cell * 2654435761u) >> 20;
+        for (int probe = 0; probe < 32; ++probe) {
+            uint32_t old = atomicCAS(&sKey[h], kBgEmpty, cell);
+            if (old == kBgEmpty || old == cell) { atomicAdd(&sVal[h], n); return; }
+            h = (h + 1) & (kBgHash - 1);
+        }
+        atomicAdd(&grouped[cell], n);
+    };
+    // tiles are handed out dynamically (signature-dense tiles take much longer than empty ones)
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(tileCursor, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= nTiles) break;
+        const uint32_t cnt = tileCnt[tile];
+        if (cnt == 0) continue;
+        const size_t src = tileBase[tile], dst = tileDst[tile];
+        for (uint32_t base = 0; base < cnt; base += 64) {  // two records per lane in flight
+            const uint32_t i0 = base + lane, i1 = base + 32 + lane;
+            const bool ok0 = i0 < cnt, ok1 = i1 < cnt;
+            PairRec r0 = {0, 1.f, 1.f, 0}, r1 = {0, 1.f, 1.f, 0};
+            if (ok0) *reinterpret_cast<uint4*>(&r0) = *reinterpret_cast<const uint4*>(&raw[src + i0]);
+            if (ok1) *reinterpret_cast<uint4*>(&r1) = *reinterpret_cast<const uint4*>(&raw[src + i1]);
+            const float fp0 = lut[round_height(r0.rp)], fm0 = lut[round_height(r0.rm)];  // heightScoreMap[0.5 + reads], :582 / :589
+            const float fp1 = lut[round_height(r1.rp)], fm1 = lut[round_height(r1.rm)];
+            uint32_t cell0 = 0, cell1 = 0;
+            if (ok0) {
+                int b = bin_of(__fmul_rn(fp0, fm0));
+                r0.misc |= (uint32_t)b << 7;
+                cell0 = ((((uint32_t)b * (uint32_t)W + (r0.misc & 31u)) * 2u + ((r0.misc >> 6) & 1u)) * 2u) + ((r0.misc >> 5) & 1u);  // bin-major table
+                *reinterpret_cast<uint4*>(&ordered[dst + i0]) = *reinterpret_cast<uint4*>(&r0);
+            }
+            if (ok1) {
+                int b = bin_of(__fmul_rn(fp1, fm1));
+                r1.misc |= (uint32_t)b << 7;
+                cell1 = ((((uint32_t)b * (uint32_t)W + (r1.misc & 31u)) * 2u + ((r1.misc >> 6) & 1u)) * 2u) + ((r1.misc >> 5) & 1u);
+                *reinterpret_cast<uint4*>(&ordered[dst + i1]) = *reinterpret_cast<uint4*>(&r1);
+            }
+            count_cell(ok0, cell0);
+            count_cell(ok1, cell1);
+        }
     }
-    sStart[tid] = before + inc - c;
-    if (tid == 0) sStart[kBgThreads] = total;
     __syncthreads();
-    if (total == 0) return;
-    const uint32_t dstBase = tileDst[blockIdx.x * kBgThreads];  // ordered index of the block's first record
-    const uint32_t rounds = (total + kBgThreads - 1) / kBgThreads;
-    for (uint32_t it = 0; it < rounds; ++it) {
-        uint32_t item = it * kBgThreads + tid;
-        bool ok = item < total;
-        PairRec r;
-        uint32_t cell = 0;
-        if (ok) {
-            int lo = 0, hi = kBgThreads;  // last tile slot whose start <= item
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (sStart[mid] <= item) lo = mid; else hi = mid;
-            }
-            *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(&raw[(size_t)sSrc[lo] + (item - sStart[lo])]);
-            float fp = lut[round_height(r.rp)];                       // heightScoreMap[0.5 + reads], :582
-            float fm = lut[round_height(r.rm)];                       // :589
-            float hs = __fmul_rn(fp, fm);
-            int b = 0, e = kBins - 1;                                 // bin = #thresholds <= hs (host-built, see api.cu)
-            while (b < e) {
-                int mid = (b + e) >> 1;
-                if (sThr[mid] <= hs) b = mid + 1; else e = mid;
-            }
-            r.misc |= (uint32_t)b << 7;
-            cell = (((r.misc & 31u) * kBins + (uint32_t)b) * 2u + ((r.misc >> 6) & 1u)) * 2u + ((r.misc >> 5) & 1u);
-            *reinterpret_cast<uint4*>(&ordered[(size_t)dstBase + item]) = *reinterpret_cast<uint4*>(&r);
-        }
-        unsigned act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            unsigned peers = __match_any_sync(act, cell);
-            if (lane == __ffs(peers) - 1) atomicAdd(&grouped[cell], (uint32_t)__popc(peers));  // :605
-        }
-    }
+    for (int k = tid; k < kBgHash; k += kBgThreads)
+        if (sKey[k] != kBgEmpty) atomicAdd(&grouped[sKey[k]], sVal[k]);
 }
 
 }  // namespace
@@ -339,7 +370,7 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int perSm = 4;
+    int perSm = 6;
     if (repr == kReprInt) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprInt>, kThreads, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprFloat>, kThreads, 0);
     if (perSm < 1) perSm = 1;
@@ -359,10 +390,17 @@ cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* f
 }
 
 cudaError_t launch_bin_group(const PairRec* raw, PairRec* ordered, const uint32_t* tileCnt, const uint32_t* tileBase, const uint32_t* tileDst, uint32_t nTiles,
-                             const float* lut, const float* thresholds, uint32_t* grouped, cudaStream_t s, int* launches) {
+                             const float* lut, const float* thresholds, float binScale, int W, uint32_t* grouped, uint32_t* tileCursor, cudaStream_t s,
+                             int* launches) {
     if (nTiles == 0) return cudaSuccess;
-    unsigned blocks = (nTiles + kBgThreads - 1) / kBgThreads;
-    k_bin_group<<<blocks, kBgThreads, 0, s>>>(raw, ordered, tileCnt, tileBase, tileDst, nTiles, lut, thresholds, grouped);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned blocks = (nTiles + kBgWarps - 1) / kBgWarps;
+    if (blocks > (unsigned)sms * 2u) blocks = (unsigned)sms * 2u;
+    cudaError_t e = cudaMemsetAsync(tileCursor, 0, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    k_bin_group<<<blocks, kBgThreads, 0, s>>>(raw, ordered, tileCnt, tileBase, tileDst, nTiles, lut, thresholds, binScale, W, grouped, tileCursor);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

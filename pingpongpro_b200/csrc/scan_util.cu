@@ -6,9 +6,9 @@
 namespace pppk {
 
 namespace {
-constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 4;
-constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr int kPrefixThreads = 1024;
+constexpr int kPrefixItems = 4;
+constexpr int kPrefixTile = kPrefixThreads * kPrefixItems;
 
 __device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
 #pragma unroll
@@ -38,12 +38,12 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* total,
     return r;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_prefix_reduce(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ blockSums) {
+__global__ void __launch_bounds__(kPrefixThreads) k_prefix_reduce(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ blockSums) {
     __shared__ uint32_t sh[33];
-    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    size_t base = (size_t)blockIdx.x * kPrefixTile + (size_t)threadIdx.x * kPrefixItems;
     uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
+    for (int k = 0; k < kPrefixItems; ++k)
         if (base + k < n) s += in[base + k];
     uint32_t total;
     block_exclusive(s, &total, sh);
@@ -51,10 +51,10 @@ __global__ void __launch_bounds__(kScanThreads) k_prefix_reduce(const uint32_t* 
 }
 
 // In-place exclusive scan of a short array by one block (loops with a carry).
-__global__ void __launch_bounds__(kScanThreads) k_prefix_single(uint32_t* data, size_t n) {
+__global__ void __launch_bounds__(kPrefixThreads) k_prefix_single(uint32_t* data, size_t n) {
     __shared__ uint32_t sh[33];
     uint32_t carry = 0;
-    for (size_t base = 0; base < n; base += kScanThreads) {
+    for (size_t base = 0; base < n; base += kPrefixThreads) {
         size_t i = base + threadIdx.x;
         uint32_t v = i < n ? data[i] : 0;
         uint32_t total;
@@ -64,36 +64,36 @@ __global__ void __launch_bounds__(kScanThreads) k_prefix_single(uint32_t* data, 
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_prefix_apply(const uint32_t* in, uint32_t* out, size_t n, const uint32_t* __restrict__ blockSums) {
+__global__ void __launch_bounds__(kPrefixThreads) k_prefix_apply(const uint32_t* in, uint32_t* out, size_t n, const uint32_t* __restrict__ blockSums) {
     __shared__ uint32_t sh[33];
-    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
+    size_t base = (size_t)blockIdx.x * kPrefixTile + (size_t)threadIdx.x * kPrefixItems;
+    uint32_t v[kPrefixItems];
     uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
+    for (int k = 0; k < kPrefixItems; ++k) {
         v[k] = base + k < n ? in[base + k] : 0;
         s += v[k];
     }
     uint32_t total;
     uint32_t ex = block_exclusive(s, &total, sh) + blockSums[blockIdx.x];
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
+    for (int k = 0; k < kPrefixItems; ++k) {
         if (base + k < n) out[base + k] = ex;
         ex += v[k];
     }
 }
 }  // namespace
 
-size_t exclusive_scan_scratch_words(size_t n) { return (n + kScanTile - 1) / kScanTile + 1; }
+size_t exclusive_scan_scratch_words(size_t n) { return (n + kPrefixTile - 1) / kPrefixTile + 1; }
 
 // out[i] = sum(in[0..i)).  in == out is allowed.  scratch: exclusive_scan_scratch_words(n) words.
 cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* scratch, size_t scratchWords, cudaStream_t s, int* launches) {
     if (n == 0) return cudaSuccess;
-    size_t nBlocks = (n + kScanTile - 1) / kScanTile;
+    size_t nBlocks = (n + kPrefixTile - 1) / kPrefixTile;
     if (scratchWords < nBlocks) return cudaErrorInvalidValue;
-    k_prefix_reduce<<<(unsigned)nBlocks, kScanThreads, 0, s>>>(in, n, scratch);
-    k_prefix_single<<<1, kScanThreads, 0, s>>>(scratch, nBlocks);
-    k_prefix_apply<<<(unsigned)nBlocks, kScanThreads, 0, s>>>(in, out, n, scratch);
+    k_prefix_reduce<<<(unsigned)nBlocks, kPrefixThreads, 0, s>>>(in, n, scratch);
+    k_prefix_single<<<1, kPrefixThreads, 0, s>>>(scratch, nBlocks);
+    k_prefix_apply<<<(unsigned)nBlocks, kPrefixThreads, 0, s>>>(in, out, n, scratch);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }

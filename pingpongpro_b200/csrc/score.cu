@@ -1,13 +1,13 @@
 // score.cu -- K4: collapseBins (pingpongpro.cpp:631-686), calculateFDRs (:695-754) and the selection of
 // the reported loci (:901-903), all on the device so that scan -> score needs no host round trip.
 //
-//   k_collapse    one CTA; the 1000 x (W x 2 x 2) table is staged through shared memory in chunks and one
-//                 warp walks the bins sequentially (the merge decision of :670 is inherently serial),
-//                 using the same float additions as :658 on counters clipped at 2^24.
-//   k_fdr_table   one thread per (collapsed bin, bias, local, overlap): background mean / sigma (:705-718)
-//                 and the 1001-step Gaussian integral of :724-734 as the same sequence of IEEE double
-//                 operations (__dadd_rn/__dmul_rn/__ddiv_rn, no FMA); x and the weights
-//                 0.01/sqrt(2 pi) * exp(-x^2/2) are tabulated by the host with the host libm.
+//   k_collapse_*  the serial merge decision of :670 runs on per-bin occupancy bit masks (one warp, prefix-OR);
+//                 the float additions of :658 (counters clipped at 2^24) are exact integer sums below 2^24.
+//   k_fdr_table   one warp per (collapsed bin, bias, local, overlap): background mean / sigma (:705-718)
+//                 and the 1001-step Gaussian integral of :724-734: terms evaluated in parallel with IEEE double
+//                 operations (__dadd_rn/__dmul_rn/__ddiv_rn, no FMA), summed by one lane in the reference's
+//                 order; x and the weights 0.01/sqrt(2 pi) * exp(-x^2/2) are tabulated by the host with the
+//                 host libm.
 //   k_score_*     per-signature FDR lookup (:750-753) fused with the -s filter (:903) and an
 //                 order-preserving compaction (count -> scan -> write) of the overlap-10 loci.
 // All of it is latency-bound bookkeeping on kilobytes .. a few megabytes.
@@ -17,68 +17,140 @@ namespace pppk {
 
 namespace {
 
-constexpr int kCollapseThreads = 256;
-constexpr int kChunkBins = 100;
+// Device tables are BIN-MAJOR: cell(bin, overlap, bias, local) = ((bin * W + overlap) * 2 + bias) * 2 + local, so
+// that the W*4 cells of one height-score bin are contiguous (the ABI transposes to [overlap][bin][bias][local]).
+constexpr int kCollapseThreads = 1024;
+constexpr int kMaxCellWords = (PPP_MAX_OVERLAPS * 4 + 31) / 32;  // occupancy bits of one bin's cells
 
-__global__ void __launch_bounds__(kCollapseThreads) k_collapse(const uint32_t* __restrict__ grouped, int W, float* __restrict__ cells,
-                                                                uint16_t* __restrict__ binMap, uint32_t* __restrict__ nBins) {
-    extern __shared__ float sChunk[];  // [kChunkBins][cellsPerBin]
-    const int cellsPerBin = W * 4;
-    const int perLane = (cellsPerBin + 31) / 32;  // <= 4
-    const int tid = threadIdx.x, lane = tid & 31;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+// collapseBins, pingpongpro.cpp:631-686.  A merged bin is closed at the first source bin after which none of its
+// W*4 cells is <= 0 (:661, :670).  Counts are >= 0 and float additions of non-negative numbers never return to 0,
+// so that decision depends only on WHICH cells of each source bin are non-zero:
+//   k_collapse_map   (one CTA) one occupancy bit per (bin, cell); then warp 0 replays the serial walk of :641-673
+//                    32 bins at a time with a prefix-OR over the lanes -> oldBinCollapsedBinMap, group starts, C;
+//   k_collapse_sum   every non-zero cell adds min(count, 2^24) (the reference's float counter) to an exact 64-bit
+//                    sum of its merged bin;
+//   k_collapse_final a sum below 2^24 equals the float additions of :658 exactly (no rounding can have happened);
+//                    a larger one is recomputed with the literal in-order float additions.
+__global__ void __launch_bounds__(kCollapseThreads) k_collapse_map(const uint32_t* __restrict__ grouped, int W, uint16_t* __restrict__ binMap,
+                                                                    uint16_t* __restrict__ groupStart, uint32_t* __restrict__ nBins) {
+    __shared__ uint32_t sOcc[kBins][kMaxCellWords];
+    const int cellsPerBin = W * 4, tid = threadIdx.x;
+    for (int k = tid; k < kBins * kMaxCellWords; k += kCollapseThreads) (&sOcc[0][0])[k] = 0;
+    __syncthreads();
+    const int total = kBins * cellsPerBin;
+    for (int k0 = tid; k0 < total; k0 += kCollapseThreads * 4) {  // 4 independent loads in flight per thread
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { int k = k0 + u * kCollapseThreads; v[u] = k < total ? grouped[k] : 0u; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v[u]) {
+                int k = k0 + u * kCollapseThreads, b = k / cellsPerBin, c = k - b * cellsPerBin;
+                atomicOr(&sOcc[b][c >> 5], 1u << (c & 31));
+            }
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+    const int lane = tid;
+    uint32_t full[kMaxCellWords], carry[kMaxCellWords];
+#pragma unroll
+    for (int w = 0; w < kMaxCellWords; ++w) {
+        int bitsHere = cellsPerBin - 32 * w;
+        full[w] = bitsHere >= 32 ? 0xffffffffu : (bitsHere > 0 ? ((1u << bitsHere) - 1u) : 0u);
+        carry[w] = 0;
+    }
     uint32_t collapsed = 0;
-    bool open = false;  // a collapsed bin is being accumulated (its merge loop has not ended)
-    for (int chunk = 0; chunk < kBins; chunk += kChunkBins) {
-        __syncthreads();
-        for (int k = tid; k < kChunkBins * cellsPerBin; k += kCollapseThreads) {
-            int b = k / cellsPerBin, c = k - b * cellsPerBin;  // c = overlap * 4 + bias * 2 + local
-            uint32_t v = grouped[((size_t)(c >> 2) * kBins + (chunk + b)) * 4 + (c & 3)];
-            sChunk[k] = (float)(v < kSaturate ? v : kSaturate);  // the reference's float counter (:605)
-        }
-        __syncthreads();
-        if (tid < 32) {
-            for (int b = 0; b < kChunkBins; ++b) {
-                if (!open) {  // :644-647
+    int lastClose = -1;
+    if (lane == 0) groupStart[0] = 0;
+    for (int chunk = 0; chunk * 32 < kBins; ++chunk) {
+        const int b = chunk * 32 + lane;
+        const bool valid = b < kBins;
+        uint32_t m[kMaxCellWords];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] = 0.f;
-                    open = true;
-                }
-                bool empty = false;
+        for (int w = 0; w < kMaxCellWords; ++w) m[w] = valid ? sOcc[b][w] : 0u;
+        int start = 0;
+        while (start < 32) {
+            uint32_t pre[kMaxCellWords];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    int c = lane + 32 * q;
-                    if (q < perLane && c < cellsPerBin) {
-                        acc[q] = __fadd_rn(acc[q], sChunk[b * cellsPerBin + c]);  // :658
-                        empty |= acc[q] <= 0.f;                                   // :661
-                    }
-                }
-                if (lane == 0) binMap[chunk + b] = (uint16_t)collapsed;            // :666
-                bool anyEmpty = __any_sync(0xffffffffu, empty);
-                bool last = (chunk + b == kBins - 1);
-                if (!anyEmpty || last) {                                           // :670
+            for (int w = 0; w < kMaxCellWords; ++w) pre[w] = lane >= start ? m[w] : 0u;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        int c = lane + 32 * q;
-                        if (q < perLane && c < cellsPerBin) cells[((size_t)(c >> 2) * kBins + collapsed) * 4 + (c & 3)] = acc[q];
-                    }
-                    ++collapsed;
-                    open = false;
+            for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                for (int w = 0; w < kMaxCellWords; ++w) {
+                    uint32_t t = __shfl_up_sync(0xffffffffu, pre[w], d);
+                    if (lane >= d) pre[w] |= t;
                 }
             }
+            bool complete = valid && lane >= start;
+#pragma unroll
+            for (int w = 0; w < kMaxCellWords; ++w) { pre[w] |= carry[w]; complete &= pre[w] == full[w]; }  // no cell <= 0 (:661)
+            const unsigned closes = __ballot_sync(0xffffffffu, complete);
+            const int fc = closes ? __ffs(closes) - 1 : 31;
+            if (valid && lane >= start && lane <= fc) binMap[b] = (uint16_t)collapsed;  // :666
+            if (!closes) {
+#pragma unroll
+                for (int w = 0; w < kMaxCellWords; ++w) carry[w] = __shfl_sync(0xffffffffu, pre[w], 31);
+                break;
+            }
+            ++collapsed;                                                                 // :670-672
+            lastClose = chunk * 32 + fc;
+            if (lane == 0 && lastClose + 1 < kBins) groupStart[collapsed] = (uint16_t)(lastClose + 1);
+#pragma unroll
+            for (int w = 0; w < kMaxCellWords; ++w) carry[w] = 0;
+            start = fc + 1;
         }
     }
-    if (tid == 0) *nBins = collapsed;
+    if (lastClose != kBins - 1) ++collapsed;  // the loop of :641 ends with the last bin, whatever is still empty
+    if (lane == 0) { groupStart[collapsed] = (uint16_t)kBins; *nBins = collapsed; }
 }
 
-__global__ void __launch_bounds__(128) k_fdr_table(const float* __restrict__ cells, const uint32_t* __restrict__ nBins, int W, int ppIdx,
-                                                   const double* __restrict__ xs, const double* __restrict__ ws, int nSteps, float* __restrict__ fdr) {
+__global__ void __launch_bounds__(256) k_collapse_sum(const uint32_t* __restrict__ grouped, int W, const uint16_t* __restrict__ binMap,
+                                                      unsigned long long* __restrict__ sums) {
+    const int cellsPerBin = W * 4;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= kBins * cellsPerBin) return;
+    uint32_t v = grouped[k];
+    if (!v) return;
+    int b = k / cellsPerBin, c = k - b * cellsPerBin;
+    atomicAdd(&sums[(size_t)binMap[b] * cellsPerBin + c], (unsigned long long)(v < kSaturate ? v : kSaturate));
+}
+
+__global__ void __launch_bounds__(256) k_collapse_final(const uint32_t* __restrict__ grouped, int W, const uint16_t* __restrict__ groupStart,
+                                                        const uint32_t* __restrict__ nBins, const unsigned long long* __restrict__ sums,
+                                                        float* __restrict__ cells) {
+    const int cellsPerBin = W * 4;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (int)*nBins * cellsPerBin) return;
+    unsigned long long total = sums[k];
+    float a;
+    if (total < kSaturate) {
+        a = (float)(uint32_t)total;
+    } else {  // partial sums may have rounded: literal in-order float additions of :658
+        int g = k / cellsPerBin, c = k - g * cellsPerBin;
+        a = 0.f;
+        for (int b = groupStart[g]; b < (int)groupStart[g + 1]; ++b) {
+            uint32_t v = grouped[(size_t)b * cellsPerBin + c];
+            a = __fadd_rn(a, (float)(v < kSaturate ? v : kSaturate));
+        }
+    }
+    cells[k] = a;
+}
+
+// calculateFDRs, pingpongpro.cpp:700-747.  One warp per (merged bin, bias, local, overlap).  The 1001 integrand terms of
+// :726-733 are independent: the lanes evaluate them (IEEE double ops, no FMA; x and w(x) from the host libm) into
+// shared memory, then ONE lane adds them in the reference's order, so the sum is the same sequence of fp64 additions.
+constexpr int kFdrWarps = 4;
+constexpr int kFdrMaxSteps = 1008;
+__global__ void __launch_bounds__(kFdrWarps * 32) k_fdr_table(const float* __restrict__ cells, const uint32_t* __restrict__ nBins, int W, int ppIdx,
+                                                               const double* __restrict__ xs, const double* __restrict__ ws, int nSteps, float* __restrict__ fdr) {
+    __shared__ double sTerm[kFdrWarps][kFdrMaxSteps];
     const uint32_t C = *nBins;
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= C * 4u * (uint32_t)W) return;
-    const uint32_t ov = t % (uint32_t)W, cell = t / (uint32_t)W;  // cell = bin * 4 + bias * 2 + local
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t item = blockIdx.x * kFdrWarps + warp;
+    if (item >= C * 4u * (uint32_t)W) return;
+    const uint32_t ov = item % (uint32_t)W, cell = item / (uint32_t)W;  // cell = bin * 4 + bias * 2 + local
     const uint32_t bin = cell >> 2, k = cell & 3u;
-    auto at = [&](int o) { return cells[((size_t)o * kBins + bin) * 4 + k]; };
+    auto at = [&](int o) { return cells[((size_t)bin * W + o) * 4 + k]; };
     float mean = 0.f;
     for (int o = 0; o < W; ++o)
         if (o != ppIdx) mean = __fadd_rn(mean, at(o));                       // :705-708
@@ -94,14 +166,18 @@ __global__ void __launch_bounds__(128) k_fdr_table(const float* __restrict__ cel
     const float c = at((int)ov);
     const double thr = (double)__fdiv_rn(__fsub_rn(c, mean), sd);            // :726
     const double dsd = (double)sd, dmean = (double)mean, dc = (double)c;
-    double acc = 0.0;
-    for (int i = 0; i < nSteps; ++i) {                                       // :724
+    for (int i = lane; i < nSteps; i += 32) {                                // :724
         double x = xs[i], w = ws[i];
-        if (x >= thr) acc = __dadd_rn(acc, w);                               // :728
-        else acc = __dadd_rn(acc, __ddiv_rn(__dmul_rn(w, __dadd_rn(__dmul_rn(x, dsd), dmean)), dc));  // :732
+        sTerm[warp][i] = (x >= thr) ? w                                                           // :728
+                                    : __ddiv_rn(__dmul_rn(w, __dadd_rn(__dmul_rn(x, dsd), dmean)), dc);  // :732
     }
-    if (acc < 0.0) acc = 0.0; else if (acc > 1.0) acc = 1.0;                 // :736-743 (NaN stays NaN)
-    fdr[((size_t)ov * kBins + bin) * 4 + k] = __double2float_rn(acc);        // :745
+    __syncwarp();
+    if (lane == 0) {
+        double acc = 0.0;
+        for (int i = 0; i < nSteps; ++i) acc = __dadd_rn(acc, sTerm[warp][i]);
+        if (acc < 0.0) acc = 0.0; else if (acc > 1.0) acc = 1.0;             // :736-743 (NaN stays NaN)
+        fdr[((size_t)bin * W + ov) * 4 + k] = __double2float_rn(acc);        // :745
+    }
 }
 
 constexpr int kScoreThreads = 256;
@@ -123,7 +199,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_count(const PairRec* __
 }
 
 __global__ void __launch_bounds__(kScoreThreads) k_score_write(const PairRec* __restrict__ pairs, size_t n, const float* __restrict__ fdrTable,
-                                                               const uint16_t* __restrict__ binMap, int ppIdx, float minHeight, const Slot* __restrict__ slots,
+                                                               const uint16_t* __restrict__ binMap, int W, int ppIdx, float minHeight, const Slot* __restrict__ slots,
                                                                uint32_t nSlots, const uint32_t* __restrict__ blockOff, uint32_t nBlocks, float* __restrict__ pairFdr,
                                                                LocusOut* __restrict__ loci, unsigned long long* nLoci) {
     __shared__ uint32_t sWarp[kScoreThreads / 32];
@@ -135,7 +211,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_write(const PairRec* __
     if (i < n) {
         *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(&pairs[i]);
         uint32_t ov = r.misc & 31u, bin = binMap[(r.misc >> 7) & 1023u];                      // :682
-        fdr = fdrTable[((size_t)ov * kBins + bin) * 4 + ((r.misc >> 6) & 1u) * 2 + ((r.misc >> 5) & 1u)];  // :753
+        fdr = fdrTable[((size_t)bin * W + ov) * 4 + ((r.misc >> 6) & 1u) * 2 + ((r.misc >> 5) & 1u)];  // :753
         pairFdr[i] = fdr;
         keep = reported(r, ppIdx, minHeight);
     }
@@ -168,22 +244,28 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_write(const PairRec* __
 
 }  // namespace
 
-cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, cudaStream_t s, int* launches) {
-    size_t smem = (size_t)kChunkBins * W * 4 * sizeof(float);
-    k_collapse<<<1, kCollapseThreads, smem, s>>>(grouped, W, cells, binMap, nBins);
+cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, uint16_t* groupStart, unsigned long long* sums,
+                            cudaStream_t s, int* launches) {
+    const int entries = kBins * W * 4;
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)entries * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    k_collapse_map<<<1, kCollapseThreads, 0, s>>>(grouped, W, binMap, groupStart, nBins);
+    k_collapse_sum<<<(entries + 255) / 256, 256, 0, s>>>(grouped, W, binMap, sums);
+    k_collapse_final<<<(entries + 255) / 256, 256, 0, s>>>(grouped, W, groupStart, nBins, sums, cells);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, uint32_t maxBins, int W, int ppIdx, const double* xs, const double* ws, int nSteps,
+                             float* fdr, cudaStream_t s, int* launches) {
+    if (nSteps > kFdrMaxSteps) return cudaErrorInvalidValue;
+    unsigned items = (unsigned)maxBins * 4u * (unsigned)W;  // upper bound on the bin count; the kernel reads the real one
+    k_fdr_table<<<(items + kFdrWarps - 1) / kFdrWarps, kFdrWarps * 32, 0, s>>>(cells, nBins, W, ppIdx, xs, ws, nSteps, fdr);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
-cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, int W, int ppIdx, const double* xs, const double* ws, int nSteps, float* fdr,
-                             cudaStream_t s, int* launches) {
-    unsigned threads = (unsigned)kBins * 4u * (unsigned)W;  // upper bound; the kernel reads the real bin count
-    k_fdr_table<<<(threads + 127) / 128, 128, 0, s>>>(cells, nBins, W, ppIdx, xs, ws, nSteps, fdr);
-    if (launches) *launches += 1;
-    return cudaGetLastError();
-}
-
-cudaError_t launch_score_pairs(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int ppIdx, uint32_t minHeight,
+cudaError_t launch_score_pairs(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
                                const Slot* slots, uint32_t nSlots, float* pairFdr, LocusOut* loci, unsigned long long* nLoci, uint32_t* blockCnt,
                                uint32_t* scanScratch, size_t scanScratchWords, cudaStream_t s, int* launches) {
     if (nPairs == 0) return cudaMemsetAsync(nLoci, 0, sizeof(unsigned long long), s);
@@ -192,7 +274,7 @@ cudaError_t launch_score_pairs(const PairRec* pairs, size_t nPairs, const float*
     k_score_count<<<blocks, kScoreThreads, 0, s>>>(pairs, nPairs, ppIdx, mh, blockCnt);
     cudaError_t e = exclusive_scan_u32(blockCnt, blockCnt, blocks, scanScratch, scanScratchWords, s, launches);
     if (e != cudaSuccess) return e;
-    k_score_write<<<blocks, kScoreThreads, 0, s>>>(pairs, nPairs, fdrTable, binMap, ppIdx, mh, slots, nSlots, blockCnt, blocks, pairFdr, loci, nLoci);
+    k_score_write<<<blocks, kScoreThreads, 0, s>>>(pairs, nPairs, fdrTable, binMap, W, ppIdx, mh, slots, nSlots, blockCnt, blocks, pairFdr, loci, nLoci);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

@@ -158,24 +158,39 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t* 
 }
 
 // ------------------------------------------------------------------ ordered fold
-// One thread per run of equal keys (the thread at the run's first element).  Within the run the records
-// are in file order (stable sort); plus- and minus-strand records of the same position are folded
-// into their own words.
+// Runs of equal keys are in file order (stable sort); plus- and minus-strand records of the same position are
+// folded into their own words.  Short runs: one thread per run (the thread at the run's first element).  Runs
+// longer than kShortRun (piRNA stacks are heavy tailed: a single position can hold > 10^6 reads) are deferred to
+// k_fold_long, where a warp loads 32 records at a time, evaluates the weights in parallel and only the
+// __fadd_rn chain itself stays serial (adding +0.0f for the other strand's records is exact).
+constexpr int kShortRun = 32;
+
+__device__ __forceinline__ float read_weight_weighted(uint32_t meta) {
+    return (float)__ddiv_rn(1.0, (double)(meta >> PPP_READ_NH_SHIFT));  // readWeight = 1.0 / multiHits, narrowed to float (:449)
+}
+
 __global__ void __launch_bounds__(kBuildThreads) k_fold_runs(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t n,
-                                                              uint32_t* __restrict__ H, uint64_t G) {
+                                                              uint32_t* __restrict__ H, uint64_t G, unsigned long long* __restrict__ longRuns,
+                                                              unsigned int* __restrict__ nLong, unsigned int longCap) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t pos = keys[i];
     if (pos == kInvalidPos) return;
     if (i > 0 && keys[i - 1] == pos) return;  // not a run head
+    size_t end = i + 1;
+    while (end < n && end - i <= (size_t)kShortRun && keys[end] == pos) ++end;
+    if (end - i > (size_t)kShortRun) {  // long run: hand over to a warp
+        unsigned int slot = atomicAdd(nLong, 1u);
+        if (slot < longCap) { longRuns[slot] = (unsigned long long)i; return; }
+        while (end < n && keys[end] == pos) ++end;  // list full (cannot happen with longCap = n / kShortRun): fold here
+    }
     uint32_t wp = H[pos], wm = H[G + pos];
     float hp = __uint_as_float(wp & kValueMask), hm = __uint_as_float(wm & kValueMask);
     uint32_t ap = wp & kA10Bit, am = wm & kA10Bit;
     bool anyP = false, anyM = false;
-    for (size_t j = i; j < n && keys[j] == pos; ++j) {
+    for (size_t j = i; j < end; ++j) {
         uint32_t meta = vals[j];
-        uint32_t nh = meta >> PPP_READ_NH_SHIFT;
-        float w = (float)__ddiv_rn(1.0, (double)nh);  // readWeight = 1.0 / multiHits, narrowed to float (:449)
+        float w = read_weight_weighted(meta);
         if (!(w > 0.0f)) continue;                     // :458
         if (meta & PPP_READ_MINUS) {
             hm = __fadd_rn(hm, w);                     // :487
@@ -189,6 +204,82 @@ __global__ void __launch_bounds__(kBuildThreads) k_fold_runs(const uint32_t* __r
     }
     if (anyP) H[pos] = (__float_as_uint(hp) & kValueMask) | ap;
     if (anyM) H[G + pos] = (__float_as_uint(hm) & kValueMask) | am;
+}
+
+__global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t n,
+                                                              uint32_t* __restrict__ H, uint64_t G, const unsigned long long* __restrict__ longRuns,
+                                                              const unsigned int* __restrict__ nLong, unsigned int longCap) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned warpsPerGrid = gridDim.x * (kBuildThreads / 32);
+    unsigned int count = *nLong;
+    if (count > longCap) count = longCap;
+    for (unsigned int run = blockIdx.x * (kBuildThreads / 32) + (threadIdx.x >> 5); run < count; run += warpsPerGrid) {
+        const size_t i = (size_t)longRuns[run];
+        const uint32_t pos = keys[i];
+        uint32_t wp = H[pos], wm = H[G + pos];
+        float hp = __uint_as_float(wp & kValueMask), hm = __uint_as_float(wm & kValueMask);
+        unsigned anyP = 0, anyM = 0, a10P = 0, a10M = 0;
+        // software pipeline: 4 x 32 records (independent loads) are fetched while the previous 128 are added
+        constexpr int kDepth = 4;
+        uint32_t kq[kDepth], vq[kDepth];
+        auto fetch = [&](size_t base) {
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u) {
+                size_t j = base + (size_t)u * 32 + lane;
+                kq[u] = j < n ? keys[j] : kInvalidPos;
+                vq[u] = j < n ? vals[j] : 0u;
+            }
+        };
+        size_t nextBase = i;
+        fetch(nextBase);
+        bool more = true;
+        while (more) {
+            uint32_t kc[kDepth], vc[kDepth];
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u) { kc[u] = kq[u]; vc[u] = vq[u]; }
+            nextBase += (size_t)kDepth * 32;
+            fetch(nextBase);  // in flight during the adds below (harmless past the end of the run)
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u) {
+                if (!more) break;
+                const bool in = kc[u] == pos;
+                const unsigned mask = __ballot_sync(0xffffffffu, in);  // a prefix of the lanes: the run is contiguous
+                const int cnt = __popc(mask);
+                if (cnt < 32) more = false;
+                if (cnt == 0) break;
+                const float w = in ? read_weight_weighted(vc[u]) : 0.0f;
+                const bool live = in && w > 0.0f;                                     // :458
+                const bool minus = (vc[u] & PPP_READ_MINUS) != 0;
+                const float addP = live && !minus ? w : 0.0f, addM = live && minus ? w : 0.0f;
+                const unsigned liveP = __ballot_sync(0xffffffffu, live && !minus), liveM = __ballot_sync(0xffffffffu, live && minus);
+                anyP |= liveP;
+                anyM |= liveM;
+                a10P |= __ballot_sync(0xffffffffu, live && !minus && (vc[u] & PPP_READ_A10));  // :483
+                a10M |= __ballot_sync(0xffffffffu, live && minus && (vc[u] & PPP_READ_A10));   // :471
+                // the adds themselves are the only serial part (:487, file order); a strand without records is skipped
+                if (liveP) {
+                    if (cnt == 32) {
+#pragma unroll
+                        for (int l = 0; l < 32; ++l) hp = __fadd_rn(hp, __shfl_sync(0xffffffffu, addP, l));
+                    } else {
+                        for (int l = 0; l < cnt; ++l) hp = __fadd_rn(hp, __shfl_sync(0xffffffffu, addP, l));
+                    }
+                }
+                if (liveM) {
+                    if (cnt == 32) {
+#pragma unroll
+                        for (int l = 0; l < 32; ++l) hm = __fadd_rn(hm, __shfl_sync(0xffffffffu, addM, l));
+                    } else {
+                        for (int l = 0; l < cnt; ++l) hm = __fadd_rn(hm, __shfl_sync(0xffffffffu, addM, l));
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            if (anyP) H[pos] = (__float_as_uint(hp) & kValueMask) | (wp & kA10Bit) | (a10P ? kA10Bit : 0u);
+            if (anyM) H[G + pos] = (__float_as_uint(hm) & kValueMask) | (wm & kA10Bit) | (a10M ? kA10Bit : 0u);
+        }
+    }
 }
 
 inline unsigned grid_for(size_t n, int threads, unsigned cap) {
@@ -233,8 +324,15 @@ cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
-    k_fold_runs<<<blocks, kBuildThreads, 0, s>>>(kin, vin, n, H, G);
-    if (launches) *launches += 1;
+    // the sort's output buffers of the last pass are free again: kout holds the long-run list, vout[0] its length
+    unsigned long long* longRuns = reinterpret_cast<unsigned long long*>(kout);
+    unsigned int* nLong = reinterpret_cast<unsigned int*>(vout);
+    unsigned int longCap = (unsigned int)(scr.capacity / 2);
+    cudaError_t e = cudaMemsetAsync(nLong, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    k_fold_runs<<<blocks, kBuildThreads, 0, s>>>(kin, vin, n, H, G, longRuns, nLong, longCap);
+    k_fold_long<<<148 * 2, kBuildThreads, 0, s>>>(kin, vin, n, H, G, longRuns, nLong, longCap);
+    if (launches) *launches += 2;
     return cudaGetLastError();
 }
 

@@ -66,8 +66,43 @@ def host_lib() -> C.CDLL:
         L.ppp_fe_n_records.restype = C.c_uint64
         L.ppp_fe_n_kept.argtypes = [C.c_void_p]
         L.ppp_fe_n_kept.restype = C.c_uint64
+        L.ppp_annot_read.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_void_p)]
+        L.ppp_annot_read.restype = C.c_int
+        L.ppp_annot_free.argtypes = [C.c_void_p]
+        L.ppp_annot_count.argtypes = [C.c_void_p]
+        L.ppp_annot_count.restype = C.c_size_t
+        L.ppp_annot_intervals.argtypes = [C.c_void_p, C.c_void_p]
+        L.ppp_annot_identifier.argtypes = [C.c_void_p, C.c_size_t]
+        L.ppp_annot_identifier.restype = C.c_char_p
+        L.ppp_annot_n_names.argtypes = [C.c_void_p]
+        L.ppp_annot_name.argtypes = [C.c_void_p, C.c_int]
+        L.ppp_annot_name.restype = C.c_char_p
         _host = L
     return _host
+
+
+ANNOT_DTYPE = np.dtype([("contig", "<u4"), ("strand", "<u4"), ("start", "<u4"), ("end", "<u4")])
+
+
+def read_annotation(paths, contig_names):
+    """Transposon intervals of annotation files (.bed .csv .gff .gtf .tsv) with the reference's parsing rules
+    (pingpongpro.cpp:993-1175).  Returns (intervals[ANNOT_DTYPE] in reference order, identifiers, extended name store)."""
+    L = host_lib()
+    pa = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    na = (C.c_char_p * len(contig_names))(*[n.encode() for n in contig_names])
+    h = C.c_void_p()
+    if L.ppp_annot_read(pa, len(paths), na, len(contig_names), C.byref(h)) != 0:
+        raise OSError("Failed to open transposon file")
+    try:
+        n = L.ppp_annot_count(h)
+        iv = np.zeros(n, ANNOT_DTYPE)
+        if n:
+            L.ppp_annot_intervals(h, iv.ctypes.data)
+        ids = [L.ppp_annot_identifier(h, i).decode(errors="replace") for i in range(n)]
+        names = [L.ppp_annot_name(h, i).decode(errors="replace") for i in range(L.ppp_annot_n_names(h))]
+        return iv, ids, names
+    finally:
+        L.ppp_annot_free(h)
 
 
 class DecodedFile:

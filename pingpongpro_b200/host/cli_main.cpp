@@ -1,0 +1,302 @@
+// cli_main.cpp -- the drop-in `pingpongpro` command: same flags, inputs, messages, exit codes and output files as
+// the reference's main() (pingpongpro.cpp:1461-1638).  Alignment decode and feature extraction run here on the
+// host (frontend.h) and feed pinned, double-buffered uploads; stacks, overlap scan, FDRs and transposon scores
+// are computed by the CUDA layer through the C ABI of ppp_b200.h.  There is no CPU fallback.
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "aln_reader.h"
+#include "annotation.h"
+#include "cli_args.h"
+#include "frontend.h"
+#include "ppp_b200.h"
+#include "writers.h"
+
+using namespace ppp;
+
+namespace {
+
+// stopwatch of pingpongpro.cpp:364-390: alternate calls start / stop, 1-second resolution, stderr, only with -v.
+unsigned stopwatch(const std::string& operation, unsigned verbosity) {
+    static time_t start = 0;
+    unsigned elapsed = 0;
+    if (start != 0) { elapsed = (unsigned)(time(nullptr) - start); start = 0; }
+    else start = time(nullptr);
+    if (verbosity >= 3) {
+        if (!operation.empty()) std::cerr << operation << " ... ";
+        else std::cerr << "done (" << elapsed << " seconds)" << std::endl;
+    }
+    std::cerr.flush();
+    return elapsed;
+}
+unsigned stopwatch(unsigned verbosity) { return stopwatch("", verbosity); }
+
+int gpuError(const char* what) {
+    std::cerr << "pingpongpro: " << what << ": " << ppp_last_error() << std::endl;
+    return 1;
+}
+
+// Pinned double buffer that streams one contig's reads to the GPU in file order.
+struct Uploader {
+    static const size_t kBatch = (size_t)1 << 20;
+    ppp_ctx* ctx = nullptr;
+    ppp_read* pinned[2] = {nullptr, nullptr};
+    int which = 0;
+    std::vector<std::vector<ppp_read> > pending;  // per contig
+    uint64_t submitted = 0;
+
+    bool init(ppp_ctx* c, size_t nContigs) {
+        ctx = c;
+        pending.assign(nContigs, std::vector<ppp_read>());
+        for (int k = 0; k < 2; ++k)
+            if (ppp_pinned_alloc(kBatch * sizeof(ppp_read), (void**)&pinned[k]) != PPP_OK) return false;
+        return true;
+    }
+    bool flush(size_t contig) {
+        std::vector<ppp_read>& v = pending[contig];
+        for (size_t o = 0; o < v.size(); o += kBatch) {
+            size_t k = std::min(kBatch, v.size() - o);
+            memcpy(pinned[which], v.data() + o, k * sizeof(ppp_read));
+            if (ppp_reads_submit(ctx, (int32_t)contig, pinned[which], k, submitted) != PPP_OK) return false;
+            submitted += k;
+            which ^= 1;  // the other buffer may be refilled as soon as this submit has returned
+        }
+        v.clear();
+        return true;
+    }
+    bool add(size_t contig, const ppp_read& r) {
+        std::vector<ppp_read>& v = pending[contig];
+        v.push_back(r);
+        return v.size() < kBatch || flush(contig);
+    }
+    bool flushAll() {
+        for (size_t c = 0; c < pending.size(); ++c)
+            if (!pending[c].empty() && !flush(c)) return false;
+        return true;
+    }
+    ~Uploader() {
+        for (int k = 0; k < 2; ++k)
+            if (pinned[k]) ppp_pinned_free(pinned[k]);
+    }
+};
+
+std::vector<ScoredTransposon> scoreTransposons(ppp_ctx* ctx, const TransposonsPerGenome& tp, bool& ok) {
+    std::vector<ScoredTransposon> rows;
+    std::vector<ppp_interval> iv;
+    for (const auto& kv : tp)
+        for (const Transposon& t : kv.second) {
+            ScoredTransposon s;
+            s.t = t;
+            s.contig = kv.first;
+            memset(&s.r, 0, sizeof s.r);
+            rows.push_back(s);
+            iv.push_back(ppp_interval{kv.first, t.strand, t.start, t.end});
+        }
+    std::vector<ppp_tp_result> res(iv.size());
+    std::vector<uint32_t> order(iv.size());
+    ok = iv.empty() || ppp_transposons(ctx, iv.data(), iv.size(), res.data(), order.data()) == PPP_OK;
+    if (ok)
+        for (size_t k = 0; k < rows.size(); ++k) rows[order[k]].r = res[k];  // results come back in (contig, start, end) order = our order
+    return rows;
+}
+
+void plotTransposons(const std::vector<ScoredTransposon>& rows, const std::string& fileName, const AppOptions& o, int W) {
+    std::vector<std::string> titles;
+    std::vector<std::vector<float> > hist;
+    for (const ScoredTransposon& s : rows) {
+        std::ostringstream ss;
+        ss << "z-scores of transposon " << s.t.identifier << std::endl << "(p-value for overlap of " << 10 << " nt = " << s.r.p_value << ")";  // :1450-1452
+        titles.push_back(ss.str());
+        hist.push_back(std::vector<float>(s.r.histogram, s.r.histogram + W));
+    }
+    plotHistograms(fileName, titles, hist, o.minOverlap, o.maxOverlap, 10);
+}
+
+}  // namespace
+
+int main(int argc, char const** argv) {
+    AppOptions options;
+    if (parseCommandLine(options, argc, argv) != PARSE_OK) return 1;  // :1465-1466 (help and version too)
+
+    std::vector<std::string> names;   // bamNameStore
+    std::vector<uint64_t> lengths;
+    ppp_ctx* ctx = nullptr;
+    Uploader up;
+    double totalReadCount = 0;
+    const int W = options.maxOverlap - options.minOverlap + 1, ppIdx = 10 - options.minOverlap;
+
+    if (options.verbosity >= 3) std::cerr << "Counting reads in SAM/BAM files" << std::endl;
+    for (const std::string& path : options.inputFiles) {
+        stopwatch(std::string("  ") + path, options.verbosity);
+        AlnReader reader;
+        if (!reader.open(path.c_str())) {
+            std::cerr << "Failed to open input file: " << path << std::endl;  // :1485
+            return 1;
+        }
+        if (!ctx) {
+            names = reader.names();
+            lengths = reader.lengths();
+            if (lengths.empty()) lengths.push_back(0);
+            ppp_config cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.device = options.device;
+            cfg.n_contigs = (uint32_t)lengths.size();
+            cfg.contig_lengths = lengths.data();
+            cfg.min_overlap = options.minOverlap;
+            cfg.max_overlap = options.maxOverlap;
+            cfg.pingpong_overlap = 10;
+            cfg.multi_hits = options.countMultiHits;
+            if (ppp_init(&cfg, &ctx) != PPP_OK) return gpuError("cannot initialise the CUDA context");
+            if (!up.init(ctx, lengths.size())) return gpuError("cannot allocate pinned upload buffers");
+        }
+        ExtractOptions eo;
+        eo.minLen = options.minAlignmentLength;
+        eo.maxLen = options.maxAlignmentLength;
+        eo.mode = options.countMultiHits;
+        AlnView v;
+        bool foreignContig = false;
+        while (!reader.atEnd()) {
+            if (reader.next(v) != 0) {
+                std::cerr << "Failed to read record" << std::endl;  // :411
+                return 1;
+            }
+            ppp_read r;
+            int32_t contig;
+            float w;
+            if (!extract_read(v, eo, r, contig, w)) continue;
+            totalReadCount += (double)w;  // :488
+            if ((size_t)contig >= up.pending.size()) { foreignContig = true; continue; }  // header differs: reported below
+            if (!up.add((size_t)contig, r)) return gpuError("upload failed");
+        }
+        if (!reader.good()) {
+            std::cerr << "Failed to read record" << std::endl;
+            return 1;
+        }
+        // @SQ lines of all inputs must be identical (:1494-1517)
+        if (foreignContig || reader.names() != names) {
+            std::cerr << "@SQ header lines of '" << path << "' differ from those of previous input files" << std::endl;  // :1514
+            return 1;
+        }
+        reader.close();
+        stopwatch(options.verbosity);
+    }
+    if (!up.flushAll()) return gpuError("upload failed");
+    if (ppp_stacks_finish(ctx) != PPP_OK) return gpuError("stack build failed");
+
+    TransposonsPerGenome transposons;
+    if (!options.transposonFiles.empty()) {
+        if (options.verbosity >= 3) std::cerr << "Loading transposon coordinates" << std::endl;
+        for (const std::string& path : options.transposonFiles) {
+            stopwatch(std::string("  ") + path, options.verbosity);
+            std::ifstream fs(path.c_str());
+            if (fs.fail()) {
+                std::cerr << "Failed to open transposon file \"" << path << "\"." << std::endl;  // :1539
+                return 1;
+            }
+            readTransposons(fs, formatFromPath(path), transposons, names);
+            stopwatch(options.verbosity);
+        }
+    }
+
+    if (!options.output.empty()) {  // :1563-1576
+        mkdir(options.output.c_str(), 0777);
+        if (chdir(options.output.c_str()) != 0) {
+            std::cerr << "Failed to open output directory: " << options.output;  // :1573
+            return 1;
+        }
+    }
+
+    stopwatch("Binning stacks", options.verbosity);
+    if (ppp_height_hist(ctx, nullptr, nullptr) != PPP_OK) return gpuError("height histogram failed");
+    if (ppp_scan(ctx, nullptr, nullptr) != PPP_OK) return gpuError("overlap scan failed");
+    stopwatch(options.verbosity);
+
+    stopwatch("Calculating FDR for putative ping-pong signatures", options.verbosity);
+    uint32_t nBins = 0;
+    std::vector<float> cells((size_t)W * PPP_HEIGHT_SCORE_BINS * 4);
+    const ppp_locus* loci = nullptr;
+    size_t nLoci = 0;
+    if (ppp_score(ctx, options.minStackHeight, &nBins, nullptr, options.plot ? cells.data() : nullptr, nullptr, &loci, &nLoci) != PPP_OK)
+        return gpuError("scoring failed");
+    stopwatch(options.verbosity);
+
+    if (options.plot) {  // generateGroupedStackCountsPlot, :944-981
+        stopwatch("Rendering plots for z-scores of ping-pong signatures", options.verbosity);
+        std::vector<std::string> titles;
+        std::vector<std::vector<float> > hist;
+        for (int i = (int)nBins - 1; i >= 0; --i)
+            for (unsigned j = 0; j < 2; ++j)
+                for (unsigned k = 0; k < 2; ++k) {
+                    std::vector<float> h(W);
+                    for (int o = 0; o < W; ++o) h[o] = cells[(((size_t)o * nBins + i) * 2 + j) * 2 + k];
+                    std::ostringstream ss;
+                    ss << "z-scores of signatures with the following properties:" << std::endl;
+                    ss << "stack height score of " << (nBins - 1 - i) << std::endl;
+                    if (j != 0) ss << "no ";
+                    ss << "adenine at position 10" << std::endl;
+                    ss << "stack height " << ((k == 0) ? "above" : "below") << " the local coverage";
+                    titles.push_back(ss.str());
+                    hist.push_back(h);
+                }
+        plotHistograms("ping-pong_signatures_z-scores", titles, hist, options.minOverlap, options.maxOverlap, 10);
+        stopwatch(options.verbosity);
+    }
+
+    stopwatch("Writing ping-pong signatures to file", options.verbosity);
+    writeSignatures(loci, nLoci, names, options.browserTracks);
+    stopwatch(options.verbosity);
+
+    if (!options.transposonFiles.empty()) {
+        stopwatch("Checking input transposons for ping-pong activity", options.verbosity);
+        bool ok = true;
+        std::vector<ScoredTransposon> rows = scoreTransposons(ctx, transposons, ok);
+        if (!ok) return gpuError("transposon scoring failed");
+        stopwatch(options.verbosity);
+        stopwatch("Writing input transposons to file", options.verbosity);
+        writeTransposons(rows, names, options.browserTracks, "transposons", totalReadCount, ppIdx);
+        stopwatch(options.verbosity);
+        if (options.plot) {
+            stopwatch("Rendering plots for z-scores of input transposons", options.verbosity);
+            plotTransposons(rows, "transposons_z-scores", options, W);
+            stopwatch(options.verbosity);
+        }
+    }
+
+    if (options.predictTransposonsRange > 0) {
+        stopwatch("Predicting transposons based on ping-pong activity", options.verbosity);
+        // prediction walks ALL overlap-10 signatures, whatever -s says (:1327)
+        if (options.minStackHeight != 0 && ppp_score(ctx, 0, nullptr, nullptr, nullptr, nullptr, &loci, &nLoci) != PPP_OK) return gpuError("scoring failed");
+        std::map<unsigned, std::vector<unsigned> > positions;
+        for (size_t i = 0; i < nLoci; ++i) positions[loci[i].contig].push_back(loci[i].position);
+        // findSuppressedTransposons has indexed the signature map with every annotated contig (:1203-1206), which
+        // leaves empty lists behind; the prediction loop stops at the first of them (:1327)
+        if (!options.transposonFiles.empty())
+            for (const auto& kv : transposons) positions[kv.first];
+        TransposonsPerGenome putative;
+        predictTransposons(positions, names, options.predictTransposonsRange, putative);
+        bool ok = true;
+        std::vector<ScoredTransposon> rows = scoreTransposons(ctx, putative, ok);
+        if (!ok) return gpuError("transposon scoring failed");
+        stopwatch(options.verbosity);
+        stopwatch("Writing predicted transposons to file", options.verbosity);
+        writeTransposons(rows, names, options.browserTracks, "predicted_transposons", totalReadCount, ppIdx);
+        stopwatch(options.verbosity);
+        if (options.plot) {
+            stopwatch("Rendering plots for z-scores of predicted transposons", options.verbosity);
+            plotTransposons(rows, "predicted_transposons_z-scores", options, W);
+            stopwatch(options.verbosity);
+        }
+    }
+    ppp_destroy(ctx);
+    return 0;
+}

@@ -1,6 +1,9 @@
 // frontend.cpp -- whole-file decode into packed per-contig reads + the C API of ppp_host.h.
 #include "frontend.h"
 
+#include <fstream>
+
+#include "annotation.h"
 #include "ppp_host.h"
 
 namespace ppp {
@@ -62,5 +65,39 @@ const ppp_read* ppp_fe_reads(const ppp_fe* fe, int c) { return fe->f.reads[c].da
 double ppp_fe_total_weight(const ppp_fe* fe) { return fe->f.totalWeight; }
 uint64_t ppp_fe_n_records(const ppp_fe* fe) { return fe->f.nRecords; }
 uint64_t ppp_fe_n_kept(const ppp_fe* fe) { return fe->f.nKept; }
+
+struct ppp_annot_impl {
+    std::vector<std::string> names;
+    std::vector<ppp_annot_interval> iv;
+    std::vector<std::string> ids;
+};
+
+int ppp_annot_read(const char* const* paths, int n_paths, const char* const* contig_names, int n_names, ppp_annot** out) {
+    *out = nullptr;
+    ppp_annot_impl* a = new ppp_annot_impl;
+    for (int i = 0; i < n_names; ++i) a->names.push_back(contig_names[i]);
+    ppp::TransposonsPerGenome tp;
+    for (int i = 0; i < n_paths; ++i) {
+        std::ifstream fs(paths[i]);
+        if (fs.fail()) { delete a; return 1; }
+        ppp::readTransposons(fs, ppp::formatFromPath(paths[i]), tp, a->names);
+    }
+    for (const auto& kv : tp)
+        for (const ppp::Transposon& t : kv.second) {
+            a->iv.push_back(ppp_annot_interval{kv.first, t.strand, t.start, t.end});
+            a->ids.push_back(t.identifier);
+        }
+    *out = reinterpret_cast<ppp_annot*>(a);
+    return 0;
+}
+void ppp_annot_free(ppp_annot* a) { delete reinterpret_cast<ppp_annot_impl*>(a); }
+size_t ppp_annot_count(const ppp_annot* a) { return reinterpret_cast<const ppp_annot_impl*>(a)->iv.size(); }
+void ppp_annot_intervals(const ppp_annot* a, ppp_annot_interval* out) {
+    const ppp_annot_impl* p = reinterpret_cast<const ppp_annot_impl*>(a);
+    for (size_t i = 0; i < p->iv.size(); ++i) out[i] = p->iv[i];
+}
+const char* ppp_annot_identifier(const ppp_annot* a, size_t i) { return reinterpret_cast<const ppp_annot_impl*>(a)->ids[i].c_str(); }
+int ppp_annot_n_names(const ppp_annot* a) { return (int)reinterpret_cast<const ppp_annot_impl*>(a)->names.size(); }
+const char* ppp_annot_name(const ppp_annot* a, int i) { return reinterpret_cast<const ppp_annot_impl*>(a)->names[i].c_str(); }
 
 }  // extern "C"
