@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(kBgThreads) k_bin_group(const PairRec* __restr
                                                           uint32_t* __restrict__ grouped, uint32_t* __restrict__ tileCursor) {
     __shared__ float sThr[kBins];
     __shared__ uint32_t sKey[kBgHash], sVal[kBgHash];
+    __shared__ uint32_t sFirst, sItemStart[33 + 16], sCnt[32], sSrc[32], sDst[32];
     const int tid = threadIdx.x, lane = tid & 31;
     for (int k = tid; k < kBins - 1; k += kBgThreads) sThr[k] = thresholds[k];
     for (int k = tid; k < kBgHash; k += kBgThreads) { sKey[k] = kBgEmpty; sVal[k] = 0; }
@@ -324,17 +325,36 @@ __global__ void __launch_bounds__(kBgThreads) k_bin_group(const PairRec* __restr
         }
         atomicAdd(&grouped[cell], n);
     };
-    // tiles are handed out dynamically (signature-dense tiles take much longer than empty ones)
+    // Work is handed out dynamically, 32 tiles per block at a time (one atomic per batch: a single global counter
+    // serialises at ~1 ns per atomic).  Signature-dense tiles hold thousands of records and every 64-record step is
+    // latency bound, so the block's warps share the 64-record items of ALL tiles of the batch instead of owning tiles.
+    const int warp = tid >> 5;
     for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(tileCursor, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= nTiles) break;
-        const uint32_t cnt = tileCnt[tile];
-        if (cnt == 0) continue;
-        const size_t src = tileBase[tile], dst = tileDst[tile];
-        for (uint32_t base = 0; base < cnt; base += 64) {  // two records per lane in flight
-            const uint32_t i0 = base + lane, i1 = base + 32 + lane;
+        if (tid == 0) sFirst = atomicAdd(tileCursor, 32u);
+        __syncthreads();
+        const uint32_t first = sFirst;
+        if (first >= nTiles) break;
+        if (warp == 0) {
+            const uint32_t tile = first + lane;
+            const uint32_t cnt = tile < nTiles ? tileCnt[tile] : 0u;
+            sCnt[lane] = cnt;
+            sSrc[lane] = tile < nTiles ? tileBase[tile] : 0u;
+            sDst[lane] = tile < nTiles ? tileDst[tile] : 0u;
+            const uint32_t items = (cnt + 63u) >> 6;
+            const uint32_t inc = warp_inclusive(items, lane);
+            sItemStart[lane] = inc - items;
+            if (lane == 31) sItemStart[32] = inc;
+        }
+        __syncthreads();
+        const uint32_t totalItems = sItemStart[32];
+        for (uint32_t item = warp; item < totalItems; item += kBgWarps) {
+            int t = 0;  // tile slot with sItemStart[t] <= item < sItemStart[t + 1] (warp-uniform)
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (sItemStart[t + step] <= item) t += step;
+            const uint32_t cnt = sCnt[t], base = (item - sItemStart[t]) << 6;
+            const size_t src = sSrc[t], dst = sDst[t];
+            const uint32_t i0 = base + lane, i1 = base + 32 + lane;  // two records per lane in flight
             const bool ok0 = i0 < cnt, ok1 = i1 < cnt;
             PairRec r0 = {0, 1.f, 1.f, 0}, r1 = {0, 1.f, 1.f, 0};
             if (ok0) *reinterpret_cast<uint4*>(&r0) = *reinterpret_cast<const uint4*>(&raw[src + i0]);
@@ -357,6 +377,7 @@ __global__ void __launch_bounds__(kBgThreads) k_bin_group(const PairRec* __restr
             count_cell(ok0, cell0);
             count_cell(ok1, cell1);
         }
+        __syncthreads();  // the batch descriptors are overwritten next
     }
     __syncthreads();
     for (int k = tid; k < kBgHash; k += kBgThreads)
@@ -397,7 +418,7 @@ cudaError_t launch_bin_group(const PairRec* raw, PairRec* ordered, const uint32_
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     unsigned blocks = (nTiles + kBgWarps - 1) / kBgWarps;
-    if (blocks > (unsigned)sms * 2u) blocks = (unsigned)sms * 2u;
+    if (blocks > (unsigned)sms * 4u) blocks = (unsigned)sms * 4u;  // 4 x 512 threads = full occupancy; the kernel is load-latency bound
     cudaError_t e = cudaMemsetAsync(tileCursor, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     k_bin_group<<<blocks, kBgThreads, 0, s>>>(raw, ordered, tileCnt, tileBase, tileDst, nTiles, lut, thresholds, binScale, W, grouped, tileCursor);
