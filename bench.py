@@ -44,6 +44,18 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_traffic(args):
+    """DRAM bytes per k_scan launch from the committed ncu --set full capture of this workload (profiles/), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_k_scan_traffic.json")) as f:
+            t = json.load(f)
+        if (t["genome"], t["reads"], t["mode"]) == (args.genome, args.reads, args.mode):
+            return t["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed regions run."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -276,7 +288,7 @@ def main():
                    "l2": "inputs (8 B x positions = %.2f GB) are far larger than the 126 MB L2; no flush between steps" % (8e-9 * words),
                    "synthetic_generation_s": t_gen},
         "roofline": {"bound": "hbm", "kernel": "k_scan (fused height histogram + overlap scan)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes,
+                     "frac": achieved / peak, "traffic": profiled_traffic(args), "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes,
                      "kernel_ms": tm["scan_ms"], "achieved_two_pass_accounting_gbs": survey_bytes / (tm["scan_ms"] * 1e-3) / 1e9,
                      "device_ms_per_step": {k: tm[k] for k in ("scan_ms", "lut_ms", "bin_ms", "score_ms")}},
         "clocks": clocks,

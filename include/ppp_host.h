@@ -18,6 +18,8 @@ typedef struct ppp_fe ppp_fe; /* a decoded input file */
  * Returns 0, or 1 = cannot open ("Failed to open input file", :1485), 2 = malformed record
  * ("Failed to read record", :411). */
 PPP_API int ppp_fe_decode(const char* path, uint32_t min_len, uint32_t max_len, int mode, ppp_fe** out);
+/* Same with `threads` BGZF inflate workers for BAM input (<= 1: sequential). */
+PPP_API int ppp_fe_decode_mt(const char* path, uint32_t min_len, uint32_t max_len, int mode, int threads, ppp_fe** out);
 PPP_API void ppp_fe_free(ppp_fe* fe);
 PPP_API int ppp_fe_n_contigs(const ppp_fe* fe);
 PPP_API const char* ppp_fe_contig_name(const ppp_fe* fe, int contig);

@@ -167,10 +167,14 @@ bool computeThresholds(float maxFreq, float* thr) {
     bool monotone = true;
     uint32_t from = loBits;
     const int topBin = binAt(topBits);
+    const double ratio = pow(10.0, (double)maxHs / 999.0);
+    double lastGuess = 1.0;
     for (int b = 1; b < PPP_HEIGHT_SCORE_BINS; ++b) {
         if (topBin < b) { thr[b - 1] = std::numeric_limits<float>::infinity(); continue; }
         // analytic estimate of the step (bin >= b  <=>  log10(hs) / maxHs * 999 >= b - 0.5), then gallop + bisect around it
-        float guessF = (float)pow(10.0, ((double)b - 0.5) / 999.0 * (double)maxHs);
+        double guessD = b == 1 ? pow(10.0, 0.5 / 999.0 * (double)maxHs) : lastGuess * ratio;  // 10^((b - 0.5) / 999 * maxHs), incrementally
+        lastGuess = guessD;
+        float guessF = (float)guessD;
         uint32_t g;
         memcpy(&g, &guessF, 4);
         if (!(guessF >= 1.0f) || g < from) g = from;
@@ -201,10 +205,8 @@ bool computeThresholds(float maxFreq, float* thr) {
         }
         memcpy(&thr[b - 1], &hi, 4);
         // local validation: a few patterns either side must respect the step
-        for (uint32_t d = 1; d <= 3; ++d) {
-            if (hi >= loBits + d && binAt(hi - d) >= b) monotone = false;
-            if (hi + d <= topBits && binAt(hi + d) < b) monotone = false;
-        }
+        if (hi >= loBits + 2 && binAt(hi - 2) >= b) monotone = false;  // (hi - 1 was already probed by the bisection)
+        if (hi + 1 <= topBits && binAt(hi + 1) < b) monotone = false;
         from = hi;
     }
     return monotone;

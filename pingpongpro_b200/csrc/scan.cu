@@ -87,7 +87,13 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
     const float fW = (float)P.W;
     const uint32_t myPos = (uint32_t)tid * kPerThread;  // this thread owns 32 consecutive positions of the tile
     const uint32_t rowSw = (uint32_t)tid & 7u;          // group permutation of this thread's row (see sw())
-    uint32_t ones = 0, localMax = 0;
+    uint32_t ones = 0, localMax = 0, small = 0;  // small: four 8-bit counters for rounded heights 0..3
+    auto flush_small = [&]() {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if ((small >> (8 * r)) & 0xffu) atomicAdd(&sHist[r], (small >> (8 * r)) & 0xffu);
+        small = 0;
+    };
 
     // register pipeline: the 32 positions are fetched as 4 sub-steps of 8 words per strand (LDG.E.256); the loads
     // of sub-step s+1 (or of the next tile's sub-step 0) are in flight while sub-step s is staged.
@@ -143,17 +149,21 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
                 uint32_t below = lo >= 32 ? 0xffffffffu : ((1u << lo) - 1u), upto = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
                 mm &= below | ~upto;
             }
+            // both strands advance together (two independent load -> classify chains per trip)
+            uint32_t nzA = nzP, nzB = mm;
+            while (nzA | nzB) {
 #pragma unroll
-            for (int strand = 0; strand < 2; ++strand) {
-                uint32_t nz = strand ? mm : nzP;
-                const uint32_t* src = strand ? sM : sP;
-                while (nz) {
+                for (int strand = 0; strand < 2; ++strand) {
+                    uint32_t& nz = strand ? nzB : nzA;
+                    if (!nz) continue;
+                    const uint32_t* src = strand ? sM : sP;
                     int b = __ffs(nz) - 1;
                     nz &= nz - 1;
                     uint32_t wv = src[myPos + ((uint32_t)b ^ (rowSw << 2))];
                     if ((wv & kValueMask) == ONE) { ++ones; continue; }
                     uint32_t r = word_round_height<REPR>(wv);
-                    if (r < kScanLowBins) atomicAdd(&sHist[r], 1u);
+                    if (r < 4u) { small += 1u << (8 * r); if ((small & 0x80808080u) != 0u) flush_small(); }  // heights 0..3: byte counters in a register
+                    else if (r < kScanLowBins) atomicAdd(&sHist[r], 1u);
                     else atomicAdd(&P.freqTail[r], 1u);
                     localMax = max(localMax, r);
                 }
@@ -216,9 +226,11 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
                     uint32_t bits = sCandBits[c];
                     const uint32_t wp = sP[sw(tp)];
                     const uint32_t w0 = tp + P.minOv;  // first window position (tile-relative)
+                    // vicinity sum / max over the PRESENT stacks only, in overlap order: an absent stack would add
+                    // +0.0f, which is an exact no-op (:564-577)
                     float sum = 0.0f, mx = 0.0f;
-                    for (int q = 0; q < P.W; ++q) {                          // :564-577 (absent stacks add +0)
-                        float mq = word_height<REPR>(sM[sw(w0 + q)]);
+                    for (uint32_t rest = bits; rest; rest &= rest - 1) {
+                        float mq = word_height<REPR>(sM[sw(w0 + (uint32_t)(__ffs(rest) - 1))]);
                         sum = __fadd_rn(sum, mq);
                         mx = fmaxf(mx, mq);
                     }
@@ -250,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
     }
 
     // flush the privatised histogram
+    flush_small();
     if (ones) { atomicAdd(&sHist[1], ones); localMax = max(localMax, 1u); }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) localMax = max(localMax, __shfl_xor_sync(0xffffffffu, localMax, d));

@@ -50,6 +50,8 @@ def host_lib() -> C.CDLL:
         L = _load("libppp_host.so", _build.build_host)
         L.ppp_fe_decode.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
         L.ppp_fe_decode.restype = C.c_int
+        L.ppp_fe_decode_mt.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.ppp_fe_decode_mt.restype = C.c_int
         L.ppp_fe_free.argtypes = [C.c_void_p]
         L.ppp_fe_n_contigs.argtypes = [C.c_void_p]
         L.ppp_fe_contig_name.argtypes = [C.c_void_p, C.c_int]
@@ -117,10 +119,10 @@ class DecodedFile:
         self.n_kept = n_kept
 
 
-def decode_file(path: str, min_len: int = 24, max_len: int = 32, mode: str = "weighted") -> DecodedFile:
+def decode_file(path: str, min_len: int = 24, max_len: int = 32, mode: str = "weighted", threads: int = 1) -> DecodedFile:
     L = host_lib()
     h = C.c_void_p()
-    rc = L.ppp_fe_decode(os.fsencode(path), min_len, max_len, MODES[mode], C.byref(h))
+    rc = L.ppp_fe_decode_mt(os.fsencode(path), min_len, max_len, MODES[mode], threads, C.byref(h))
     if rc == 1:
         raise OSError(f"Failed to open input file: {path}")
     if rc != 0:

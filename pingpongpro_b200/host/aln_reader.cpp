@@ -3,8 +3,13 @@
 
 #include <zlib.h>
 
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <unordered_map>
 
 namespace ppp {
@@ -15,10 +20,149 @@ struct AlnReader::NameMap {
 
 static const size_t kRawChunk = 4u << 20;
 
+// ---------------------------------------------------------------------------
+// parallel BGZF inflate: one reader thread cuts the file into jobs of whole blocks, a pool inflates them, the
+// consumer takes the jobs back in file order.  BGZF blocks are independent deflate streams, so this is exact.
+// ---------------------------------------------------------------------------
+struct AlnReader::Pipeline {
+    struct Block { size_t off, clen; uint32_t isize; size_t outOff; };
+    struct Job {
+        std::vector<uint8_t> raw, out;
+        std::vector<Block> blocks;
+        bool done = false, bad = false;
+    };
+    FILE* fp;
+    std::mutex mu;
+    std::condition_variable cvWork, cvDone, cvSpace;
+    std::deque<std::shared_ptr<Job> > todo, ordered;  // ordered: every job in file order until consumed
+    bool eof = false, stop = false, readError = false;
+    size_t maxOutstanding;
+    std::thread reader;
+    std::vector<std::thread> workers;
+    std::shared_ptr<Job> current;  // keeps the chunk handed to the consumer alive
+
+    Pipeline(FILE* f, int threads) : fp(f), maxOutstanding((size_t)threads * 3 + 2) {
+        reader = std::thread([this] { readLoop(); });
+        for (int i = 0; i < threads; ++i) workers.emplace_back([this] { workLoop(); });
+    }
+    ~Pipeline() {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            stop = true;
+        }
+        cvWork.notify_all();
+        cvSpace.notify_all();
+        cvDone.notify_all();
+        reader.join();
+        for (auto& w : workers) w.join();
+    }
+    void readLoop() {
+        const size_t kJobBytes = 1u << 20;
+        for (;;) {
+            auto job = std::make_shared<Job>();
+            size_t outTotal = 0;
+            bool fileEnd = false, bad = false;
+            while (job->raw.size() < kJobBytes) {
+                uint8_t hdr[12];
+                size_t got = fread(hdr, 1, 12, fp);
+                if (got == 0) { fileEnd = true; break; }
+                if (got != 12 || hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) { bad = true; break; }
+                uint32_t xlen = hdr[10] | (hdr[11] << 8);
+                uint8_t extra[65536];
+                if (fread(extra, 1, xlen, fp) != xlen) { bad = true; break; }
+                int bsize = -1;
+                for (uint32_t i = 0; i + 4 <= xlen;) {
+                    uint32_t slen = extra[i + 2] | (extra[i + 3] << 8);
+                    if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2) bsize = extra[i + 4] | (extra[i + 5] << 8);
+                    i += 4 + slen;
+                }
+                if (bsize < 0) { bad = true; break; }
+                size_t clen = (size_t)bsize + 1 - xlen - 12 - 8;
+                size_t off = job->raw.size();
+                job->raw.resize(off + clen + 8);
+                if (fread(job->raw.data() + off, 1, clen + 8, fp) != clen + 8) { bad = true; break; }
+                uint32_t isize;
+                memcpy(&isize, job->raw.data() + off + clen + 4, 4);
+                job->blocks.push_back(Block{off, clen, isize, outTotal});
+                outTotal += isize;
+            }
+            job->out.resize(outTotal);
+            job->bad = bad;
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cvSpace.wait(l, [this] { return stop || ordered.size() < maxOutstanding; });
+                if (stop) return;
+                if (!job->blocks.empty() || bad) {
+                    ordered.push_back(job);
+                    if (bad) { job->done = true; cvDone.notify_all(); }
+                    else { todo.push_back(job); cvWork.notify_one(); }
+                }
+                if (fileEnd || bad) { eof = true; cvDone.notify_all(); cvWork.notify_all(); return; }
+            }
+        }
+    }
+    void workLoop() {
+        for (;;) {
+            std::shared_ptr<Job> job;
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cvWork.wait(l, [this] { return stop || !todo.empty() || eof; });
+                if (stop) return;
+                if (todo.empty()) { if (eof) return; continue; }
+                job = todo.front();
+                todo.pop_front();
+            }
+            bool bad = false;
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) bad = true;
+            for (const Block& b : job->blocks) {
+                if (bad) break;
+                if (b.isize == 0) continue;
+                inflateReset(&zs);
+                zs.next_in = job->raw.data() + b.off;
+                zs.avail_in = (uInt)b.clen;
+                zs.next_out = job->out.data() + b.outOff;
+                zs.avail_out = b.isize;
+                int rc = inflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END || zs.avail_out != 0) bad = true;
+            }
+            inflateEnd(&zs);
+            std::vector<uint8_t>().swap(job->raw);
+            {
+                std::lock_guard<std::mutex> l(mu);
+                job->bad = job->bad || bad;
+                job->done = true;
+            }
+            cvDone.notify_all();
+        }
+    }
+    // Next inflated chunk in file order; false at end of file.  `bad` is set on a malformed block.
+    bool next(const uint8_t*& data, size_t& len, bool& bad) {
+        std::unique_lock<std::mutex> l(mu);
+        cvDone.wait(l, [this] { return (!ordered.empty() && ordered.front()->done) || (ordered.empty() && eof); });
+        if (ordered.empty()) return false;
+        current = ordered.front();
+        ordered.pop_front();
+        cvSpace.notify_one();
+        bad = current->bad;
+        data = current->out.data();
+        len = current->out.size();
+        return true;
+    }
+};
+
 AlnReader::AlnReader() {}
 AlnReader::~AlnReader() { close(); }
 
+void AlnReader::setThreads(int n) {
+    if (!isBam_ || !good_ || pipe_ || n <= 1) return;
+    pipe_ = new Pipeline(fp_, n);  // continues at the current file offset (after the blocks already consumed)
+}
+
 void AlnReader::close() {
+    delete pipe_;
+    pipe_ = nullptr;
     if (fp_) fclose(fp_);
     fp_ = nullptr;
     delete nameMap_;
@@ -75,6 +219,20 @@ bool AlnReader::readBgzfBlock() {
 bool AlnReader::fill() {
     if (eofRaw_) return false;
     compact(buf_, cur_, end_);
+    if (isBam_ && pipe_) {
+        const uint8_t* data;
+        size_t len;
+        bool bad = false;
+        size_t before = end_;
+        while (end_ == before) {
+            if (!pipe_->next(data, len, bad)) { eofRaw_ = true; return false; }
+            if (bad) { good_ = false; eofRaw_ = true; return false; }
+            if (buf_.size() < end_ + len) buf_.resize(end_ + len + kRawChunk);
+            memcpy(buf_.data() + end_, data, len);
+            end_ += len;
+        }
+        return true;
+    }
     if (isBam_) {
         size_t before = end_;
         while (!eofRaw_ && end_ == before) readBgzfBlock();

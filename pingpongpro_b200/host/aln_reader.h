@@ -71,6 +71,10 @@ public:
     // Records decoded so far.
     uint64_t recordCount() const { return nRecords_; }
 
+    // BAM only: inflate BGZF blocks on `n` worker threads (read-ahead, in order).  Call after open(); n <= 1 keeps the
+    // sequential path.  Record decoding itself stays on the calling thread.
+    void setThreads(int n);
+
 private:
     bool fill();                  // refill raw buffer (decompressing BGZF blocks for BAM)
     bool ensure(size_t n);        // make >= n bytes available at cur_ (BAM)
@@ -97,6 +101,8 @@ private:
     NameMap* nameMap_ = nullptr;
     bool pendingLine_ = false;    // SAM: first alignment line was consumed while reading the header
     std::string pending_;
+    struct Pipeline;
+    Pipeline* pipe_ = nullptr;    // parallel BGZF inflate (setThreads)
 };
 
 }  // namespace ppp

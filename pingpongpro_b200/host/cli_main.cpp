@@ -13,6 +13,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "aln_reader.h"
@@ -142,6 +143,10 @@ int main(int argc, char const** argv) {
         if (!reader.open(path.c_str())) {
             std::cerr << "Failed to open input file: " << path << std::endl;  // :1485
             return 1;
+        }
+        {
+            int nt = options.threads > 0 ? options.threads : (int)std::thread::hardware_concurrency();
+            reader.setThreads(nt > 1 ? nt - 1 : 1);  // one thread stays free for the record walk
         }
         if (!ctx) {
             names = reader.names();

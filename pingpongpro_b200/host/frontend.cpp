@@ -8,9 +8,10 @@
 
 namespace ppp {
 
-int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out) {
+int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int threads) {
     AlnReader rd;
     if (!rd.open(path)) return 1;
+    rd.setThreads(threads);
     out.names = rd.names();
     out.lengths = rd.lengths();
     out.reads.assign(out.names.size(), std::vector<ppp_read>());
@@ -45,13 +46,17 @@ struct ppp_fe {
 extern "C" {
 
 int ppp_fe_decode(const char* path, uint32_t min_len, uint32_t max_len, int mode, ppp_fe** out) {
+    return ppp_fe_decode_mt(path, min_len, max_len, mode, 1, out);
+}
+
+int ppp_fe_decode_mt(const char* path, uint32_t min_len, uint32_t max_len, int mode, int threads, ppp_fe** out) {
     *out = nullptr;
     ppp_fe* fe = new ppp_fe;
     ppp::ExtractOptions o;
     o.minLen = min_len;
     o.maxLen = max_len;
     o.mode = mode;
-    int rc = ppp::decode_file(path, o, fe->f);
+    int rc = ppp::decode_file(path, o, fe->f, threads);
     if (rc != 0) { delete fe; return rc; }
     *out = fe;
     return 0;

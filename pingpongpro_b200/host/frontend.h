@@ -68,6 +68,6 @@ struct DecodedFile {
 };
 
 // 0 = ok, 1 = cannot open, 2 = malformed record.
-int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out);
+int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int threads = 1);
 
 }  // namespace ppp
