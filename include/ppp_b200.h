@@ -115,6 +115,10 @@ typedef int (*ppp_allreduce_fn)(void* user, void* device_buffer, size_t count, i
 PPP_API const char* ppp_last_error(void);
 PPP_API int ppp_device_count(int* n);
 
+/* Creates the CUDA context of `device` (the one-off driver initialisation, ~1 s).  Optional: lets a host driver
+ * overlap that latency with input decoding by calling it from a helper thread before ppp_init. */
+PPP_API int ppp_warmup(int32_t device);
+
 /* Context: allocates and zeroes the dense per-strand stack arrays (TReadStacksPerGenome, :103-105). */
 PPP_API int ppp_init(const ppp_config* cfg, ppp_ctx** ctx);
 PPP_API void ppp_destroy(ppp_ctx* ctx);

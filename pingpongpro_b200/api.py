@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
     L.ppp_last_error.restype = C.c_char_p
     L.ppp_device_count.argtypes = [C.POINTER(C.c_int)]
     L.ppp_init.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.ppp_warmup.argtypes = [C.c_int32]
     L.ppp_destroy.argtypes = [vp]
     L.ppp_destroy.restype = None
     L.ppp_reset.argtypes = [vp]
@@ -98,7 +99,7 @@ def lib() -> C.CDLL:
     L.ppp_timings_get.argtypes = [vp, C.POINTER(Timings)]
     L.ppp_timings_reset.argtypes = [vp]
     L.ppp_layout.argtypes = [vp, u64p, u64p]
-    for name in ("ppp_device_count", "ppp_init", "ppp_reset", "ppp_set_allreduce", "ppp_pinned_alloc", "ppp_pinned_free", "ppp_reads_submit",
+    for name in ("ppp_device_count", "ppp_warmup", "ppp_init", "ppp_reset", "ppp_set_allreduce", "ppp_pinned_alloc", "ppp_pinned_free", "ppp_reads_submit",
                  "ppp_reads_submit_device", "ppp_stacks_finish", "ppp_reads_foreign", "ppp_stacks_download", "ppp_height_hist", "ppp_scan", "ppp_score",
                  "ppp_pairs_download", "ppp_transposons", "ppp_timings_get", "ppp_timings_reset", "ppp_layout"):
         getattr(L, name).restype = C.c_int

@@ -2,9 +2,11 @@
 // host arithmetic that must use the HOST libm to stay bit-identical to the reference (log10f-based bin
 // thresholds, exp-based Gaussian weights).  No CPU fallback exists anywhere in this file: every entry point
 // that computes launches CUDA kernels and fails with PPP_ERR_CUDA when that is impossible.
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -353,6 +355,12 @@ int ppp_device_count(int* n) {
     return PPP_OK;
 }
 
+int ppp_warmup(int32_t device) {
+    CK(cudaSetDevice(device));
+    CK(cudaFree(nullptr));
+    return PPP_OK;
+}
+
 int ppp_pinned_alloc(size_t bytes, void** ptr) {
     CK(cudaMallocHost(ptr, bytes));
     return PPP_OK;
@@ -362,8 +370,15 @@ int ppp_pinned_free(void* ptr) {
     return PPP_OK;
 }
 
+static void initMark(const char* what) {  // PPP_TIMING=1: where the start-up time goes
+    static const bool on = getenv("PPP_TIMING") != nullptr;
+    static const auto t0 = std::chrono::steady_clock::now();
+    if (on) fprintf(stderr, "[ppp_init %7.3f s] %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), what);
+}
+
 int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     if (!cfg || !out) return fail(PPP_ERR_ARG, "null argument");
+    initMark("enter");
     *out = nullptr;
     if (cfg->n_contigs == 0 || !cfg->contig_lengths) return fail(PPP_ERR_ARG, "no contigs");
     if (cfg->min_overlap < 0 || cfg->max_overlap < cfg->min_overlap || cfg->max_overlap > 32 || cfg->pingpong_overlap < cfg->min_overlap ||
@@ -375,7 +390,10 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     if (e != cudaSuccess || nDev == 0)
         return fail(PPP_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= nDev) return fail(PPP_ERR_ARG, "device %d out of range (%d devices)", cfg->device, nDev);
+    initMark("cudaGetDeviceCount");
     CK(cudaSetDevice(cfg->device));
+    CK(cudaFree(nullptr));
+    initMark("context created");
     ppp_ctx* c = new ppp_ctx;
     c->device = cfg->device;
     c->minOv = cfg->min_overlap;
@@ -398,6 +416,7 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     size_t hWords = 2 * c->G + 64;
     CKI(cudaMalloc(&c->H, hWords * sizeof(uint32_t)));
     CKI(cudaMemsetAsync(c->H, 0, hWords * sizeof(uint32_t), c->stream));
+    initMark("stack arrays allocated");
     if (!c->ownedSlots.empty()) {
         CKI(cudaMalloc(&c->dSlots, c->ownedSlots.size() * sizeof(Slot)));
         CKI(cudaMemcpyAsync(c->dSlots, c->ownedSlots.data(), c->ownedSlots.size() * sizeof(Slot), cudaMemcpyHostToDevice, c->stream));
@@ -431,6 +450,7 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     CKI(cudaMalloc(&c->dNBins, sizeof(uint32_t)));
     CKI(cudaMalloc(&c->dTileCursor, sizeof(uint32_t)));
     CKI(cudaMalloc(&c->dThresholds, kBins * sizeof(float)));
+    initMark("device tables allocated");
     CKI(cudaMallocHost(&c->hThresholds, kBins * sizeof(float)));
     CKI(cudaMallocHost(&c->hs, sizeof(PinnedScalars)));
     memset(c->hs, 0, sizeof(PinnedScalars));
@@ -441,7 +461,9 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     CKI(cudaMalloc(&c->dWs, ws.size() * sizeof(double)));
     CKI(cudaMemcpyAsync(c->dXs, xs.data(), xs.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CKI(cudaMemcpyAsync(c->dWs, ws.data(), ws.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    initMark("pinned + tables");
     CKI(cudaStreamSynchronize(c->stream));
+    initMark("synchronised");
 #undef CKI
     *out = c;
     return PPP_OK;
