@@ -69,6 +69,8 @@ struct ppp_ctx {
 
     cudaStream_t stream = nullptr, copyStream = nullptr;
     uint32_t* H = nullptr;
+    uint32_t* occ = nullptr;  // occupancy bitmap of H (2G bits + padding)
+    size_t occWords = 0;
     Slot* dSlots = nullptr;
     unsigned long long* dCounters = nullptr;  // [0] foreign, [1] range errors
 
@@ -310,11 +312,11 @@ int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n) {
     int rc = timerStart(c, t);
     if (rc) return rc;
     if (c->repr == kReprInt) {
-        CK(launch_stack_build_int(dReads, n, c->H, c->G, slot, c->mode, c->dCounters, c->stream, &c->launches));
+        CK(launch_stack_build_int(dReads, n, c->H, c->G, c->occ, slot, c->mode, c->dCounters, c->stream, &c->launches));
     } else {
         rc = ensureSortScratch(c);
         if (rc) return rc;
-        CK(launch_stack_build_weighted(dReads, n, c->H, c->G, slot, c->dCounters, c->sort, c->stream, &c->launches));
+        CK(launch_stack_build_weighted(dReads, n, c->H, c->G, c->occ, slot, c->dCounters, c->sort, c->stream, &c->launches));
     }
     rc = timerStop(c, t);
     if (rc) return rc;
@@ -416,6 +418,9 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     size_t hWords = 2 * c->G + 64;
     CKI(cudaMalloc(&c->H, hWords * sizeof(uint32_t)));
     CKI(cudaMemsetAsync(c->H, 0, hWords * sizeof(uint32_t), c->stream));
+    c->occWords = (size_t)(2 * c->G / 32) + 64;
+    CKI(cudaMalloc(&c->occ, c->occWords * sizeof(uint32_t)));
+    CKI(cudaMemsetAsync(c->occ, 0, c->occWords * sizeof(uint32_t), c->stream));
     initMark("stack arrays allocated");
     if (!c->ownedSlots.empty()) {
         CKI(cudaMalloc(&c->dSlots, c->ownedSlots.size() * sizeof(Slot)));
@@ -475,7 +480,7 @@ void ppp_destroy(ppp_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     foldBuildTimers(c);
-    void* dev[] = {c->H, c->dSlots, c->dCounters, c->dStage[0], c->dStage[1], c->sort.keysA, c->sort.keysB, c->sort.valsA, c->sort.valsB, c->sort.blockHist,
+    void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dStage[0], c->dStage[1], c->sort.keysA, c->sort.keysB, c->sort.valsA, c->sort.valsB, c->sort.blockHist,
                    c->sort.scanScratch, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
                    c->dPairFdr, c->dLoci, c->dTileCnt, c->dTileBase, c->dTileDst, c->dScanScratch, c->dBlockCnt, c->dGrouped, c->dThresholds, c->dCells,
                    c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dTileCursor};
@@ -500,6 +505,7 @@ int ppp_reset(ppp_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->copyStream));
     CK(cudaMemsetAsync(c->H, 0, (2 * c->G + 64) * sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(c->occ, 0, c->occWords * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->dCounters, 0, 2 * sizeof(unsigned long long), c->stream));
     c->readsSubmitted = 0;
     c->finished = false;
@@ -615,7 +621,8 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
     if (!c->finished) return fail(PPP_ERR_STATE, "call ppp_stacks_finish before ppp_height_hist");
     CK(cudaSetDevice(c->device));
     invalidateResults(c);
-    uint64_t want = c->cfgPairCapacity ? c->cfgPairCapacity : std::max<uint64_t>((uint64_t)1 << 20, c->readsSubmitted);
+    // signatures are ~0.1-0.3 per read on real densities; a scan that overflows the store reports the exact count and is re-run once
+    uint64_t want = c->cfgPairCapacity ? c->cfgPairCapacity : std::max<uint64_t>((uint64_t)1 << 20, c->readsSubmitted / 3);
     if (want < c->pairCapacity) want = c->pairCapacity;
     int rc = ensurePairCapacity(c, want);
     if (rc) return rc;
@@ -628,6 +635,7 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
         CK(cudaMemsetAsync(c->dCursor, 0, sizeof(unsigned long long), c->stream));
         ScanParams p;
         p.H = c->H;
+        p.occ = c->occ;
         p.G = c->G;
         p.nTiles = c->nTiles;
         p.minOv = c->minOv;

@@ -8,6 +8,7 @@
 //   integer representation (-m unique / discard): bits 0..30 = number of reads, bit 31 = A10 flag
 //   float   representation (-m weighted)        : bits 0..30 = IEEE-754 bits of the height, bit 31 = A10
 // (heights are > 0, so the sign bit is free).  TReadStack of pingpongpro.cpp:91-99.
+// An occupancy bitmap (bit i set <=> word i of H is non-zero) is maintained beside H by the stack builder.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,7 +23,7 @@ constexpr uint32_t kValueMask = 0x7fffffffu;
 constexpr uint32_t kSaturate = 1u << 24;        // float counters stop at 2^24
 constexpr int kBins = 1000;                     // HEIGHT_SCORE_BINS, pingpongpro.cpp:164
 constexpr uint32_t kScanLowBins = 512;          // smem-privatised part of the height histogram
-constexpr int kScanTile = 4096;                 // positions per CTA iteration of the fused scan (G is a multiple)
+constexpr int kScanTile = 8192;                 // positions per CTA iteration of the fused scan (G is a multiple)
 constexpr uint32_t kFreqCapacity = kSaturate + 1;  // rounded heights never exceed 2^24
 constexpr uint32_t kInvalidPos = 0xffffffffu;
 
@@ -49,6 +50,7 @@ struct __align__(16) PairRec {
 
 struct ScanParams {
     const uint32_t* H;      // both strands
+    const uint32_t* occ;    // occupancy bitmap: bit i <-> word i of H (plus strand words [0, G/32), minus [G/32, 2G/32))
     uint64_t G;             // words per strand
     uint32_t nTiles;
     int minOv, W;
@@ -83,15 +85,15 @@ __device__ __forceinline__ uint32_t word_round_height(uint32_t w) {
 cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* scratch, size_t scratchWords, cudaStream_t s, int* launches);
 size_t exclusive_scan_scratch_words(size_t n);
 
-cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, Slot slot, int mode, unsigned long long* counters,
-                                   cudaStream_t s, int* launches);
+cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, uint32_t* occ, Slot slot, int mode,
+                                   unsigned long long* counters, cudaStream_t s, int* launches);
 struct SortScratch {
     uint32_t *keysA, *keysB, *valsA, *valsB, *blockHist, *scanScratch;
     size_t capacity, blockHistWords, scanScratchWords;
 };
 size_t sort_block_hist_words(size_t n);
-cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, Slot slot, unsigned long long* counters,
-                                        const SortScratch& scr, cudaStream_t s, int* launches);
+cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, uint32_t* occ, Slot slot,
+                                        unsigned long long* counters, const SortScratch& scr, cudaStream_t s, int* launches);
 
 cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* launches);
 cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* freqTail, const uint32_t* maxHeight, float* lut,

@@ -1,49 +1,41 @@
 // scan.cu -- the streaming pass over the dense stack arrays (K2 + K3 of SURVEY.md §8(a)).
 //
-// k_scan (fused): ONE pass over H+ and H- (8 bytes per genome position) that
+// k_scan (fused, occupancy driven): ONE pass that
 //   (K2) builds the height -> frequency histogram of mapHeightsToScores (pingpongpro.cpp:502-509), and
 //   (K3) finds, for every plus stack, the minus stacks at overlaps min..max (:559-577), computes the vicinity
 //        mean / max (:570-578), the local-height bin (:597-599) and the base-bias bin (:602) and appends
 //        one record per (plus stack, minus stack, overlap) (:608).
 // Everything of countStacksByGroup that needs the finished histogram (the height-score bin :589-594 and the
 // grouped counter :605) is deferred to k_bin_group, which touches only the (few) signature records.
-// Fusing the two passes halves the DRAM traffic of "K2 + K3" from 16 to 8 bytes per position.
 //
-// Tiling: a CTA of 128 threads walks tiles of 4096 positions; each thread owns 32 CONSECUTIVE positions, i.e.
-// exactly one 32-bit occupancy word per strand.  They are fetched as four 256-bit streaming loads per strand
-// (LDG.E.256, L1::no_allocate, one full 32-byte sector each) through a two-deep register pipeline that also
-// prefetches the next tile, and staged in shared memory with the 1-bit/word occupancy mask of the minus strand;
-// the window test of a plus stack is then one 64-bit funnel shift over two mask words instead of `W` loads.
-// The stack arrays are sparse, but in a 32-wide warp "some lane has a stack here" is almost always true, so
-// per-position branches buy nothing.  Instead all per-stack work loops over the SET BITS of the thread's own
-// occupancy words (trip count = the busiest lane's stack count; 32 positions per thread amortise it), and all
-// per-signature work is made dense: candidates are ranked with a block scan, listed in shared memory, and one
-// thread per CANDIDATE evaluates the window and writes its records.  The records of a tile are written
-// contiguously (one atomicAdd on a global cursor) in (position, overlap) order and the tile's run is published in
-// tileBase/tileCnt; k_bin_group later copies the runs into global position order.
-// Histogram: bins < 512 are privatised per CTA in shared memory (height 1, by far the most common, is
-// counted in a register), the rare tall stacks go to a global table with red.add.
+// The dense stack arrays are ~96 % zeros.  A streaming version of this kernel (8 bytes per position, 256-bit loads,
+// shared-memory staging; 0.38 ms on configs[1] = 50 % of the HBM roofline, 70-80 % on the sparser mouse / human
+// sized genomes -- profiles/README.md) spent ~1500 instructions per 64 words mostly discovering that.  This version
+// reads the OCCUPANCY BITMAPS that the stack builder maintains (1 bit per word: G/4 bytes instead of 8 G) and gathers
+// only the words that exist, so the work is proportional to the number of stacks, like the reference's std::map walk
+// -- but over 8192 positions per CTA iteration in parallel:
+//   * a thread owns 32 consecutive positions = one bitmap word per strand (prefetched one tile ahead);
+//   * histogram: loop over the set bits, gather the word (one 32-byte sector), classify (height 1 in a register,
+//     heights 0..3 in packed byte counters, bins < 512 in shared memory, the tall tail by red.add to a global table);
+//   * the window test of a plus stack is one 64-bit funnel shift over two minus-strand bitmap words in shared memory;
+//   * all per-signature work is dense: block scan of (records, candidates), candidate list in shared memory, one
+//     thread per CANDIDATE gathers the present window words, evaluates the float expressions in the reference's
+//     order and writes its records.  The records of a tile are written contiguously (one atomicAdd on a global
+//     cursor) in (position, overlap) order; k_bin_group later copies the runs into global position order.
 //
-// Bound: HBM bandwidth.  Algorithmic bytes per launch: 8 * G + 16 * P  (G padded positions, P signatures).
+// Bound: DRAM sector gathers (32 B per touched sector) + latency.  Algorithmic bytes in SURVEY §8(d)'s dense
+// accounting stay 8 * G + 16 * P per launch; the traffic actually moved is G/4 + 32 B per occupied sector + 16 * P.
 #include "common.cuh"
 
 namespace pppk {
 
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kPerThread = 32;                 // consecutive positions owned by one thread = one occupancy word
-constexpr int kTile = kScanTile;               // 4096 positions per CTA iteration
-constexpr int kHalo = 32;
-constexpr int kMaskWords = kTile / 32 + 2;
-constexpr int kCandCap = 224;                  // candidates staged per round
+constexpr int kThreads = 256;
+constexpr int kPerThread = 32;                 // consecutive positions owned by one thread = one occupancy word per strand
+constexpr int kTile = kScanTile;               // 8192 positions per CTA iteration
+constexpr int kCandCap = 512;                  // candidates staged per round (a tile rarely has more)
 static_assert(kTile == kThreads * kPerThread, "tile geometry");
-
-__device__ __forceinline__ void ld_stream256(uint32_t (&r)[8], const uint32_t* p) {  // LDG.E.256, 32-byte aligned
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "l"(p));
-}
 
 __device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
 #pragma unroll
@@ -54,23 +46,9 @@ __device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
     return v;
 }
 
-// Shared-memory index of tile position p.  A thread owns one 32-word row; without a swizzle every 128-bit store of a
-// warp would hit the same 4 banks (32-way conflict).  The 4-word groups of a row are XOR-permuted with the row
-// number, so 8 consecutive rows cover all 32 banks; positions stay addressable one by one (the window reads cross rows).
-__device__ __forceinline__ uint32_t sw(uint32_t p) { return p ^ (((p >> 5) & 7u) << 2); }
-
-__device__ __forceinline__ uint32_t nz_byte(const uint32_t (&w)[8]) {
-    uint32_t m = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) m |= (w[j] != 0u ? 1u : 0u) << j;
-    return m;
-}
-
 template <int REPR>
-__global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
-    __shared__ __align__(32) uint32_t sP[kTile];          // plus strand of the tile
-    __shared__ __align__(32) uint32_t sM[kTile + kHalo];  // minus strand + right halo
-    __shared__ uint32_t sMask[kMaskWords];                // 1 bit per minus word: stack present
+__global__ void __launch_bounds__(kThreads, 8) k_scan(ScanParams P) {
+    __shared__ uint32_t sMask[2][kThreads + 2];  // minus-strand occupancy words of the tile + the word after it
     __shared__ uint32_t sHist[kScanLowBins];
     __shared__ uint32_t sWarpTot[kThreads / 32];
     __shared__ unsigned long long sBase;
@@ -79,14 +57,17 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < (int)kScanLowBins; k += kThreads) sHist[k] = 0;
-    if (tid == 0) sMask[kMaskWords - 1] = 0;
+    if (tid < 2) sMask[tid][kThreads + 1] = 0;
     __syncthreads();
 
     const uint32_t ONE = REPR == kReprInt ? 1u : 0x3f800000u;
     const uint32_t wMask = P.W >= 32 ? 0xffffffffu : ((1u << P.W) - 1u);
     const float fW = (float)P.W;
     const uint32_t myPos = (uint32_t)tid * kPerThread;  // this thread owns 32 consecutive positions of the tile
-    const uint32_t rowSw = (uint32_t)tid & 7u;          // group permutation of this thread's row (see sw())
+    const uint32_t* __restrict__ occP = P.occ;
+    const uint32_t* __restrict__ occM = P.occ + P.G / 32;
+    const uint32_t* __restrict__ Hp = P.H;
+    const uint32_t* __restrict__ Hm = P.H + P.G;
     uint32_t ones = 0, localMax = 0, small = 0;  // small: four 8-bit counters for rounded heights 0..3
     auto flush_small = [&]() {
 #pragma unroll
@@ -95,52 +76,25 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
         small = 0;
     };
 
-    // register pipeline: the 32 positions are fetched as 4 sub-steps of 8 words per strand (LDG.E.256); the loads
-    // of sub-step s+1 (or of the next tile's sub-step 0) are in flight while sub-step s is staged.
-    uint32_t pa[8], ma[8], pb[8], mb[8], hw[8];
-    auto issue = [&](uint32_t (&p)[8], uint32_t (&m)[8], uint32_t t, int sub) {
-        const uint32_t* src = P.H + (size_t)t * kTile + myPos + sub * 8;
-        ld_stream256(p, src);
-        ld_stream256(m, src + P.G);
+    // the occupancy words of the next tile are fetched while the current one is processed
+    uint32_t nextP = 0, nextM = 0, nextHalo = 0;
+    auto fetch = [&](uint32_t t) {
+        const size_t w = (size_t)t * kThreads;
+        nextP = __ldg(occP + w + tid);
+        nextM = __ldg(occM + w + tid);
+        if (tid == 0) nextHalo = __ldg(occM + w + kThreads);
     };
-    if (blockIdx.x < P.nTiles) issue(pa, ma, blockIdx.x, 0);
+    if (blockIdx.x < P.nTiles) fetch(blockIdx.x);
 
-    for (uint32_t tile = blockIdx.x; tile < P.nTiles; tile += gridDim.x) {
+    int buf = 0;
+    for (uint32_t tile = blockIdx.x; tile < P.nTiles; tile += gridDim.x, buf ^= 1) {
         const uint32_t tileBase = tile * (uint32_t)kTile;
-        if (tid < kHalo / 8) ld_stream256(hw, P.H + P.G + tileBase + kTile + tid * 8);
-        uint32_t nzP = 0, nzM = 0;
-        auto stage = [&](const uint32_t (&p)[8], const uint32_t (&m)[8], int sub) {
-            const uint32_t g0 = myPos + (((uint32_t)(sub * 2) ^ rowSw) << 2), g1 = myPos + (((uint32_t)(sub * 2 + 1) ^ rowSw) << 2);
-            *reinterpret_cast<uint4*>(&sP[g0]) = make_uint4(p[0], p[1], p[2], p[3]);
-            *reinterpret_cast<uint4*>(&sP[g1]) = make_uint4(p[4], p[5], p[6], p[7]);
-            *reinterpret_cast<uint4*>(&sM[g0]) = make_uint4(m[0], m[1], m[2], m[3]);
-            *reinterpret_cast<uint4*>(&sM[g1]) = make_uint4(m[4], m[5], m[6], m[7]);
-            nzP |= nz_byte(p) << (sub * 8);
-            nzM |= nz_byte(m) << (sub * 8);
-        };
-        issue(pb, mb, tile, 1);
-        stage(pa, ma, 0);
-        issue(pa, ma, tile, 2);
-        stage(pb, mb, 1);
-        issue(pb, mb, tile, 3);
-        stage(pa, ma, 2);
-        if (tile + gridDim.x < P.nTiles) issue(pa, ma, tile + gridDim.x, 0);  // next tile, in flight during the phases below
-        stage(pb, mb, 3);
-        sMask[tid] = nzM;
-        if (warp == 0) {
-            uint32_t v = 0;
-            if (lane < kHalo / 8) {
-                *reinterpret_cast<uint4*>(&sM[kTile + lane * 8]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(&sM[kTile + lane * 8 + 4]) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-                v = nz_byte(hw) << (8 * lane);
-            }
-            v |= __shfl_xor_sync(0xffffffffu, v, 1);
-            v |= __shfl_xor_sync(0xffffffffu, v, 2);
-            if (lane == 0) sMask[kTile / 32] = v;
-        }
+        const uint32_t nzP = nextP, nzM = nextM;
+        sMask[buf][tid] = nzM;
+        if (tid == 0) sMask[buf][kThreads] = nextHalo;
+        if (tile + gridDim.x < P.nTiles) fetch(tile + gridDim.x);
 
-        // K2: height histogram.  Loop over the set bits of this thread's own occupancy words (iterations = the
-        // busiest lane's stack count, not 64), re-reading the word it staged itself.
+        // K2: height histogram over the stacks that exist (set bits), gathered from the dense arrays.
         {
             uint32_t mm = nzM;
             if (tileBase < P.haloHi && tileBase + kTile > P.haloLo) {  // halo copies of a neighbouring shard are not counted
@@ -149,19 +103,19 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
                 uint32_t below = lo >= 32 ? 0xffffffffu : ((1u << lo) - 1u), upto = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
                 mm &= below | ~upto;
             }
-            // both strands advance together (two independent load -> classify chains per trip)
+            // up to four gathers (two per strand) are in flight per trip before any of them is classified
             uint32_t nzA = nzP, nzB = mm;
             while (nzA | nzB) {
+                uint32_t wv[4] = {0u, 0u, 0u, 0u};
+                if (nzA) { wv[0] = __ldg(Hp + tileBase + myPos + (uint32_t)(__ffs(nzA) - 1)); nzA &= nzA - 1; }
+                if (nzB) { wv[1] = __ldg(Hm + tileBase + myPos + (uint32_t)(__ffs(nzB) - 1)); nzB &= nzB - 1; }
+                if (nzA) { wv[2] = __ldg(Hp + tileBase + myPos + (uint32_t)(__ffs(nzA) - 1)); nzA &= nzA - 1; }
+                if (nzB) { wv[3] = __ldg(Hm + tileBase + myPos + (uint32_t)(__ffs(nzB) - 1)); nzB &= nzB - 1; }
 #pragma unroll
-                for (int strand = 0; strand < 2; ++strand) {
-                    uint32_t& nz = strand ? nzB : nzA;
-                    if (!nz) continue;
-                    const uint32_t* src = strand ? sM : sP;
-                    int b = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    uint32_t wv = src[myPos + ((uint32_t)b ^ (rowSw << 2))];
-                    if ((wv & kValueMask) == ONE) { ++ones; continue; }
-                    uint32_t r = word_round_height<REPR>(wv);
+                for (int k = 0; k < 4; ++k) {
+                    if (!wv[k]) continue;
+                    if ((wv[k] & kValueMask) == ONE) { ++ones; continue; }
+                    uint32_t r = word_round_height<REPR>(wv[k]);
                     if (r < 4u) { small += 1u << (8 * r); if ((small & 0x80808080u) != 0u) flush_small(); }  // heights 0..3: byte counters in a register
                     else if (r < kScanLowBins) atomicAdd(&sHist[r], 1u);
                     else atomicAdd(&P.freqTail[r], 1u);
@@ -169,9 +123,9 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
                 }
             }
         }
-        __syncthreads();  // (A) both strands + mask are complete
+        __syncthreads();  // (A) the tile's minus occupancy words are complete
 
-        // K3: candidates = plus stacks with at least one minus stack at overlaps min..max
+        // K3: candidates = plus stacks with at least one minus stack at overlaps min..max (bitmaps only)
         uint32_t cnt = 0, ncand = 0, cand = 0;
         {
             uint32_t nz = nzP;
@@ -179,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
                 int b = __ffs(nz) - 1;
                 nz &= nz - 1;
                 uint32_t bit = myPos + b + P.minOv;
-                uint32_t bits = __funnelshift_r(sMask[bit >> 5], sMask[(bit >> 5) + 1], bit & 31) & wMask;
+                uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
                 if (bits) { cnt += __popc(bits); ++ncand; cand |= 1u << b; }
             }
         }
@@ -213,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
                     int b = __ffs(cm) - 1;
                     cm &= cm - 1;
                     uint32_t tp = myPos + b, bit = tp + P.minOv;
-                    uint32_t bits = __funnelshift_r(sMask[bit >> 5], sMask[(bit >> 5) + 1], bit & 31) & wMask;
+                    uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
                     uint32_t slot = rank - cbase;  // wraps to a huge value for earlier rounds
                     if (slot < (uint32_t)kCandCap) { sCandTp[slot] = (uint16_t)tp; sCandBits[slot] = bits; sCandOff[slot] = off; }
                     off += __popc(bits);
@@ -224,13 +178,13 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
                 for (uint32_t c = tid; c < nIn; c += kThreads) {
                     const uint32_t tp = sCandTp[c];
                     uint32_t bits = sCandBits[c];
-                    const uint32_t wp = sP[sw(tp)];
-                    const uint32_t w0 = tp + P.minOv;  // first window position (tile-relative)
+                    const uint32_t wp = __ldg(Hp + tileBase + tp);
+                    const uint32_t* win = Hm + tileBase + tp + P.minOv;  // first window word
                     // vicinity sum / max over the PRESENT stacks only, in overlap order: an absent stack would add
                     // +0.0f, which is an exact no-op (:564-577)
                     float sum = 0.0f, mx = 0.0f;
                     for (uint32_t rest = bits; rest; rest &= rest - 1) {
-                        float mq = word_height<REPR>(sM[sw(w0 + (uint32_t)(__ffs(rest) - 1))]);
+                        float mq = word_height<REPR>(__ldg(win + (__ffs(rest) - 1)));
                         sum = __fadd_rn(sum, mq);
                         mx = fmaxf(mx, mq);
                     }
@@ -240,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
                     while (bits) {                                            // :584-586
                         const int o = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        const uint32_t wm = sM[sw(w0 + o)];
+                        const uint32_t wm = __ldg(win + o);  // second touch: served by L1
                         const float mo = word_height<REPR>(wm);
                         const float local = __fdiv_rn(__fsub_rn(mo, __fsub_rn(mean, __fdiv_rn(mo, fW))), mx);  // :597
                         const uint32_t lbin = ((double)local < 0.2) ? 1u : 0u;     // :599
@@ -258,7 +212,6 @@ __global__ void __launch_bounds__(kThreads, 6) k_scan(ScanParams P) {
                 }
             }
         }
-        __syncthreads();  // (E) the staged tile is no longer read
     }
 
     // flush the privatised histogram
@@ -305,6 +258,8 @@ __global__ void __launch_bounds__(256) k_freq_lut(const unsigned long long* __re
 constexpr int kBgThreads = 512;
 constexpr int kBgWarps = kBgThreads / 32;
 constexpr int kBgHash = 4096;
+constexpr int kBgPerLane = 2;               // records per lane in flight
+constexpr int kBgItem = 32 * kBgPerLane;    // records per work item
 constexpr uint32_t kBgEmpty = 0xffffffffu;
 __global__ void __launch_bounds__(kBgThreads) k_bin_group(const PairRec* __restrict__ raw, PairRec* __restrict__ ordered, const uint32_t* __restrict__ tileCnt,
                                                           const uint32_t* __restrict__ tileBase, const uint32_t* __restrict__ tileDst, uint32_t nTiles,
@@ -353,7 +308,7 @@ __global__ void __launch_bounds__(kBgThreads) k_bin_group(const PairRec* __restr
             sCnt[lane] = cnt;
             sSrc[lane] = tile < nTiles ? tileBase[tile] : 0u;
             sDst[lane] = tile < nTiles ? tileDst[tile] : 0u;
-            const uint32_t items = (cnt + 63u) >> 6;
+            const uint32_t items = (cnt + (uint32_t)kBgItem - 1u) / (uint32_t)kBgItem;
             const uint32_t inc = warp_inclusive(items, lane);
             sItemStart[lane] = inc - items;
             if (lane == 31) sItemStart[32] = inc;
@@ -365,30 +320,34 @@ __global__ void __launch_bounds__(kBgThreads) k_bin_group(const PairRec* __restr
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1)
                 if (sItemStart[t + step] <= item) t += step;
-            const uint32_t cnt = sCnt[t], base = (item - sItemStart[t]) << 6;
+            const uint32_t cnt = sCnt[t], base = (item - sItemStart[t]) * (uint32_t)kBgItem;
             const size_t src = sSrc[t], dst = sDst[t];
-            const uint32_t i0 = base + lane, i1 = base + 32 + lane;  // two records per lane in flight
-            const bool ok0 = i0 < cnt, ok1 = i1 < cnt;
-            PairRec r0 = {0, 1.f, 1.f, 0}, r1 = {0, 1.f, 1.f, 0};
-            if (ok0) *reinterpret_cast<uint4*>(&r0) = *reinterpret_cast<const uint4*>(&raw[src + i0]);
-            if (ok1) *reinterpret_cast<uint4*>(&r1) = *reinterpret_cast<const uint4*>(&raw[src + i1]);
-            const float fp0 = lut[round_height(r0.rp)], fm0 = lut[round_height(r0.rm)];  // heightScoreMap[0.5 + reads], :582 / :589
-            const float fp1 = lut[round_height(r1.rp)], fm1 = lut[round_height(r1.rm)];
-            uint32_t cell0 = 0, cell1 = 0;
-            if (ok0) {
-                int b = bin_of(__fmul_rn(fp0, fm0));
-                r0.misc |= (uint32_t)b << 7;
-                cell0 = ((((uint32_t)b * (uint32_t)W + (r0.misc & 31u)) * 2u + ((r0.misc >> 6) & 1u)) * 2u) + ((r0.misc >> 5) & 1u);  // bin-major table
-                *reinterpret_cast<uint4*>(&ordered[dst + i0]) = *reinterpret_cast<uint4*>(&r0);
+            PairRec r[kBgPerLane];
+            bool ok[kBgPerLane];
+            float fp[kBgPerLane], fm[kBgPerLane];
+#pragma unroll
+            for (int u = 0; u < kBgPerLane; ++u) {  // kBgPerLane independent record loads in flight per lane
+                const uint32_t i = base + u * 32 + lane;
+                ok[u] = i < cnt;
+                r[u] = PairRec{0, 1.f, 1.f, 0};
+                if (ok[u]) *reinterpret_cast<uint4*>(&r[u]) = *reinterpret_cast<const uint4*>(&raw[src + i]);
             }
-            if (ok1) {
-                int b = bin_of(__fmul_rn(fp1, fm1));
-                r1.misc |= (uint32_t)b << 7;
-                cell1 = ((((uint32_t)b * (uint32_t)W + (r1.misc & 31u)) * 2u + ((r1.misc >> 6) & 1u)) * 2u) + ((r1.misc >> 5) & 1u);
-                *reinterpret_cast<uint4*>(&ordered[dst + i1]) = *reinterpret_cast<uint4*>(&r1);
+#pragma unroll
+            for (int u = 0; u < kBgPerLane; ++u) {  // heightScoreMap[0.5 + reads], :582 / :589
+                fp[u] = lut[round_height(r[u].rp)];
+                fm[u] = lut[round_height(r[u].rm)];
             }
-            count_cell(ok0, cell0);
-            count_cell(ok1, cell1);
+#pragma unroll
+            for (int u = 0; u < kBgPerLane; ++u) {
+                uint32_t cell = 0;
+                if (ok[u]) {
+                    int b = bin_of(__fmul_rn(fp[u], fm[u]));
+                    r[u].misc |= (uint32_t)b << 7;
+                    cell = ((((uint32_t)b * (uint32_t)W + (r[u].misc & 31u)) * 2u + ((r[u].misc >> 6) & 1u)) * 2u) + ((r[u].misc >> 5) & 1u);  // bin-major table
+                    *reinterpret_cast<uint4*>(&ordered[dst + base + u * 32 + lane]) = *reinterpret_cast<uint4*>(&r[u]);
+                }
+                count_cell(ok[u], cell);
+            }
         }
         __syncthreads();  // the batch descriptors are overwritten next
     }
@@ -404,7 +363,7 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int perSm = 6;
+    int perSm = 8;
     if (repr == kReprInt) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprInt>, kThreads, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprFloat>, kThreads, 0);
     if (perSm < 1) perSm = 1;

@@ -14,6 +14,10 @@
 // keys is folded sequentially with __fadd_rn, continuing from the word's current value so that
 // successive batches extend the same left-to-right sum.
 //
+// Both paths also maintain the OCCUPANCY BITMAP (1 bit per word of H, same index space: word i of H <-> bit i):
+// the thread that turns a word from 0 to non-zero sets its bit.  The scan (scan.cu) reads the bitmaps instead of
+// streaming the ~96 % empty arrays.
+//
 // Bound: L2 atomic throughput / 32-byte sector read-modify-write traffic, not streaming bandwidth.
 // Algorithmic bytes: 8 N (records) + 8 N (word read+write) + 8 G (zero fill at init/reset).
 #include "common.cuh"
@@ -39,7 +43,7 @@ __device__ __forceinline__ bool locate(const ppp_read r, const Slot& slot, int m
 }
 
 __global__ void __launch_bounds__(kBuildThreads) k_stack_build_int(const ppp_read* __restrict__ reads, size_t n, uint32_t* __restrict__ H, uint64_t G,
-                                                                    Slot slot, int mode, unsigned long long* counters) {
+                                                                    uint32_t* __restrict__ occ, Slot slot, int mode, unsigned long long* counters) {
     const unsigned lane = threadIdx.x & 31;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t nRound = (n + 31) & ~(size_t)31;  // whole warps stay converged for the warp primitives
@@ -59,7 +63,8 @@ __global__ void __launch_bounds__(kBuildThreads) k_stack_build_int(const ppp_rea
             unsigned peers = __match_any_sync(active, widx);       // lanes that hit the same word
             unsigned a10 = __ballot_sync(active, (r.meta & PPP_READ_A10) != 0);
             if (lane == (unsigned)(__ffs(peers) - 1)) {
-                atomicAdd(&H[widx], (uint32_t)__popc(peers));       // reads += 1 per read (:487)
+                uint32_t old = atomicAdd(&H[widx], (uint32_t)__popc(peers));  // reads += 1 per read (:487)
+                if ((old & kValueMask) == 0u) atomicOr(&occ[widx >> 5], 1u << (widx & 31u));  // first read of this stack: mark it occupied
                 if (a10 & peers) atomicOr(&H[widx], kA10Bit);       // AAtPosition10 = true (:471/:483)
             }
         }
@@ -170,8 +175,8 @@ __device__ __forceinline__ float read_weight_weighted(uint32_t meta) {
 }
 
 __global__ void __launch_bounds__(kBuildThreads) k_fold_runs(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t n,
-                                                              uint32_t* __restrict__ H, uint64_t G, unsigned long long* __restrict__ longRuns,
-                                                              unsigned int* __restrict__ nLong, unsigned int longCap) {
+                                                              uint32_t* __restrict__ H, uint64_t G, uint32_t* __restrict__ occ,
+                                                              unsigned long long* __restrict__ longRuns, unsigned int* __restrict__ nLong, unsigned int longCap) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t pos = keys[i];
@@ -202,13 +207,20 @@ __global__ void __launch_bounds__(kBuildThreads) k_fold_runs(const uint32_t* __r
             anyP = true;
         }
     }
-    if (anyP) H[pos] = (__float_as_uint(hp) & kValueMask) | ap;
-    if (anyM) H[G + pos] = (__float_as_uint(hm) & kValueMask) | am;
+    if (anyP) {
+        H[pos] = (__float_as_uint(hp) & kValueMask) | ap;
+        if (wp == 0u) atomicOr(&occ[pos >> 5], 1u << (pos & 31u));  // new stack: mark it occupied
+    }
+    if (anyM) {
+        H[G + pos] = (__float_as_uint(hm) & kValueMask) | am;
+        if (wm == 0u) atomicOr(&occ[(G + pos) >> 5], 1u << (pos & 31u));
+    }
 }
 
 __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t n,
-                                                              uint32_t* __restrict__ H, uint64_t G, const unsigned long long* __restrict__ longRuns,
-                                                              const unsigned int* __restrict__ nLong, unsigned int longCap) {
+                                                              uint32_t* __restrict__ H, uint64_t G, uint32_t* __restrict__ occ,
+                                                              const unsigned long long* __restrict__ longRuns, const unsigned int* __restrict__ nLong,
+                                                              unsigned int longCap) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned warpsPerGrid = gridDim.x * (kBuildThreads / 32);
     unsigned int count = *nLong;
@@ -276,8 +288,14 @@ __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __r
             }
         }
         if (lane == 0) {
-            if (anyP) H[pos] = (__float_as_uint(hp) & kValueMask) | (wp & kA10Bit) | (a10P ? kA10Bit : 0u);
-            if (anyM) H[G + pos] = (__float_as_uint(hm) & kValueMask) | (wm & kA10Bit) | (a10M ? kA10Bit : 0u);
+            if (anyP) {
+                H[pos] = (__float_as_uint(hp) & kValueMask) | (wp & kA10Bit) | (a10P ? kA10Bit : 0u);
+                if (wp == 0u) atomicOr(&occ[pos >> 5], 1u << (pos & 31u));
+            }
+            if (anyM) {
+                H[G + pos] = (__float_as_uint(hm) & kValueMask) | (wm & kA10Bit) | (a10M ? kA10Bit : 0u);
+                if (wm == 0u) atomicOr(&occ[(G + pos) >> 5], 1u << (pos & 31u));
+            }
         }
     }
 }
@@ -290,18 +308,18 @@ inline unsigned grid_for(size_t n, int threads, unsigned cap) {
 
 }  // namespace
 
-cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, Slot slot, int mode, unsigned long long* counters,
-                                   cudaStream_t s, int* launches) {
+cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, uint32_t* occ, Slot slot, int mode,
+                                   unsigned long long* counters, cudaStream_t s, int* launches) {
     if (n == 0) return cudaSuccess;
-    k_stack_build_int<<<grid_for(n, kBuildThreads, 148 * 16), kBuildThreads, 0, s>>>(reads, n, H, G, slot, mode, counters);
+    k_stack_build_int<<<grid_for(n, kBuildThreads, 148 * 16), kBuildThreads, 0, s>>>(reads, n, H, G, occ, slot, mode, counters);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
 size_t sort_block_hist_words(size_t n) { return ((n + kSortTile - 1) / kSortTile) * 256; }
 
-cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, Slot slot, unsigned long long* counters,
-                                        const SortScratch& scr, cudaStream_t s, int* launches) {
+cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, uint32_t* occ, Slot slot,
+                                        unsigned long long* counters, const SortScratch& scr, cudaStream_t s, int* launches) {
     if (n == 0) return cudaSuccess;
     if (n > scr.capacity) return cudaErrorInvalidValue;
     unsigned blocks = (unsigned)((n + kBuildThreads - 1) / kBuildThreads);
@@ -330,8 +348,8 @@ cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_
     unsigned int longCap = (unsigned int)(scr.capacity / 2);
     cudaError_t e = cudaMemsetAsync(nLong, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;
-    k_fold_runs<<<blocks, kBuildThreads, 0, s>>>(kin, vin, n, H, G, longRuns, nLong, longCap);
-    k_fold_long<<<148 * 2, kBuildThreads, 0, s>>>(kin, vin, n, H, G, longRuns, nLong, longCap);
+    k_fold_runs<<<blocks, kBuildThreads, 0, s>>>(kin, vin, n, H, G, occ, longRuns, nLong, longCap);
+    k_fold_long<<<148 * 2, kBuildThreads, 0, s>>>(kin, vin, n, H, G, occ, longRuns, nLong, longCap);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

@@ -168,20 +168,20 @@ def test_max_overlap_sweep_and_min_stack_height():
     """BASELINE.json config 5: -s 1..20 and background range up to 30 nt."""
     m = host.SynthModel(None, n_reads=120_000, seed=9, lengths=[60000, 40000])
     reads = m.generate(mode="weighted")
-    for max_ov in (23, 26, 30):
-        o, sigs = oracle_reference(m.lengths, reads, "weighted", 3, max_ov, 10)
-        with api.Context(m.lengths, mode="weighted", max_overlap=max_ov) as ctx:
+    for min_ov, max_ov in ((3, 23), (3, 26), (3, 30), (1, 32), (0, 31), (8, 12)):
+        o, sigs = oracle_reference(m.lengths, reads, "weighted", min_ov, max_ov, 10)
+        with api.Context(m.lengths, mode="weighted", min_overlap=min_ov, max_overlap=max_ov) as ctx:
             for c, r in enumerate(reads):
                 ctx.count_reads(c, r)
             ctx.finish()
             ctx.map_heights_to_scores()
             g = ctx.count_stacks_by_group()
             assert np.array_equal(np.minimum(g, 1 << 24).astype(np.float32), o.grouped_pre())
-            sel = sigs[sigs["ov"] == 7]
+            sel = sigs[sigs["ov"] == 10 - min_ov]
             for s in (0, 1, 2, 3, 5, 8, 13, 20):
                 sc = ctx.calculate_fdrs(s)
                 keep = sel[(sel["rp"] >= np.float32(s)) & (sel["rm"] >= np.float32(s))]
-                assert len(sc.loci) == len(keep), (max_ov, s)
+                assert len(sc.loci) == len(keep), (min_ov, max_ov, s)
                 assert np.array_equal(sc.loci["position"], keep["pos"]) and np.array_equal(bits(sc.loci["fdr"]), bits(keep["fdr"]))
 
 
