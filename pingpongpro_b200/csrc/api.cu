@@ -67,7 +67,7 @@ struct ppp_ctx {
     uint64_t G = 0, ownedPositions = 0;
     uint32_t nTiles = 0, haloLo = 0, haloHi = 0;
 
-    cudaStream_t stream = nullptr, copyStream = nullptr;
+    cudaStream_t stream = nullptr, copyStream = nullptr, sortStream = nullptr;
     uint32_t* H = nullptr;
     uint32_t* occ = nullptr;  // occupancy bitmap of H (2G bits + padding)
     size_t occWords = 0;
@@ -83,7 +83,11 @@ struct ppp_ctx {
     uint64_t readsSubmitted = 0;
     std::vector<Timer> buildTimers;
     float buildMs = 0.f;
-    SortScratch sort = {};
+    // -m weighted: the sort of batch k+1 (sortStream) overlaps the fold of batch k (stream); two scratch sets
+    SortScratch sort[2] = {};
+    cudaEvent_t evSorted[2] = {nullptr, nullptr}, evFolded[2] = {nullptr, nullptr}, evReset = nullptr;
+    bool sortUsed[2] = {false, false};
+    unsigned batchCount = 0;
 
     // scan state
     unsigned long long* dFreqLow = nullptr;
@@ -128,13 +132,13 @@ struct ppp_ctx {
 
 namespace {
 
-int timerStart(ppp_ctx* c, Timer& t) {
+int timerStart(ppp_ctx* c, Timer& t, cudaStream_t s = nullptr) {
     if (!t.a) { CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b)); }
-    CK(cudaEventRecord(t.a, c->stream));
+    CK(cudaEventRecord(t.a, s ? s : c->stream));
     return PPP_OK;
 }
-int timerStop(ppp_ctx* c, Timer& t) {
-    CK(cudaEventRecord(t.b, c->stream));
+int timerStop(ppp_ctx* c, Timer& t, cudaStream_t s = nullptr) {
+    CK(cudaEventRecord(t.b, s ? s : c->stream));
     t.used = true;
     return PPP_OK;
 }
@@ -175,9 +179,9 @@ bool computeThresholds(float maxFreq, float* thr) {
     double lastGuess = 1.0;
     for (int b = 1; b < PPP_HEIGHT_SCORE_BINS; ++b) {
         if (topBin < b) { thr[b - 1] = std::numeric_limits<float>::infinity(); continue; }
-        // analytic estimate of the step (bin >= b  <=>  log10(hs) / maxHs * 999 >= b - 0.5), then gallop + bisect around it
-        double guessD = b == 1 ? pow(10.0, 0.5 / 999.0 * (double)maxHs) : lastGuess * ratio;  // 10^((b - 0.5) / 999 * maxHs), incrementally
-        lastGuess = guessD;
+        // thresholds form a geometric sequence (bin >= b  <=>  log10(hs) >= (b - 0.5) / 999 * maxHs): the previous exact
+        // threshold times the common ratio lands within a few float steps of the next one
+        double guessD = b == 1 ? pow(10.0, 0.5 / 999.0 * (double)maxHs) : lastGuess * ratio;
         float guessF = (float)guessD;
         uint32_t g;
         memcpy(&g, &guessF, 4);
@@ -208,6 +212,7 @@ bool computeThresholds(float maxFreq, float* thr) {
             if (binAt(mid) >= b) hi = mid; else lo = mid + 1;
         }
         memcpy(&thr[b - 1], &hi, 4);
+        lastGuess = (double)thr[b - 1];
         // local validation: a few patterns either side must respect the step
         if (hi >= loBits + 2 && binAt(hi - 2) >= b) monotone = false;  // (hi - 1 was already probed by the bisection)
         if (hi + 1 <= topBits && binAt(hi + 1) < b) monotone = false;
@@ -291,9 +296,9 @@ int ensurePairCapacity(ppp_ctx* c, uint64_t want) {
     return PPP_OK;
 }
 
-int ensureSortScratch(ppp_ctx* c) {
-    if (c->sort.keysA) return PPP_OK;
-    SortScratch& s = c->sort;
+int ensureSortScratch(ppp_ctx* c, int set) {
+    SortScratch& s = c->sort[set];
+    if (s.keysA) return PPP_OK;
     s.capacity = kChunk;
     CK(cudaMalloc(&s.keysA, kChunk * 4));
     CK(cudaMalloc(&s.keysB, kChunk * 4));
@@ -303,24 +308,47 @@ int ensureSortScratch(ppp_ctx* c) {
     CK(cudaMalloc(&s.blockHist, s.blockHistWords * 4));
     s.scanScratchWords = exclusive_scan_scratch_words(s.blockHistWords);
     CK(cudaMalloc(&s.scanScratch, s.scanScratchWords * 4));
+    CK(cudaEventCreateWithFlags(&c->evSorted[set], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evFolded[set], cudaEventDisableTiming));
     return PPP_OK;
 }
 
-// Stack-builder kernels for n device-resident records of one contig (n <= kChunk).
-int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n) {
+// Stack-builder kernels for n device-resident records of one contig (n <= kChunk).  `ready` (may be null): the
+// records are valid once it has fired; `consumed` (may be null) is recorded when the kernels no longer read them.
+int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n, cudaEvent_t ready, cudaEvent_t consumed) {
     Timer t;
-    int rc = timerStart(c, t);
-    if (rc) return rc;
+    int rc;
     if (c->repr == kReprInt) {
+        if (ready) CK(cudaStreamWaitEvent(c->stream, ready, 0));
+        if ((rc = timerStart(c, t))) return rc;
         CK(launch_stack_build_int(dReads, n, c->H, c->G, c->occ, slot, c->mode, c->dCounters, c->stream, &c->launches));
-    } else {
-        rc = ensureSortScratch(c);
-        if (rc) return rc;
-        CK(launch_stack_build_weighted(dReads, n, c->H, c->G, c->occ, slot, c->dCounters, c->sort, c->stream, &c->launches));
+        if ((rc = timerStop(c, t))) return rc;
+        if (consumed) CK(cudaEventRecord(consumed, c->stream));
+        c->buildTimers.push_back(t);
+        return PPP_OK;
     }
-    rc = timerStop(c, t);
-    if (rc) return rc;
+    // the additions of one position must happen in file order, so folds stay on `stream` in submission order; the
+    // sort has no such constraint and runs ahead on its own stream while the previous batch's long stacks are folded
+    const int set = (int)(c->batchCount & 1u);
+    if ((rc = ensureSortScratch(c, set))) return rc;
+    if (ready) CK(cudaStreamWaitEvent(c->sortStream, ready, 0));
+    if (c->sortUsed[set]) CK(cudaStreamWaitEvent(c->sortStream, c->evFolded[set], 0));  // scratch set free again
+    SortedRun run;
+    if ((rc = timerStart(c, t, c->sortStream))) return rc;
+    CK(launch_stack_sort(dReads, n, c->G, slot, c->dCounters, c->sort[set], c->sortStream, &c->launches, &run));
+    if ((rc = timerStop(c, t, c->sortStream))) return rc;
     c->buildTimers.push_back(t);
+    if (consumed) CK(cudaEventRecord(consumed, c->sortStream));
+    CK(cudaEventRecord(c->evSorted[set], c->sortStream));
+    CK(cudaStreamWaitEvent(c->stream, c->evSorted[set], 0));
+    Timer tf;
+    if ((rc = timerStart(c, tf))) return rc;
+    CK(launch_stack_fold(run, c->H, c->G, c->occ, c->sort[set].capacity, c->stream, &c->launches));
+    if ((rc = timerStop(c, tf))) return rc;
+    c->buildTimers.push_back(tf);
+    CK(cudaEventRecord(c->evFolded[set], c->stream));
+    c->sortUsed[set] = true;
+    c->batchCount++;
     return PPP_OK;
 }
 
@@ -415,6 +443,8 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     } while (0)
     CKI(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CKI(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    CKI(cudaStreamCreateWithFlags(&c->sortStream, cudaStreamNonBlocking));
+    CKI(cudaEventCreateWithFlags(&c->evReset, cudaEventDisableTiming));
     size_t hWords = 2 * c->G + 64;
     CKI(cudaMalloc(&c->H, hWords * sizeof(uint32_t)));
     CKI(cudaMemsetAsync(c->H, 0, hWords * sizeof(uint32_t), c->stream));
@@ -479,9 +509,11 @@ void ppp_destroy(ppp_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    if (c->sortStream) cudaStreamSynchronize(c->sortStream);
     foldBuildTimers(c);
-    void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dStage[0], c->dStage[1], c->sort.keysA, c->sort.keysB, c->sort.valsA, c->sort.valsB, c->sort.blockHist,
-                   c->sort.scanScratch, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
+    void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dStage[0], c->dStage[1], c->sort[0].keysA, c->sort[0].keysB, c->sort[0].valsA, c->sort[0].valsB, c->sort[0].blockHist,
+                   c->sort[0].scanScratch, c->sort[1].keysA, c->sort[1].keysB, c->sort[1].valsA, c->sort[1].valsB, c->sort[1].blockHist,
+                   c->sort[1].scanScratch, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
                    c->dPairFdr, c->dLoci, c->dTileCnt, c->dTileBase, c->dTileDst, c->dScanScratch, c->dBlockCnt, c->dGrouped, c->dThresholds, c->dCells,
                    c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dTileCursor};
     for (void* p : dev)
@@ -492,11 +524,15 @@ void ppp_destroy(ppp_ctx* c) {
     for (int k = 0; k < 2; ++k) {
         if (c->evCopied[k]) cudaEventDestroy(c->evCopied[k]);
         if (c->evConsumed[k]) cudaEventDestroy(c->evConsumed[k]);
+        if (c->evSorted[k]) cudaEventDestroy(c->evSorted[k]);
+        if (c->evFolded[k]) cudaEventDestroy(c->evFolded[k]);
     }
     for (Timer* t : {&c->tScan, &c->tLut, &c->tBin, &c->tScore, &c->tTransposon})
         if (t->a) { cudaEventDestroy(t->a); cudaEventDestroy(t->b); }
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
+    if (c->sortStream) cudaStreamDestroy(c->sortStream);
+    if (c->evReset) cudaEventDestroy(c->evReset);
     delete c;
 }
 
@@ -507,6 +543,8 @@ int ppp_reset(ppp_ctx* c) {
     CK(cudaMemsetAsync(c->H, 0, (2 * c->G + 64) * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->occ, 0, c->occWords * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->dCounters, 0, 2 * sizeof(unsigned long long), c->stream));
+    CK(cudaEventRecord(c->evReset, c->stream));  // the sort stream's kernels count into dCounters
+    CK(cudaStreamWaitEvent(c->sortStream, c->evReset, 0));
     c->readsSubmitted = 0;
     c->finished = false;
     invalidateResults(c);
@@ -529,7 +567,7 @@ int ppp_reads_submit_device(ppp_ctx* c, int32_t contig, const ppp_read* dReads, 
     const Slot& slot = c->slotOfContig[contig];
     for (size_t o = 0; o < n; o += kChunk) {
         size_t k = std::min(kChunk, n - o);
-        int rc = buildChunk(c, slot, dReads + o, k);
+        int rc = buildChunk(c, slot, dReads + o, k, nullptr, nullptr);
         if (rc) return rc;
     }
     c->readsSubmitted += n;
@@ -564,10 +602,8 @@ int ppp_reads_submit(ppp_ctx* c, int32_t contig, const ppp_read* reads, size_t n
         if (c->slotUsed[s]) CK(cudaStreamWaitEvent(c->copyStream, c->evConsumed[s], 0));  // kernels done with dStage[s]
         CK(cudaMemcpyAsync(c->dStage[s], src, k * sizeof(ppp_read), cudaMemcpyHostToDevice, c->copyStream));
         CK(cudaEventRecord(c->evCopied[s], c->copyStream));
-        CK(cudaStreamWaitEvent(c->stream, c->evCopied[s], 0));
-        int rc = buildChunk(c, slot, c->dStage[s], k);
+        int rc = buildChunk(c, slot, c->dStage[s], k, c->evCopied[s], c->evConsumed[s]);
         if (rc) return rc;
-        CK(cudaEventRecord(c->evConsumed[s], c->stream));
         c->slotUsed[s] = true;
         c->submitCount++;
     }
@@ -579,6 +615,7 @@ int ppp_stacks_finish(ppp_ctx* c) {
     if (!c) return fail(PPP_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->copyStream));
+    CK(cudaStreamSynchronize(c->sortStream));
     CK(cudaMemcpyAsync(c->hs->counters, c->dCounters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     foldBuildTimers(c);

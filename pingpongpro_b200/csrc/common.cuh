@@ -92,8 +92,15 @@ struct SortScratch {
     size_t capacity, blockHistWords, scanScratchWords;
 };
 size_t sort_block_hist_words(size_t n);
-cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, uint32_t* occ, Slot slot,
-                                        unsigned long long* counters, const SortScratch& scr, cudaStream_t s, int* launches);
+// -m weighted, in two halves so that the sort of one batch can overlap the (latency-bound) fold of the previous one:
+// the sort leaves (position, meta) records ordered by position, file order within a position; the fold adds them to H.
+struct SortedRun {
+    uint32_t *keys, *vals, *spareA, *spareB;
+    size_t n;
+};
+cudaError_t launch_stack_sort(const ppp_read* reads, size_t n, uint64_t G, Slot slot, unsigned long long* counters, const SortScratch& scr,
+                              cudaStream_t s, int* launches, SortedRun* out);
+cudaError_t launch_stack_fold(const SortedRun& r, uint32_t* H, uint64_t G, uint32_t* occ, size_t capacity, cudaStream_t s, int* launches);
 
 cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* launches);
 cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* freqTail, const uint32_t* maxHeight, float* lut,

@@ -166,12 +166,21 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t* 
 // Runs of equal keys are in file order (stable sort); plus- and minus-strand records of the same position are
 // folded into their own words.  Short runs: one thread per run (the thread at the run's first element).  Runs
 // longer than kShortRun (piRNA stacks are heavy tailed: a single position can hold > 10^6 reads) are deferred to
-// k_fold_long, where a warp loads 32 records at a time, evaluates the weights in parallel and only the
-// __fadd_rn chain itself stays serial (adding +0.0f for the other strand's records is exact).
+// k_fold_long, where a warp finds the end of the run, streams its records with a deep software pipeline, evaluates
+// the weights 32 at a time and only the __fadd_rn chain itself stays serial (adding +0.0f for the other strand's
+// records is exact).
 constexpr int kShortRun = 32;
+constexpr int kFoldBlock = 256;  // records per pipeline stage of k_fold_long
+constexpr int kWeightLut = 64;
 
 __device__ __forceinline__ float read_weight_weighted(uint32_t meta) {
-    return (float)__ddiv_rn(1.0, (double)(meta >> PPP_READ_NH_SHIFT));  // readWeight = 1.0 / multiHits, narrowed to float (:449)
+    // readWeight = 1.0 / multiHits in double, narrowed to float (:449).  For multiHits < 2^24 the correctly rounded
+    // single-precision reciprocal is the same number: 1/n stays at least 2^-24/n (relative) away from every
+    // rounding tie of the float format, far more than the 2^-53 the intermediate double could move it
+    // (checked exhaustively in tests/test_frontend.py).
+    const uint32_t nh = meta >> PPP_READ_NH_SHIFT;
+    if (nh < (1u << 24)) return __frcp_rn((float)nh);
+    return (float)__ddiv_rn(1.0, (double)nh);
 }
 
 __global__ void __launch_bounds__(kBuildThreads) k_fold_runs(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t n,
@@ -217,76 +226,123 @@ __global__ void __launch_bounds__(kBuildThreads) k_fold_runs(const uint32_t* __r
     }
 }
 
+// End of the run of `pos` that starts at keys[i] (keys are sorted, keys[i + kShortRun] == pos is known): the whole warp
+// gallops (lane l probes i + 32 * 2^l) and then narrows the bracket 32-fold per round of independent loads.
+__device__ __forceinline__ size_t warp_run_end(const uint32_t* __restrict__ keys, size_t i, size_t n, uint32_t pos, unsigned lane) {
+    size_t p = i + ((size_t)kShortRun << lane);
+    unsigned hit = __ballot_sync(0xffffffffu, lane < 26 && p < n && keys[p] == pos);  // a prefix of the lanes
+    int k = __popc(hit);                                                              // >= 1 (lane 0 probes i + 32)
+    size_t lo = i + ((size_t)kShortRun << (k - 1));                                   // keys[lo] == pos
+    size_t hi = i + ((size_t)kShortRun << k);                                         // keys[hi] != pos (or hi >= n)
+    if (hi > n) hi = n;
+    while (hi - lo > 1) {
+        const size_t step = (hi - lo + 31) / 32;
+        p = lo + (size_t)(lane + 1) * step;
+        hit = __ballot_sync(0xffffffffu, p < hi && keys[p] == pos);
+        k = __popc(hit);
+        const size_t nlo = lo + (size_t)k * step, nhi = lo + (size_t)(k + 1) * step;
+        lo = nlo;
+        if (nhi < hi) hi = nhi;
+    }
+    return hi;
+}
+
 __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t n,
                                                               uint32_t* __restrict__ H, uint64_t G, uint32_t* __restrict__ occ,
                                                               const unsigned long long* __restrict__ longRuns, const unsigned int* __restrict__ nLong,
                                                               unsigned int longCap) {
+    __shared__ __align__(16) float stage[kBuildThreads / 32][2][kFoldBlock];
+    __shared__ float weightOf[kWeightLut];  // weights of the common multiplicities (the reciprocal is ~1/4 of the warp's instructions otherwise)
+    if (threadIdx.x < kWeightLut) weightOf[threadIdx.x] = read_weight_weighted((uint32_t)threadIdx.x << PPP_READ_NH_SHIFT);
+    __syncthreads();
     const unsigned lane = threadIdx.x & 31;
+    float* const stageP = stage[threadIdx.x >> 5][0];
+    float* const stageM = stage[threadIdx.x >> 5][1];
     const unsigned warpsPerGrid = gridDim.x * (kBuildThreads / 32);
     unsigned int count = *nLong;
     if (count > longCap) count = longCap;
     for (unsigned int run = blockIdx.x * (kBuildThreads / 32) + (threadIdx.x >> 5); run < count; run += warpsPerGrid) {
         const size_t i = (size_t)longRuns[run];
         const uint32_t pos = keys[i];
+        const size_t end = warp_run_end(keys, i, n, pos, lane);
         uint32_t wp = H[pos], wm = H[G + pos];
         float hp = __uint_as_float(wp & kValueMask), hm = __uint_as_float(wm & kValueMask);
-        unsigned anyP = 0, anyM = 0, a10P = 0, a10M = 0;
-        // software pipeline: 4 x 32 records (independent loads) are fetched while the previous 128 are added
-        constexpr int kDepth = 4;
-        uint32_t kq[kDepth], vq[kDepth];
+        unsigned anyP = 0, anyM = 0, accP = 0, accM = 0;
+        // One warp owns the run, so nothing hides latency but the warp itself.  Records move in blocks of 256: while
+        // one block is added, the next one's loads are in flight.  The weights of a block are evaluated 32 at a time
+        // (off the serial chain) and staged in shared memory per strand, so the chain reads them back with
+        // broadcast 128-bit loads and is nothing but dependent additions (:487, file order).
+        constexpr int kDepth = kFoldBlock / 32;
+        uint32_t vq[kDepth];
         auto fetch = [&](size_t base) {
+            const uint32_t* src = vals + base + lane;
+            const unsigned left = (unsigned)min((size_t)kFoldBlock, end - base);
 #pragma unroll
-            for (int u = 0; u < kDepth; ++u) {
-                size_t j = base + (size_t)u * 32 + lane;
-                kq[u] = j < n ? keys[j] : kInvalidPos;
-                vq[u] = j < n ? vals[j] : 0u;
-            }
+            for (int u = 0; u < kDepth; ++u) vq[u] = u * 32 + lane < left ? src[u * 32] : 0u;
         };
-        size_t nextBase = i;
-        fetch(nextBase);
-        bool more = true;
-        while (more) {
-            uint32_t kc[kDepth], vc[kDepth];
+        size_t base = i;
+        fetch(base);
+        while (base < end) {
+            uint32_t vc[kDepth];
 #pragma unroll
-            for (int u = 0; u < kDepth; ++u) { kc[u] = kq[u]; vc[u] = vq[u]; }
-            nextBase += (size_t)kDepth * 32;
-            fetch(nextBase);  // in flight during the adds below (harmless past the end of the run)
+            for (int u = 0; u < kDepth; ++u) vc[u] = vq[u];
+            const size_t nextBase = base + (size_t)kFoldBlock;
+            if (nextBase < end) fetch(nextBase);
+            unsigned laneP = 0, laneM = 0;
+            const unsigned left = (unsigned)min((size_t)kFoldBlock, end - base);
 #pragma unroll
             for (int u = 0; u < kDepth; ++u) {
-                if (!more) break;
-                const bool in = kc[u] == pos;
-                const unsigned mask = __ballot_sync(0xffffffffu, in);  // a prefix of the lanes: the run is contiguous
-                const int cnt = __popc(mask);
-                if (cnt < 32) more = false;
-                if (cnt == 0) break;
-                const float w = in ? read_weight_weighted(vc[u]) : 0.0f;
-                const bool live = in && w > 0.0f;                                     // :458
+                const bool in = u * 32 + lane < left;
+                const uint32_t nh = vc[u] >> PPP_READ_NH_SHIFT;
+                const float wt = nh < kWeightLut ? weightOf[nh] : read_weight_weighted(vc[u]);
+                const bool live = in && wt > 0.0f;  // :458
                 const bool minus = (vc[u] & PPP_READ_MINUS) != 0;
-                const float addP = live && !minus ? w : 0.0f, addM = live && minus ? w : 0.0f;
-                const unsigned liveP = __ballot_sync(0xffffffffu, live && !minus), liveM = __ballot_sync(0xffffffffu, live && minus);
-                anyP |= liveP;
-                anyM |= liveM;
-                a10P |= __ballot_sync(0xffffffffu, live && !minus && (vc[u] & PPP_READ_A10));  // :483
-                a10M |= __ballot_sync(0xffffffffu, live && minus && (vc[u] & PPP_READ_A10));   // :471
-                // the adds themselves are the only serial part (:487, file order); a strand without records is skipped
-                if (liveP) {
-                    if (cnt == 32) {
+                stageP[u * 32 + lane] = live && !minus ? wt : 0.0f;  // adding +0.0f is exact
+                stageM[u * 32 + lane] = live && minus ? wt : 0.0f;
+                laneP |= live && !minus ? vc[u] | 0x80000000u : 0u;  // A10 flag: :483
+                laneM |= live && minus ? vc[u] | 0x80000000u : 0u;   // :471
+            }
+            accP |= laneP;
+            accM |= laneM;
+            const unsigned blockP = __ballot_sync(0xffffffffu, laneP != 0), blockM = __ballot_sync(0xffffffffu, laneM != 0);
+            anyP |= blockP;
+            anyM |= blockM;
+            __syncwarp();
+            const float4* qp = reinterpret_cast<const float4*>(stageP);
+            const float4* qm = reinterpret_cast<const float4*>(stageM);
+            if (nextBase <= end) {  // a full block
+                if (blockM == 0) {
 #pragma unroll
-                        for (int l = 0; l < 32; ++l) hp = __fadd_rn(hp, __shfl_sync(0xffffffffu, addP, l));
-                    } else {
-                        for (int l = 0; l < cnt; ++l) hp = __fadd_rn(hp, __shfl_sync(0xffffffffu, addP, l));
+                    for (int t = 0; t < kFoldBlock / 4; ++t) {
+                        const float4 v = qp[t];
+                        hp = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hp, v.x), v.y), v.z), v.w);
+                    }
+                } else if (blockP == 0) {
+#pragma unroll
+                    for (int t = 0; t < kFoldBlock / 4; ++t) {
+                        const float4 v = qm[t];
+                        hm = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hm, v.x), v.y), v.z), v.w);
+                    }
+                } else {  // both strands at this position: two independent chains
+#pragma unroll
+                    for (int t = 0; t < kFoldBlock / 4; ++t) {
+                        const float4 v = qp[t], x = qm[t];
+                        hp = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hp, v.x), v.y), v.z), v.w);
+                        hm = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hm, x.x), x.y), x.z), x.w);
                     }
                 }
-                if (liveM) {
-                    if (cnt == 32) {
-#pragma unroll
-                        for (int l = 0; l < 32; ++l) hm = __fadd_rn(hm, __shfl_sync(0xffffffffu, addM, l));
-                    } else {
-                        for (int l = 0; l < cnt; ++l) hm = __fadd_rn(hm, __shfl_sync(0xffffffffu, addM, l));
-                    }
+            } else {  // the run ends inside this block (records past its end were staged as zeros)
+                const int quads = (int)((end - base + 3) / 4);
+                for (int t = 0; t < quads; ++t) {
+                    const float4 v = qp[t], x = qm[t];
+                    hp = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hp, v.x), v.y), v.z), v.w);
+                    hm = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hm, x.x), x.y), x.z), x.w);
                 }
             }
+            __syncwarp();
+            base = nextBase;
         }
+        const unsigned a10P = __ballot_sync(0xffffffffu, (accP & PPP_READ_A10) != 0), a10M = __ballot_sync(0xffffffffu, (accM & PPP_READ_A10) != 0);
         if (lane == 0) {
             if (anyP) {
                 H[pos] = (__float_as_uint(hp) & kValueMask) | (wp & kA10Bit) | (a10P ? kA10Bit : 0u);
@@ -318,8 +374,9 @@ cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H,
 
 size_t sort_block_hist_words(size_t n) { return ((n + kSortTile - 1) / kSortTile) * 256; }
 
-cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, uint32_t* occ, Slot slot,
-                                        unsigned long long* counters, const SortScratch& scr, cudaStream_t s, int* launches) {
+cudaError_t launch_stack_sort(const ppp_read* reads, size_t n, uint64_t G, Slot slot, unsigned long long* counters, const SortScratch& scr,
+                              cudaStream_t s, int* launches, SortedRun* out) {
+    out->n = 0;
     if (n == 0) return cudaSuccess;
     if (n > scr.capacity) return cudaErrorInvalidValue;
     unsigned blocks = (unsigned)((n + kBuildThreads - 1) / kBuildThreads);
@@ -342,14 +399,25 @@ cudaError_t launch_stack_build_weighted(const ppp_read* reads, size_t n, uint32_
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
-    // the sort's output buffers of the last pass are free again: kout holds the long-run list, vout[0] its length
-    unsigned long long* longRuns = reinterpret_cast<unsigned long long*>(kout);
-    unsigned int* nLong = reinterpret_cast<unsigned int*>(vout);
-    unsigned int longCap = (unsigned int)(scr.capacity / 2);
+    out->keys = kin;
+    out->vals = vin;
+    out->spareA = kout;
+    out->spareB = vout;
+    out->n = n;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stack_fold(const SortedRun& r, uint32_t* H, uint64_t G, uint32_t* occ, size_t capacity, cudaStream_t s, int* launches) {
+    if (r.n == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((r.n + kBuildThreads - 1) / kBuildThreads);
+    // the sort's output buffers of the last pass are free again: spareA holds the long-run list, spareB[0] its length
+    unsigned long long* longRuns = reinterpret_cast<unsigned long long*>(r.spareA);
+    unsigned int* nLong = reinterpret_cast<unsigned int*>(r.spareB);
+    unsigned int longCap = (unsigned int)(capacity / 2);
     cudaError_t e = cudaMemsetAsync(nLong, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;
-    k_fold_runs<<<blocks, kBuildThreads, 0, s>>>(kin, vin, n, H, G, occ, longRuns, nLong, longCap);
-    k_fold_long<<<148 * 2, kBuildThreads, 0, s>>>(kin, vin, n, H, G, occ, longRuns, nLong, longCap);
+    k_fold_runs<<<blocks, kBuildThreads, 0, s>>>(r.keys, r.vals, r.n, H, G, occ, longRuns, nLong, longCap);
+    k_fold_long<<<148 * 2, kBuildThreads, 0, s>>>(r.keys, r.vals, r.n, H, G, occ, longRuns, nLong, longCap);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

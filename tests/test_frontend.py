@@ -130,3 +130,12 @@ def test_parallel_bgzf_inflate_equals_sequential(tmp_path):
     for t in (1, 4):
         with pytest.raises(ValueError):
             host.decode_file(str(trunc), threads=t)
+
+
+def test_weight_reciprocal_single_equals_double_narrowed():
+    """The device evaluates the -m weighted read weight (float)(1.0 / (double)NH) (pingpongpro.cpp:449) as a correctly
+    rounded single-precision reciprocal for NH < 2^24; the two are the same number for every such NH."""
+    n = np.arange(1, 1 << 24, dtype=np.uint32)
+    narrowed = (1.0 / n.astype(np.float64)).astype(np.float32)
+    single = np.float32(1.0) / n.astype(np.float32)
+    assert np.array_equal(narrowed.view(np.uint32), single.view(np.uint32))
