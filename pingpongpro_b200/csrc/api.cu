@@ -40,6 +40,8 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr uint32_t kKeySlack = 64;          // keys up to contig length + 63 are accepted (a - key may equal the length, :464)
 constexpr size_t kChunk = (size_t)1 << 23;  // records per upload / sort chunk (64 MB)
+constexpr int kFoldStreams = 4;
+constexpr int kStages = 4;                  // depth of the upload -> sort -> fold pipeline (buffers are allocated on first use)
 constexpr int kTile = kScanTile;
 
 struct Timer {
@@ -68,6 +70,7 @@ struct ppp_ctx {
     uint32_t nTiles = 0, haloLo = 0, haloHi = 0;
 
     cudaStream_t stream = nullptr, copyStream = nullptr, sortStream = nullptr;
+    cudaStream_t foldStream[kFoldStreams] = {};  // -m weighted: folds of different contigs may overlap (see buildChunk)
     uint32_t* H = nullptr;
     uint32_t* occ = nullptr;  // occupancy bitmap of H (2G bits + padding)
     size_t occWords = 0;
@@ -75,18 +78,20 @@ struct ppp_ctx {
     unsigned long long* dCounters = nullptr;  // [0] foreign, [1] range errors
 
     // upload double buffers
-    ppp_read* dStage[2] = {nullptr, nullptr};
+    // upload ring: kStages device buffers (a long fold must not hold up the copies and sorts behind it), two pinned
+    // bounce buffers for callers whose memory is pageable
+    ppp_read* dStage[kStages] = {};
     ppp_read* hStage[2] = {nullptr, nullptr};
-    cudaEvent_t evCopied[2] = {nullptr, nullptr}, evConsumed[2] = {nullptr, nullptr};
-    bool slotUsed[2] = {false, false};
+    cudaEvent_t evCopied[kStages] = {}, evConsumed[kStages] = {};
+    bool slotUsed[kStages] = {};
     unsigned submitCount = 0;
     uint64_t readsSubmitted = 0;
     std::vector<Timer> buildTimers;
     float buildMs = 0.f;
-    // -m weighted: the sort of batch k+1 (sortStream) overlaps the fold of batch k (stream); two scratch sets
-    SortScratch sort[2] = {};
-    cudaEvent_t evSorted[2] = {nullptr, nullptr}, evFolded[2] = {nullptr, nullptr}, evReset = nullptr;
-    bool sortUsed[2] = {false, false};
+    // -m weighted: the sorts of the next batches (sortStream) overlap the fold of batch k (stream); one scratch set per stage
+    SortScratch sort[kStages] = {};
+    cudaEvent_t evSorted[kStages] = {}, evFolded[kStages] = {}, evReset = nullptr;
+    bool sortUsed[kStages] = {};
     unsigned batchCount = 0;
 
     // scan state
@@ -327,9 +332,12 @@ int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n, c
         c->buildTimers.push_back(t);
         return PPP_OK;
     }
-    // the additions of one position must happen in file order, so folds stay on `stream` in submission order; the
-    // sort has no such constraint and runs ahead on its own stream while the previous batch's long stacks are folded
-    const int set = (int)(c->batchCount & 1u);
+    // The additions of one position must happen in file order: the folds of one contig stay on one stream, in
+    // submission order.  Contigs share no positions, so their folds may overlap -- the tail of a fold is a single
+    // warp working through the tallest stack.  The sort has no ordering constraint at all and runs ahead on its
+    // own stream.
+    cudaStream_t fs = c->foldStream[(unsigned)slot.contig % kFoldStreams];
+    const int set = (int)(c->batchCount % kStages);
     if ((rc = ensureSortScratch(c, set))) return rc;
     if (ready) CK(cudaStreamWaitEvent(c->sortStream, ready, 0));
     if (c->sortUsed[set]) CK(cudaStreamWaitEvent(c->sortStream, c->evFolded[set], 0));  // scratch set free again
@@ -340,13 +348,13 @@ int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n, c
     c->buildTimers.push_back(t);
     if (consumed) CK(cudaEventRecord(consumed, c->sortStream));
     CK(cudaEventRecord(c->evSorted[set], c->sortStream));
-    CK(cudaStreamWaitEvent(c->stream, c->evSorted[set], 0));
+    CK(cudaStreamWaitEvent(fs, c->evSorted[set], 0));
     Timer tf;
-    if ((rc = timerStart(c, tf))) return rc;
-    CK(launch_stack_fold(run, c->H, c->G, c->occ, c->sort[set].capacity, c->stream, &c->launches));
-    if ((rc = timerStop(c, tf))) return rc;
+    if ((rc = timerStart(c, tf, fs))) return rc;
+    CK(launch_stack_fold(run, c->H, c->G, c->occ, c->sort[set].capacity, fs, &c->launches));
+    if ((rc = timerStop(c, tf, fs))) return rc;
     c->buildTimers.push_back(tf);
-    CK(cudaEventRecord(c->evFolded[set], c->stream));
+    CK(cudaEventRecord(c->evFolded[set], fs));
     c->sortUsed[set] = true;
     c->batchCount++;
     return PPP_OK;
@@ -444,6 +452,7 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     CKI(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CKI(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
     CKI(cudaStreamCreateWithFlags(&c->sortStream, cudaStreamNonBlocking));
+    for (int k = 0; k < kFoldStreams; ++k) CKI(cudaStreamCreateWithFlags(&c->foldStream[k], cudaStreamNonBlocking));
     CKI(cudaEventCreateWithFlags(&c->evReset, cudaEventDisableTiming));
     size_t hWords = 2 * c->G + 64;
     CKI(cudaMalloc(&c->H, hWords * sizeof(uint32_t)));
@@ -458,7 +467,7 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     }
     CKI(cudaMalloc(&c->dCounters, 2 * sizeof(unsigned long long)));
     CKI(cudaMemsetAsync(c->dCounters, 0, 2 * sizeof(unsigned long long), c->stream));
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kStages; ++k) {
         CKI(cudaEventCreateWithFlags(&c->evCopied[k], cudaEventDisableTiming));
         CKI(cudaEventCreateWithFlags(&c->evConsumed[k], cudaEventDisableTiming));
     }
@@ -510,18 +519,23 @@ void ppp_destroy(ppp_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     if (c->sortStream) cudaStreamSynchronize(c->sortStream);
+    for (int k = 0; k < kFoldStreams; ++k)
+        if (c->foldStream[k]) cudaStreamSynchronize(c->foldStream[k]);
     foldBuildTimers(c);
-    void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dStage[0], c->dStage[1], c->sort[0].keysA, c->sort[0].keysB, c->sort[0].valsA, c->sort[0].valsB, c->sort[0].blockHist,
-                   c->sort[0].scanScratch, c->sort[1].keysA, c->sort[1].keysB, c->sort[1].valsA, c->sort[1].valsB, c->sort[1].blockHist,
-                   c->sort[1].scanScratch, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
+    void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
                    c->dPairFdr, c->dLoci, c->dTileCnt, c->dTileBase, c->dTileDst, c->dScanScratch, c->dBlockCnt, c->dGrouped, c->dThresholds, c->dCells,
                    c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dTileCursor};
     for (void* p : dev)
         if (p) cudaFree(p);
+    for (int k = 0; k < kStages; ++k) {
+        void* stage[] = {c->dStage[k], c->sort[k].keysA, c->sort[k].keysB, c->sort[k].valsA, c->sort[k].valsB, c->sort[k].blockHist, c->sort[k].scanScratch};
+        for (void* p : stage)
+            if (p) cudaFree(p);
+    }
     void* pinned[] = {c->hStage[0], c->hStage[1], c->hThresholds, c->hs, c->hLoci};
     for (void* p : pinned)
         if (p) cudaFreeHost(p);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kStages; ++k) {
         if (c->evCopied[k]) cudaEventDestroy(c->evCopied[k]);
         if (c->evConsumed[k]) cudaEventDestroy(c->evConsumed[k]);
         if (c->evSorted[k]) cudaEventDestroy(c->evSorted[k]);
@@ -532,6 +546,8 @@ void ppp_destroy(ppp_ctx* c) {
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     if (c->sortStream) cudaStreamDestroy(c->sortStream);
+    for (int k = 0; k < kFoldStreams; ++k)
+        if (c->foldStream[k]) cudaStreamDestroy(c->foldStream[k]);
     if (c->evReset) cudaEventDestroy(c->evReset);
     delete c;
 }
@@ -540,11 +556,13 @@ int ppp_reset(ppp_ctx* c) {
     if (!c) return fail(PPP_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->copyStream));
+    for (int k = 0; k < kFoldStreams; ++k) CK(cudaStreamSynchronize(c->foldStream[k]));  // folds still in flight write H
     CK(cudaMemsetAsync(c->H, 0, (2 * c->G + 64) * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->occ, 0, c->occWords * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->dCounters, 0, 2 * sizeof(unsigned long long), c->stream));
     CK(cudaEventRecord(c->evReset, c->stream));  // the sort stream's kernels count into dCounters
     CK(cudaStreamWaitEvent(c->sortStream, c->evReset, 0));
+    for (int k = 0; k < kFoldStreams; ++k) CK(cudaStreamWaitEvent(c->foldStream[k], c->evReset, 0));
     c->readsSubmitted = 0;
     c->finished = false;
     invalidateResults(c);
@@ -588,16 +606,17 @@ int ppp_reads_submit(ppp_ctx* c, int32_t contig, const ppp_read* reads, size_t n
     cudaGetLastError();
     for (size_t o = 0; o < n; o += kChunk) {
         size_t k = std::min(kChunk, n - o);
-        int s = (int)(c->submitCount & 1u), prev = s ^ 1;
-        // the double-buffer contract: the copy of the previous submission has left its host buffer
+        const int s = (int)(c->submitCount % kStages), prev = (int)((c->submitCount + kStages - 1) % kStages);
+        // the double-buffer contract: the copy of the previous submission has left its host buffer (copies run in
+        // order on one stream, so every earlier one has, too)
         if (c->slotUsed[prev]) CK(cudaEventSynchronize(c->evCopied[prev]));
         if (!c->dStage[s]) CK(cudaMalloc(&c->dStage[s], kChunk * sizeof(ppp_read)));
         const ppp_read* src = reads + o;
         if (!pinned) {
-            if (!c->hStage[s]) CK(cudaMallocHost(&c->hStage[s], kChunk * sizeof(ppp_read)));
-            if (c->slotUsed[s]) CK(cudaEventSynchronize(c->evCopied[s]));  // staging buffer free again
-            memcpy(c->hStage[s], src, k * sizeof(ppp_read));
-            src = c->hStage[s];
+            const int hs = (int)(c->submitCount & 1u);  // last used two submissions ago: that copy is complete (see above)
+            if (!c->hStage[hs]) CK(cudaMallocHost(&c->hStage[hs], kChunk * sizeof(ppp_read)));
+            memcpy(c->hStage[hs], src, k * sizeof(ppp_read));
+            src = c->hStage[hs];
         }
         if (c->slotUsed[s]) CK(cudaStreamWaitEvent(c->copyStream, c->evConsumed[s], 0));  // kernels done with dStage[s]
         CK(cudaMemcpyAsync(c->dStage[s], src, k * sizeof(ppp_read), cudaMemcpyHostToDevice, c->copyStream));
@@ -616,6 +635,7 @@ int ppp_stacks_finish(ppp_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->copyStream));
     CK(cudaStreamSynchronize(c->sortStream));
+    for (int k = 0; k < kFoldStreams; ++k) CK(cudaStreamSynchronize(c->foldStream[k]));
     CK(cudaMemcpyAsync(c->hs->counters, c->dCounters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     foldBuildTimers(c);

@@ -288,19 +288,28 @@ __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __r
             for (int u = 0; u < kDepth; ++u) vc[u] = vq[u];
             const size_t nextBase = base + (size_t)kFoldBlock;
             if (nextBase < end) fetch(nextBase);
-            unsigned laneP = 0, laneM = 0;
+            // (every weight of this mode is positive -- 1 / NH, +inf for NH:i:0 -- so the `weight > 0` test of :458 is moot)
+            unsigned laneP = 0, laneM = 0, big = 0;
             const unsigned left = (unsigned)min((size_t)kFoldBlock, end - base);
 #pragma unroll
-            for (int u = 0; u < kDepth; ++u) {
+            for (int u = 0; u < kDepth; ++u) {  // branch free: the eight table look-ups are in flight together
                 const bool in = u * 32 + lane < left;
                 const uint32_t nh = vc[u] >> PPP_READ_NH_SHIFT;
-                const float wt = nh < kWeightLut ? weightOf[nh] : read_weight_weighted(vc[u]);
-                const bool live = in && wt > 0.0f;  // :458
+                const float wt = weightOf[min(nh, (uint32_t)kWeightLut - 1u)];
+                big |= nh;
                 const bool minus = (vc[u] & PPP_READ_MINUS) != 0;
-                stageP[u * 32 + lane] = live && !minus ? wt : 0.0f;  // adding +0.0f is exact
-                stageM[u * 32 + lane] = live && minus ? wt : 0.0f;
-                laneP |= live && !minus ? vc[u] | 0x80000000u : 0u;  // A10 flag: :483
-                laneM |= live && minus ? vc[u] | 0x80000000u : 0u;   // :471
+                stageP[u * 32 + lane] = in && !minus ? wt : 0.0f;  // adding +0.0f is exact
+                stageM[u * 32 + lane] = in && minus ? wt : 0.0f;
+                laneP |= in && !minus ? vc[u] | 0x80000000u : 0u;  // A10 flag: :483
+                laneM |= in && minus ? vc[u] | 0x80000000u : 0u;   // :471
+            }
+            if (__any_sync(0xffffffffu, big >= (uint32_t)kWeightLut)) {  // a multiplicity beyond the table: evaluate those records
+#pragma unroll  // (registers cannot be indexed dynamically)
+                for (int u = 0; u < kDepth; ++u) {
+                    if ((vc[u] >> PPP_READ_NH_SHIFT) < (uint32_t)kWeightLut || !(u * 32 + lane < left)) continue;
+                    const float wt = read_weight_weighted(vc[u]);
+                    if (vc[u] & PPP_READ_MINUS) stageM[u * 32 + lane] = wt; else stageP[u * 32 + lane] = wt;
+                }
             }
             accP |= laneP;
             accM |= laneM;
