@@ -1,4 +1,4 @@
-"""Where the end-to-end step goes: host enqueue, device completion of the stack build, the scan/score pass."""
+"""python -m pingpongpro_b200.tools.e2e_probe: where the end-to-end step goes: host enqueue, device completion of the stack build, the scan/score pass."""
 import time
 import numpy as np
 from pingpongpro_b200 import api, host

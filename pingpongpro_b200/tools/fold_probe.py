@@ -1,4 +1,4 @@
-"""One long run (a single stack of N reads on one strand) through the weighted stack builder."""
+"""python -m pingpongpro_b200.tools.fold_probe [N]: one long run (a single stack of N reads on one strand) through the weighted stack builder."""
 import sys
 import numpy as np
 from pingpongpro_b200 import api, host
