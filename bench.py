@@ -115,14 +115,14 @@ def run_harness(args, steps, warmup, genome_size):
                 f"{timed[0]['records']} decoded records held in memory, {timed[0]['pairs']} signatures")
 
 
-def reference_arm(args, rank, world):
+def reference_arm(args, rank, world, json_out):
     if rank != 0:
         return
     from pingpongpro_b200 import host
     m = host.SynthModel(args.genome, n_reads=args.reads, seed=SEED)
     h = run_harness(args, args.steps, args.warmup, m.genome_size)
     if h is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ppp_harness was not built (needs /root/reference at build time)"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ppp_harness was not built (needs /root/reference at build time)"}), file=json_out, flush=True)
         return
     full = [r["t_count"] + r["t_heights"] + r["t_group"] + r["t_collapse"] + r["t_fdr"] for r in h["rows"]]
     scan = [r["t_heights"] + r["t_group"] + r["t_collapse"] + r["t_fdr"] for r in h["rows"]]
@@ -140,7 +140,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
 
 
 def main():
@@ -154,12 +154,17 @@ def main():
     ap.add_argument("--mode", default="weighted")
     ap.add_argument("--min-stack-height", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "torch"], help="N>1: the library's NCCL binding, or the torch.distributed hook")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        reference_arm(args, rank, world)
+        reference_arm(args, rank, world, json_out)
         return
 
     import numpy as np
@@ -213,7 +218,10 @@ def main():
 
     ctx = api.Context(lengths, mode=args.mode, device=local_rank, range_begin=rank * G, range_end=(rank + 1) * G)
     if world > 1:
-        ctx.set_allreduce(pdist.torch_allreduce_hook())
+        if args.collective == "torch":
+            ctx.set_allreduce(pdist.torch_allreduce_hook())
+        else:
+            pdist.attach_nccl(ctx)
     words, owned = ctx.layout()
 
     def upload():
@@ -308,7 +316,7 @@ def main():
                                         "stage_seconds": {k: r[k] for k in ("t_count", "t_heights", "t_group", "t_collapse", "t_fdr")}}
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
     if tdist is not None:
         tdist.destroy_process_group()
 

@@ -126,6 +126,15 @@ PPP_API void ppp_destroy(ppp_ctx* ctx);
 PPP_API int ppp_reset(ppp_ctx* ctx);
 PPP_API int ppp_set_allreduce(ppp_ctx* ctx, ppp_allreduce_fn fn, void* user);
 
+/* Built-in collective for the hook above: NCCL all-reduces on the context's stream.  libnccl.so.2 is loaded at run
+ * time (PPP_NCCL_LIB overrides the path; a copy already loaded into the process is preferred), so single-GPU runs
+ * do not need it.  Rank 0 creates the 128-byte id and hands it to the other ranks by any means (MPI, a socket,
+ * torch.distributed); every rank then attaches, which creates its communicator (collective call) and installs it
+ * with ppp_set_allreduce.  ppp_destroy destroys the communicator. */
+#define PPP_NCCL_UNIQUE_ID_BYTES 128
+PPP_API int ppp_nccl_unique_id(void* id);
+PPP_API int ppp_nccl_attach(ppp_ctx* ctx, const void* id, int rank, int world);
+
 /* Pinned host memory for the double-buffered uploads. */
 PPP_API int ppp_pinned_alloc(size_t bytes, void** ptr);
 PPP_API int ppp_pinned_free(void* ptr);

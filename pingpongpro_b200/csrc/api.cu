@@ -2,6 +2,8 @@
 // host arithmetic that must use the HOST libm to stay bit-identical to the reference (log10f-based bin
 // thresholds, exp-based Gaussian weights).  No CPU fallback exists anywhere in this file: every entry point
 // that computes launches CUDA kernels and fails with PPP_ERR_CUDA when that is impossible.
+#include <dlfcn.h>
+
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -9,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -130,6 +133,7 @@ struct ppp_ctx {
 
     ppp_allreduce_fn allreduce = nullptr;
     void* allreduceUser = nullptr;
+    void* ncclComm = nullptr;  // communicator of the built-in collective (ppp_nccl_attach)
 
     Timer tScan, tLut, tBin, tScore, tTransposon;
     int launches = 0;
@@ -379,6 +383,47 @@ int hookReduce(ppp_ctx* c, void* buf, size_t count, int dtype, int op) {
 
 void invalidateResults(ppp_ctx* c) { c->haveHist = c->haveScan = c->haveScore = false; }
 
+// ---- built-in collective: NCCL, bound at run time ------------------------------------------------
+// Only four entry points are needed; their signatures and the enum values below have been stable since NCCL 2.0.
+// libnccl is not a link-time dependency: a single-GPU run never touches it.
+struct NcclId { char internal[PPP_NCCL_UNIQUE_ID_BYTES]; };
+struct NcclApi {
+    int (*getUniqueId)(NcclId*) = nullptr;
+    int (*commInitRank)(void** comm, int nranks, NcclId id, int rank) = nullptr;
+    int (*allReduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t stream) = nullptr;
+    int (*commDestroy)(void* comm) = nullptr;
+    const char* (*getErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = nullptr;
+        const char* env = getenv("PPP_NCCL_LIB");
+        if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy the process already uses (e.g. torch's)
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { api.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+        api.getUniqueId = reinterpret_cast<decltype(api.getUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+        api.commInitRank = reinterpret_cast<decltype(api.commInitRank)>(dlsym(h, "ncclCommInitRank"));
+        api.allReduce = reinterpret_cast<decltype(api.allReduce)>(dlsym(h, "ncclAllReduce"));
+        api.commDestroy = reinterpret_cast<decltype(api.commDestroy)>(dlsym(h, "ncclCommDestroy"));
+        api.getErrorString = reinterpret_cast<decltype(api.getErrorString)>(dlsym(h, "ncclGetErrorString"));
+        api.ok = api.getUniqueId && api.commInitRank && api.allReduce && api.commDestroy && api.getErrorString;
+        if (!api.ok) api.why = "libnccl.so.2 lacks an expected entry point";
+    });
+    return api;
+}
+int ncclFail(const char* what, int rc) { return fail(PPP_ERR_CUDA, "%s: %s", what, nccl().getErrorString(rc)); }
+
+// ppp_allreduce_fn over the context's communicator; dtype / op codes of ppp_b200.h -> ncclUint32 (3) / ncclUint64 (5), ncclSum (0) / ncclMax (2)
+int ncclHook(void* user, void* buf, size_t count, int dtype, int op, void* stream) {
+    ppp_ctx* c = static_cast<ppp_ctx*>(user);
+    return nccl().allReduce(buf, buf, count, dtype == 1 ? 5 : 3, op == 1 ? 2 : 0, c->ncclComm, static_cast<cudaStream_t>(stream));
+}
+
 }  // namespace
 
 extern "C" {
@@ -522,6 +567,7 @@ void ppp_destroy(ppp_ctx* c) {
     for (int k = 0; k < kFoldStreams; ++k)
         if (c->foldStream[k]) cudaStreamSynchronize(c->foldStream[k]);
     foldBuildTimers(c);
+    if (c->ncclComm) nccl().commDestroy(c->ncclComm);
     void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
                    c->dPairFdr, c->dLoci, c->dTileCnt, c->dTileBase, c->dTileDst, c->dScanScratch, c->dBlockCnt, c->dGrouped, c->dThresholds, c->dCells,
                    c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dTileCursor};
@@ -573,6 +619,28 @@ int ppp_set_allreduce(ppp_ctx* c, ppp_allreduce_fn fn, void* user) {
     if (!c) return fail(PPP_ERR_ARG, "null context");
     c->allreduce = fn;
     c->allreduceUser = user;
+    return PPP_OK;
+}
+
+int ppp_nccl_unique_id(void* id) {
+    if (!id) return fail(PPP_ERR_ARG, "null argument");
+    if (!nccl().ok) return fail(PPP_ERR_STATE, "%s", nccl().why.c_str());
+    int rc = nccl().getUniqueId(static_cast<NcclId*>(id));
+    return rc ? ncclFail("ncclGetUniqueId", rc) : PPP_OK;
+}
+
+int ppp_nccl_attach(ppp_ctx* c, const void* id, int rank, int world) {
+    if (!c || !id) return fail(PPP_ERR_ARG, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(PPP_ERR_ARG, "rank %d of %d", rank, world);
+    if (c->ncclComm) return fail(PPP_ERR_STATE, "a communicator is already attached");
+    if (!nccl().ok) return fail(PPP_ERR_STATE, "%s", nccl().why.c_str());
+    CK(cudaSetDevice(c->device));
+    NcclId nid;
+    memcpy(&nid, id, sizeof nid);
+    int rc = nccl().commInitRank(&c->ncclComm, world, nid, rank);
+    if (rc) { c->ncclComm = nullptr; return ncclFail("ncclCommInitRank", rc); }
+    c->allreduce = ncclHook;
+    c->allreduceUser = c;
     return PPP_OK;
 }
 

@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: one process per GPU, each holding one position-range shard of the genome
 (SURVEY.md §8(e)).  The data path has no collective; the only exchange is the all-reduce of three small
 tables (maximum stack height, height -> frequency histogram, grouped overlap counts), which the CUDA layer
-requests through its collective hook (ppp_set_allreduce).  Here the hook is bound to torch.distributed
-(NCCL over NVLink on GPUs; gloo in the CPU tests of the sharding logic).
+requests through its collective hook (ppp_set_allreduce).  On GPUs the hook is the library's own NCCL binding
+(attach_nccl: torch.distributed only carries the 128-byte communicator id to the other ranks); a
+torch.distributed-backed hook is kept for comparison, and gloo stands in for the CPU tests of the sharding logic.
 
 PyTorch is plumbing only: it never touches the stack arrays or the kernels.
 """
@@ -29,6 +30,18 @@ def device_tensor(ptr: int, count: int, dtype: int):
 def shard_ranges(total_positions: int, world_size: int):
     """Equal position ranges of the concatenated genome; rank r owns [cuts[r], cuts[r+1])."""
     return [total_positions * k // world_size for k in range(world_size + 1)]
+
+
+def attach_nccl(ctx, group=None):
+    """Binds the context's all-reduce hook to the library's NCCL communicator.  Collective over `group`."""
+    import torch.distributed as dist
+
+    from . import api
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [api.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.attach_nccl(box[0], rank, world)
 
 
 def torch_allreduce_hook(group=None):

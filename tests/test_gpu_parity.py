@@ -347,3 +347,26 @@ def test_range_sharding_equals_single_context(mode, n_shards):
     for p in parts:
         assert p[0].n_bins == single["score"].n_bins
         assert np.array_equal(bits(p[0].fdr_table), bits(single["score"].fdr_table))
+
+
+def test_builtin_nccl_collective_single_rank():
+    """ppp_nccl_attach: the library's own NCCL binding behind the all-reduce hook (a one-rank communicator here; the
+    multi-rank use is bench.py --gpus N).  The three reductions then run through ncclAllReduce on the context's
+    stream and must leave every result unchanged."""
+    m = host.SynthModel("tiny", n_reads=120_000, seed=5)
+    reads = m.generate(mode="weighted")
+    single = run_gpu(m.lengths, reads, "weighted")
+    with api.Context(m.lengths, mode="weighted") as ctx:
+        ctx.attach_nccl(api.nccl_unique_id(), 0, 1)
+        with pytest.raises(api.PppError):
+            ctx.attach_nccl(api.nccl_unique_id(), 0, 1)  # one communicator per context
+        for c, r in enumerate(reads):
+            if len(r):
+                ctx.count_reads(c, r)
+        ctx.finish()
+        ctx.map_heights_to_scores(False)
+        ctx.count_stacks_by_group(False)
+        sc = ctx.calculate_fdrs(0)
+        assert np.array_equal(sc.loci, single["score"].loci)
+        assert np.array_equal(ctx.signatures(), single["signatures"])
+        assert np.array_equal(bits(sc.fdr_table), bits(single["score"].fdr_table))
