@@ -5,13 +5,15 @@
 
 Metric: overlap-scan genome positions / second (BASELINE.json `metric`):
   value  G / (one pass of mapHeightsToScores + countStacksByGroup + collapseBins + calculateFDRs through the
-         C ABI), stacks resident in HBM when the timed region starts, result loci copied back every step;
+         C ABI), stacks resident in HBM when the timed region starts, the scored loci resident in HBM (and
+         their count on the host) when it ends;
   e2e    the same metric through the C ABI from HOST buffers: packed reads in pinned memory -> H2D ->
          stack build -> the pass above -> loci in host memory (reads/s of the same region reported beside it).
 A step is one pass over the whole synthetic data set.  N=1 workload: BASELINE.json configs[1] (50 M reads,
 dm6-sized genome, default parameters).  N>1: weak scaling -- every rank holds one dm6-sized position range of
 an N-times larger genome (range sharding of SURVEY §8(e)); the data path has no collective, the histogram
-tables are all-reduced over NCCL.
+tables are all-reduced over NCCL.  --scaling strong cuts ONE genome into N position ranges instead (the
+human-sized configs[3] study: --genome human --reads 500000000).
 
 --impl reference times the UNMODIFIED reference (oracle/_ref/ppp_harness, its own functions on decoded records
 held in memory) on one host core, on a bounded genome-range sample of the same workload.
@@ -154,6 +156,8 @@ def main():
     ap.add_argument("--mode", default="weighted")
     ap.add_argument("--min-stack-height", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = one genome + read set per GPU (default); strong = one genome cut into N position ranges")
     ap.add_argument("--collective", default="nccl", choices=["nccl", "torch"], help="N>1: the library's NCCL binding, or the torch.distributed hook")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr
@@ -199,11 +203,24 @@ def main():
         tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- workload: rank r owns copy r of the genome (contigs [r*nc, (r+1)*nc)) with its own seeded read set
-    model = host.SynthModel(args.genome, n_reads=args.reads, seed=SEED + rank)
+    # ---- workload.  weak (default): rank r owns copy r of the genome (contigs [r*nc, (r+1)*nc)) with its own seeded
+    # read set.  strong: ONE genome and read set, cut into `world` equal position ranges; every rank
+    # generates the reads of its range plus the minus-strand halo.
+    strong = args.scaling == "strong" and world > 1
+    model = host.SynthModel(args.genome, n_reads=args.reads, seed=SEED + (0 if strong else rank))
     nc = len(model.lengths)
-    lengths = model.lengths * world
     G = model.genome_size
+    if strong:
+        lengths = list(model.lengths)
+        cuts = pdist.shard_ranges(G, world)
+        r_lo, r_hi = cuts[rank], cuts[rank + 1]
+        contig0 = 0
+        work_positions = G           # whole-job positions per step
+    else:
+        lengths = model.lengths * world
+        r_lo, r_hi = rank * G, (rank + 1) * G
+        contig0 = rank * nc
+        work_positions = world * G
     t_gen = time.perf_counter()
     pinned = []
 
@@ -212,11 +229,14 @@ def main():
         pinned.append(b)
         return b.array
 
-    reads = model.generate(mode=args.mode, alloc=alloc)
+    if strong:  # (+64: keys at or just past a contig's end belong to the shard holding its last base)
+        reads = model.generate(mode=args.mode, alloc=alloc, g_lo=r_lo, g_hi=r_hi, halo=23 + 64)
+    else:
+        reads = model.generate(mode=args.mode, alloc=alloc)
     t_gen = time.perf_counter() - t_gen
     n_reads = sum(len(r) for r in reads)
 
-    ctx = api.Context(lengths, mode=args.mode, device=local_rank, range_begin=rank * G, range_end=(rank + 1) * G)
+    ctx = api.Context(lengths, mode=args.mode, device=local_rank, range_begin=r_lo, range_end=r_hi)
     if world > 1:
         if args.collective == "torch":
             ctx.set_allreduce(pdist.torch_allreduce_hook())
@@ -228,48 +248,53 @@ def main():
         ctx.reset()
         for c, b in enumerate(pinned):
             if b.n:
-                ctx.count_reads(rank * nc + c, b)
+                ctx.count_reads(contig0 + c, b)
         ctx.finish()
 
-    def scan_and_score():
-        ctx.map_heights_to_scores(want_table=False)
+    max_height = [0]
+
+    def scan_and_score(loci_to_host):
+        max_height[0] = ctx.map_heights_to_scores(want_table=False)[1]
         ctx.count_stacks_by_group(want_table=False)
-        return ctx.calculate_fdrs(args.min_stack_height, want_tables=False, want_loci=True, copy_loci=False)  # loci land in pinned host memory
+        # loci_to_host: the compacted loci are also copied into the library's pinned host buffer (20 B per locus)
+        return ctx.calculate_fdrs(args.min_stack_height, want_tables=False, want_loci=loci_to_host, copy_loci=False)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_clock0 = time.perf_counter()
 
-    # ---- value: stacks resident in HBM (1.1 GB per strand pair >> 126 MB L2: no L2 flush needed)
+    # ---- value: stacks resident in HBM (1.1 GB per strand pair >> 126 MB L2: no L2 flush needed); the step ends
+    # with the compacted, scored loci resident in HBM and their count on the host (the device->host copy of the
+    # loci themselves belongs to the end-to-end figure below)
     upload()
     for _ in range(args.warmup):
-        res = scan_and_score()
+        res = scan_and_score(False)
     ctx.timings_reset()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = scan_and_score()
+        res = scan_and_score(False)
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
     tm = ctx.timings()  # device time of the LAST step's kernels (CUDA events on the context's stream)
     launches_per_step = tm["launches"] / args.steps
     n_pairs, n_loci = ctx.n_pairs, res.n_loci
-    value = world * G / (dt / args.steps)
+    value = work_positions / (dt / args.steps)
 
     # ---- e2e: host buffers -> H2D -> stack build -> scan + score -> loci on the host
     for _ in range(args.warmup):
         upload()
-        scan_and_score()
+        scan_and_score(True)
     ctx.timings_reset()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         upload()
-        res = scan_and_score()
+        res = scan_and_score(True)
     barrier()
     dt_e2e = max_over_ranks(time.perf_counter() - t0)
     tm_e2e = ctx.timings()
     t_clock1 = time.perf_counter()
-    e2e_value = world * G / (dt_e2e / args.steps)
+    e2e_value = work_positions / (dt_e2e / args.steps)
     total_reads = sum_over_ranks(float(n_reads))
     total_pairs = sum_over_ranks(float(n_pairs))
     total_loci = sum_over_ranks(float(n_loci))
@@ -286,13 +311,16 @@ def main():
     scan_bytes = 8.0 * words + 16.0 * n_pairs
     achieved = scan_bytes / (tm["scan_ms"] * 1e-3) / 1e9
     survey_bytes = 16.0 * words + 16.0 * n_pairs  # SURVEY §8(d) counts K2 and K3 as two passes of 8 B/position
+    which = {("dm6", 50_000_000): "configs[1]", ("mouse", 200_000_000): "configs[2]", ("human", 500_000_000): "configs[3]"}.get((args.genome, args.reads), "(custom size)")
+    per = "in total" if strong else "per GPU"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE.json configs[1]: {args.reads} synthetic piRNA-seq reads per GPU on a {args.genome}-sized genome ({G} positions per GPU), "
-                               f"-m {args.mode}, overlaps 3..23, default parameters", "positions_per_gpu": G, "reads_per_gpu_after_filters": n_reads,
-                   "signatures": total_pairs, "loci": total_loci, "sharding": "position ranges, one per rank" if world > 1 else "none",
+        "config": {"workload": f"BASELINE.json {which}: {args.reads} synthetic piRNA-seq reads {per} on a {args.genome}-sized genome ({G} positions {per}), "
+                               f"-m {args.mode}, overlaps 3..23, default parameters", "positions_per_gpu": owned, "reads_per_gpu_after_filters": n_reads,
+                   "signatures": total_pairs, "loci": total_loci, "max_stack_height": max_height[0],
+                   "sharding": ("one genome cut into equal position ranges, one per rank" if strong else "one genome per rank (a position range of the concatenation)") if world > 1 else "none",
                    "l2": "inputs (8 B x positions = %.2f GB) are far larger than the 126 MB L2; no flush between steps" % (8e-9 * words),
                    "synthetic_generation_s": t_gen},
         "roofline": {"bound": "hbm", "kernel": "k_scan (fused height histogram + overlap scan)", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -300,7 +328,7 @@ def main():
                      "kernel_ms": tm["scan_ms"], "achieved_two_pass_accounting_gbs": survey_bytes / (tm["scan_ms"] * 1e-3) / 1e9,
                      "device_ms_per_step": {k: tm[k] for k in ("scan_ms", "lut_ms", "bin_ms", "score_ms")}},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_reads, "d2h_bytes_per_step": 20 * n_loci + 64,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * total_reads), "d2h_bytes_per_step": int(20 * total_loci + 64 * world),
                 "ms_per_step": 1e3 * dt_e2e / args.steps, "reads_per_s": total_reads / (dt_e2e / args.steps),
                 "stack_build_device_ms_per_step": tm_e2e["stack_build_ms"] / args.steps},
         "gpu_launches": int(round(launches_per_step * args.steps)),

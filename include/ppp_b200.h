@@ -125,6 +125,10 @@ PPP_API void ppp_destroy(ppp_ctx* ctx);
 /* Empties the stack store and all results (a new run over the same genome). */
 PPP_API int ppp_reset(ppp_ctx* ctx);
 PPP_API int ppp_set_allreduce(ppp_ctx* ctx, ppp_allreduce_fn fn, void* user);
+/* Optional with a custom hook (ppp_nccl_attach does it itself): tells the context which of `world` shards it is.
+ * The rare tall stacks (rounded height >= 512) are then exchanged as one compact list per rank inside a single
+ * sum all-reduce, instead of a reduction over height tables as long as the tallest stack. */
+PPP_API int ppp_set_rank(ppp_ctx* ctx, int rank, int world);
 
 /* Built-in collective for the hook above: NCCL all-reduces on the context's stream.  libnccl.so.2 is loaded at run
  * time (PPP_NCCL_LIB overrides the path; a copy already loaded into the process is preferred), so single-GPU runs

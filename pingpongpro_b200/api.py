@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.ppp_destroy.restype = None
     L.ppp_reset.argtypes = [vp]
     L.ppp_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
+    L.ppp_set_rank.argtypes = [vp, C.c_int, C.c_int]
     L.ppp_nccl_unique_id.argtypes = [vp]
     L.ppp_nccl_attach.argtypes = [vp, vp, C.c_int, C.c_int]
     L.ppp_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -101,7 +102,7 @@ def lib() -> C.CDLL:
     L.ppp_timings_get.argtypes = [vp, C.POINTER(Timings)]
     L.ppp_timings_reset.argtypes = [vp]
     L.ppp_layout.argtypes = [vp, u64p, u64p]
-    for name in ("ppp_device_count", "ppp_warmup", "ppp_init", "ppp_reset", "ppp_set_allreduce", "ppp_nccl_unique_id", "ppp_nccl_attach", "ppp_pinned_alloc", "ppp_pinned_free", "ppp_reads_submit",
+    for name in ("ppp_device_count", "ppp_warmup", "ppp_init", "ppp_reset", "ppp_set_allreduce", "ppp_set_rank", "ppp_nccl_unique_id", "ppp_nccl_attach", "ppp_pinned_alloc", "ppp_pinned_free", "ppp_reads_submit",
                  "ppp_reads_submit_device", "ppp_stacks_finish", "ppp_reads_foreign", "ppp_stacks_download", "ppp_height_hist", "ppp_scan", "ppp_score",
                  "ppp_pairs_download", "ppp_transposons", "ppp_timings_get", "ppp_timings_reset", "ppp_layout"):
         getattr(L, name).restype = C.c_int
@@ -301,6 +302,10 @@ class Context:
                 return 1
         self._hook = ALLREDUCE_FN(tramp)
         _check(lib().ppp_set_allreduce(self._h, self._hook, None))
+
+    def set_rank(self, rank: int, world: int):
+        """With a custom hook: which of `world` shards this context is (enables the compact exchange of tall stacks)."""
+        _check(lib().ppp_set_rank(self._h, rank, world))
 
     def attach_nccl(self, unique_id: bytes, rank: int, world: int):
         """Built-in collective: creates this rank's NCCL communicator from the id of nccl_unique_id() (collective call)."""

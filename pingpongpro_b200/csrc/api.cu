@@ -44,6 +44,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr uint32_t kKeySlack = 64;          // keys up to contig length + 63 are accepted (a - key may equal the length, :464)
 constexpr size_t kChunk = (size_t)1 << 23;  // records per upload / sort chunk (64 MB)
 constexpr int kFoldStreams = 4;
+constexpr uint32_t kTallCap = 1u << 16;      // tall stacks (rounded height >= kScanLowBins) per rank in the compact exchange
 constexpr int kStages = 4;                  // depth of the upload -> sort -> fold pipeline (buffers are allocated on first use)
 constexpr int kTile = kScanTile;
 
@@ -55,6 +56,8 @@ struct Timer {
 struct PinnedScalars {
     uint32_t maxHeight;
     uint32_t nBins;
+    uint32_t tallOverflow;
+    uint32_t pad;
     unsigned long long cursor;
     unsigned long long maxCount;
     unsigned long long nLoci;
@@ -134,6 +137,11 @@ struct ppp_ctx {
     ppp_allreduce_fn allreduce = nullptr;
     void* allreduceUser = nullptr;
     void* ncclComm = nullptr;  // communicator of the built-in collective (ppp_nccl_attach)
+    int rank = 0, world = 0;   // known (ppp_set_rank / ppp_nccl_attach): tall stacks are exchanged as compact lists
+    uint32_t* dGather = nullptr;  // [world][kTallHeader + tallCap], see launch_tall_apply
+    uint32_t tallCap = 0;
+    uint32_t* dOverflow = nullptr;
+    bool denseTail = false;    // a list overflowed once: this context reduces the dense tables from then on
 
     Timer tScan, tLut, tBin, tScore, tTransposon;
     int launches = 0;
@@ -381,6 +389,20 @@ int hookReduce(ppp_ctx* c, void* buf, size_t count, int dtype, int op) {
     return PPP_OK;
 }
 
+// PPP_TRACE=1: host wall time between the phases of one call, to stderr (where a multi-GPU step waits)
+struct Trace {
+    bool on;
+    const char* call;
+    std::chrono::steady_clock::time_point t;
+    explicit Trace(const char* name) : on(getenv("PPP_TRACE") != nullptr), call(name), t(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ppp_trace %s] %-28s +%.3f ms\n", call, what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 void invalidateResults(ppp_ctx* c) { c->haveHist = c->haveScan = c->haveScore = false; }
 
 // ---- built-in collective: NCCL, bound at run time ------------------------------------------------
@@ -568,6 +590,8 @@ void ppp_destroy(ppp_ctx* c) {
         if (c->foldStream[k]) cudaStreamSynchronize(c->foldStream[k]);
     foldBuildTimers(c);
     if (c->ncclComm) nccl().commDestroy(c->ncclComm);
+    if (c->dGather) cudaFree(c->dGather);
+    if (c->dOverflow) cudaFree(c->dOverflow);
     void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
                    c->dPairFdr, c->dLoci, c->dTileCnt, c->dTileBase, c->dTileDst, c->dScanScratch, c->dBlockCnt, c->dGrouped, c->dThresholds, c->dCells,
                    c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dTileCursor};
@@ -622,6 +646,18 @@ int ppp_set_allreduce(ppp_ctx* c, ppp_allreduce_fn fn, void* user) {
     return PPP_OK;
 }
 
+int ppp_set_rank(ppp_ctx* c, int rank, int world) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (world < 1 || rank < 0 || rank >= world) return fail(PPP_ERR_ARG, "rank %d of %d", rank, world);
+    if (c->dGather) return fail(PPP_ERR_STATE, "the rank cannot change after the first scan");
+    c->rank = rank;
+    c->world = world;
+    c->tallCap = kTallCap;
+    if (const char* e = getenv("PPP_TALL_CAP")) c->tallCap = (uint32_t)std::max(1L, atol(e));  // test knob: forces the dense fall-back
+    c->tallCap = (c->tallCap + 1u) & ~1u;  // slots stay 8-byte aligned (64-bit low bins inside)
+    return PPP_OK;
+}
+
 int ppp_nccl_unique_id(void* id) {
     if (!id) return fail(PPP_ERR_ARG, "null argument");
     if (!nccl().ok) return fail(PPP_ERR_STATE, "%s", nccl().why.c_str());
@@ -641,7 +677,7 @@ int ppp_nccl_attach(ppp_ctx* c, const void* id, int rank, int world) {
     if (rc) { c->ncclComm = nullptr; return ncclFail("ncclCommInitRank", rc); }
     c->allreduce = ncclHook;
     c->allreduceUser = c;
-    return PPP_OK;
+    return ppp_set_rank(c, rank, world);
 }
 
 int ppp_reads_submit_device(ppp_ctx* c, int32_t contig, const ppp_read* dReads, size_t n) {
@@ -746,6 +782,7 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
     if (!c->finished) return fail(PPP_ERR_STATE, "call ppp_stacks_finish before ppp_height_hist");
     CK(cudaSetDevice(c->device));
     invalidateResults(c);
+    Trace tr("height_hist");
     // signatures are ~0.1-0.3 per read on real densities; a scan that overflows the store reports the exact count and is re-run once
     uint64_t want = c->cfgPairCapacity ? c->cfgPairCapacity : std::max<uint64_t>((uint64_t)1 << 20, c->readsSubmitted / 3);
     if (want < c->pairCapacity) want = c->pairCapacity;
@@ -775,16 +812,44 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
         p.capacity = c->pairCapacity;
         p.tileCnt = c->dTileCnt;
         p.tileBase = c->dTileBase;
+        // multi-GPU with known rank: heights beyond the shared-memory bins go to this rank's slot of the gather buffer
+        const bool gatherTall = c->allreduce && c->world > 1 && !c->denseTail;
+        const size_t slotWords = (size_t)kTallHeader + c->tallCap;
+        p.tallList = nullptr;
+        p.tallCount = nullptr;
+        p.tallCap = 0;
+        if (gatherTall) {
+            if (!c->dGather) {
+                CK(cudaMalloc(&c->dGather, (size_t)c->world * slotWords * sizeof(uint32_t)));
+                CK(cudaMalloc(&c->dOverflow, sizeof(uint32_t)));
+            }
+            CK(cudaMemsetAsync(c->dGather, 0, (size_t)c->world * slotWords * sizeof(uint32_t), c->stream));
+            CK(cudaMemsetAsync(c->dOverflow, 0, sizeof(uint32_t), c->stream));
+            uint32_t* slot = c->dGather + (size_t)c->rank * slotWords;
+            p.tallCount = slot;
+            p.maxHeight = slot + 1;
+            p.freqLow = reinterpret_cast<unsigned long long*>(slot + kTallLow);
+            p.tallList = slot + kTallHeader;
+            p.tallCap = c->tallCap;
+        }
+        c->hs->tallOverflow = 0;
         if ((rc = timerStart(c, c->tScan))) return rc;
         CK(launch_scan(p, c->repr, c->stream, &c->launches));
         if ((rc = timerStop(c, c->tScan))) return rc;
-        if (c->allreduce) {
+        if (gatherTall) {
+            // one all-reduce carries every rank's low bins, tall stacks and maximum height; no host round trip in between
+            if ((rc = hookReduce(c, c->dGather, (size_t)c->world * slotWords, 0, 0))) return rc;
+            CK(launch_tall_apply(c->dGather, c->world, c->tallCap, c->dFreqLow, c->dFreqTail, c->dMaxHeight, c->dOverflow, c->stream, &c->launches));
+            CK(cudaMemcpyAsync(&c->hs->tallOverflow, c->dOverflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        } else if (c->allreduce) {
             // sizes of the table reductions depend on the global maximum height: one extra round trip
             if ((rc = hookReduce(c, c->dMaxHeight, 1, 0, 1))) return rc;
             CK(cudaMemcpyAsync(&c->hs->maxHeight, c->dMaxHeight, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
+            tr.mark("scan + max-height reduce");
             if ((rc = hookReduce(c, c->dFreqLow, kScanLowBins, 1, 0))) return rc;
             if (c->hs->maxHeight >= kScanLowBins && (rc = hookReduce(c, c->dFreqTail + kScanLowBins, (size_t)c->hs->maxHeight - kScanLowBins + 1, 0, 0))) return rc;
+            if (tr.on) { CK(cudaStreamSynchronize(c->stream)); tr.mark("histogram reduce"); }
         }
         if ((rc = timerStart(c, c->tLut))) return rc;
         CK(launch_freq_lut(c->dFreqLow, c->dFreqTail, c->dMaxHeight, c->dLut, c->dMaxCount, c->stream, &c->launches));
@@ -793,7 +858,12 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
         CK(cudaMemcpyAsync(&c->hs->cursor, c->dCursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(&c->hs->maxCount, c->dMaxCount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
+        tr.mark("histogram reduce + table");
         c->prevMaxHeight = std::max(c->prevMaxHeight, c->hs->maxHeight);
+        if (c->hs->tallOverflow) {  // (the same on every rank: it is read from the reduced buffer) -> dense tables, once and for all
+            c->denseTail = true;
+            continue;
+        }
         if (c->hs->cursor <= c->pairCapacity) break;
         if (attempt >= 2) return fail(PPP_ERR_NOMEM, "signature store overflow");
         if ((rc = ensurePairCapacity(c, c->hs->cursor + c->hs->cursor / 8 + 1024))) return rc;  // rerun with room for every record
@@ -811,6 +881,7 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
         return fail(PPP_ERR_DEGENERATE, "every rounded stack height occurs once: the reference's height score is 0/0 (pingpongpro.cpp:551/:593)");
     }
     CK(cudaMemcpyAsync(c->dThresholds, c->hThresholds, kBins * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    tr.mark("bin thresholds (host)");
 
     if (freq) {
         uint32_t mh = c->maxHeight;
@@ -863,6 +934,7 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     CK(cudaSetDevice(c->device));
     int rc;
     const int ppIdx = c->ppOv - c->minOv;
+    Trace tr("score");
     if ((rc = timerStart(c, c->tScore))) return rc;
     CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dCellSums, c->stream, &c->launches));
     CK(launch_fdr_table(c->dCells, c->dNBins, kBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
@@ -872,6 +944,7 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     CK(cudaMemcpyAsync(&c->hs->nLoci, c->dNLoci, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&c->hs->nBins, c->dNBins, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    tr.mark("binning + reduce + scoring");
     size_t n = (size_t)c->hs->nLoci;
     uint32_t C = c->hs->nBins;
     if (loci) {
@@ -891,6 +964,7 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     if (fdrTable) { tmpFdr.resize(tableWords); CK(cudaMemcpyAsync(tmpFdr.data(), c->dFdr, tableWords * 4, cudaMemcpyDeviceToHost, c->stream)); }
     if (binMap) CK(cudaMemcpyAsync(binMap, c->dBinMap, kBins * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
     if (loci || cells || fdrTable || binMap) CK(cudaStreamSynchronize(c->stream));
+    tr.mark("loci to host");
     // device tables are bin-major; the ABI returns them as [overlap][C][bias][local]
     for (int o = 0; o < c->W; ++o)
         for (uint32_t b = 0; b < C; ++b)

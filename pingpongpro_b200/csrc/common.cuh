@@ -58,6 +58,10 @@ struct ScanParams {
     unsigned long long* freqLow;  // [kScanLowBins]
     uint32_t* freqTail;           // [kFreqCapacity] (entries >= kScanLowBins used)
     uint32_t* maxHeight;
+    // multi-GPU: rounded heights >= kScanLowBins are appended here instead of counted in freqTail (see launch_tall_apply)
+    uint32_t* tallList;           // null: count in freqTail
+    unsigned int* tallCount;
+    uint32_t tallCap;
     PairRec* pairsRaw;
     unsigned long long* cursor;   // total records produced (may exceed capacity)
     uint64_t capacity;
@@ -103,6 +107,15 @@ cudaError_t launch_stack_sort(const ppp_read* reads, size_t n, uint64_t G, Slot 
 cudaError_t launch_stack_fold(const SortedRun& r, uint32_t* H, uint64_t G, uint32_t* occ, size_t capacity, cudaStream_t s, int* launches);
 
 cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* launches);
+// Multi-GPU exchange of the height histogram in ONE collective.  `gather` holds one slot of kTallHeader + cap words
+// per rank: [count of tall stacks, local maximum height, the rank's low bins (kScanLowBins x u64), tall heights...];
+// every rank fills its own slot of a zeroed buffer and a sum all-reduce turns that into an all-gather.  The kernel
+// sums the low bins, adds every listed tall height to freqTail and leaves the global maximum height; *overflow
+// becomes non-zero when some rank had more than `cap` tall stacks (the caller then falls back to reducing the tables).
+constexpr uint32_t kTallLow = 2;                            // word offset of the low bins inside a slot
+constexpr uint32_t kTallHeader = kTallLow + 2 * kScanLowBins;
+cudaError_t launch_tall_apply(const uint32_t* gather, int world, uint32_t cap, unsigned long long* freqLow, uint32_t* freqTail, uint32_t* maxHeight,
+                              uint32_t* overflow, cudaStream_t s, int* launches);
 cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* freqTail, const uint32_t* maxHeight, float* lut,
                             unsigned long long* maxCount, cudaStream_t s, int* launches);
 cudaError_t launch_bin_group(const PairRec* raw, PairRec* ordered, const uint32_t* tileCnt, const uint32_t* tileBase, const uint32_t* tileDst, uint32_t nTiles,

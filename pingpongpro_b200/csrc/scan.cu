@@ -46,6 +46,16 @@ __device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
     return v;
 }
 
+// a stack taller than the shared-memory bins (rare): out of line, so that it costs the streaming loop no registers
+__device__ __noinline__ void count_tall(uint32_t* freqTail, uint32_t* tallList, unsigned int* tallCount, uint32_t tallCap, uint32_t r) {
+    if (tallList) {
+        unsigned int i = atomicAdd(tallCount, 1u);
+        if (i < tallCap) tallList[i] = r;
+    } else {
+        atomicAdd(&freqTail[r], 1u);
+    }
+}
+
 template <int REPR>
 __global__ void __launch_bounds__(kThreads, 8) k_scan(ScanParams P) {
     __shared__ uint32_t sMask[2][kThreads + 2];  // minus-strand occupancy words of the tile + the word after it
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_scan(ScanParams P) {
                     uint32_t r = word_round_height<REPR>(wv[k]);
                     if (r < 4u) { small += 1u << (8 * r); if ((small & 0x80808080u) != 0u) flush_small(); }  // heights 0..3: byte counters in a register
                     else if (r < kScanLowBins) atomicAdd(&sHist[r], 1u);
-                    else atomicAdd(&P.freqTail[r], 1u);
+                    else count_tall(P.freqTail, P.tallList, P.tallCount, P.tallCap, r);
                     localMax = max(localMax, r);
                 }
             }
@@ -225,6 +235,26 @@ __global__ void __launch_bounds__(kThreads, 8) k_scan(ScanParams P) {
         uint32_t c = sHist[k];
         if (c) atomicAdd(&P.freqLow[k], (unsigned long long)c);
     }
+}
+
+// see launch_tall_apply in common.cuh
+__global__ void __launch_bounds__(256) k_tall_apply(const uint32_t* __restrict__ gather, int world, uint32_t cap, unsigned long long* __restrict__ freqLow,
+                                                    uint32_t* __restrict__ freqTail, uint32_t* __restrict__ maxHeight, uint32_t* __restrict__ overflow) {
+    const size_t slotWords = (size_t)kTallHeader + cap;
+    uint32_t best = 0;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < kScanLowBins; k += gridDim.x * blockDim.x) {
+        unsigned long long sum = 0;
+        for (int r = 0; r < world; ++r) sum += reinterpret_cast<const unsigned long long*>(gather + (size_t)r * slotWords + kTallLow)[k];
+        freqLow[k] = sum;
+    }
+    for (int r = 0; r < world; ++r) {
+        const uint32_t* slot = gather + (size_t)r * slotWords;
+        uint32_t n = slot[0];
+        best = max(best, slot[1]);
+        if (n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1u; n = cap; }
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&freqTail[slot[kTallHeader + i]], 1u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *maxHeight = best;
 }
 
 // freq LUT: lut[h] = float(min(count[h], 2^24)) -- the value the reference's float counter holds (:508) --
@@ -371,6 +401,13 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
     if (grid > p.nTiles) grid = p.nTiles;
     if (repr == kReprInt) k_scan<kReprInt><<<grid, kThreads, 0, s>>>(p);
     else k_scan<kReprFloat><<<grid, kThreads, 0, s>>>(p);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tall_apply(const uint32_t* gather, int world, uint32_t cap, unsigned long long* freqLow, uint32_t* freqTail, uint32_t* maxHeight,
+                              uint32_t* overflow, cudaStream_t s, int* launches) {
+    k_tall_apply<<<148, 256, 0, s>>>(gather, world, cap, freqLow, freqTail, maxHeight, overflow);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -287,7 +287,7 @@ def test_saturation_of_float_counters():
         assert len(s) == 1 and s["reads_plus"][0] == np.float32(1 << 24) and s["overlap"][0] == 10
 
 
-def _sharded(lengths, reads, mode, n_shards, min_stack_height=0):
+def _sharded(lengths, reads, mode, n_shards, min_stack_height=0, known_rank=False):
     """n_shards contexts on one GPU, one host thread each; the collective hook is a host-side barrier exchange."""
     total = sum(lengths)
     cuts = [total * k // n_shards for k in range(n_shards + 1)]
@@ -312,6 +312,8 @@ def _sharded(lengths, reads, mode, n_shards, min_stack_height=0):
                     t.copy_(torch.from_numpy(acc))
                     torch.cuda.synchronize()
                 ctx.set_allreduce(hook)
+                if known_rank:
+                    ctx.set_rank(rank, n_shards)
                 for c, r in enumerate(reads):
                     if len(r):
                         ctx.count_reads(c, r)  # broadcast: every shard keeps what it owns (+ its halo)
@@ -332,14 +334,19 @@ def _sharded(lengths, reads, mode, n_shards, min_stack_height=0):
     return out
 
 
-@pytest.mark.parametrize("mode,n_shards", [("weighted", 2), ("unique", 3), ("weighted", 8)])
-def test_range_sharding_equals_single_context(mode, n_shards):
+@pytest.mark.parametrize("mode,n_shards,exchange", [("weighted", 2, "tables"), ("unique", 3, "lists"), ("weighted", 8, "lists"), ("weighted", 4, "overflow")])
+def test_range_sharding_equals_single_context(mode, n_shards, exchange, monkeypatch):
     """SURVEY §8(e): shards with a max-overlap halo + all-reduced histograms reproduce the single-GPU result;
-    loci concatenated in rank order are globally sorted."""
+    loci concatenated in rank order are globally sorted.  `exchange`: how the tall stacks' heights travel -- reduced
+    height tables (rank unknown to the context), one compact list per rank (ppp_set_rank), or lists that overflow
+    and fall back to the tables."""
     m = host.SynthModel("tiny", n_reads=150_000, seed=12)
     reads = m.generate(mode=mode)
     single = run_gpu(m.lengths, reads, mode)
-    parts = _sharded(m.lengths, reads, mode, n_shards)
+    assert single["max_height"] >= 512  # the exchange under test is that of the heights beyond the shared-memory bins
+    if exchange == "overflow":
+        monkeypatch.setenv("PPP_TALL_CAP", "3")
+    parts = _sharded(m.lengths, reads, mode, n_shards, known_rank=exchange != "tables")
     loci = np.concatenate([p[0].loci for p in parts])
     sigs = np.concatenate([p[1] for p in parts])
     assert np.array_equal(loci, single["score"].loci)
