@@ -152,17 +152,275 @@ struct AlnReader::Pipeline {
     }
 };
 
+// ---------------------------------------------------------------------------
+// SAM line parser and its worker-thread pipeline
+// ---------------------------------------------------------------------------
+static inline bool parseU32(const char* s, size_t n, uint32_t& v) {
+    if (n == 0) return false;
+    uint64_t x = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        x = x * 10 + (uint64_t)(s[i] - '0');
+        if (x > 0xffffffffull) return false;
+    }
+    v = (uint32_t)x;
+    return true;
+}
+
+static inline int cigarOpCode(char c) {
+    switch (c) {
+        case 'M': return 0; case 'I': return 1; case 'D': return 2; case 'N': return 3; case 'S': return 4;
+        case 'H': return 5; case 'P': return 6; case '=': return 7; case 'X': return 8; default: return -1;
+    }
+}
+
+// One alignment line (without its terminator).  `names` is only read.  Returns 0 = ok, 1 = malformed, 2 = RNAME is not in
+// `names` (everything else is filled in; the caller decides whether the name store grows).  CIGAR elements are appended
+// to `cigars` from out.cigarOff on; SEQ is referenced by its offset in the line.
+struct SamFields {
+    int32_t rID, beginPos;
+    uint32_t flag, cigarOff, nCigar, seqOff, lSeq, nh, nameOff, nameLen;
+    bool hasNH;
+};
+static int parseSamLine(const char* line, size_t len, const std::unordered_map<std::string, int32_t>& names, std::string& lastName, int32_t& lastId,
+                        std::vector<uint32_t>& cigars, SamFields& out) {
+    // split the 11 mandatory fields
+    const char* f[12];
+    size_t fl[12];
+    int nf = 0;
+    size_t i = 0;
+    while (nf < 11) {
+        const char* t = (const char*)memchr(line + i, '\t', len - i);
+        size_t j = t ? (size_t)(t - line) : len;
+        f[nf] = line + i;
+        fl[nf] = j - i;
+        ++nf;
+        if (j >= len) { i = len; break; }
+        i = j + 1;
+    }
+    if (nf < 11) return 1;
+    uint32_t flag, pos;
+    if (!parseU32(f[1], fl[1], flag) || !parseU32(f[3], fl[3], pos)) return 1;
+    out.flag = flag;
+    out.beginPos = (int32_t)pos - 1;
+    out.nameOff = (uint32_t)(f[2] - line);
+    out.nameLen = (uint32_t)fl[2];
+    int rc = 0;
+    if (fl[2] == 1 && f[2][0] == '*') {
+        out.rID = -1;
+    } else if (lastId >= 0 && lastName.size() == fl[2] && memcmp(lastName.data(), f[2], fl[2]) == 0) {
+        out.rID = lastId;  // sorted input: long runs of one contig
+    } else {
+        auto it = names.find(std::string(f[2], fl[2]));
+        if (it == names.end()) { out.rID = -2; rc = 2; }
+        else { out.rID = it->second; lastName.assign(f[2], fl[2]); lastId = it->second; }
+    }
+    // CIGAR
+    out.cigarOff = (uint32_t)cigars.size();
+    if (!(fl[5] == 1 && f[5][0] == '*')) {
+        uint64_t cnt = 0;
+        bool haveDigit = false;
+        for (size_t k = 0; k < fl[5]; ++k) {
+            char c = f[5][k];
+            if (c >= '0' && c <= '9') { cnt = cnt * 10 + (uint64_t)(c - '0'); haveDigit = true; if (cnt >= (1ull << 28)) return 1; }
+            else {
+                int op = cigarOpCode(c);
+                if (op < 0 || !haveDigit) return 1;
+                cigars.push_back((uint32_t)(cnt << 4) | (uint32_t)op);
+                cnt = 0;
+                haveDigit = false;
+            }
+        }
+        if (haveDigit) return 1;
+    }
+    out.nCigar = (uint32_t)cigars.size() - out.cigarOff;
+    // SEQ
+    out.seqOff = (uint32_t)(f[9] - line);
+    out.lSeq = (fl[9] == 1 && f[9][0] == '*') ? 0u : (uint32_t)fl[9];
+    // optional fields: look for NH:i:<n>
+    out.hasNH = false;
+    out.nh = 1;
+    while (i < len) {
+        const char* t = (const char*)memchr(line + i, '\t', len - i);
+        size_t j = t ? (size_t)(t - line) : len;
+        if (j - i >= 6 && line[i] == 'N' && line[i + 1] == 'H' && line[i + 2] == ':' && line[i + 3] == 'i' && line[i + 4] == ':') {
+            const char* sv = line + i + 5;
+            size_t n = j - i - 5;
+            bool neg = (n && sv[0] == '-');
+            uint32_t v;
+            if (parseU32(sv + (neg ? 1 : 0), n - (neg ? 1 : 0), v)) {
+                out.hasNH = true;
+                out.nh = neg ? (uint32_t)(-(int64_t)v) : v;
+            }
+            break;
+        }
+        i = j + 1;
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// parallel SAM parsing: one reader thread cuts the text into jobs of whole lines, a pool parses them (name lookups
+// against the header's contig table, which no longer changes), the consumer takes the jobs back in file order and
+// only copies the parsed fields into its AlnView.  A line whose RNAME is not in the header is left to the consumer,
+// which parses it itself and extends the name store exactly as the sequential reader does.
+// ---------------------------------------------------------------------------
+struct AlnReader::SamPipeline {
+    struct Rec { SamFields f; uint32_t lineOff, lineLen; };
+    struct Job {
+        std::unique_ptr<char[]> text;  // (not a vector: no zero fill of the read buffer)
+        size_t textLen = 0;
+        std::vector<Rec> recs;
+        std::vector<uint32_t> cigars;
+        bool bad = false;  // the line after recs.back() is malformed
+        bool done = false;
+    };
+    FILE* fp;
+    const std::unordered_map<std::string, int32_t>& names;
+    std::vector<char> carry;  // bytes already read by the header parser, then the partial last line of each block
+    std::mutex mu;
+    std::condition_variable cvWork, cvDone, cvSpace;
+    std::deque<std::shared_ptr<Job> > todo, ordered;
+    bool eof = false, stop = false;
+    size_t maxOutstanding;
+    std::thread reader;
+    std::vector<std::thread> workers;
+
+    SamPipeline(FILE* f, int threads, const uint8_t* initial, size_t nInitial, const std::unordered_map<std::string, int32_t>& nm)
+        : fp(f), names(nm), carry((const char*)initial, (const char*)initial + nInitial), maxOutstanding((size_t)threads * 3 + 2) {
+        reader = std::thread([this] { readLoop(); });
+        for (int i = 0; i < threads; ++i) workers.emplace_back([this] { workLoop(); });
+    }
+    ~SamPipeline() {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            stop = true;
+        }
+        cvWork.notify_all();
+        cvSpace.notify_all();
+        cvDone.notify_all();
+        reader.join();
+        for (auto& w : workers) w.join();
+    }
+    void readLoop() {
+        const size_t kJobBytes = 2u << 20;
+        bool fileEnd = false;
+        while (!fileEnd) {
+            auto job = std::make_shared<Job>();
+            const size_t have = carry.size();
+            job->text.reset(new char[have + kJobBytes]);
+            if (have) memcpy(job->text.get(), carry.data(), have);
+            size_t got = fread(job->text.get() + have, 1, kJobBytes, fp);
+            size_t total = have + got;
+            if (got == 0) {
+                fileEnd = true;  // the rest (a last line without '\n') is the final job
+                carry.clear();
+            } else {
+                size_t cut = total;
+                while (cut > 0 && job->text[cut - 1] != '\n') --cut;
+                if (cut == 0) { carry.assign(job->text.get(), job->text.get() + total); continue; }  // no complete line yet
+                carry.assign(job->text.get() + cut, job->text.get() + total);
+                total = cut;
+            }
+            job->textLen = total;
+            std::unique_lock<std::mutex> l(mu);
+            cvSpace.wait(l, [this] { return stop || ordered.size() < maxOutstanding; });
+            if (stop) return;
+            if (job->textLen) {
+                ordered.push_back(job);
+                todo.push_back(job);
+                cvWork.notify_one();
+            }
+        }
+        std::lock_guard<std::mutex> l(mu);
+        eof = true;
+        cvDone.notify_all();
+        cvWork.notify_all();
+    }
+    void workLoop() {
+        std::string lastName;
+        int32_t lastId = -1;
+        for (;;) {
+            std::shared_ptr<Job> job;
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cvWork.wait(l, [this] { return stop || !todo.empty() || eof; });
+                if (stop) return;
+                if (todo.empty()) { if (eof) return; continue; }
+                job = todo.front();
+                todo.pop_front();
+            }
+            const char* t = job->text.get();
+            const size_t n = job->textLen;
+            job->recs.reserve(n / 96);
+            size_t p = 0;
+            while (p < n) {
+                if (t[p] == '\n' || t[p] == '\r') { ++p; continue; }  // blank lines are not records
+                const char* nl = (const char*)memchr(t + p, '\n', n - p);
+                size_t e = nl ? (size_t)(nl - t) : n, len = e - p;
+                if (len && t[p + len - 1] == '\r') --len;
+                Rec r;
+                r.lineOff = (uint32_t)p;
+                r.lineLen = (uint32_t)len;
+                int rc = parseSamLine(t + p, len, names, lastName, lastId, job->cigars, r.f);
+                if (rc == 1) { job->bad = true; break; }
+                job->recs.push_back(r);
+                p = e + 1;
+            }
+            {
+                std::lock_guard<std::mutex> l(mu);
+                job->done = true;
+            }
+            cvDone.notify_all();
+        }
+    }
+    // Next parsed job in file order; null at end of file.
+    std::shared_ptr<Job> next() {
+        std::unique_lock<std::mutex> l(mu);
+        cvDone.wait(l, [this] { return (!ordered.empty() && ordered.front()->done) || (ordered.empty() && eof); });
+        if (ordered.empty()) return nullptr;
+        std::shared_ptr<Job> j = ordered.front();
+        ordered.pop_front();
+        cvSpace.notify_one();
+        return j;
+    }
+    // consumer state
+    std::shared_ptr<Job> cur;
+    size_t idx = 0;
+    bool finished = false;
+    // makes cur/idx point at the next record (or at a job's malformed line); false at end of input
+    bool advance() {
+        while (!finished) {
+            if (cur && (idx < cur->recs.size() || cur->bad)) return true;
+            cur = next();
+            idx = 0;
+            if (!cur) finished = true;
+        }
+        return false;
+    }
+};
+
 AlnReader::AlnReader() {}
 AlnReader::~AlnReader() { close(); }
 
 void AlnReader::setThreads(int n) {
-    if (!isBam_ || !good_ || pipe_ || n <= 1) return;
-    pipe_ = new Pipeline(fp_, n);  // continues at the current file offset (after the blocks already consumed)
+    if (!good_ || pipe_ || samPipe_ || n <= 1) return;
+    if (isBam_) {
+        pipe_ = new Pipeline(fp_, n);  // continues at the current file offset (after the blocks already consumed)
+    } else {
+        samPipe_ = new SamPipeline(fp_, n, buf_.data() + cur_, end_ - cur_, nameMap_->m);  // takes over what the header parser had read ahead
+        cur_ = end_ = 0;
+    }
 }
 
 void AlnReader::close() {
     delete pipe_;
     pipe_ = nullptr;
+    delete samPipe_;
+    samPipe_ = nullptr;
+    extraNames_.clear();
+    lastName_.clear();
+    lastId_ = -1;
     if (fp_) fclose(fp_);
     fp_ = nullptr;
     delete nameMap_;
@@ -356,6 +614,7 @@ bool AlnReader::open(const char* path) {
 
 bool AlnReader::atEnd() {
     if (!good_ && !fp_) return true;
+    if (samPipe_) return !samPipe_->advance();
     for (;;) {
         if (!isBam_)  // SAM: blank lines (e.g. a trailing newline) are not records
             while (cur_ < end_ && (buf_[cur_] == '\n' || buf_[cur_] == '\r')) ++cur_;
@@ -367,105 +626,47 @@ bool AlnReader::atEnd() {
 // ---------------------------------------------------------------------------
 // SAM record
 // ---------------------------------------------------------------------------
-static inline bool parseU32(const char* s, size_t n, uint32_t& v) {
-    if (n == 0) return false;
-    uint64_t x = 0;
-    for (size_t i = 0; i < n; ++i) {
-        if (s[i] < '0' || s[i] > '9') return false;
-        x = x * 10 + (uint64_t)(s[i] - '0');
-        if (x > 0xffffffffull) return false;
-    }
-    v = (uint32_t)x;
-    return true;
-}
-
-static inline int cigarOpCode(char c) {
-    switch (c) {
-        case 'M': return 0; case 'I': return 1; case 'D': return 2; case 'N': return 3; case 'S': return 4;
-        case 'H': return 5; case 'P': return 6; case '=': return 7; case 'X': return 8; default: return -1;
-    }
-}
-
 int AlnReader::nextSam(AlnView& out) {
+    SamFields fld;
     const char* line;
-    size_t len;
-    if (atEnd() || !getLine(line, len) || len == 0) return 1;
-    // split the 11 mandatory fields
-    const char* f[12];
-    size_t fl[12];
-    int nf = 0;
-    size_t i = 0;
-    while (nf < 11) {
-        size_t j = i;
-        while (j < len && line[j] != '\t') ++j;
-        f[nf] = line + i;
-        fl[nf] = j - i;
-        ++nf;
-        if (j >= len) { i = len; break; }
-        i = j + 1;
-    }
-    if (nf < 11) return 1;
-    uint32_t flag, pos;
-    if (!parseU32(f[1], fl[1], flag) || !parseU32(f[3], fl[3], pos)) return 1;
-    out.flag = flag;
-    out.beginPos = (int32_t)pos - 1;
-    if (fl[2] == 1 && f[2][0] == '*') {
-        out.rID = -1;
+    if (samPipe_) {
+        if (!samPipe_->advance()) return 1;
+        SamPipeline::Job& job = *samPipe_->cur;
+        if (samPipe_->idx >= job.recs.size()) return 1;  // the malformed line of this job
+        const SamPipeline::Rec& r = job.recs[samPipe_->idx++];
+        fld = r.f;
+        line = job.text.get() + r.lineOff;
+        out.cigar = job.cigars.data() + fld.cigarOff;
     } else {
-        auto it = nameMap_->m.find(std::string(f[2], fl[2]));
-        if (it == nameMap_->m.end()) {  // contig missing from the header: extend the name store
+        size_t len;
+        if (atEnd() || !getLine(line, len) || len == 0) return 1;
+        cigarScratch_.clear();
+        int rc = parseSamLine(line, len, nameMap_->m, lastName_, lastId_, cigarScratch_, fld);
+        if (rc == 1) return 1;
+        out.cigar = cigarScratch_.data();
+    }
+    if (fld.rID == -2) {  // contig missing from the header: extend the name store
+        std::string name(line + fld.nameOff, fld.nameLen);
+        auto it = extraNames_.find(name);
+        if (it == extraNames_.end()) {
             int32_t id = (int32_t)names_.size();
-            nameMap_->m.emplace(std::string(f[2], fl[2]), id);
-            names_.push_back(std::string(f[2], fl[2]));
+            extraNames_.emplace(name, id);
+            names_.push_back(name);
             lengths_.push_back(0);
-            out.rID = id;
+            fld.rID = id;
         } else {
-            out.rID = it->second;
+            fld.rID = it->second;
         }
     }
-    // CIGAR
-    cigarScratch_.clear();
-    if (!(fl[5] == 1 && f[5][0] == '*')) {
-        uint64_t cnt = 0;
-        bool haveDigit = false;
-        for (size_t k = 0; k < fl[5]; ++k) {
-            char c = f[5][k];
-            if (c >= '0' && c <= '9') { cnt = cnt * 10 + (uint64_t)(c - '0'); haveDigit = true; if (cnt >= (1ull << 28)) return 1; }
-            else {
-                int op = cigarOpCode(c);
-                if (op < 0 || !haveDigit) return 1;
-                cigarScratch_.push_back((uint32_t)(cnt << 4) | (uint32_t)op);
-                cnt = 0;
-                haveDigit = false;
-            }
-        }
-        if (haveDigit) return 1;
-    }
-    out.cigar = cigarScratch_.data();
-    out.nCigar = (uint32_t)cigarScratch_.size();
-    // SEQ
+    out.rID = fld.rID;
+    out.beginPos = fld.beginPos;
+    out.flag = fld.flag;
+    out.nCigar = fld.nCigar;
     out.seq4 = nullptr;
-    if (fl[9] == 1 && f[9][0] == '*') { out.seqText = f[9]; out.lSeq = 0; }
-    else { out.seqText = f[9]; out.lSeq = (uint32_t)fl[9]; }
-    // optional fields: look for NH:i:<n>
-    out.hasNH = false;
-    out.nh = 1;
-    while (i < len) {
-        size_t j = i;
-        while (j < len && line[j] != '\t') ++j;
-        if (j - i >= 6 && line[i] == 'N' && line[i + 1] == 'H' && line[i + 2] == ':' && line[i + 3] == 'i' && line[i + 4] == ':') {
-            const char* s = line + i + 5;
-            size_t n = j - i - 5;
-            bool neg = (n && s[0] == '-');
-            uint32_t v;
-            if (parseU32(s + (neg ? 1 : 0), n - (neg ? 1 : 0), v)) {
-                out.hasNH = true;
-                out.nh = neg ? (uint32_t)(-(int64_t)v) : v;
-            }
-            break;
-        }
-        i = j + 1;
-    }
+    out.seqText = line + fld.seqOff;
+    out.lSeq = fld.lSeq;
+    out.hasNH = fld.hasNH;
+    out.nh = fld.nh;
     ++nRecords_;
     return 0;
 }

@@ -1,4 +1,4 @@
-// aln_reader.h -- sequential SAM / BGZF-BAM record walker (own code, zlib only).
+// aln_reader.h -- SAM / BGZF-BAM record walker, optionally with worker threads (own code, zlib only).
 //
 // This is the ONE alignment decoder of the project.  It replaces the SeqAn 1.4
 // BamStream the reference uses at pingpongpro.cpp:402-415 and :1482-1520 and is
@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace ppp {
@@ -71,8 +72,9 @@ public:
     // Records decoded so far.
     uint64_t recordCount() const { return nRecords_; }
 
-    // BAM only: inflate BGZF blocks on `n` worker threads (read-ahead, in order).  Call after open(); n <= 1 keeps the
-    // sequential path.  Record decoding itself stays on the calling thread.
+    // Worker threads (read-ahead, results in file order).  BAM: BGZF blocks are inflated on `n` threads and the record
+    // walk stays on the calling thread.  SAM: whole lines are parsed on `n` threads and the calling thread only copies
+    // the parsed fields.  Call after open(); n <= 1 keeps the sequential path.
     void setThreads(int n);
 
 private:
@@ -103,6 +105,11 @@ private:
     std::string pending_;
     struct Pipeline;
     Pipeline* pipe_ = nullptr;    // parallel BGZF inflate (setThreads)
+    struct SamPipeline;
+    SamPipeline* samPipe_ = nullptr;  // parallel SAM line parsing (setThreads)
+    std::unordered_map<std::string, int32_t> extraNames_;  // SAM contigs that are missing from the header, in order of appearance
+    std::string lastName_;        // SAM: the previous record's RNAME (sorted input repeats it)
+    int32_t lastId_ = -1;
 };
 
 }  // namespace ppp

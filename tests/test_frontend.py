@@ -139,3 +139,56 @@ def test_weight_reciprocal_single_equals_double_narrowed():
     narrowed = (1.0 / n.astype(np.float64)).astype(np.float32)
     single = np.float32(1.0) / n.astype(np.float32)
     assert np.array_equal(narrowed.view(np.uint32), single.view(np.uint32))
+
+
+def _decoded_equal(a, b):
+    assert a.names == b.names and a.lengths == b.lengths
+    assert a.n_records == b.n_records and a.n_kept == b.n_kept and a.total_weight == b.total_weight
+    for x, y in zip(a.reads, b.reads):
+        assert np.array_equal(x, y)
+
+
+SAM_EDGE = (
+    "@HD\tVN:1.0\n@SQ\tSN:c1\tLN:5000\n@SQ\tSN:c2\tLN:400\n"
+    "r1\t0\tc1\t100\t255\t25M\t*\t0\t0\tACGTACGTAAACGTACGTACGTACG\t*\tNH:i:2\n"
+    "\n\r\n"                                                                          # blank lines are not records
+    "r2\t16\tc2\t50\t255\t2S24M\t*\t0\t0\tACGTACGTACGTACGTACGTACGTAC\t*\tXX:Z:NH:i:7\tNH:i:3\r\n"   # CRLF, decoy tag
+    "r3\t0\tlate\t7\t255\t30M\t*\t0\t0\tACGTACGTAAACGTACGTACGTACGTACGT\t*\n"          # contig that is missing from the header
+    "r4\t0\t*\t0\t0\t*\t*\t0\t0\t*\t*\n"                                                # unmapped
+    "r5\t0\tlate\t9\t255\t24M\t*\t0\t0\tACGTACGTAAACGTACGTACGTAC\t*\tNH:i:-1\n"
+    "r6\t16\tc1\t4000\t255\t26M\t*\t0\t0\tACGTACGTACGTACGTTCGTACGTAC\t*"               # last line without a terminator
+)
+
+
+@pytest.mark.parametrize("threads", [2, 5])
+def test_parallel_sam_parser_equals_sequential_reader(tmp_path, threads):
+    """AlnReader::setThreads on SAM text: worker-parsed lines come back in file order and decode to the same records,
+    including blank lines, CRLF, a contig missing from the header (the name store grows in order of appearance), a
+    negative NH, and a last line without '\\n'.  Also on a file large enough for many parser jobs."""
+    p = tmp_path / "edge.sam"
+    p.write_bytes(SAM_EDGE.encode())
+    seq = host.decode_file(str(p), threads=1)
+    assert seq.names == ["c1", "c2", "late"] and seq.n_records == 6 and seq.n_kept == 5
+    _decoded_equal(seq, host.decode_file(str(p), threads=threads))
+    (tmp_path / "headerless.sam").write_bytes(SAM_EDGE[SAM_EDGE.index("r1"):].encode())
+    _decoded_equal(host.decode_file(str(tmp_path / "headerless.sam"), threads=1), host.decode_file(str(tmp_path / "headerless.sam"), threads=threads))
+    big = tmp_path / "big.sam"
+    subprocess.check_call([os.path.join(_build.BIN, "ppp_synth"), "--genome", "tiny", "--reads", "120000", "--seed", "9", "--out", str(big)])
+    assert big.stat().st_size > 3 * (2 << 20)  # several jobs of 2 MB
+    _decoded_equal(host.decode_file(str(big), threads=1), host.decode_file(str(big), threads=threads))
+    for mode in ("unique", "discard"):
+        _decoded_equal(host.decode_file(str(big), mode=mode, threads=1), host.decode_file(str(big), mode=mode, threads=threads))
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_malformed_sam_record_fails_at_the_same_place(tmp_path, threads):
+    """'Failed to read record' (pingpongpro.cpp:411): a malformed line stops the parallel parser exactly like the
+    sequential one (the CLI exits with 1 either way)."""
+    good = "r\t0\tc1\t100\t255\t25M\t*\t0\t0\tACGTACGTAAACGTACGTACGTACG\t*\n"
+    p = tmp_path / "bad.sam"
+    p.write_text("@SQ\tSN:c1\tLN:5000\n" + good * 3 + "r\tnotanumber\tc1\t5\t255\t25M\t*\t0\t0\tACGT\tIIII\n" + good)
+    with pytest.raises(ValueError, match="Failed to read record"):
+        host.decode_file(str(p), threads=threads)
+    p.write_text("@SQ\tSN:c1\tLN:5000\n" + good * 2 + "r\t0\tc1\t5\t255\t25Q\t*\t0\t0\tACGT\tIIII\n")  # bad CIGAR operation
+    with pytest.raises(ValueError, match="Failed to read record"):
+        host.decode_file(str(p), threads=threads)
