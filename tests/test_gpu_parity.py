@@ -377,3 +377,48 @@ def test_builtin_nccl_collective_single_rank():
         assert np.array_equal(sc.loci, single["score"].loci)
         assert np.array_equal(ctx.signatures(), single["signatures"])
         assert np.array_equal(bits(sc.fdr_table), bits(single["score"].fdr_table))
+
+
+def _fold_f32(weights):
+    """reads += w in single precision, in order (pingpongpro.cpp:487)."""
+    h = np.float32(0.0)
+    for w in weights:
+        h = np.float32(h + w)
+    return h
+
+
+@pytest.mark.parametrize("batches", [1, 3])
+def test_tall_stacks_fold_in_file_order(batches):
+    """-m weighted on tall stacks (the warp-cooperative fold): run lengths around its 32-record and 256-record
+    boundaries, both strands interleaved at one position, multiplicities beyond the weight table and beyond 2^24,
+    and sums continued across submissions.  Expected value: the literal single-precision loop."""
+    rng = np.random.default_rng(7)
+    nh_pool = np.array([1, 1, 1, 1, 2, 3, 5, 7, 10, 63, 64, 100, (1 << 24) - 1, (1 << 24) + 3, 1 << 29], dtype=np.uint32)
+    lengths_of_runs = [31, 32, 33, 34, 255, 256, 257, 511, 512, 513, 777, 5000, 40000]
+    key, minus, a10, nh = [], [], [], []
+    for i, n in enumerate(lengths_of_runs):
+        pos = 100 + 50 * i
+        key.append(np.full(n, pos, np.uint32))
+        both = i % 3 != 0                      # every third position holds one strand only
+        minus.append(rng.random(n) < 0.5 if both else np.full(n, i % 2 == 0))
+        a10.append(rng.random(n) < 0.01)
+        nh.append(rng.choice(nh_pool, size=n))
+    key, minus, a10, nh = map(np.concatenate, (key, minus, a10, nh))
+    order = rng.permutation(len(key))         # positions interleaved in the "file"; the order within a position is what matters
+    key, minus, a10, nh = key[order], minus[order], a10[order], nh[order]
+    reads = host.pack_reads(key, minus, a10, nh)
+    w = (1.0 / nh.astype(np.float64)).astype(np.float32)   # :449
+    with api.Context([2000], mode="weighted") as ctx:
+        cuts = [len(reads) * k // batches for k in range(batches + 1)]
+        for k in range(batches):
+            ctx.count_reads(0, reads[cuts[k]:cuts[k + 1]])
+        ctx.finish()
+        for strand in (0, 1):
+            h, a = ctx.stacks(0, strand, 0, 2000)
+            for i, n in enumerate(lengths_of_runs):
+                pos = 100 + 50 * i
+                sel = (key == pos) & (minus == bool(strand))
+                want = _fold_f32(w[sel])
+                assert bits(np.array([h[pos]]))[0] == bits(np.array([want]))[0], (strand, n, h[pos], want)
+                assert bool(a[pos]) == bool(a10[sel].any())
+            assert np.count_nonzero(h) == sum(1 for i in range(len(lengths_of_runs)) if ((key == 100 + 50 * i) & (minus == bool(strand))).any())
