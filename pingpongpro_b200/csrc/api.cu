@@ -141,6 +141,7 @@ struct ppp_ctx {
     uint32_t* dGather = nullptr;  // [world][kTallHeader + tallCap], see launch_tall_apply
     uint32_t tallCap = 0;
     uint32_t* dOverflow = nullptr;
+    float thresholdFreq = 0.f;  // the maximum frequency hThresholds was built for (0: none)
     bool denseTail = false;    // a list overflowed once: this context reduces the dense tables from then on
 
     Timer tScan, tLut, tBin, tScore, tTransposon;
@@ -176,8 +177,9 @@ inline int heightScoreBin(float hs, float maxHeightScore) {
 // thresholds[b-1] = smallest float hs in [1, maxFreq^2] whose bin is >= b (b = 1..999); +inf when no product
 // reaches bin b.  bin() is a monotone step function of hs, so the device computes it as the
 // number of thresholds <= hs.  Bisection runs on float bit patterns (order-isomorphic for positive floats).
-// Returns false when bin() is found non-monotone around a threshold (never observed with glibc).
-bool computeThresholds(float maxFreq, float* thr) {
+// The search assumes that bin() is a monotone step function; validateThresholds() checks that assumption around
+// every step afterwards (off the critical path: the caller runs it while the binning kernel is executing).
+void computeThresholds(float maxFreq, float* thr) {
     float maxHs = log10f(maxFreq * maxFreq);  // :551
     float top = maxFreq * maxFreq;
     uint32_t loBits, topBits;
@@ -189,7 +191,6 @@ bool computeThresholds(float maxFreq, float* thr) {
         memcpy(&f, &bits, 4);
         return heightScoreBin(f, maxHs);
     };
-    bool monotone = true;
     uint32_t from = loBits;
     const int topBin = binAt(topBits);
     const double ratio = pow(10.0, (double)maxHs / 999.0);
@@ -230,12 +231,35 @@ bool computeThresholds(float maxFreq, float* thr) {
         }
         memcpy(&thr[b - 1], &hi, 4);
         lastGuess = (double)thr[b - 1];
-        // local validation: a few patterns either side must respect the step
-        if (hi >= loBits + 2 && binAt(hi - 2) >= b) monotone = false;  // (hi - 1 was already probed by the bisection)
-        if (hi + 1 <= topBits && binAt(hi + 1) < b) monotone = false;
         from = hi;
     }
-    return monotone;
+}
+
+// False when bin() is found non-monotone around a threshold (never observed with glibc): the patterns just below a
+// threshold must fall below bin b, the threshold itself and the pattern above it must reach it.
+bool validateThresholds(float maxFreq, const float* thr) {
+    const float maxHs = log10f(maxFreq * maxFreq);
+    const float top = maxFreq * maxFreq;
+    uint32_t loBits, topBits;
+    const float one = 1.0f;
+    memcpy(&loBits, &one, 4);
+    memcpy(&topBits, &top, 4);
+    auto binAt = [&](uint32_t bits) {
+        float f;
+        memcpy(&f, &bits, 4);
+        return heightScoreBin(f, maxHs);
+    };
+    for (int b = 1; b < PPP_HEIGHT_SCORE_BINS; ++b) {
+        if (std::isinf(thr[b - 1])) continue;
+        uint32_t hi;
+        memcpy(&hi, &thr[b - 1], 4);
+        if (binAt(hi) < b) return false;
+        if (hi >= loBits + 1 && (b == 1 || thr[b - 2] < thr[b - 1]) && binAt(hi - 1) >= b) return false;
+        if (hi >= loBits + 2 && (b == 1 || thr[b - 2] < thr[b - 1]) && binAt(hi - 2) >= b) return false;
+        if (hi + 1 <= topBits && binAt(hi + 1) < b) return false;
+        if (b > 1 && thr[b - 2] > thr[b - 1]) return false;
+    }
+    return true;
 }
 
 // x and w(x) of the integral at pingpongpro.cpp:724-734: for (double x = -5; x <= 5; x += 0.01)
@@ -875,8 +899,9 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
     float maxFreq = (float)(c->hs->maxCount < kSaturate ? (uint32_t)c->hs->maxCount : kSaturate);  // :547-550
     for (int b = 0; b < kBins; ++b) c->hThresholds[b] = std::numeric_limits<float>::infinity();
     c->binScale = maxFreq > 1.0f ? 999.0f / log10f(maxFreq * maxFreq) : 0.0f;
+    c->thresholdFreq = maxFreq > 1.0f ? maxFreq : 0.0f;
     if (maxFreq > 1.0f) {
-        if (!computeThresholds(maxFreq, c->hThresholds)) return fail(PPP_ERR_STATE, "host log10f is not monotone around a bin threshold");
+        computeThresholds(maxFreq, c->hThresholds);
     } else if (c->nPairs > 0 && !c->allreduce) {
         return fail(PPP_ERR_DEGENERATE, "every rounded stack height occurs once: the reference's height score is 0/0 (pingpongpro.cpp:551/:593)");
     }
@@ -914,6 +939,9 @@ int ppp_scan(ppp_ctx* c, uint64_t* grouped, uint64_t* nPairs) {
     CK(launch_bin_group(c->dPairsRaw, c->dPairs, c->dTileCnt, c->dTileBase, c->dTileDst, c->nTiles, c->dLut, c->dThresholds, c->binScale, c->W, c->dGrouped, c->dTileCursor, c->stream,
                         &c->launches));
     if ((rc = timerStop(c, c->tBin))) return rc;
+    // while the binning kernel runs: the monotonicity assumption behind the threshold table is checked on the host
+    if (c->thresholdFreq > 1.0f && !validateThresholds(c->thresholdFreq, c->hThresholds))
+        return fail(PPP_ERR_STATE, "host log10f is not monotone around a bin threshold");
     if ((rc = hookReduce(c, c->dGrouped, tableWords, 0, 0))) return rc;
     if (grouped) {
         std::vector<uint32_t> g(tableWords);

@@ -137,18 +137,29 @@ struct AlnReader::Pipeline {
             cvDone.notify_all();
         }
     }
-    // Next inflated chunk in file order; false at end of file.  `bad` is set on a malformed block.
-    bool next(const uint8_t*& data, size_t& len, bool& bad) {
+    // Next inflated chunk in file order; false at end of file (or after requestStop).  `bad` is set on a malformed
+    // block.  `keep` (optional) receives shared ownership of the chunk; otherwise it lives until the next call.
+    bool next(const uint8_t*& data, size_t& len, bool& bad, std::shared_ptr<Job>* keep = nullptr) {
         std::unique_lock<std::mutex> l(mu);
-        cvDone.wait(l, [this] { return (!ordered.empty() && ordered.front()->done) || (ordered.empty() && eof); });
-        if (ordered.empty()) return false;
+        cvDone.wait(l, [this] { return stop || (!ordered.empty() && ordered.front()->done) || (ordered.empty() && eof); });
+        if (stop || ordered.empty()) return false;
         current = ordered.front();
         ordered.pop_front();
         cvSpace.notify_one();
         bad = current->bad;
         data = current->out.data();
         len = current->out.size();
+        if (keep) { *keep = current; current.reset(); }
         return true;
+    }
+    void requestStop() {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            stop = true;
+        }
+        cvWork.notify_all();
+        cvSpace.notify_all();
+        cvDone.notify_all();
     }
 };
 
@@ -260,22 +271,40 @@ static int parseSamLine(const char* line, size_t len, const std::unordered_map<s
 }
 
 // ---------------------------------------------------------------------------
-// parallel SAM parsing: one reader thread cuts the text into jobs of whole lines, a pool parses them (name lookups
-// against the header's contig table, which no longer changes), the consumer takes the jobs back in file order and
-// only copies the parsed fields into its AlnView.  A line whose RNAME is not in the header is left to the consumer,
-// which parses it itself and extends the name store exactly as the sequential reader does.
+// SAM batch mode: one reader thread cuts the text into jobs of whole lines, a pool parses them (name lookups against
+// the header's contig table, which no longer changes) and applies the record function, the consumer takes the jobs'
+// outputs back in file order.  A job with an RNAME that is not in the header is redone by the consumer, which
+// extends the name store exactly as the sequential reader does.
 // ---------------------------------------------------------------------------
+static inline void fillView(AlnView& out, const SamFields& f, const char* line, const uint32_t* cigars) {
+    out.rID = f.rID;
+    out.beginPos = f.beginPos;
+    out.flag = f.flag;
+    out.cigar = cigars + f.cigarOff;
+    out.nCigar = f.nCigar;
+    out.seq4 = nullptr;
+    out.seqText = line + f.seqOff;
+    out.lSeq = f.lSeq;
+    out.hasNH = f.hasNH;
+    out.nh = f.nh;
+}
+
 struct AlnReader::SamPipeline {
+    typedef AlnReader::RecordFn RecordFn;
     struct Rec { SamFields f; uint32_t lineOff, lineLen; };
     struct Job {
         std::unique_ptr<char[]> text;  // (not a vector: no zero fill of the read buffer)
-        size_t textLen = 0;
+        size_t textLen = 0, textCap = 0;
         std::vector<Rec> recs;
         std::vector<uint32_t> cigars;
-        bool bad = false;  // the line after recs.back() is malformed
+        std::vector<uint8_t> out;  // batch mode: what the record function kept
+        bool bad = false;          // the line after recs.back() is malformed
+        bool unknownName = false;  // batch mode: a contig that is missing from the header -- the consumer redoes this job
         bool done = false;
     };
     FILE* fp;
+    RecordFn fn = nullptr;
+    void* user = nullptr;
     const std::unordered_map<std::string, int32_t>& names;
     std::vector<char> carry;  // bytes already read by the header parser, then the partial last line of each block
     std::mutex mu;
@@ -285,9 +314,31 @@ struct AlnReader::SamPipeline {
     size_t maxOutstanding;
     std::thread reader;
     std::vector<std::thread> workers;
+    // consumed jobs are reused: their buffers keep their capacity, so the steady state allocates nothing (fresh
+    // multi-megabyte allocations mean mmap / page faults / munmap, which serialise the threads on the address space)
+    std::vector<std::shared_ptr<Job> > pool;
+    std::shared_ptr<Job> obtain() {
+        std::lock_guard<std::mutex> l(mu);
+        if (pool.empty()) return std::make_shared<Job>();
+        std::shared_ptr<Job> j = pool.back();
+        pool.pop_back();
+        return j;
+    }
+    void recycle(std::shared_ptr<Job>& j) {
+        if (!j) return;
+        j->recs.clear();
+        j->cigars.clear();
+        j->out.clear();
+        j->bad = j->unknownName = j->done = false;
+        j->textLen = 0;
+        std::lock_guard<std::mutex> l(mu);
+        pool.push_back(std::move(j));
+        j.reset();
+    }
 
-    SamPipeline(FILE* f, int threads, const uint8_t* initial, size_t nInitial, const std::unordered_map<std::string, int32_t>& nm)
-        : fp(f), names(nm), carry((const char*)initial, (const char*)initial + nInitial), maxOutstanding((size_t)threads * 3 + 2) {
+    SamPipeline(FILE* f, int threads, const uint8_t* initial, size_t nInitial, const std::unordered_map<std::string, int32_t>& nm, RecordFn fn_ = nullptr,
+                void* user_ = nullptr)
+        : fp(f), fn(fn_), user(user_), names(nm), carry((const char*)initial, (const char*)initial + nInitial), maxOutstanding((size_t)threads * 3 + 2) {
         reader = std::thread([this] { readLoop(); });
         for (int i = 0; i < threads; ++i) workers.emplace_back([this] { workLoop(); });
     }
@@ -306,9 +357,12 @@ struct AlnReader::SamPipeline {
         const size_t kJobBytes = 2u << 20;
         bool fileEnd = false;
         while (!fileEnd) {
-            auto job = std::make_shared<Job>();
+            std::shared_ptr<Job> job = obtain();
             const size_t have = carry.size();
-            job->text.reset(new char[have + kJobBytes]);
+            if (job->textCap < have + kJobBytes) {
+                job->textCap = have + kJobBytes + (64u << 10);
+                job->text.reset(new char[job->textCap]);
+            }
             if (have) memcpy(job->text.get(), carry.data(), have);
             size_t got = fread(job->text.get() + have, 1, kJobBytes, fp);
             size_t total = have + got;
@@ -318,7 +372,7 @@ struct AlnReader::SamPipeline {
             } else {
                 size_t cut = total;
                 while (cut > 0 && job->text[cut - 1] != '\n') --cut;
-                if (cut == 0) { carry.assign(job->text.get(), job->text.get() + total); continue; }  // no complete line yet
+                if (cut == 0) { carry.assign(job->text.get(), job->text.get() + total); recycle(job); continue; }  // no complete line yet
                 carry.assign(job->text.get() + cut, job->text.get() + total);
                 total = cut;
             }
@@ -365,7 +419,15 @@ struct AlnReader::SamPipeline {
                 int rc = parseSamLine(t + p, len, names, lastName, lastId, job->cigars, r.f);
                 if (rc == 1) { job->bad = true; break; }
                 job->recs.push_back(r);
+                if (rc == 2) job->unknownName = true;
                 p = e + 1;
+            }
+            if (fn && !job->unknownName) {
+                AlnView v;
+                for (const Rec& r : job->recs) {
+                    fillView(v, r.f, t + r.lineOff, job->cigars.data());
+                    fn(user, v, job->out);
+                }
             }
             {
                 std::lock_guard<std::mutex> l(mu);
@@ -384,19 +446,254 @@ struct AlnReader::SamPipeline {
         cvSpace.notify_one();
         return j;
     }
-    // consumer state
-    std::shared_ptr<Job> cur;
-    size_t idx = 0;
-    bool finished = false;
-    // makes cur/idx point at the next record (or at a job's malformed line); false at end of input
-    bool advance() {
-        while (!finished) {
-            if (cur && (idx < cur->recs.size() || cur->bad)) return true;
-            cur = next();
-            idx = 0;
-            if (!cur) finished = true;
+};
+
+// ---------------------------------------------------------------------------
+// BAM record decoding (shared by the sequential walk and the batch workers)
+// ---------------------------------------------------------------------------
+static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type);
+
+static size_t bamTypeSize(char t) {
+    switch (t) {
+        case 'A': case 'c': case 'C': return 1;
+        case 's': case 'S': return 2;
+        case 'i': case 'I': case 'f': return 4;
+        default: return 0;
+    }
+}
+
+static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type) {
+    size_t sz = bamTypeSize(type);
+    if (sz) { if (n < sz) return false; used = sz; return true; }
+    if (type == 'Z' || type == 'H') {
+        const void* z = memchr(p, 0, n);
+        if (!z) return false;
+        used = (size_t)((const uint8_t*)z - p) + 1;
+        return true;
+    }
+    if (type == 'B') {
+        if (n < 5) return false;
+        size_t es = bamTypeSize((char)p[0]);
+        uint32_t cnt;
+        memcpy(&cnt, p + 1, 4);
+        if (!es || n < 5 + es * (size_t)cnt) return false;
+        used = 5 + es * (size_t)cnt;
+        return true;
+    }
+    return false;
+}
+
+// `p` points behind the block_size word of one record of `blockSize` bytes.  False: malformed.
+static bool parseBamRecord(const uint8_t* p, uint32_t blockSize, std::vector<uint32_t>& cigarScratch, AlnView& out) {
+    if (blockSize < 32) return false;
+    int32_t refID, pos;
+    memcpy(&refID, p, 4);
+    memcpy(&pos, p + 4, 4);
+    uint32_t lReadName = p[8];
+    uint16_t nCigar, flag;
+    memcpy(&nCigar, p + 12, 2);
+    memcpy(&flag, p + 14, 2);
+    uint32_t lSeq;
+    memcpy(&lSeq, p + 16, 4);
+    size_t off = 32 + lReadName;
+    size_t need = off + 4 * (size_t)nCigar + ((size_t)lSeq + 1) / 2 + lSeq;
+    if (need > blockSize) return false;
+    out.rID = refID;
+    out.beginPos = pos;
+    out.flag = flag;
+    cigarScratch.resize(nCigar);
+    if (nCigar) memcpy(cigarScratch.data(), p + off, 4 * (size_t)nCigar);  // unaligned source
+    out.cigar = cigarScratch.data();
+    out.nCigar = nCigar;
+    off += 4 * (size_t)nCigar;
+    out.seqText = nullptr;
+    out.seq4 = p + off;
+    out.lSeq = lSeq;
+    off += ((size_t)lSeq + 1) / 2 + lSeq;
+    // tags
+    out.hasNH = false;
+    out.nh = 1;
+    const uint8_t* t = p + off;
+    size_t n = blockSize - off;
+    while (n >= 3) {
+        char type = (char)t[2];
+        size_t used = 0;
+        if (!skipBamTag(t + 3, n - 3, used, type)) break;
+        if (t[0] == 'N' && t[1] == 'H') {
+            const uint8_t* v = t + 3;
+            switch (type) {
+                case 'c': out.hasNH = true; out.nh = (uint32_t)(int32_t)(int8_t)v[0]; break;
+                case 'C': out.hasNH = true; out.nh = v[0]; break;
+                case 's': { int16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = (uint32_t)(int32_t)x; break; }
+                case 'S': { uint16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = x; break; }
+                case 'i': { int32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = (uint32_t)x; break; }
+                case 'I': { uint32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = x; break; }
+                default: break;
+            }
+            break;
         }
-        return false;
+        t += 3 + used;
+        n -= 3 + used;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// BAM batch mode, the third stage behind the parallel inflate: ONE thread walks the record boundaries of the inflated
+// chunks (4 bytes per record; a record that straddles two chunks is stitched into a side buffer), the workers decode
+// the records of a chunk and apply the record function, the consumer receives the outputs in file order.
+// ---------------------------------------------------------------------------
+struct AlnReader::BamBatcher {
+    typedef AlnReader::RecordFn RecordFn;
+    struct Batch {
+        std::shared_ptr<Pipeline::Job> chunk;  // keeps the inflated bytes alive
+        std::vector<uint8_t> stitched;         // records that began in an earlier chunk (block_size word included)
+        std::vector<uint32_t> stitchedOff, chunkOff;  // offsets of the block_size words, file order: stitched first
+        std::vector<uint8_t> out;
+        uint64_t nRecords = 0;
+        bool bad = false, done = false;
+    };
+    Pipeline* src;
+    RecordFn fn;
+    void* user;
+    std::vector<uint8_t> carry;  // bytes the sequential header parser had read ahead, then incomplete records
+    std::mutex mu;
+    std::condition_variable cvWork, cvDone, cvSpace;
+    std::deque<std::shared_ptr<Batch> > todo, ordered;
+    bool eof = false, stop = false;
+    size_t maxOutstanding;
+    std::thread walker;
+    std::vector<std::thread> workers;
+
+    BamBatcher(Pipeline* p, int threads, RecordFn f, void* u, const uint8_t* initial, size_t nInitial)
+        : src(p), fn(f), user(u), carry(initial, initial + nInitial), maxOutstanding((size_t)threads * 3 + 2) {
+        walker = std::thread([this] { walkLoop(); });
+        for (int i = 0; i < threads; ++i) workers.emplace_back([this] { workLoop(); });
+    }
+    ~BamBatcher() {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            stop = true;
+        }
+        cvWork.notify_all();
+        cvSpace.notify_all();
+        cvDone.notify_all();
+        // the walker may be waiting inside src->next(): stopping the source first releases it
+        src->requestStop();
+        walker.join();
+        for (auto& w : workers) w.join();
+    }
+    bool push(std::shared_ptr<Batch> b) {
+        std::unique_lock<std::mutex> l(mu);
+        cvSpace.wait(l, [this] { return stop || ordered.size() < maxOutstanding; });
+        if (stop) return false;
+        ordered.push_back(b);
+        todo.push_back(b);
+        cvWork.notify_one();
+        return true;
+    }
+    void finish(bool bad) {
+        if (bad) {
+            auto b = std::make_shared<Batch>();
+            b->bad = true;
+            b->done = true;
+            std::lock_guard<std::mutex> l(mu);
+            ordered.push_back(b);
+        }
+        std::lock_guard<std::mutex> l(mu);
+        eof = true;
+        cvDone.notify_all();
+        cvWork.notify_all();
+    }
+    void walkLoop() {
+        for (;;) {
+            const uint8_t* data = nullptr;
+            size_t len = 0;
+            bool bad = false;
+            std::shared_ptr<Pipeline::Job> chunk;
+            if (!src->next(data, len, bad, &chunk)) { finish(!carry.empty()); return; }  // a truncated record at the end is malformed
+            if (bad) { finish(true); return; }
+            auto b = std::make_shared<Batch>();
+            b->chunk = chunk;
+            size_t p = 0;
+            // records that began earlier (the carry may hold several: the header parser reads whole blocks ahead)
+            size_t cpos = 0;
+            while (cpos < carry.size()) {
+                size_t have = carry.size() - cpos;
+                size_t want = 4;
+                if (have >= 4) {
+                    uint32_t bs;
+                    memcpy(&bs, carry.data() + cpos, 4);
+                    want = (size_t)bs + 4;
+                }
+                if (have >= want && want > 4) {
+                    b->stitchedOff.push_back((uint32_t)b->stitched.size());
+                    b->stitched.insert(b->stitched.end(), carry.begin() + cpos, carry.begin() + cpos + want);
+                    cpos += want;
+                    continue;
+                }
+                if (have >= 4 && want == 4) { b->stitchedOff.push_back((uint32_t)b->stitched.size()); b->stitched.insert(b->stitched.end(), carry.begin() + cpos, carry.begin() + cpos + 4); cpos += 4; continue; }  // block_size 0: the decoder rejects it
+                if (p >= len) break;  // chunk exhausted, record still incomplete
+                size_t take = std::min(want - have, len - p);
+                carry.insert(carry.end(), data + p, data + p + take);
+                p += take;
+            }
+            if (cpos) carry.erase(carry.begin(), carry.begin() + cpos);
+            // whole records inside this chunk
+            while (carry.empty() && len - p >= 4) {
+                uint32_t bs;
+                memcpy(&bs, data + p, 4);
+                if (len - p < (size_t)bs + 4) break;
+                b->chunkOff.push_back((uint32_t)p);
+                p += (size_t)bs + 4;
+            }
+            if (carry.empty() && p < len) carry.assign(data + p, data + len);
+            if (!push(b)) return;
+        }
+    }
+    void workLoop() {
+        std::vector<uint32_t> cigarScratch;
+        AlnView v;
+        for (;;) {
+            std::shared_ptr<Batch> b;
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cvWork.wait(l, [this] { return stop || !todo.empty() || eof; });
+                if (stop) return;
+                if (todo.empty()) { if (eof) return; continue; }
+                b = todo.front();
+                todo.pop_front();
+            }
+            b->out.reserve((b->stitchedOff.size() + b->chunkOff.size()) * 12);
+            auto one = [&](const uint8_t* rec) {
+                uint32_t bs;
+                memcpy(&bs, rec, 4);
+                if (!parseBamRecord(rec + 4, bs, cigarScratch, v)) return false;
+                fn(user, v, b->out);
+                ++b->nRecords;
+                return true;
+            };
+            bool ok = true;
+            for (size_t k = 0; ok && k < b->stitchedOff.size(); ++k) ok = one(b->stitched.data() + b->stitchedOff[k]);
+            const uint8_t* base = b->chunk ? b->chunk->out.data() : nullptr;
+            for (size_t k = 0; ok && k < b->chunkOff.size(); ++k) ok = one(base + b->chunkOff[k]);
+            {
+                std::lock_guard<std::mutex> l(mu);
+                b->bad = !ok;
+                b->done = true;
+                b->chunk.reset();
+            }
+            cvDone.notify_all();
+        }
+    }
+    std::shared_ptr<Batch> next() {
+        std::unique_lock<std::mutex> l(mu);
+        cvDone.wait(l, [this] { return (!ordered.empty() && ordered.front()->done) || (ordered.empty() && eof); });
+        if (ordered.empty()) return nullptr;
+        std::shared_ptr<Batch> b = ordered.front();
+        ordered.pop_front();
+        cvSpace.notify_one();
+        return b;
     }
 };
 
@@ -404,16 +701,15 @@ AlnReader::AlnReader() {}
 AlnReader::~AlnReader() { close(); }
 
 void AlnReader::setThreads(int n) {
-    if (!good_ || pipe_ || samPipe_ || n <= 1) return;
-    if (isBam_) {
-        pipe_ = new Pipeline(fp_, n);  // continues at the current file offset (after the blocks already consumed)
-    } else {
-        samPipe_ = new SamPipeline(fp_, n, buf_.data() + cur_, end_ - cur_, nameMap_->m);  // takes over what the header parser had read ahead
-        cur_ = end_ = 0;
-    }
+    if (!isBam_ || !good_ || pipe_ || n <= 1) return;
+    pipe_ = new Pipeline(fp_, n);  // continues at the current file offset (after the blocks already consumed)
 }
 
 void AlnReader::close() {
+    delete bamBatch_;  // (before its source)
+    bamBatch_ = nullptr;
+    batchFn_ = nullptr;
+    batchFailed_ = false;
     delete pipe_;
     pipe_ = nullptr;
     delete samPipe_;
@@ -569,7 +865,6 @@ bool AlnReader::open(const char* path) {
     cur_ = end_ = 0;
     eofRaw_ = false;
     nRecords_ = 0;
-    pendingLine_ = false;
     good_ = true;
     int c0 = fgetc(fp_), c1 = fgetc(fp_);
     isBam_ = (c0 == 31 && c1 == 139);
@@ -614,7 +909,6 @@ bool AlnReader::open(const char* path) {
 
 bool AlnReader::atEnd() {
     if (!good_ && !fp_) return true;
-    if (samPipe_) return !samPipe_->advance();
     for (;;) {
         if (!isBam_)  // SAM: blank lines (e.g. a trailing newline) are not records
             while (cur_ < end_ && (buf_[cur_] == '\n' || buf_[cur_] == '\r')) ++cur_;
@@ -629,83 +923,30 @@ bool AlnReader::atEnd() {
 int AlnReader::nextSam(AlnView& out) {
     SamFields fld;
     const char* line;
-    if (samPipe_) {
-        if (!samPipe_->advance()) return 1;
-        SamPipeline::Job& job = *samPipe_->cur;
-        if (samPipe_->idx >= job.recs.size()) return 1;  // the malformed line of this job
-        const SamPipeline::Rec& r = job.recs[samPipe_->idx++];
-        fld = r.f;
-        line = job.text.get() + r.lineOff;
-        out.cigar = job.cigars.data() + fld.cigarOff;
-    } else {
-        size_t len;
-        if (atEnd() || !getLine(line, len) || len == 0) return 1;
-        cigarScratch_.clear();
-        int rc = parseSamLine(line, len, nameMap_->m, lastName_, lastId_, cigarScratch_, fld);
-        if (rc == 1) return 1;
-        out.cigar = cigarScratch_.data();
-    }
-    if (fld.rID == -2) {  // contig missing from the header: extend the name store
-        std::string name(line + fld.nameOff, fld.nameLen);
-        auto it = extraNames_.find(name);
-        if (it == extraNames_.end()) {
-            int32_t id = (int32_t)names_.size();
-            extraNames_.emplace(name, id);
-            names_.push_back(name);
-            lengths_.push_back(0);
-            fld.rID = id;
-        } else {
-            fld.rID = it->second;
-        }
-    }
-    out.rID = fld.rID;
-    out.beginPos = fld.beginPos;
-    out.flag = fld.flag;
-    out.nCigar = fld.nCigar;
-    out.seq4 = nullptr;
-    out.seqText = line + fld.seqOff;
-    out.lSeq = fld.lSeq;
-    out.hasNH = fld.hasNH;
-    out.nh = fld.nh;
+    size_t len;
+    if (atEnd() || !getLine(line, len) || len == 0) return 1;
+    cigarScratch_.clear();
+    if (parseSamLine(line, len, nameMap_->m, lastName_, lastId_, cigarScratch_, fld) == 1) return 1;
+    if (fld.rID == -2) fld.rID = internExtraName(std::string(line + fld.nameOff, fld.nameLen));
+    fillView(out, fld, line, cigarScratch_.data());
     ++nRecords_;
     return 0;
+}
+
+// A contig that is missing from the header: the name store grows in order of appearance.
+int32_t AlnReader::internExtraName(const std::string& name) {
+    auto it = extraNames_.find(name);
+    if (it != extraNames_.end()) return it->second;
+    int32_t id = (int32_t)names_.size();
+    extraNames_.emplace(name, id);
+    names_.push_back(name);
+    lengths_.push_back(0);
+    return id;
 }
 
 // ---------------------------------------------------------------------------
 // BAM record
 // ---------------------------------------------------------------------------
-static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type);
-
-static size_t bamTypeSize(char t) {
-    switch (t) {
-        case 'A': case 'c': case 'C': return 1;
-        case 's': case 'S': return 2;
-        case 'i': case 'I': case 'f': return 4;
-        default: return 0;
-    }
-}
-
-static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type) {
-    size_t sz = bamTypeSize(type);
-    if (sz) { if (n < sz) return false; used = sz; return true; }
-    if (type == 'Z' || type == 'H') {
-        const void* z = memchr(p, 0, n);
-        if (!z) return false;
-        used = (size_t)((const uint8_t*)z - p) + 1;
-        return true;
-    }
-    if (type == 'B') {
-        if (n < 5) return false;
-        size_t es = bamTypeSize((char)p[0]);
-        uint32_t cnt;
-        memcpy(&cnt, p + 1, 4);
-        if (!es || n < 5 + es * (size_t)cnt) return false;
-        used = 5 + es * (size_t)cnt;
-        return true;
-    }
-    return false;
-}
-
 int AlnReader::nextBam(AlnView& out) {
     if (!ensure(4)) return 1;
     uint32_t blockSize;
@@ -713,57 +954,60 @@ int AlnReader::nextBam(AlnView& out) {
     if (blockSize < 32 || !ensure((size_t)blockSize + 4)) return 1;
     const uint8_t* p = buf_.data() + cur_ + 4;
     cur_ += (size_t)blockSize + 4;
-    int32_t refID, pos;
-    memcpy(&refID, p, 4);
-    memcpy(&pos, p + 4, 4);
-    uint32_t lReadName = p[8];
-    uint16_t nCigar, flag;
-    memcpy(&nCigar, p + 12, 2);
-    memcpy(&flag, p + 14, 2);
-    uint32_t lSeq;
-    memcpy(&lSeq, p + 16, 4);
-    size_t off = 32 + lReadName;
-    size_t need = off + 4 * (size_t)nCigar + ((size_t)lSeq + 1) / 2 + lSeq;
-    if (need > blockSize) return 1;
-    out.rID = refID;
-    out.beginPos = pos;
-    out.flag = flag;
-    cigarScratch_.resize(nCigar);
-    if (nCigar) memcpy(cigarScratch_.data(), p + off, 4 * (size_t)nCigar);  // unaligned source
-    out.cigar = cigarScratch_.data();
-    out.nCigar = nCigar;
-    off += 4 * (size_t)nCigar;
-    out.seqText = nullptr;
-    out.seq4 = p + off;
-    out.lSeq = lSeq;
-    off += ((size_t)lSeq + 1) / 2 + lSeq;
-    // tags
-    out.hasNH = false;
-    out.nh = 1;
-    const uint8_t* t = p + off;
-    size_t n = blockSize - off;
-    while (n >= 3) {
-        char type = (char)t[2];
-        size_t used = 0;
-        if (!skipBamTag(t + 3, n - 3, used, type)) break;
-        if (t[0] == 'N' && t[1] == 'H') {
-            const uint8_t* v = t + 3;
-            switch (type) {
-                case 'c': out.hasNH = true; out.nh = (uint32_t)(int32_t)(int8_t)v[0]; break;
-                case 'C': out.hasNH = true; out.nh = v[0]; break;
-                case 's': { int16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = (uint32_t)(int32_t)x; break; }
-                case 'S': { uint16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = x; break; }
-                case 'i': { int32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = (uint32_t)x; break; }
-                case 'I': { uint32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = x; break; }
-                default: break;
-            }
-            break;
-        }
-        t += 3 + used;
-        n -= 3 + used;
-    }
+    if (!parseBamRecord(p, blockSize, cigarScratch_, out)) return 1;
     ++nRecords_;
     return 0;
+}
+
+// ---------------------------------------------------------------------------
+// batch mode
+// ---------------------------------------------------------------------------
+void AlnReader::startBatches(int threads, RecordFn fn, void* user) {
+    if (!good_ || pipe_ || samPipe_ || bamBatch_ || !fn) return;
+    if (threads < 1) threads = 1;
+    batchFn_ = fn;
+    batchUser_ = user;
+    if (isBam_) {
+        pipe_ = new Pipeline(fp_, threads);
+        bamBatch_ = new BamBatcher(pipe_, threads, fn, user, buf_.data() + cur_, end_ - cur_);
+    } else {
+        samPipe_ = new SamPipeline(fp_, threads, buf_.data() + cur_, end_ - cur_, nameMap_->m, fn, user);
+    }
+    cur_ = end_ = 0;
+}
+
+bool AlnReader::nextBatch(std::vector<uint8_t>& out, uint64_t& nRecords, int& error) {
+    out.clear();
+    nRecords = 0;
+    error = 0;
+    if (batchFailed_ || !batchFn_) return false;
+    if (bamBatch_) {
+        std::shared_ptr<BamBatcher::Batch> b = bamBatch_->next();
+        if (!b) return false;
+        out.swap(b->out);
+        nRecords = b->nRecords;
+        nRecords_ += nRecords;
+        if (b->bad) { error = 1; batchFailed_ = true; }
+        return true;
+    }
+    std::shared_ptr<SamPipeline::Job> j = samPipe_->next();
+    if (!j) return false;
+    if (j->unknownName) {  // a contig that is missing from the header: this job is redone here, where the name store may grow
+        AlnView v;
+        for (const SamPipeline::Rec& r : j->recs) {
+            SamFields f = r.f;
+            const char* line = j->text.get() + r.lineOff;
+            if (f.rID == -2) f.rID = internExtraName(std::string(line + f.nameOff, f.nameLen));
+            fillView(v, f, line, j->cigars.data());
+            batchFn_(batchUser_, v, j->out);
+        }
+    }
+    out.swap(j->out);  // (the caller's previous buffer goes back into the pool with the job)
+    nRecords = j->recs.size();
+    nRecords_ += nRecords;
+    if (j->bad) { error = 1; batchFailed_ = true; }
+    samPipe_->recycle(j);
+    return true;
 }
 
 int AlnReader::next(AlnView& out) {

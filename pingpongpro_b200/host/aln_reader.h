@@ -72,10 +72,20 @@ public:
     // Records decoded so far.
     uint64_t recordCount() const { return nRecords_; }
 
-    // Worker threads (read-ahead, results in file order).  BAM: BGZF blocks are inflated on `n` threads and the record
-    // walk stays on the calling thread.  SAM: whole lines are parsed on `n` threads and the calling thread only copies
-    // the parsed fields.  Call after open(); n <= 1 keeps the sequential path.
+    // BAM only: inflate BGZF blocks on `n` worker threads (read-ahead, in order) while next() keeps walking the records
+    // on the calling thread.  Call after open(); n <= 1 keeps the sequential path.
     void setThreads(int n);
+
+    // Batch mode: the per-record work runs on the worker threads as well.  `fn` is called for every record (on any
+    // thread, concurrently; it appends what it wants to keep to `out`), and nextBatch() hands the bytes produced for
+    // consecutive records back in file order.  BAM: blocks are inflated in parallel, one thread walks the record
+    // boundaries, the workers decode the records.  SAM: the workers parse whole lines.  Use either atEnd()/next() or
+    // startBatches()/nextBatch() on one file, not both.
+    typedef void (*RecordFn)(void* user, const AlnView& v, std::vector<uint8_t>& out);
+    void startBatches(int threads, RecordFn fn, void* user);
+    // False at the end of the input.  error != 0: a malformed record follows the records of this batch
+    // ("Failed to read record"); the call after that returns false.
+    bool nextBatch(std::vector<uint8_t>& out, uint64_t& nRecords, int& error);
 
 private:
     bool fill();                  // refill raw buffer (decompressing BGZF blocks for BAM)
@@ -85,6 +95,7 @@ private:
     int nextSam(AlnView& out);
     int nextBam(AlnView& out);
     bool getLine(const char*& line, size_t& len);
+    int32_t internExtraName(const std::string& name);
 
     FILE* fp_ = nullptr;
     bool good_ = false;
@@ -101,12 +112,15 @@ private:
     // name -> rID lookup for SAM
     struct NameMap;
     NameMap* nameMap_ = nullptr;
-    bool pendingLine_ = false;    // SAM: first alignment line was consumed while reading the header
-    std::string pending_;
     struct Pipeline;
     Pipeline* pipe_ = nullptr;    // parallel BGZF inflate (setThreads)
     struct SamPipeline;
-    SamPipeline* samPipe_ = nullptr;  // parallel SAM line parsing (setThreads)
+    SamPipeline* samPipe_ = nullptr;  // parallel SAM line parsing (startBatches)
+    struct BamBatcher;
+    BamBatcher* bamBatch_ = nullptr;  // record boundary walk + parallel record decoding (startBatches)
+    RecordFn batchFn_ = nullptr;
+    void* batchUser_ = nullptr;
+    bool batchFailed_ = false;
     std::unordered_map<std::string, int32_t> extraNames_;  // SAM contigs that are missing from the header, in order of appearance
     std::string lastName_;        // SAM: the previous record's RNAME (sorted input repeats it)
     int32_t lastId_ = -1;

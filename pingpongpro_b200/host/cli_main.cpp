@@ -155,10 +155,6 @@ int main(int argc, char const** argv) {
             std::cerr << "Failed to open input file: " << path << std::endl;  // :1485
             return 1;
         }
-        {
-            int nt = options.threads > 0 ? options.threads : (int)std::thread::hardware_concurrency();
-            reader.setThreads(nt > 1 ? nt - 1 : 1);  // one thread stays free for the record walk
-        }
         if (!ctx) {
             names = reader.names();
             lengths = reader.lengths();
@@ -184,20 +180,25 @@ int main(int argc, char const** argv) {
         eo.minLen = options.minAlignmentLength;
         eo.maxLen = options.maxAlignmentLength;
         eo.mode = options.countMultiHits;
-        AlnView v;
         bool foreignContig = false;
-        while (!reader.atEnd()) {
-            if (reader.next(v) != 0) {
+        // inflate / line parsing, record decoding and extraction run on worker threads; this thread appends the kept
+        // reads in file order (the order of the float additions of -m weighted, :487) and feeds the uploads
+        int nt = options.threads > 0 ? options.threads : (int)std::thread::hardware_concurrency();
+        reader.startBatches(nt > 2 ? nt - 2 : 1, extract_record_fn, &eo);
+        std::vector<uint8_t> bytes;
+        uint64_t nRecords;
+        int err;
+        while (reader.nextBatch(bytes, nRecords, err)) {
+            const ExtractedRead* e = reinterpret_cast<const ExtractedRead*>(bytes.data());
+            for (size_t k = 0, m = bytes.size() / sizeof(ExtractedRead); k < m; ++k) {
+                totalReadCount += (double)e[k].weight;  // :488
+                if ((size_t)e[k].contig >= up.pending.size()) { foreignContig = true; continue; }  // header differs: reported below
+                if (!up.add((size_t)e[k].contig, e[k].read)) return gpuError("upload failed");
+            }
+            if (err) {
                 std::cerr << "Failed to read record" << std::endl;  // :411
                 return 1;
             }
-            ppp_read r;
-            int32_t contig;
-            float w;
-            if (!extract_read(v, eo, r, contig, w)) continue;
-            totalReadCount += (double)w;  // :488
-            if ((size_t)contig >= up.pending.size()) { foreignContig = true; continue; }  // header differs: reported below
-            if (!up.add((size_t)contig, r)) return gpuError("upload failed");
         }
         if (!reader.good()) {
             std::cerr << "Failed to read record" << std::endl;

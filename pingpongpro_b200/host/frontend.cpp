@@ -8,13 +8,43 @@
 
 namespace ppp {
 
+void extract_record_fn(void* user, const AlnView& v, std::vector<uint8_t>& out) {
+    ExtractedRead e;
+    if (!extract_read(v, *static_cast<const ExtractOptions*>(user), e.read, e.contig, e.weight)) return;
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(&e);
+    out.insert(out.end(), p, p + sizeof e);
+}
+
 int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int threads) {
     AlnReader rd;
     if (!rd.open(path)) return 1;
-    rd.setThreads(threads);
     out.names = rd.names();
     out.lengths = rd.lengths();
     out.reads.assign(out.names.size(), std::vector<ppp_read>());
+    if (threads > 1) {
+        ExtractOptions opts = o;
+        rd.startBatches(threads, extract_record_fn, &opts);
+        std::vector<uint8_t> bytes;
+        uint64_t n;
+        int err;
+        while (rd.nextBatch(bytes, n, err)) {
+            out.nRecords += n;
+            const ExtractedRead* e = reinterpret_cast<const ExtractedRead*>(bytes.data());
+            for (size_t k = 0, m = bytes.size() / sizeof(ExtractedRead); k < m; ++k) {
+                if ((size_t)e[k].contig >= out.reads.size()) {  // contig that is missing from the header
+                    out.names = rd.names();
+                    out.lengths = rd.lengths();
+                    out.reads.resize(out.names.size());
+                    if ((size_t)e[k].contig >= out.reads.size()) return 2;
+                }
+                out.reads[e[k].contig].push_back(e[k].read);
+                out.totalWeight += (double)e[k].weight;  // :488, file order
+                ++out.nKept;
+            }
+            if (err) return 2;
+        }
+        return rd.good() ? 0 : 2;
+    }
     AlnView v;
     while (!rd.atEnd()) {
         if (rd.next(v) != 0) return 2;

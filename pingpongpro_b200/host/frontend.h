@@ -58,6 +58,15 @@ static inline bool extract_read(const AlnView& v, const ExtractOptions& o, ppp_r
     return true;
 }
 
+// What the worker threads keep of a record in batch mode (AlnReader::startBatches): 16 bytes.
+struct ExtractedRead {
+    int32_t contig;
+    ppp_read read;
+    float weight;  // the value added at :487-488
+};
+// AlnReader::RecordFn over extract_read; `user` is the ExtractOptions.
+void extract_record_fn(void* user, const AlnView& v, std::vector<uint8_t>& out);
+
 // A fully decoded input file: reads per contig in file order.
 struct DecodedFile {
     std::vector<std::string> names;
@@ -68,6 +77,8 @@ struct DecodedFile {
 };
 
 // 0 = ok, 1 = cannot open, 2 = malformed record.
+// threads <= 1: the sequential record walk; otherwise inflate / line parsing, record decoding and extraction all run on
+// `threads` workers and this thread only appends the kept reads in file order.
 int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int threads = 1);
 
 }  // namespace ppp

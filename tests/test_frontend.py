@@ -132,6 +132,47 @@ def test_parallel_bgzf_inflate_equals_sequential(tmp_path):
             host.decode_file(str(trunc), threads=t)
 
 
+def _bgzf_payload(path):
+    import zlib
+    raw, out, off = open(path, "rb").read(), [], 0
+    while off + 18 <= len(raw):
+        size = int.from_bytes(raw[off + 16:off + 18], "little") + 1  # BSIZE of the BC subfield (xlen = 6)
+        out.append(zlib.decompress(raw[off + 18:off + size - 8], -15))
+        off += size
+    return b"".join(out)
+
+
+def _bgzf_write(path, payload, block_bytes):
+    import zlib
+    with open(path, "wb") as f:
+        for o in list(range(0, len(payload), block_bytes)) + [None]:
+            chunk = b"" if o is None else payload[o:o + block_bytes]  # None: the empty end-of-file block
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            body = c.compress(chunk) + c.flush()
+            f.write(bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0]) + (len(body) + 25).to_bytes(2, "little") + body
+                    + zlib.crc32(chunk).to_bytes(4, "little") + len(chunk).to_bytes(4, "little"))
+
+
+@pytest.mark.parametrize("block_bytes", [601, 7919, 65280])
+def test_bam_records_straddling_bgzf_blocks(tmp_path, block_bytes):
+    """BAM writers cut BGZF blocks wherever the buffer fills, so records (and their block_size words) straddle blocks
+    and the worker jobs made of them.  The boundary walker of the batch mode must stitch them exactly like the
+    sequential reader; a file that ends inside a record is a read error for both."""
+    src = str(tmp_path / "src.bam")
+    subprocess.check_call([os.path.join(_build.BIN, "ppp_synth"), "--genome", "tiny", "--reads", "60000", "--seed", "34", "--out", src])
+    payload = _bgzf_payload(src)
+    f = str(tmp_path / "reblocked.bam")
+    _bgzf_write(f, payload, block_bytes)
+    seq = host.decode_file(f, threads=1)
+    _decoded_equal(seq, host.decode_file(src, threads=1))
+    for t in (2, 5):
+        _decoded_equal(seq, host.decode_file(f, threads=t))
+    _bgzf_write(f, payload[: len(payload) - 37], block_bytes)  # the last record is incomplete
+    for t in (1, 4):
+        with pytest.raises(ValueError, match="Failed to read record"):
+            host.decode_file(f, threads=t)
+
+
 def test_weight_reciprocal_single_equals_double_narrowed():
     """The device evaluates the -m weighted read weight (float)(1.0 / (double)NH) (pingpongpro.cpp:449) as a correctly
     rounded single-precision reciprocal for NH < 2^24; the two are the same number for every such NH."""
