@@ -2,10 +2,13 @@
 // ios::scientific and the default precision 6 (:883-889, :1387-1389).
 #include "writers.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <sstream>
+#include <thread>
 
 namespace ppp {
 
@@ -41,14 +44,40 @@ bool writeSignatures(const ppp_locus* loci, size_t n, const std::vector<std::str
         minus << "track type=bedGraph name=\"read stacks on - strand\" description=\"height of read stacks on the - strand\" visibility=full\n";
         scores << "track type=bedGraph name=\"scores\" description=\"scores of ping-pong signatures (1 - FDR)\" visibility=full viewLimits=0.0:1.0 autoScale=off\n";
     }
-    for (size_t i = 0; i < n; ++i) {
-        const ppp_locus& l = loci[i];
-        const std::string& contig = names[l.contig];
-        tsv << contig << '\t' << l.position << '\t' << l.fdr << '\t' << l.reads_plus << '\t' << l.reads_minus << '\n';  // :905-910
-        if (browserTracks) {
-            plus << contig << '\t' << l.position << '\t' << (l.position + 1) << '\t' << l.reads_plus << '\n';
-            minus << contig << '\t' << l.position << '\t' << (l.position + 1) << '\t' << l.reads_minus << '\n';
-            scores << contig << '\t' << l.position << '\t' << (l.position + 1) << '\t' << (1 - l.fdr) << '\n';  // :927
+    // Rows are formatted on several threads (each with its own stream object carrying the same flags, so the text is
+    // what the single stream would have produced) and appended to the files in order, one wave at a time.
+    const size_t kChunk = 32768;
+    const unsigned nThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    struct Text { std::string tsv, plus, minus, scores; };
+    std::vector<Text> wave(nThreads);
+    for (size_t base = 0; base < n; base += kChunk * nThreads) {
+        auto format = [&](unsigned t) {
+            const size_t a = std::min(n, base + t * kChunk), b = std::min(n, a + kChunk);
+            std::ostringstream o, p, m, sc;
+            o.setf(std::ios::scientific, std::ios::floatfield);
+            p.setf(std::ios::scientific, std::ios::floatfield);
+            m.setf(std::ios::scientific, std::ios::floatfield);
+            sc.setf(std::ios::scientific, std::ios::floatfield);
+            for (size_t i = a; i < b; ++i) {
+                const ppp_locus& l = loci[i];
+                const std::string& contig = names[l.contig];
+                o << contig << '\t' << l.position << '\t' << l.fdr << '\t' << l.reads_plus << '\t' << l.reads_minus << '\n';  // :905-910
+                if (browserTracks) {
+                    p << contig << '\t' << l.position << '\t' << (l.position + 1) << '\t' << l.reads_plus << '\n';
+                    m << contig << '\t' << l.position << '\t' << (l.position + 1) << '\t' << l.reads_minus << '\n';
+                    sc << contig << '\t' << l.position << '\t' << (l.position + 1) << '\t' << (1 - l.fdr) << '\n';  // :927
+                }
+            }
+            wave[t].tsv = o.str();
+            if (browserTracks) { wave[t].plus = p.str(); wave[t].minus = m.str(); wave[t].scores = sc.str(); }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nThreads && base + t * kChunk < n; ++t) th.emplace_back(format, t);
+        format(0);
+        for (std::thread& x : th) x.join();
+        for (unsigned t = 0; t < nThreads && base + t * kChunk < n; ++t) {
+            tsv << wave[t].tsv;
+            if (browserTracks) { plus << wave[t].plus; minus << wave[t].minus; scores << wave[t].scores; }
         }
     }
     return true;

@@ -3,6 +3,7 @@
 #   bench lines (N=1, both arms), ncu launch list of bench.py, ncu --set full of k_scan, big-genome bench lines,
 #   command-line end-to-end timing against the reference binary.  Everything lands in gpurun_out/.
 set -u
+export PYTHONPATH=$PWD
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $O/gpu.csv
@@ -19,3 +20,6 @@ python bench.py --steps 5 --warmup 3 --no-cpu-baseline --genome mouse --reads 20
 # command line end to end (decode included) against the reference binary
 python -m pingpongpro_b200.tools.cli_e2e --reads 50000000 > $O/cli_e2e_50M_bam.json 2> $O/cli_e2e_50M_bam.err
 python -m pingpongpro_b200.tools.cli_e2e --reads 1000000 --format sam > $O/cli_e2e_1M_sam.json 2> $O/cli_e2e_1M_sam.err
+python -m pingpongpro_b200.tools.cli_e2e --reads 20000000 --format sam > $O/cli_e2e_20M_sam.json 2> $O/cli_e2e_20M_sam.err
+# where the end-to-end step goes (host enqueue / device completion / scan + score)
+python -m pingpongpro_b200.tools.e2e_probe > $O/e2e_probe.log 2>&1
