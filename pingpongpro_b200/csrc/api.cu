@@ -96,7 +96,7 @@ struct ppp_ctx {
     float buildMs = 0.f;
     // -m weighted: the sorts of the next batches (sortStream) overlap the fold of batch k (stream); one scratch set per stage
     SortScratch sort[kStages] = {};
-    cudaEvent_t evSorted[kStages] = {}, evFolded[kStages] = {}, evReset = nullptr;
+    cudaEvent_t evSorted[kStages] = {}, evFolded[kStages] = {}, evReset = nullptr, evFork = nullptr, evJoin = nullptr;
     bool sortUsed[kStages] = {};
     unsigned batchCount = 0;
 
@@ -545,6 +545,8 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     CKI(cudaStreamCreateWithFlags(&c->sortStream, cudaStreamNonBlocking));
     for (int k = 0; k < kFoldStreams; ++k) CKI(cudaStreamCreateWithFlags(&c->foldStream[k], cudaStreamNonBlocking));
     CKI(cudaEventCreateWithFlags(&c->evReset, cudaEventDisableTiming));
+    CKI(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    CKI(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
     size_t hWords = 2 * c->G + 64;
     CKI(cudaMalloc(&c->H, hWords * sizeof(uint32_t)));
     CKI(cudaMemsetAsync(c->H, 0, hWords * sizeof(uint32_t), c->stream));
@@ -643,6 +645,8 @@ void ppp_destroy(ppp_ctx* c) {
     for (int k = 0; k < kFoldStreams; ++k)
         if (c->foldStream[k]) cudaStreamDestroy(c->foldStream[k]);
     if (c->evReset) cudaEventDestroy(c->evReset);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
     delete c;
 }
 
@@ -964,10 +968,17 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     const int ppIdx = c->ppOv - c->minOv;
     Trace tr("score");
     if ((rc = timerStart(c, c->tScore))) return rc;
+    // which signatures are reported (and where) does not depend on the tables: counted on the sort stream (idle by now)
+    // while collapse and the FDR table run here
+    CK(cudaEventRecord(c->evFork, c->stream));
+    CK(cudaStreamWaitEvent(c->sortStream, c->evFork, 0));
+    CK(launch_score_count(c->dPairs, c->nPairs, ppIdx, minStackHeight, c->dBlockCnt, c->dScanScratch, c->scanScratchWords, c->sortStream, &c->launches));
+    CK(cudaEventRecord(c->evJoin, c->sortStream));
     CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dCellSums, c->stream, &c->launches));
     CK(launch_fdr_table(c->dCells, c->dNBins, kBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
-    CK(launch_score_pairs(c->dPairs, c->nPairs, c->dFdr, c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dPairFdr, c->dLoci,
-                          c->dNLoci, c->dBlockCnt, c->dScanScratch, c->scanScratchWords, c->stream, &c->launches));
+    CK(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
+    CK(launch_score_write(c->dPairs, c->nPairs, c->dFdr, c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dPairFdr, c->dLoci,
+                          c->dNLoci, c->dBlockCnt, c->stream, &c->launches));
     if ((rc = timerStop(c, c->tScore))) return rc;
     CK(cudaMemcpyAsync(&c->hs->nLoci, c->dNLoci, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&c->hs->nBins, c->dNBins, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -129,8 +129,12 @@ struct LocusOut {
     uint32_t contig, position;
     float fdr, rp, rm;
 };
-cudaError_t launch_score_pairs(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
-                               const Slot* slots, uint32_t nSlots, float* pairFdr, LocusOut* loci, unsigned long long* nLoci, uint32_t* blockCnt,
-                               uint32_t* scanScratch, size_t scanScratchWords, cudaStream_t s, int* launches);
+// K4 in two halves: the per-block counts of reported loci (and their prefix sum) do not depend on the FDR table, so the
+// caller runs them beside collapse + FDR table on a second stream; the write needs both.
+cudaError_t launch_score_count(const PairRec* pairs, size_t nPairs, int ppIdx, uint32_t minHeight, uint32_t* blockCnt, uint32_t* scanScratch,
+                               size_t scanScratchWords, cudaStream_t s, int* launches);
+cudaError_t launch_score_write(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
+                               const Slot* slots, uint32_t nSlots, float* pairFdr, LocusOut* loci, unsigned long long* nLoci, const uint32_t* blockCnt,
+                               cudaStream_t s, int* launches);
 
 }  // namespace pppk

@@ -265,17 +265,24 @@ cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, uint32_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_score_pairs(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
-                               const Slot* slots, uint32_t nSlots, float* pairFdr, LocusOut* loci, unsigned long long* nLoci, uint32_t* blockCnt,
-                               uint32_t* scanScratch, size_t scanScratchWords, cudaStream_t s, int* launches) {
-    if (nPairs == 0) return cudaMemsetAsync(nLoci, 0, sizeof(unsigned long long), s);
+cudaError_t launch_score_count(const PairRec* pairs, size_t nPairs, int ppIdx, uint32_t minHeight, uint32_t* blockCnt, uint32_t* scanScratch,
+                               size_t scanScratchWords, cudaStream_t s, int* launches) {
+    if (nPairs == 0) return cudaSuccess;
     unsigned blocks = (unsigned)((nPairs + kScoreThreads - 1) / kScoreThreads);
     float mh = (float)minHeight;  // `reads >= minStackHeight` compares float with unsigned converted to float (:903)
     k_score_count<<<blocks, kScoreThreads, 0, s>>>(pairs, nPairs, ppIdx, mh, blockCnt);
-    cudaError_t e = exclusive_scan_u32(blockCnt, blockCnt, blocks, scanScratch, scanScratchWords, s, launches);
-    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+    return exclusive_scan_u32(blockCnt, blockCnt, blocks, scanScratch, scanScratchWords, s, launches);
+}
+
+cudaError_t launch_score_write(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
+                               const Slot* slots, uint32_t nSlots, float* pairFdr, LocusOut* loci, unsigned long long* nLoci, const uint32_t* blockCnt,
+                               cudaStream_t s, int* launches) {
+    if (nPairs == 0) return cudaMemsetAsync(nLoci, 0, sizeof(unsigned long long), s);
+    unsigned blocks = (unsigned)((nPairs + kScoreThreads - 1) / kScoreThreads);
+    float mh = (float)minHeight;
     k_score_write<<<blocks, kScoreThreads, 0, s>>>(pairs, nPairs, fdrTable, binMap, W, ppIdx, mh, slots, nSlots, blockCnt, blocks, pairFdr, loci, nLoci);
-    if (launches) *launches += 2;
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
