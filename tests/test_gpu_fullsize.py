@@ -7,7 +7,8 @@ genome, one GPU) checked through size-independent properties, where the CPU orac
   * idempotence: a second scan + score over the same stacks returns identical tables and loci;
   * monotone -s filter: loci(s) is exactly the subset of loci(0) with both heights >= s;
   * order independence in unique mode: reversing the read order changes nothing;
-  * a 2-way range-sharded run reproduces the single-context loci (config 2)."""
+  * a 2-way range-sharded run reproduces the single-context loci (config 2);
+  * config 3 (200 M reads, mouse-sized genome, annotation): per-transposon sums recomputed from the signatures."""
 import numpy as np
 import pytest
 
@@ -93,3 +94,49 @@ def test_config4_human_500m_single_gpu():
         assert owned == m.genome_size and words * 8 > 24e9  # 24.8 GB of stack arrays on one B200
         build(ctx, reads)
         check_properties(ctx, reads, "unique", n_kept)
+
+
+def test_config3_mouse_200m_annotation():
+    """configs[2]: 200 M reads on the mouse-sized genome with a transposon annotation.  The per-transposon sums of
+    findSuppressedTransposons (pingpongpro.cpp:1221-1240) are recomputed for a sample of the (non-overlapping, sorted)
+    intervals straight from the downloaded signatures with the literal single-precision loop."""
+    m = host.SynthModel("mouse", n_reads=200_000_000, seed=3)
+    reads = m.generate(mode="weighted")
+    ivs = m.intervals()
+    iv = np.zeros(len(ivs), api.INTERVAL_DTYPE)
+    iv["contig"], iv["start"], iv["end"] = ivs[:, 0], ivs[:, 1], ivs[:, 2] - 1
+    with api.Context(m.lengths, mode="weighted") as ctx:
+        build(ctx, reads)
+        del reads
+        freq, max_h, grouped, sc = pass_over(ctx)
+        assert int(grouped.sum()) == ctx.n_pairs and int(grouped[10 - ctx.min_overlap].sum()) == len(sc.loci)
+        tp, order = ctx.find_suppressed_transposons(iv)
+        sig = ctx.signatures()
+    assert len(tp) == len(iv) and np.all((tp["p_value"] >= 0) & (tp["p_value"] <= 1)) and np.all((tp["q_value"] >= 0) & (tp["q_value"] <= 1))
+    srt = iv[order]  # results come back in (contig, start, end) order
+    assert np.all((srt["contig"][1:] > srt["contig"][:-1]) | ((srt["contig"][1:] == srt["contig"][:-1]) & (srt["start"][1:] >= srt["start"][:-1])))
+    W, pp = 21, 10 - 3
+    key = sig["contig"].astype(np.uint64) << np.uint64(32) | sig["position"].astype(np.uint64)
+    rng = np.random.default_rng(1)
+    checked = 0
+    for k in rng.choice(len(srt), size=400, replace=False):
+        t = srt[k]
+        lo = np.searchsorted(key, (np.uint64(t["contig"]) << np.uint64(32)) | np.uint64(t["start"]), "left")
+        hi = np.searchsorted(key, (np.uint64(t["contig"]) << np.uint64(32)) | np.uint64(t["end"]), "right")
+        s = sig[lo:hi]
+        hist = np.zeros(W, np.float32)
+        rp = rm = np.float32(0)
+        for o in range(W):
+            so = s[s["overlap"] == o + 3]
+            h = np.float32(0)
+            for a, b, f in zip(so["reads_plus"], so["reads_minus"], so["fdr"]):
+                h = np.float32(h + np.float32(np.float32(a + b) * np.float32(np.float32(1) - f)))  # :1227
+            hist[o] = h
+            if o == pp:
+                for a, b in zip(so["reads_plus"], so["reads_minus"]):
+                    rp, rm = np.float32(rp + a), np.float32(rm + b)                                    # :1230-1234
+        got = tp[k]
+        assert np.array_equal(got["histogram"][:W].view(np.uint32), hist.view(np.uint32)), (k, got["histogram"][:W], hist)
+        assert np.float32(got["reads_plus"]) == rp and np.float32(got["reads_minus"]) == rm
+        checked += len(s) > 0
+    assert checked > 100
