@@ -244,11 +244,15 @@ def main():
             pdist.attach_nccl(ctx)
     words, owned = ctx.layout()
 
+    # contigs are independent, so the caller is free to choose their order: largest first, so that the copy -> sort ->
+    # fold pipeline drains on the small ones
+    submit_order = sorted(range(len(pinned)), key=lambda c: -pinned[c].n)
+
     def upload():
         ctx.reset()
-        for c, b in enumerate(pinned):
-            if b.n:
-                ctx.count_reads(contig0 + c, b)
+        for c in submit_order:
+            if pinned[c].n:
+                ctx.count_reads(contig0 + c, pinned[c])
         ctx.finish()
 
     max_height = [0]
