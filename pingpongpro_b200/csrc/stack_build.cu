@@ -247,120 +247,143 @@ __device__ __forceinline__ size_t warp_run_end(const uint32_t* __restrict__ keys
     return hi;
 }
 
+// Barrier among the 64 threads of one warp pair (named barriers 1..; 0 is __syncthreads).
+__device__ __forceinline__ void pair_barrier(unsigned pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+// One WARP PAIR per long run.  Nothing hides latency for a run but the threads that own it, so the work is split by
+// kind: the producer warp streams the records (256 per stage, the next stage's loads in flight), turns NH into
+// weights 32 at a time through a shared-memory table and stages them per strand in shared memory; the consumer warp
+// reads a staged block back with broadcast 128-bit loads and does nothing but the dependent additions (:487, file
+// order) -- 4.5 cycles per read (tools/ub_chain.cu) instead of 6.8 when one warp did both.  Two staging buffers; one
+// pair barrier per block.
 __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t n,
                                                               uint32_t* __restrict__ H, uint64_t G, uint32_t* __restrict__ occ,
                                                               const unsigned long long* __restrict__ longRuns, const unsigned int* __restrict__ nLong,
                                                               unsigned int longCap) {
-    __shared__ __align__(16) float stage[kBuildThreads / 32][2][kFoldBlock];
-    __shared__ float weightOf[kWeightLut];  // weights of the common multiplicities (the reciprocal is ~1/4 of the warp's instructions otherwise)
+    constexpr int kPairs = kBuildThreads / 64;
+    constexpr int kDepth = kFoldBlock / 32;
+    __shared__ __align__(16) float stage[kPairs][2][2][kFoldBlock];  // [pair][buffer][strand][record]
+    __shared__ unsigned sMask[kPairs][2][2];                        // [pair][buffer][strand]: lanes that staged a record of that strand
+    __shared__ unsigned long long sEnd[kPairs];
+    __shared__ unsigned sFlags[kPairs][2];                          // per strand: OR of the metas (A10), bit 31 = any record
+    __shared__ float weightOf[kWeightLut];  // weights of the common multiplicities (the reciprocal is ~1/4 of the instructions otherwise)
     if (threadIdx.x < kWeightLut) weightOf[threadIdx.x] = read_weight_weighted((uint32_t)threadIdx.x << PPP_READ_NH_SHIFT);
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
-    float* const stageP = stage[threadIdx.x >> 5][0];
-    float* const stageM = stage[threadIdx.x >> 5][1];
-    const unsigned warpsPerGrid = gridDim.x * (kBuildThreads / 32);
+    const unsigned pair = threadIdx.x >> 6;
+    const bool producer = ((threadIdx.x >> 5) & 1u) == 0;
+    const unsigned pairsPerGrid = gridDim.x * kPairs;
     unsigned int count = *nLong;
     if (count > longCap) count = longCap;
-    for (unsigned int run = blockIdx.x * (kBuildThreads / 32) + (threadIdx.x >> 5); run < count; run += warpsPerGrid) {
+    for (unsigned int run = blockIdx.x * kPairs + pair; run < count; run += pairsPerGrid) {
         const size_t i = (size_t)longRuns[run];
         const uint32_t pos = keys[i];
-        const size_t end = warp_run_end(keys, i, n, pos, lane);
-        uint32_t wp = H[pos], wm = H[G + pos];
-        float hp = __uint_as_float(wp & kValueMask), hm = __uint_as_float(wm & kValueMask);
-        unsigned anyP = 0, anyM = 0, accP = 0, accM = 0;
-        // One warp owns the run, so nothing hides latency but the warp itself.  Records move in blocks of 256: while
-        // one block is added, the next one's loads are in flight.  The weights of a block are evaluated 32 at a time
-        // (off the serial chain) and staged in shared memory per strand, so the chain reads them back with
-        // broadcast 128-bit loads and is nothing but dependent additions (:487, file order).
-        constexpr int kDepth = kFoldBlock / 32;
-        uint32_t vq[kDepth];
-        auto fetch = [&](size_t base) {
-            const uint32_t* src = vals + base + lane;
-            const unsigned left = (unsigned)min((size_t)kFoldBlock, end - base);
+        if (producer) {
+            const size_t end = warp_run_end(keys, i, n, pos, lane);
+            if (lane == 0) sEnd[pair] = end;
+            const size_t nBlocks = (end - i + kFoldBlock - 1) / kFoldBlock;
+            uint32_t vq[kDepth];
+            auto fetch = [&](size_t blk) {
+                const size_t base = i + blk * kFoldBlock;
+                const uint32_t* src = vals + base + lane;
+                const unsigned left = (unsigned)min((size_t)kFoldBlock, end - base);
 #pragma unroll
-            for (int u = 0; u < kDepth; ++u) vq[u] = u * 32 + lane < left ? src[u * 32] : 0u;
-        };
-        size_t base = i;
-        fetch(base);
-        while (base < end) {
-            uint32_t vc[kDepth];
+                for (int u = 0; u < kDepth; ++u) vq[u] = u * 32 + lane < left ? src[u * 32] : 0u;
+            };
+            unsigned accP = 0, accM = 0;
+            // weights of block `blk` (held in vq) -> shared memory, branch free (the eight table look-ups are in flight
+            // together).  Every weight of this mode is positive (1 / NH, +inf for NH:i:0), so `weight > 0` of :458 is moot.
+            auto stageBlock = [&](size_t blk) {
+                float* sp = stage[pair][blk & 1][0];
+                float* sm = stage[pair][blk & 1][1];
+                const unsigned left = (unsigned)min((size_t)kFoldBlock, end - (i + blk * kFoldBlock));
+                uint32_t vc[kDepth];
 #pragma unroll
-            for (int u = 0; u < kDepth; ++u) vc[u] = vq[u];
-            const size_t nextBase = base + (size_t)kFoldBlock;
-            if (nextBase < end) fetch(nextBase);
-            // (every weight of this mode is positive -- 1 / NH, +inf for NH:i:0 -- so the `weight > 0` test of :458 is moot)
-            unsigned laneP = 0, laneM = 0, big = 0;
-            const unsigned left = (unsigned)min((size_t)kFoldBlock, end - base);
+                for (int u = 0; u < kDepth; ++u) vc[u] = vq[u];
+                if (blk + 1 < nBlocks) fetch(blk + 1);  // in flight while this block is staged and the previous one is added
+                unsigned laneP = 0, laneM = 0, big = 0;
 #pragma unroll
-            for (int u = 0; u < kDepth; ++u) {  // branch free: the eight table look-ups are in flight together
-                const bool in = u * 32 + lane < left;
-                const uint32_t nh = vc[u] >> PPP_READ_NH_SHIFT;
-                const float wt = weightOf[min(nh, (uint32_t)kWeightLut - 1u)];
-                big |= nh;
-                const bool minus = (vc[u] & PPP_READ_MINUS) != 0;
-                stageP[u * 32 + lane] = in && !minus ? wt : 0.0f;  // adding +0.0f is exact
-                stageM[u * 32 + lane] = in && minus ? wt : 0.0f;
-                laneP |= in && !minus ? vc[u] | 0x80000000u : 0u;  // A10 flag: :483
-                laneM |= in && minus ? vc[u] | 0x80000000u : 0u;   // :471
-            }
-            if (__any_sync(0xffffffffu, big >= (uint32_t)kWeightLut)) {  // a multiplicity beyond the table: evaluate those records
-#pragma unroll  // (registers cannot be indexed dynamically)
                 for (int u = 0; u < kDepth; ++u) {
-                    if ((vc[u] >> PPP_READ_NH_SHIFT) < (uint32_t)kWeightLut || !(u * 32 + lane < left)) continue;
-                    const float wt = read_weight_weighted(vc[u]);
-                    if (vc[u] & PPP_READ_MINUS) stageM[u * 32 + lane] = wt; else stageP[u * 32 + lane] = wt;
+                    const bool in = u * 32 + lane < left;
+                    const uint32_t nh = vc[u] >> PPP_READ_NH_SHIFT;
+                    const float wt = weightOf[min(nh, (uint32_t)kWeightLut - 1u)];
+                    big |= nh;
+                    const bool minus = (vc[u] & PPP_READ_MINUS) != 0;
+                    sp[u * 32 + lane] = in && !minus ? wt : 0.0f;  // adding +0.0f is exact
+                    sm[u * 32 + lane] = in && minus ? wt : 0.0f;
+                    laneP |= in && !minus ? vc[u] | 0x80000000u : 0u;  // A10 flag: :483
+                    laneM |= in && minus ? vc[u] | 0x80000000u : 0u;   // :471
                 }
+                if (__any_sync(0xffffffffu, big >= (uint32_t)kWeightLut)) {  // a multiplicity beyond the table: evaluate those records
+#pragma unroll  // (registers cannot be indexed dynamically)
+                    for (int u = 0; u < kDepth; ++u) {
+                        if ((vc[u] >> PPP_READ_NH_SHIFT) < (uint32_t)kWeightLut || !(u * 32 + lane < left)) continue;
+                        const float wt = read_weight_weighted(vc[u]);
+                        if (vc[u] & PPP_READ_MINUS) sm[u * 32 + lane] = wt; else sp[u * 32 + lane] = wt;
+                    }
+                }
+                accP |= laneP;
+                accM |= laneM;
+                const unsigned mp = __ballot_sync(0xffffffffu, laneP != 0), mm = __ballot_sync(0xffffffffu, laneM != 0);
+                if (lane == 0) { sMask[pair][blk & 1][0] = mp; sMask[pair][blk & 1][1] = mm; }
+            };
+            fetch(0);
+            stageBlock(0);
+            pair_barrier(pair);  // block 0 (and the run's end) visible to the consumer
+            for (size_t blk = 0; blk < nBlocks; ++blk) {
+                if (blk + 1 < nBlocks) stageBlock(blk + 1);  // the other buffer: its previous block was consumed before the last barrier
+                if (blk + 1 == nBlocks) {
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) { accP |= __shfl_xor_sync(0xffffffffu, accP, d); accM |= __shfl_xor_sync(0xffffffffu, accM, d); }
+                    if (lane == 0) { sFlags[pair][0] = accP; sFlags[pair][1] = accM; }
+                }
+                pair_barrier(pair);  // block blk added, block blk + 1 staged
             }
-            accP |= laneP;
-            accM |= laneM;
-            const unsigned blockP = __ballot_sync(0xffffffffu, laneP != 0), blockM = __ballot_sync(0xffffffffu, laneM != 0);
-            anyP |= blockP;
-            anyM |= blockM;
-            __syncwarp();
-            const float4* qp = reinterpret_cast<const float4*>(stageP);
-            const float4* qm = reinterpret_cast<const float4*>(stageM);
-            if (nextBase <= end) {  // a full block
-                if (blockM == 0) {
+            pair_barrier(pair);      // the consumer has read the flags of this run
+        } else {
+            const uint32_t wp = H[pos], wm = H[G + pos];
+            float hp = __uint_as_float(wp & kValueMask), hm = __uint_as_float(wm & kValueMask);
+            pair_barrier(pair);
+            const size_t end = (size_t)sEnd[pair];
+            const size_t nBlocks = (end - i + kFoldBlock - 1) / kFoldBlock;
+            for (size_t blk = 0; blk < nBlocks; ++blk) {
+                const float4* qp = reinterpret_cast<const float4*>(stage[pair][blk & 1][0]);
+                const float4* qm = reinterpret_cast<const float4*>(stage[pair][blk & 1][1]);
+                const unsigned maskP = sMask[pair][blk & 1][0], maskM = sMask[pair][blk & 1][1];
+                const unsigned left = (unsigned)min((size_t)kFoldBlock, end - (i + blk * kFoldBlock));
+                if (left == (unsigned)kFoldBlock && (maskP == 0 || maskM == 0)) {  // a full block of one strand (the common case by far)
+                    const bool isMinus = maskP == 0;
+                    const float4* q = isMinus ? qm : qp;
+                    float h = isMinus ? hm : hp;
 #pragma unroll
                     for (int t = 0; t < kFoldBlock / 4; ++t) {
-                        const float4 v = qp[t];
-                        hp = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hp, v.x), v.y), v.z), v.w);
+                        const float4 v = q[t];
+                        h = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(h, v.x), v.y), v.z), v.w);
                     }
-                } else if (blockP == 0) {
-#pragma unroll
-                    for (int t = 0; t < kFoldBlock / 4; ++t) {
-                        const float4 v = qm[t];
-                        hm = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hm, v.x), v.y), v.z), v.w);
-                    }
-                } else {  // both strands at this position: two independent chains
-#pragma unroll
-                    for (int t = 0; t < kFoldBlock / 4; ++t) {
+                    if (isMinus) hm = h; else hp = h;
+                } else {  // both strands at this position (two independent chains), or the run ends inside this block
+                    const int quads = (int)((left + 3) / 4);  // records past the end of the run were staged as zeros
+#pragma unroll 4
+                    for (int t = 0; t < quads; ++t) {
                         const float4 v = qp[t], x = qm[t];
                         hp = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hp, v.x), v.y), v.z), v.w);
                         hm = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hm, x.x), x.y), x.z), x.w);
                     }
                 }
-            } else {  // the run ends inside this block (records past its end were staged as zeros)
-                const int quads = (int)((end - base + 3) / 4);
-                for (int t = 0; t < quads; ++t) {
-                    const float4 v = qp[t], x = qm[t];
-                    hp = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hp, v.x), v.y), v.z), v.w);
-                    hm = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(hm, x.x), x.y), x.z), x.w);
+                pair_barrier(pair);
+            }
+            const unsigned flagsP = sFlags[pair][0], flagsM = sFlags[pair][1];
+            if (lane == 0) {
+                if (flagsP) {
+                    H[pos] = (__float_as_uint(hp) & kValueMask) | (wp & kA10Bit) | ((flagsP & PPP_READ_A10) ? kA10Bit : 0u);
+                    if (wp == 0u) atomicOr(&occ[pos >> 5], 1u << (pos & 31u));
+                }
+                if (flagsM) {
+                    H[G + pos] = (__float_as_uint(hm) & kValueMask) | (wm & kA10Bit) | ((flagsM & PPP_READ_A10) ? kA10Bit : 0u);
+                    if (wm == 0u) atomicOr(&occ[(G + pos) >> 5], 1u << (pos & 31u));
                 }
             }
-            __syncwarp();
-            base = nextBase;
-        }
-        const unsigned a10P = __ballot_sync(0xffffffffu, (accP & PPP_READ_A10) != 0), a10M = __ballot_sync(0xffffffffu, (accM & PPP_READ_A10) != 0);
-        if (lane == 0) {
-            if (anyP) {
-                H[pos] = (__float_as_uint(hp) & kValueMask) | (wp & kA10Bit) | (a10P ? kA10Bit : 0u);
-                if (wp == 0u) atomicOr(&occ[pos >> 5], 1u << (pos & 31u));
-            }
-            if (anyM) {
-                H[G + pos] = (__float_as_uint(hm) & kValueMask) | (wm & kA10Bit) | (a10M ? kA10Bit : 0u);
-                if (wm == 0u) atomicOr(&occ[(G + pos) >> 5], 1u << (pos & 31u));
-            }
+            pair_barrier(pair);
         }
     }
 }
