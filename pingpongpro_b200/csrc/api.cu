@@ -267,6 +267,15 @@ int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n, c
     // warp working through the tallest stack.  The sort has no ordering constraint at all and runs ahead on its
     // own stream.
     cudaStream_t fs = c->foldStream[(unsigned)slot.contig % kFoldStreams];
+    if (n <= (size_t)kSmallBatch) {  // one launch instead of ~25 (many small contigs, tails of files)
+        if (ready) CK(cudaStreamWaitEvent(fs, ready, 0));
+        if ((rc = timerStart(c, t, fs))) return rc;
+        CK(launch_small_batch(dReads, n, c->H, c->G, c->occ, slot, c->dCounters, fs, &c->launches));
+        if ((rc = timerStop(c, t, fs))) return rc;
+        c->buildTimers.push_back(t);
+        if (consumed) CK(cudaEventRecord(consumed, fs));
+        return PPP_OK;
+    }
     const int set = (int)(c->batchCount % kStages);
     if ((rc = ensureSortScratch(c, set))) return rc;
     if (ready) CK(cudaStreamWaitEvent(c->sortStream, ready, 0));

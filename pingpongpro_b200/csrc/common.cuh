@@ -104,6 +104,10 @@ struct SortedRun {
 };
 cudaError_t launch_stack_sort(const ppp_read* reads, size_t n, uint64_t G, Slot slot, unsigned long long* counters, const SortScratch& scr,
                               cudaStream_t s, int* launches, SortedRun* out);
+// -m weighted, a batch of at most kSmallBatch records: sort and fold in one launch of one block.
+constexpr int kSmallBatch = 4096;
+cudaError_t launch_small_batch(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, uint32_t* occ, Slot slot, unsigned long long* counters,
+                               cudaStream_t s, int* launches);
 cudaError_t launch_stack_fold(const SortedRun& r, uint32_t* H, uint64_t G, uint32_t* occ, size_t capacity, cudaStream_t s, int* launches);
 
 cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* launches);

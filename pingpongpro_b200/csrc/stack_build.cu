@@ -388,6 +388,57 @@ __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __r
     }
 }
 
+// ------------------------------------------------------------------ small batches (-m weighted)
+// A batch of at most kSmallBatch records (a small contig of a fragmented assembly, the last reads of a file) in ONE
+// launch of one block instead of the ~25 launches of the radix sort + folds: the records' word indices are sorted in
+// shared memory together with their index in the batch (bitonic network over 64-bit composites, hence stable), then
+// one thread per run of equal words folds it in file order, continuing from the word's current value like the big path.
+__global__ void __launch_bounds__(kBuildThreads) k_small_batch(const ppp_read* __restrict__ reads, uint32_t n, Slot slot, uint32_t* __restrict__ H, uint64_t G,
+                                                                uint32_t* __restrict__ occ, unsigned long long* counters) {
+    __shared__ unsigned long long item[kSmallBatch];  // (word index of H, both strands) << 12 | index in the batch
+    constexpr unsigned long long kNone = ~0ull;
+    uint32_t m = 1;
+    while (m < n) m <<= 1;  // bitonic networks want a power of two; the padding sorts to the end
+    for (uint32_t i = threadIdx.x; i < m; i += kBuildThreads) {
+        unsigned long long v = kNone;
+        if (i < n) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reads) + i);
+            const ppp_read r = {raw.x, raw.y};
+            uint32_t pos;
+            if (locate<true>(r, slot, PPP_MULTIHITS_WEIGHTED, pos, counters))
+                v = ((((r.meta & PPP_READ_MINUS) ? G : 0ull) + pos) << 12) | i;
+        }
+        item[i] = v;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < m / 2; t += kBuildThreads) {
+                const uint32_t a = ((t & ~(j - 1)) << 1) | (t & (j - 1)), b = a | j;  // the pair of this compare-exchange
+                const bool up = (a & k) == 0;
+                const unsigned long long x = item[a], y = item[b];
+                if ((x > y) == up) { item[a] = y; item[b] = x; }
+            }
+            __syncthreads();
+        }
+    for (uint32_t j = threadIdx.x; j < n; j += kBuildThreads) {
+        const unsigned long long v = item[j];
+        if (v == kNone) continue;
+        const unsigned long long word = v >> 12;
+        if (j > 0 && (item[j - 1] >> 12) == word) continue;  // not a run head
+        const uint32_t w0 = H[word];
+        float h = __uint_as_float(w0 & kValueMask);
+        uint32_t a10 = w0 & kA10Bit;
+        for (uint32_t e = j; e < n && (item[e] >> 12) == word; ++e) {
+            const uint32_t meta = __ldg(&reads[item[e] & 4095u].meta);
+            h = __fadd_rn(h, read_weight_weighted(meta));  // :487 (every weight of this mode is positive, :458)
+            if (meta & PPP_READ_A10) a10 = kA10Bit;         // :471 / :483
+        }
+        H[word] = (__float_as_uint(h) & kValueMask) | a10;
+        if (w0 == 0u) atomicOr(&occ[word >> 5], 1u << (word & 31u));
+    }
+}
+
 inline unsigned grid_for(size_t n, int threads, unsigned cap) {
     size_t b = (n + threads - 1) / threads;
     if (b < 1) b = 1;
@@ -400,6 +451,15 @@ cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H,
                                    unsigned long long* counters, cudaStream_t s, int* launches) {
     if (n == 0) return cudaSuccess;
     k_stack_build_int<<<grid_for(n, kBuildThreads, 148 * 16), kBuildThreads, 0, s>>>(reads, n, H, G, occ, slot, mode, counters);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_small_batch(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, uint32_t* occ, Slot slot, unsigned long long* counters,
+                               cudaStream_t s, int* launches) {
+    if (n == 0) return cudaSuccess;
+    if (n > (size_t)kSmallBatch) return cudaErrorInvalidValue;
+    k_small_batch<<<1, kBuildThreads, 0, s>>>(reads, (uint32_t)n, slot, H, G, occ, counters);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -387,7 +387,7 @@ def _fold_f32(weights):
     return h
 
 
-@pytest.mark.parametrize("batches", [1, 3])
+@pytest.mark.parametrize("batches", [1, 3, 40])  # 40: batches below 4096 records take the single-launch path
 def test_tall_stacks_fold_in_file_order(batches):
     """-m weighted on tall stacks (the warp-cooperative fold): run lengths around its 32-record and 256-record
     boundaries, both strands interleaved at one position, multiplicities beyond the weight table and beyond 2^24,
