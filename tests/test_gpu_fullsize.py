@@ -8,7 +8,8 @@ genome, one GPU) checked through size-independent properties, where the CPU orac
   * monotone -s filter: loci(s) is exactly the subset of loci(0) with both heights >= s;
   * order independence in unique mode: reversing the read order changes nothing;
   * a 2-way range-sharded run reproduces the single-context loci (config 2);
-  * config 3 (200 M reads, mouse-sized genome, annotation): per-transposon sums recomputed from the signatures."""
+  * config 3 (200 M reads, mouse-sized genome, annotation): per-transposon sums recomputed from the signatures;
+  * config 5 (the 50 M-read set, background range 3..30, -s 1..20): same properties, same overlap-10 loci."""
 import numpy as np
 import pytest
 
@@ -83,6 +84,29 @@ def test_config2_dm6_50m(mode):
         merged[: len(f)] += f
     assert np.array_equal(merged, freq)
     assert sum(p[1] for p in parts) >= n_kept - 64  # each read is foreign to exactly one shard (halo copies excepted)
+
+
+def test_config5_dm6_50m_background_range_30():
+    """configs[4]: the 50 M-read set with the background overlap range widened to 3..30 (28 overlaps) and the -s sweep;
+    the same size-independent properties must hold, and the overlap-10 loci must be those of the default range (the
+    window only adds background overlaps: a locus exists iff both stacks exist, :580-608)."""
+    m = host.SynthModel("dm6", n_reads=50_000_000, seed=2)
+    reads = m.generate(mode="unique")
+    n_kept = sum(len(r) for r in reads)
+    with api.Context(m.lengths, mode="unique") as ctx:
+        build(ctx, reads)
+        _, _, sc23 = check_properties(ctx, reads, "unique", n_kept)
+        pairs23 = ctx.n_pairs
+    with api.Context(m.lengths, mode="unique", max_overlap=30) as ctx:
+        assert ctx.W == 28
+        build(ctx, reads)
+        _, grouped, sc30 = check_properties(ctx, reads, "unique", n_kept)
+        assert ctx.n_pairs > pairs23 and grouped.shape[0] == 28
+        for col in ("contig", "position", "reads_plus", "reads_minus"):
+            assert np.array_equal(sc30.loci[col], sc23.loci[col])
+        for s in range(1, 21):  # -s 1..20
+            sub = ctx.calculate_fdrs(s).loci
+            assert np.array_equal(sub, sc30.loci[(sc30.loci["reads_plus"] >= s) & (sc30.loci["reads_minus"] >= s)])
 
 
 def test_config4_human_500m_single_gpu():
