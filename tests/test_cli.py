@@ -67,6 +67,23 @@ def test_committed_reference_outputs(cli, tag, tmp_path):
     assert_same_tree(str(out), want)
 
 
+@pytest.mark.parametrize("threads", ["1", "2", "3", "7"])
+def test_thread_counts_give_identical_output(cli, threads, tmp_path):
+    """--threads only changes how many workers inflate / parse / extract; the file order of the reads (which fixes the
+    float additions of -m weighted, :487) and therefore every output byte must not depend on it.  The input is large
+    enough for several worker jobs per format, and the signature table spans several formatting chunks."""
+    f = tmp_path / "in.bam"
+    subprocess.check_call([SYNTH, "--contigs", "c1:900000,c2:300000,c3:40000", "--reads", "400000", "--seed", "91", "--out", str(f),
+                           "--annot", str(tmp_path / "annot.tsv")])
+    subprocess.check_call([SYNTH, "--contigs", "c1:900000,c2:300000,c3:40000", "--reads", "100000", "--seed", "92", "--out", str(tmp_path / "more.sam")])
+    args = ["-i", str(f), "-i", str(tmp_path / "more.sam"), "-t", str(tmp_path / "annot.tsv"), "-b"]
+    base, other = tmp_path / "base", tmp_path / "other"
+    assert run(cli, [*args, "-o", str(base)]).returncode == 0
+    assert run(cli, [*args, "-o", str(other), "--threads", threads]).returncode == 0
+    for name in sorted(os.listdir(base)):
+        assert filecmp.cmp(base / name, other / name, shallow=False), name
+
+
 def test_sam_equals_bam(cli, tmp_path):
     a, b = tmp_path / "a", tmp_path / "b"
     assert run(cli, ["-i", os.path.join(FILES, "input.sam"), "-o", str(a), "-b"]).returncode == 0
