@@ -21,6 +21,10 @@ PPP_API int ppp_fe_decode(const char* path, uint32_t min_len, uint32_t max_len, 
 /* Same with `threads` BGZF inflate workers for BAM input (<= 1: sequential). */
 PPP_API int ppp_fe_decode_mt(const char* path, uint32_t min_len, uint32_t max_len, int mode, int threads, ppp_fe** out);
 PPP_API void ppp_fe_free(ppp_fe* fe);
+
+/* The raw-DEFLATE decoder the BGZF reader tries before zlib (test hook): 1 = `in` decoded into exactly out_len bytes,
+ * 0 = declined (invalid stream, wrong size); the reader then hands the block to zlib. */
+PPP_API int ppp_fast_inflate(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len);
 PPP_API int ppp_fe_n_contigs(const ppp_fe* fe);
 PPP_API const char* ppp_fe_contig_name(const ppp_fe* fe, int contig);
 PPP_API uint64_t ppp_fe_contig_length(const ppp_fe* fe, int contig);

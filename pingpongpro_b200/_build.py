@@ -55,7 +55,7 @@ def _headers() -> list[str]:
 def build_host() -> str:
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, "libppp_host.so")
-    src = [os.path.join(HOST, "aln_reader.cpp"), os.path.join(HOST, "frontend.cpp"), os.path.join(HOST, "annotation.cpp")]
+    src = [os.path.join(HOST, f) for f in ("aln_reader.cpp", "fast_inflate.cpp", "frontend.cpp", "annotation.cpp")]
     if _newer(out, src + _headers()):
         _run([CXX, *CXXFLAGS, "-shared", "-o", out, *src, "-lz", "-lpthread"])
     return out
@@ -87,7 +87,7 @@ def build_cuda() -> str:
 def build_cli() -> str:
     os.makedirs(BIN, exist_ok=True)
     out = os.path.join(BIN, "pingpongpro")
-    src = [os.path.join(HOST, f) for f in ("cli_main.cpp", "cli_args.cpp", "annotation.cpp", "writers.cpp", "pipeline.cpp", "aln_reader.cpp", "frontend.cpp")]
+    src = [os.path.join(HOST, f) for f in ("cli_main.cpp", "cli_args.cpp", "annotation.cpp", "writers.cpp", "pipeline.cpp", "aln_reader.cpp", "fast_inflate.cpp", "frontend.cpp")]
     src = [s for s in src if os.path.exists(s)]
     if not os.path.exists(os.path.join(HOST, "cli_main.cpp")):
         return ""
@@ -104,7 +104,7 @@ def build_oracle() -> None:
     ref_src = os.environ.get("PPP_REFERENCE_SOURCE", "/root/reference/pingpongpro.cpp")
     harness = os.path.join(odir, "_ref", "ppp_harness")
     deps = [os.path.join(odir, "harness.cpp"), os.path.join(odir, "seqan_shim", "seqan", "shim_impl.h"),
-            os.path.join(HOST, "aln_reader.cpp"), os.path.join(HOST, "aln_reader.h"), os.path.join(TOOLS, "synth_core.h")]
+            os.path.join(HOST, "aln_reader.cpp"), os.path.join(HOST, "aln_reader.h"), os.path.join(HOST, "fast_inflate.cpp"), os.path.join(TOOLS, "synth_core.h")]
     if os.path.exists(ref_src) and _newer(harness, deps):
         _run(["make", "-s", "-C", odir, "ref", f"REF={ref_src}"])
 

@@ -1,6 +1,8 @@
 // aln_reader.cpp -- see aln_reader.h.  Own implementation over the system zlib.
 #include "aln_reader.h"
 
+#include "fast_inflate.h"
+
 #include <zlib.h>
 
 #include <condition_variable>
@@ -114,11 +116,17 @@ struct AlnReader::Pipeline {
             }
             bool bad = false;
             z_stream zs;
-            memset(&zs, 0, sizeof zs);
-            if (inflateInit2(&zs, -15) != Z_OK) bad = true;
+            bool zsLive = false;
             for (const Block& b : job->blocks) {
                 if (bad) break;
                 if (b.isize == 0) continue;
+                // own decoder first; zlib takes over (and judges the block) whenever that one declines
+                if (fast_inflate(job->raw.data() + b.off, b.clen, job->out.data() + b.outOff, b.isize)) continue;
+                if (!zsLive) {
+                    memset(&zs, 0, sizeof zs);
+                    if (inflateInit2(&zs, -15) != Z_OK) { bad = true; break; }
+                    zsLive = true;
+                }
                 inflateReset(&zs);
                 zs.next_in = job->raw.data() + b.off;
                 zs.avail_in = (uInt)b.clen;
@@ -127,7 +135,7 @@ struct AlnReader::Pipeline {
                 int rc = inflate(&zs, Z_FINISH);
                 if (rc != Z_STREAM_END || zs.avail_out != 0) bad = true;
             }
-            inflateEnd(&zs);
+            if (zsLive) inflateEnd(&zs);
             std::vector<uint8_t>().swap(job->raw);
             {
                 std::lock_guard<std::mutex> l(mu);
@@ -756,6 +764,10 @@ bool AlnReader::readBgzfBlock() {
     memcpy(&isize, zin_.data() + clen + 4, 4);
     if (isize == 0) return true;  // empty block (e.g. the EOF marker)
     if (buf_.size() < end_ + isize) buf_.resize(end_ + isize + kRawChunk);
+    if (fast_inflate(zin_.data(), clen, buf_.data() + end_, isize)) {
+        end_ += isize;
+        return true;
+    }
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (inflateInit2(&zs, -15) != Z_OK) { good_ = false; return false; }

@@ -4,6 +4,7 @@
 #include <fstream>
 
 #include "annotation.h"
+#include "fast_inflate.h"
 #include "ppp_host.h"
 
 namespace ppp {
@@ -91,6 +92,7 @@ int ppp_fe_decode_mt(const char* path, uint32_t min_len, uint32_t max_len, int m
     *out = fe;
     return 0;
 }
+int ppp_fast_inflate(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) { return ppp::fast_inflate(in, in_len, out, out_len) ? 1 : 0; }
 void ppp_fe_free(ppp_fe* fe) { delete fe; }
 int ppp_fe_n_contigs(const ppp_fe* fe) { return (int)fe->f.names.size(); }
 const char* ppp_fe_contig_name(const ppp_fe* fe, int c) { return fe->f.names[c].c_str(); }
