@@ -3,7 +3,10 @@
 // host (frontend.h) and feed pinned, double-buffered uploads; stacks, overlap scan, FDRs and transposon scores
 // are computed by the CUDA layer through the C ABI of ppp_b200.h.  There is no CPU fallback.
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <unistd.h>
+
+#include <cerrno>
 
 #include <chrono>
 #include <cstdio>
@@ -135,7 +138,8 @@ void plotTransposons(const std::vector<ScoredTransposon>& rows, const std::strin
 
 }  // namespace
 
-int main(int argc, char const** argv) {
+// The whole program; returns the exit status (the CUDA runtime's own process-exit teardown is skipped by the caller).
+static int run(int argc, char const** argv) {
     AppOptions options;
     if (parseCommandLine(options, argc, argv) != PARSE_OK) return 1;  // :1465-1466 (help and version too)
     mark("start");
@@ -323,7 +327,50 @@ int main(int argc, char const** argv) {
         }
     }
     mark("outputs written");
-    // every output stream has been closed; skip the CUDA runtime's process-exit teardown (~0.3 s)
-    fflush(nullptr);
-    _exit(0);
+    return 0;
+}
+
+// Releasing a CUDA context (here: > 1 GB of device memory and the pinned buffers) costs the driver 0.3-0.4 s when the
+// process exits -- after every output byte is on disk.  The work therefore runs in a child process, which hands its
+// exit status to this tiny parent the moment it is done; the parent returns to the caller at once and the driver's
+// teardown of the child proceeds in the background.  (The fork happens before anything touches CUDA.)
+// PPP_NO_FORK=1 runs everything in one process.
+int main(int argc, char const** argv) {
+    int fds[2];
+    if (getenv("PPP_NO_FORK") || pipe(fds) != 0) {
+        int rc = run(argc, argv);
+        fflush(nullptr);
+        _exit(rc);  // every output stream has been closed; skip the CUDA runtime's atexit teardown
+    }
+    pid_t pid = fork();
+    if (pid < 0) {
+        close(fds[0]);
+        close(fds[1]);
+        int rc = run(argc, argv);
+        fflush(nullptr);
+        _exit(rc);
+    }
+    if (pid == 0) {
+        close(fds[0]);
+        int rc = run(argc, argv);
+        fflush(nullptr);
+        std::cout.flush();
+        std::cerr.flush();
+        unsigned char status = (unsigned char)rc;
+        ssize_t w = write(fds[1], &status, 1);
+        (void)w;
+        close(fds[1]);
+        close(0);
+        close(1);  // a caller that captures stdout / stderr must not wait for the background teardown
+        close(2);
+        _exit(rc);
+    }
+    close(fds[1]);
+    unsigned char status = 1;
+    ssize_t n;
+    do n = read(fds[0], &status, 1); while (n < 0 && errno == EINTR);
+    if (n == 1) _exit(status);
+    int st = 0;  // the child died without reporting: pass on how
+    if (waitpid(pid, &st, 0) == pid && WIFEXITED(st)) _exit(WEXITSTATUS(st));
+    _exit(WIFSIGNALED(st) ? 128 + WTERMSIG(st) : 1);
 }
