@@ -42,6 +42,26 @@ struct AlnReader::Pipeline {
     std::thread reader;
     std::vector<std::thread> workers;
     std::shared_ptr<Job> current;  // keeps the chunk handed to the consumer alive
+    // finished jobs are reused (their buffers keep their capacity): fresh multi-megabyte allocations mean mmap / page
+    // faults / munmap, which serialise the worker threads on the address space
+    std::vector<std::shared_ptr<Job> > pool;
+    std::shared_ptr<Job> obtain() {
+        std::lock_guard<std::mutex> l(mu);
+        if (pool.empty()) return std::make_shared<Job>();
+        std::shared_ptr<Job> j = pool.back();
+        pool.pop_back();
+        return j;
+    }
+    void recycle(std::shared_ptr<Job>& j) {
+        if (!j) return;
+        j->raw.clear();
+        j->out.clear();
+        j->blocks.clear();
+        j->done = j->bad = false;
+        std::lock_guard<std::mutex> l(mu);
+        if (pool.size() < 256) pool.push_back(std::move(j));
+        j.reset();
+    }
 
     Pipeline(FILE* f, int threads) : fp(f), maxOutstanding((size_t)threads * 3 + 2) {
         reader = std::thread([this] { readLoop(); });
@@ -61,7 +81,7 @@ struct AlnReader::Pipeline {
     void readLoop() {
         const size_t kJobBytes = 1u << 20;
         for (;;) {
-            auto job = std::make_shared<Job>();
+            std::shared_ptr<Job> job = obtain();
             size_t outTotal = 0;
             bool fileEnd = false, bad = false;
             while (job->raw.size() < kJobBytes) {
@@ -136,7 +156,6 @@ struct AlnReader::Pipeline {
                 if (rc != Z_STREAM_END || zs.avail_out != 0) bad = true;
             }
             if (zsLive) inflateEnd(&zs);
-            std::vector<uint8_t>().swap(job->raw);
             {
                 std::lock_guard<std::mutex> l(mu);
                 job->bad = job->bad || bad;
@@ -151,6 +170,13 @@ struct AlnReader::Pipeline {
         std::unique_lock<std::mutex> l(mu);
         cvDone.wait(l, [this] { return stop || (!ordered.empty() && ordered.front()->done) || (ordered.empty() && eof); });
         if (stop || ordered.empty()) return false;
+        if (current) {  // record mode: the chunk handed out last time is no longer referenced
+            current->raw.clear();
+            current->out.clear();
+            current->blocks.clear();
+            current->done = current->bad = false;
+            if (pool.size() < 256) pool.push_back(current);
+        }
         current = ordered.front();
         ordered.pop_front();
         cvSpace.notify_one();
@@ -689,8 +715,8 @@ struct AlnReader::BamBatcher {
                 std::lock_guard<std::mutex> l(mu);
                 b->bad = !ok;
                 b->done = true;
-                b->chunk.reset();
             }
+            src->recycle(b->chunk);  // the inflated bytes are no longer needed: only the extracted output waits for the consumer
             cvDone.notify_all();
         }
     }

@@ -165,8 +165,9 @@ static int run(int argc, char const** argv) {
             if (lengths.empty()) lengths.push_back(0);
             mark("header read");
             up.prepare(lengths.size());
-            // CUDA start-up (cuInit + context creation, 0.4-0.8 s on the measured boxes) is a fixed cost; running it on a
-            // helper thread beside the decode loop was measured to be slower (it contends with the decoder's page faults)
+            // CUDA start-up (cuInit + context creation, 0.4-0.8 s on the measured boxes) is a fixed cost.  Letting the
+            // decode workers run ahead meanwhile (on a helper thread, or simply by starting them first) was measured
+            // twice and does not pay: with all cores busy the driver's start-up takes 1.1-1.4 s instead of 0.5 s.
             ppp_config cfg;
             memset(&cfg, 0, sizeof cfg);
             cfg.device = options.device;
