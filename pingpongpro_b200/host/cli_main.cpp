@@ -88,9 +88,12 @@ struct Uploader {
         v.clear();
         return true;
     }
-    bool add(size_t contig, const ppp_read& r) {
+    // appends n consecutive reads of one contig (file order)
+    bool addRun(size_t contig, const ExtractedRead* e, size_t n) {
         std::vector<ppp_read>& v = pending[contig];
-        v.push_back(r);
+        const size_t old = v.size();
+        v.resize(old + n);
+        for (size_t i = 0; i < n; ++i) v[old + i] = e[i].read;
         return v.size() < kBatch || !ctx || flush(contig);  // without a context yet, reads simply accumulate
     }
     bool flushAll() {
@@ -195,10 +198,13 @@ static int run(int argc, char const** argv) {
         int err;
         while (reader.nextBatch(bytes, nRecords, err)) {
             const ExtractedRead* e = reinterpret_cast<const ExtractedRead*>(bytes.data());
-            for (size_t k = 0, m = bytes.size() / sizeof(ExtractedRead); k < m; ++k) {
-                totalReadCount += (double)e[k].weight;  // :488
-                if ((size_t)e[k].contig >= up.pending.size()) { foreignContig = true; continue; }  // header differs: reported below
-                if (!up.add((size_t)e[k].contig, e[k].read)) return gpuError("upload failed");
+            for (size_t k = 0, m = bytes.size() / sizeof(ExtractedRead); k < m;) {  // runs of one contig are appended in bulk
+                const int32_t contig = e[k].contig;
+                size_t j = k;
+                for (; j < m && e[j].contig == contig; ++j) totalReadCount += (double)e[j].weight;  // :488, file order
+                if ((size_t)contig >= up.pending.size()) foreignContig = true;  // header differs: reported below
+                else if (!up.addRun((size_t)contig, e + k, j - k)) return gpuError("upload failed");
+                k = j;
             }
             if (err) {
                 std::cerr << "Failed to read record" << std::endl;  // :411
