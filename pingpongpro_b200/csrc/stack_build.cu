@@ -12,7 +12,10 @@
 // unordered scatter can reproduce bit-exactly.  Each batch is therefore stably radix-sorted by word index
 // (own LSD sort, 8-bit digits: block histograms -> device scan -> stable scatter) and every run of equal
 // keys is folded sequentially with __fadd_rn, continuing from the word's current value so that
-// successive batches extend the same left-to-right sum.
+// successive batches extend the same left-to-right sum: runs of up to 32 records by one thread each
+// (k_fold_runs), longer ones by a producer/consumer warp pair (k_fold_long), batches of up to 4096 records
+// in a single launch (k_small_batch).  The launchers are split into a sort half and a fold half so that the
+// caller (api.cu: buildChunk) can run the sort of the next batches beside the folds of earlier ones.
 //
 // Both paths also maintain the OCCUPANCY BITMAP (1 bit per word of H, same index space: word i of H <-> bit i):
 // the thread that turns a word from 0 to non-zero sets its bit.  The scan (scan.cu) reads the bitmaps instead of
