@@ -29,9 +29,14 @@ static const size_t kRawChunk = 4u << 20;
 struct AlnReader::Pipeline {
     struct Block { size_t off, clen; uint32_t isize; size_t outOff; };
     struct Job {
-        std::vector<uint8_t> raw, out;
+        // plain arrays, not vectors: resizing a vector zero-fills it, and clearing ~5 bytes of output per byte of input
+        // on the ONE reader thread was the slowest stage of the whole BAM path
+        std::unique_ptr<uint8_t[]> raw, out;
+        size_t rawCap = 0, outCap = 0, outLen = 0;
         std::vector<Block> blocks;
         bool done = false, bad = false;
+        void needRaw(size_t n) { if (rawCap < n) { raw.reset(new uint8_t[n]); rawCap = n; } }
+        void needOut(size_t n) { if (outCap < n) { out.reset(new uint8_t[n]); outCap = n; } }
     };
     FILE* fp;
     std::mutex mu;
@@ -54,8 +59,7 @@ struct AlnReader::Pipeline {
     }
     void recycle(std::shared_ptr<Job>& j) {
         if (!j) return;
-        j->raw.clear();
-        j->out.clear();
+        j->outLen = 0;
         j->blocks.clear();
         j->done = j->bad = false;
         std::lock_guard<std::mutex> l(mu);
@@ -78,37 +82,49 @@ struct AlnReader::Pipeline {
         reader.join();
         for (auto& w : workers) w.join();
     }
+    // One large read per job (straight into the job's buffer), block headers parsed in place; a block that the read cut
+    // in two is carried over to the front of the next job.
     void readLoop() {
         const size_t kJobBytes = 1u << 20;
+        std::vector<uint8_t> carry;
         for (;;) {
             std::shared_ptr<Job> job = obtain();
-            size_t outTotal = 0;
-            bool fileEnd = false, bad = false;
-            while (job->raw.size() < kJobBytes) {
-                uint8_t hdr[12];
-                size_t got = fread(hdr, 1, 12, fp);
-                if (got == 0) { fileEnd = true; break; }
-                if (got != 12 || hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) { bad = true; break; }
-                uint32_t xlen = hdr[10] | (hdr[11] << 8);
-                uint8_t extra[65536];
-                if (fread(extra, 1, xlen, fp) != xlen) { bad = true; break; }
+            const size_t have = carry.size();
+            job->needRaw(have + kJobBytes + 8);  // (+8: the decoder's bit reader may look a few bytes past a block)
+            if (have) memcpy(job->raw.get(), carry.data(), have);
+            const size_t got = fread(job->raw.get() + have, 1, kJobBytes, fp);
+            const size_t total = have + got;
+            const uint8_t* r = job->raw.get();
+            size_t off = 0, outTotal = 0;
+            bool bad = false;
+            while (total - off >= 18) {
+                if (r[off] != 31 || r[off + 1] != 139 || r[off + 2] != 8 || !(r[off + 3] & 4)) { bad = true; break; }
+                const uint32_t xlen = r[off + 10] | (r[off + 11] << 8);
+                if (total - off < 12 + (size_t)xlen) break;  // header incomplete
                 int bsize = -1;
                 for (uint32_t i = 0; i + 4 <= xlen;) {
-                    uint32_t slen = extra[i + 2] | (extra[i + 3] << 8);
-                    if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2) bsize = extra[i + 4] | (extra[i + 5] << 8);
+                    const uint8_t* x = r + off + 12 + i;
+                    const uint32_t slen = x[2] | (x[3] << 8);
+                    if (x[0] == 'B' && x[1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = x[4] | (x[5] << 8);
                     i += 4 + slen;
                 }
-                if (bsize < 0) { bad = true; break; }
-                size_t clen = (size_t)bsize + 1 - xlen - 12 - 8;
-                size_t off = job->raw.size();
-                job->raw.resize(off + clen + 8);
-                if (fread(job->raw.data() + off, 1, clen + 8, fp) != clen + 8) { bad = true; break; }
+                if (bsize < 0 || (size_t)bsize + 1 < 12 + (size_t)xlen + 8) { bad = true; break; }
+                const size_t blockLen = (size_t)bsize + 1;
+                if (total - off < blockLen) break;  // block incomplete
                 uint32_t isize;
-                memcpy(&isize, job->raw.data() + off + clen + 4, 4);
-                job->blocks.push_back(Block{off, clen, isize, outTotal});
+                memcpy(&isize, r + off + blockLen - 4, 4);
+                job->blocks.push_back(Block{off + 12 + xlen, blockLen - xlen - 12 - 8, isize, outTotal});
                 outTotal += isize;
+                off += blockLen;
             }
-            job->out.resize(outTotal);
+            const bool fileEnd = got == 0;
+            if (!bad) {
+                carry.assign(r + off, r + total);
+                if (fileEnd && !carry.empty()) bad = true;  // the file ends inside a block
+                if (!fileEnd && off == 0 && total >= kJobBytes + 65536 + 18) bad = true;  // no block fits: not BGZF
+            }
+            job->needOut(outTotal + 16);
+            job->outLen = outTotal;
             job->bad = bad;
             {
                 std::unique_lock<std::mutex> l(mu);
@@ -141,16 +157,16 @@ struct AlnReader::Pipeline {
                 if (bad) break;
                 if (b.isize == 0) continue;
                 // own decoder first; zlib takes over (and judges the block) whenever that one declines
-                if (fast_inflate(job->raw.data() + b.off, b.clen, job->out.data() + b.outOff, b.isize)) continue;
+                if (fast_inflate(job->raw.get() + b.off, b.clen, job->out.get() + b.outOff, b.isize)) continue;
                 if (!zsLive) {
                     memset(&zs, 0, sizeof zs);
                     if (inflateInit2(&zs, -15) != Z_OK) { bad = true; break; }
                     zsLive = true;
                 }
                 inflateReset(&zs);
-                zs.next_in = job->raw.data() + b.off;
+                zs.next_in = job->raw.get() + b.off;
                 zs.avail_in = (uInt)b.clen;
-                zs.next_out = job->out.data() + b.outOff;
+                zs.next_out = job->out.get() + b.outOff;
                 zs.avail_out = b.isize;
                 int rc = inflate(&zs, Z_FINISH);
                 if (rc != Z_STREAM_END || zs.avail_out != 0) bad = true;
@@ -171,8 +187,7 @@ struct AlnReader::Pipeline {
         cvDone.wait(l, [this] { return stop || (!ordered.empty() && ordered.front()->done) || (ordered.empty() && eof); });
         if (stop || ordered.empty()) return false;
         if (current) {  // record mode: the chunk handed out last time is no longer referenced
-            current->raw.clear();
-            current->out.clear();
+            current->outLen = 0;
             current->blocks.clear();
             current->done = current->bad = false;
             if (pool.size() < 256) pool.push_back(current);
@@ -181,8 +196,8 @@ struct AlnReader::Pipeline {
         ordered.pop_front();
         cvSpace.notify_one();
         bad = current->bad;
-        data = current->out.data();
-        len = current->out.size();
+        data = current->out.get();
+        len = current->outLen;
         if (keep) { *keep = current; current.reset(); }
         return true;
     }
@@ -714,7 +729,7 @@ struct AlnReader::BamBatcher {
             };
             bool ok = true;
             for (size_t k = 0; ok && k < b->stitchedOff.size(); ++k) ok = one(b->stitched.data() + b->stitchedOff[k]);
-            const uint8_t* base = b->chunk ? b->chunk->out.data() : nullptr;
+            const uint8_t* base = b->chunk ? b->chunk->out.get() : nullptr;
             for (size_t k = 0; ok && k < b->chunkOff.size(); ++k) ok = one(base + b->chunkOff[k]);
             {
                 std::lock_guard<std::mutex> l(mu);
