@@ -67,3 +67,70 @@ def test_port_equals_reference_run_live(tmp_path, contigs, n_reads, seed, mode, 
     for k in ("p", "q", "reads_plus", "reads_minus"):
         assert np.array_equal(bits(tp[k]), bits(t[k])), k
     assert np.array_equal(bits(tp["hist"][:, :W]), bits(t["hist"]))
+
+
+def _random_sam(rng, n_records, contigs):
+    """Adversarial but well-formed records: every CIGAR operation, soft and hard clips at either end, reference skips,
+    lengths around the 24..32 filter, mixed-case bases, both strands, flags the reference ignores, NH tags in any
+    position among other tags.  (Kept out: SEQ shorter than clip + 10, which the reference reads out of bounds.)"""
+    lines = ["@HD\tVN:1.0"] + [f"@SQ\tSN:{n}\tLN:{L}" for n, L in contigs]
+    for i in range(n_records):
+        name, L = contigs[rng.integers(len(contigs))]
+        flag = int(rng.choice([0, 16, 16, 0, 256, 272, 1024, 1040, 4, 20]))
+        pos = 0 if flag & 4 and rng.random() < 0.5 else int(rng.integers(1, max(2, L - 40)))
+        ops, query = [], 0
+        if rng.random() < 0.1:
+            ops.append((int(rng.integers(1, 4)), "H"))
+        if rng.random() < 0.3:
+            k = int(rng.integers(1, 6)); ops.append((k, "S")); query += k
+        core = int(rng.integers(20, 36))       # aligned length lands on both sides of the 24..32 filter
+        first = True
+        while core > 0:
+            k = int(min(core, rng.integers(1, 30))) if not first else int(min(core, rng.integers(12, 30)))
+            op = "M" if first else str(rng.choice(["M", "M", "=", "X", "D", "N"]))
+            first = False
+            ops.append((k, op)); core -= k
+            if op in "M=X":
+                query += k
+            if rng.random() < 0.2:
+                j = int(rng.integers(1, 4)); ops.append((j, "I")); query += j
+            if rng.random() < 0.05:
+                ops.append((int(rng.integers(1, 3)), "P"))
+        if ops[-1][1] in "IP":
+            ops.append((1, "M")); query += 1
+        if rng.random() < 0.3:
+            k = int(rng.integers(1, 6)); ops.append((k, "S")); query += k
+        if rng.random() < 0.1:
+            ops.append((int(rng.integers(1, 4)), "H"))
+        cigar = "".join(f"{k}{op}" for k, op in ops)
+        seq = "".join(rng.choice(list("ACGTacgtNn"), query))
+        tags = []
+        if rng.random() < 0.5:
+            tags.append("AS:i:%d" % rng.integers(0, 60))
+        if rng.random() < 0.6:
+            tags.append("NH:i:%d" % rng.integers(1, 13))
+        if rng.random() < 0.5:
+            tags.append("XS:Z:NH:i:9")
+        rng.shuffle(tags)
+        lines.append("\t".join([f"r{i}", str(flag), name, str(pos), "255", cigar, "*", "0", "0", seq, "*", *tags]))
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.skipif(not have_ref(23), reason="oracle/_ref was not built here")
+@pytest.mark.parametrize("mode", ["weighted", "unique", "discard"])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_record_extraction_equals_the_reference_on_adversarial_records(tmp_path, mode, seed):
+    """pingpongpro.cpp:415-484 (CIGAR length, NH weight, strand, 5'-end key, A10 with soft clips) as restated in
+    host/frontend.h: the stacks built from OUR extraction must be the stacks the reference builds from the same file."""
+    rng = np.random.default_rng(1000 + seed)
+    sam = tmp_path / "adv.sam"
+    sam.write_text(_random_sam(rng, 6000, [("c1", 3000), ("c2", 900), ("c3", 120)]))
+    ref = run_harness(str(tmp_path / "dump.bin"), [str(sam)], mode=mode)
+    for threads in (1, 3):
+        dec = host.decode_file(str(sam), mode=mode, threads=threads)
+        st = Oracle(dec.reads, mode=mode).stacks()
+        assert len(st["key"]) == len(ref["stacks"]) and len(st["key"]) > 500
+        for k in ("strand", "contig", "key", "a10"):
+            assert np.array_equal(st[k], ref["stacks"][k]), k
+        assert np.array_equal(bits(st["reads"]), bits(ref["stacks"]["reads"]))
+        assert dec.total_weight == ref["total"]
