@@ -134,3 +134,69 @@ def test_record_extraction_equals_the_reference_on_adversarial_records(tmp_path,
             assert np.array_equal(st[k], ref["stacks"][k]), k
         assert np.array_equal(bits(st["reads"]), bits(ref["stacks"]["reads"]))
         assert dec.total_weight == ref["total"]
+
+
+def _sam_to_bam(sam_text: str, block_bytes: int = 9000) -> bytes:
+    """Minimal SAM -> BAM encoder for the tests (integer tags typed like samtools does: smallest type that fits)."""
+    import struct
+    import zlib
+
+    header = [ln for ln in sam_text.splitlines() if ln.startswith("@")]
+    refs = [(f.split("\t")[1][3:], int(f.split("\t")[2][3:])) for f in header if f.startswith("@SQ")]
+    rid = {n: i for i, (n, _) in enumerate(refs)}
+    text = ("\n".join(header) + "\n").encode()
+    out = b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    for n, L in refs:
+        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", L)
+    for ln in sam_text.splitlines():
+        if ln.startswith("@") or not ln:
+            continue
+        f = ln.split("\t")
+        name, flag, rname, pos, cigar, seq = f[0], int(f[1]), f[2], int(f[3]), f[5], f[9]
+        ops, num = [], ""
+        for ch in cigar:
+            if ch.isdigit():
+                num += ch
+            else:
+                ops.append((int(num) << 4) | "MIDNSHP=X".index(ch)); num = ""
+        codes = ["=ACMGRSVTWYHKDBN".index(c.upper()) for c in seq]
+        packed = bytes(((codes[i] << 4) | (codes[i + 1] if i + 1 < len(codes) else 0)) for i in range(0, len(codes), 2))
+        tags = b""
+        for t in f[11:]:
+            key, typ, val = t.split(":", 2)
+            if typ == "i":
+                v = int(val)
+                for code, fmt, lo, hi in (("C", "<B", 0, 255), ("c", "<b", -128, 127), ("S", "<H", 0, 65535), ("s", "<h", -32768, 32767), ("I", "<I", 0, 2**32 - 1), ("i", "<i", -2**31, 2**31 - 1)):
+                    if lo <= v <= hi:
+                        tags += key.encode() + code.encode() + struct.pack(fmt, v)
+                        break
+            else:
+                tags += key.encode() + b"Z" + val.encode() + b"\0"
+        body = struct.pack("<iiBBHHHIiii", rid.get(rname, -1), pos - 1, len(name) + 1, 255, 4680, len(ops), flag, len(seq), -1, -1, 0)
+        body += name.encode() + b"\0" + b"".join(struct.pack("<I", o) for o in ops) + packed + b"\xff" * len(seq) + tags
+        out += struct.pack("<i", len(body)) + body
+    bam = b""
+    for o in list(range(0, len(out), block_bytes)) + [None]:
+        chunk = b"" if o is None else out[o:o + block_bytes]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        z = c.compress(chunk) + c.flush()
+        bam += bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0]) + (len(z) + 25).to_bytes(2, "little") + z + zlib.crc32(chunk).to_bytes(4, "little") + len(chunk).to_bytes(4, "little")
+    return bam
+
+
+@pytest.mark.parametrize("mode", ["weighted", "unique"])
+def test_sam_and_bam_parsers_agree_on_adversarial_records(tmp_path, mode):
+    """Two independent code paths (text fields vs binary fields, letters vs 4-bit codes, NH:i text vs typed binary
+    integers) must extract the same reads; blocks of 9000 bytes make records straddle BGZF blocks."""
+    rng = np.random.default_rng(77)
+    text = _random_sam(rng, 5000, [("c1", 3000), ("c2", 900), ("c3", 120)])
+    (tmp_path / "a.sam").write_text(text)
+    (tmp_path / "a.bam").write_bytes(_sam_to_bam(text))
+    want = host.decode_file(str(tmp_path / "a.sam"), mode=mode)
+    assert want.n_kept > 1000
+    for threads in (1, 4):
+        got = host.decode_file(str(tmp_path / "a.bam"), mode=mode, threads=threads)
+        assert got.names == want.names and got.lengths == want.lengths
+        assert got.n_records == want.n_records and got.n_kept == want.n_kept and got.total_weight == want.total_weight
+        for a, b in zip(got.reads, want.reads):
+            assert np.array_equal(a, b)
