@@ -49,6 +49,11 @@ typedef struct ppp_annot_interval {
     uint32_t end;
 } ppp_annot_interval;
 PPP_API int ppp_annot_read(const char* const* paths, int n_paths, const char* const* contig_names, int n_names, ppp_annot** out);
+/* -T: clusters overlap-10 loci (given in (contig, position) order) that lie within `range` of each other into putative
+ * transposons, predictSuppressedTransposons pingpongpro.cpp:1326-1354 -- the last cluster of a contig is never
+ * emitted and clusters must be longer than 30 nt, as in the reference.  Results through the accessors below. */
+PPP_API int ppp_annot_predict(const uint32_t* contigs, const uint32_t* positions, size_t n, const char* const* contig_names, int n_names, uint32_t range,
+                              ppp_annot** out);
 PPP_API void ppp_annot_free(ppp_annot* a);
 PPP_API size_t ppp_annot_count(const ppp_annot* a);
 PPP_API void ppp_annot_intervals(const ppp_annot* a, ppp_annot_interval* out);

@@ -107,6 +107,27 @@ def read_annotation(paths, contig_names):
         L.ppp_annot_free(h)
 
 
+def predict_transposons(contigs, positions, contig_names, rng: int):
+    """-T: putative transposons from overlap-10 loci in (contig, position) order (pingpongpro.cpp:1326-1354).
+    Returns (intervals[ANNOT_DTYPE], identifiers)."""
+    L = host_lib()
+    c = np.ascontiguousarray(contigs, dtype=np.uint32)
+    p = np.ascontiguousarray(positions, dtype=np.uint32)
+    na = (C.c_char_p * len(contig_names))(*[n.encode() for n in contig_names])
+    h = C.c_void_p()
+    L.ppp_annot_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
+    if L.ppp_annot_predict(c.ctypes.data, p.ctypes.data, len(c), na, len(contig_names), rng, C.byref(h)) != 0:
+        raise ValueError("contig id out of range")
+    try:
+        n = L.ppp_annot_count(h)
+        iv = np.zeros(n, ANNOT_DTYPE)
+        if n:
+            L.ppp_annot_intervals(h, iv.ctypes.data)
+        return iv, [L.ppp_annot_identifier(h, i).decode(errors="replace") for i in range(n)]
+    finally:
+        L.ppp_annot_free(h)
+
+
 class DecodedFile:
     """Result of decoding one SAM/BAM file: contig table + packed reads per contig (file order)."""
 

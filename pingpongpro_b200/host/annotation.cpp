@@ -144,10 +144,8 @@ void predictTransposons(const std::map<unsigned, std::vector<unsigned> >& positi
                 end = p + 1;
             } else {
                 if (start + 30u < end) {  // PREDICT_TRANSPOSONS_MIN_LENGTH, :220, :1339
-                    std::ostringstream id;
-                    id << names[kv.first] << ":" << start << "-" << end;
                     Transposon t;
-                    t.identifier = id.str();
+                    t.identifier = names[kv.first] + ":" + std::to_string(start) + "-" + std::to_string(end);  // :1341-1343
                     t.strand = 0;
                     t.start = start;
                     t.end = end;

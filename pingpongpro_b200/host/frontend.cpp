@@ -2,6 +2,7 @@
 #include "frontend.h"
 
 #include <fstream>
+#include <map>
 
 #include "annotation.h"
 #include "fast_inflate.h"
@@ -119,6 +120,26 @@ int ppp_annot_read(const char* const* paths, int n_paths, const char* const* con
         if (fs.fail()) { delete a; return 1; }
         ppp::readTransposons(fs, ppp::formatFromPath(paths[i]), tp, a->names);
     }
+    for (const auto& kv : tp)
+        for (const ppp::Transposon& t : kv.second) {
+            a->iv.push_back(ppp_annot_interval{kv.first, t.strand, t.start, t.end});
+            a->ids.push_back(t.identifier);
+        }
+    *out = reinterpret_cast<ppp_annot*>(a);
+    return 0;
+}
+int ppp_annot_predict(const uint32_t* contigs, const uint32_t* positions, size_t n, const char* const* contig_names, int n_names, uint32_t range,
+                      ppp_annot** out) {
+    *out = nullptr;
+    ppp_annot_impl* a = new ppp_annot_impl;
+    for (int i = 0; i < n_names; ++i) a->names.push_back(contig_names[i]);
+    std::map<unsigned, std::vector<unsigned> > perContig;  // loci arrive in (contig, position) order
+    for (size_t i = 0; i < n; ++i) {
+        if (contigs[i] >= (uint32_t)n_names) { delete a; return 1; }
+        perContig[contigs[i]].push_back(positions[i]);
+    }
+    ppp::TransposonsPerGenome tp;
+    ppp::predictTransposons(perContig, a->names, range, tp);
     for (const auto& kv : tp)
         for (const ppp::Transposon& t : kv.second) {
             a->iv.push_back(ppp_annot_interval{kv.first, t.strand, t.start, t.end});

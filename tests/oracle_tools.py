@@ -150,6 +150,7 @@ class Oracle:
 
     def sigs(self):
         """Signatures in the reference's list order (overlap, contig, position)."""
+        self.score()
         n = self.L.ppo_n_sigs(self.h)
         ints = np.empty((n, 7), np.uint32)
         flts = np.empty((n, 3), np.float32)

@@ -200,3 +200,34 @@ def test_sam_and_bam_parsers_agree_on_adversarial_records(tmp_path, mode):
         assert got.n_records == want.n_records and got.n_kept == want.n_kept and got.total_weight == want.total_weight
         for a, b in zip(got.reads, want.reads):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.skipif(not have_ref(23), reason="oracle/_ref was not built here")
+@pytest.mark.parametrize("rng_nt,seed", [(30, 201), (60, 202), (300, 203), (5000, 204)])
+def test_predicted_transposons_equal_the_reference(tmp_path, rng_nt, seed):
+    """-T RANGE without -t (pingpongpro.cpp:1324-1357): the clustering of the host library on the oracle's overlap-10
+    loci, scored by the oracle, against the reference's own prediction + scoring -- including the cluster that the
+    reference never emits at the end of a contig and the > 30 nt rule."""
+    sam = str(tmp_path / "in.sam")
+    subprocess.check_call([SYNTH, "--contigs", "c1:90000,c2:61000,c3:30000,c4:2000", "--reads", "60000", "--seed", str(seed), "--out", sam])
+    ref = run_harness(str(tmp_path / "dump.bin"), [sam], mode="weighted", predict=rng_nt)
+    dec = host.decode_file(sam, mode="weighted")
+    o = Oracle(dec.reads, mode="weighted")
+    s = o.sigs()
+    pp = s["ov"] == 10 - 3  # overlap index of the ping-pong overlap
+    order = np.lexsort((s["pos"][pp], s["contig"][pp]))
+    iv, ids = host.predict_transposons(s["contig"][pp][order], s["pos"][pp][order], dec.names, rng_nt)
+    t = ref["predicted"]
+    assert len(iv) == len(t)
+    if rng_nt <= 300:
+        assert len(iv) > 3
+    for k in ("contig", "strand", "start", "end"):
+        assert np.array_equal(iv[k], t[k]), k
+    assert all(i == f"{dec.names[c]}:{a}-{b}" for i, c, a, b in zip(ids, iv["contig"], iv["start"], iv["end"]))
+    q = np.zeros(len(iv), IV_DTYPE)
+    for k in ("contig", "strand", "start", "end"):
+        q[k] = iv[k]
+    tp = o.transposons(q)
+    for k in ("p", "q", "reads_plus", "reads_minus"):
+        assert np.array_equal(bits(tp[k]), bits(t[k])), k
+    assert np.array_equal(bits(tp["hist"][:, :21]), bits(t["hist"]))
