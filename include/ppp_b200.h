@@ -196,6 +196,13 @@ PPP_API int ppp_pairs_download(ppp_ctx* ctx, ppp_pair* out, size_t capacity, siz
  * permutation `order[i]` = input index of result i (optional). */
 PPP_API int ppp_transposons(ppp_ctx* ctx, const ppp_interval* intervals, size_t n, ppp_tp_result* results, uint32_t* order);
 
+/* Test hook, host only (no device needed): the height-score bin thresholds the binning kernel works with.
+ * thresholds[b-1] (b = 1..999) = smallest float product hs = freq[h+] * freq[h-] whose bin
+ * (int)(0.5 + log10f(hs) / log10f(max_freq * max_freq) * 999) (pingpongpro.cpp:551, :591-594) is >= b, evaluated
+ * with the host libm; +inf when max_freq^2 does not reach bin b.  max_freq must be > 1.  Returns PPP_ERR_STATE when
+ * the host's log10f is not monotone around a threshold (the device-side bin = number of thresholds <= hs needs that). */
+PPP_API int ppp_host_bin_thresholds(float max_freq, float* thresholds /* 999 */);
+
 PPP_API int ppp_timings_get(ppp_ctx* ctx, ppp_timings* out);
 PPP_API int ppp_timings_reset(ppp_ctx* ctx);
 /* Padded length (32-bit words per strand) of the dense stack arrays of this context. */

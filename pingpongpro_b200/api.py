@@ -102,9 +102,10 @@ def lib() -> C.CDLL:
     L.ppp_timings_get.argtypes = [vp, C.POINTER(Timings)]
     L.ppp_timings_reset.argtypes = [vp]
     L.ppp_layout.argtypes = [vp, u64p, u64p]
+    L.ppp_host_bin_thresholds.argtypes = [C.c_float, vp]
     for name in ("ppp_device_count", "ppp_warmup", "ppp_init", "ppp_reset", "ppp_set_allreduce", "ppp_set_rank", "ppp_nccl_unique_id", "ppp_nccl_attach", "ppp_pinned_alloc", "ppp_pinned_free", "ppp_reads_submit",
                  "ppp_reads_submit_device", "ppp_stacks_finish", "ppp_reads_foreign", "ppp_stacks_download", "ppp_height_hist", "ppp_scan", "ppp_score",
-                 "ppp_pairs_download", "ppp_transposons", "ppp_timings_get", "ppp_timings_reset", "ppp_layout"):
+                 "ppp_pairs_download", "ppp_transposons", "ppp_timings_get", "ppp_timings_reset", "ppp_layout", "ppp_host_bin_thresholds"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -113,6 +114,13 @@ def lib() -> C.CDLL:
 def _check(rc: int) -> None:
     if rc != 0:
         raise PppError(rc, lib().ppp_last_error().decode(errors="replace"))
+
+
+def bin_thresholds(max_freq: float) -> np.ndarray:
+    """The 999 height-score bin thresholds for a maximum frequency (host only; pingpongpro.cpp:551, :591-594)."""
+    out = np.empty(999, dtype=np.float32)
+    _check(lib().ppp_host_bin_thresholds(C.c_float(max_freq), out.ctypes.data_as(C.c_void_p)))
+    return out
 
 
 def device_count() -> int:

@@ -950,6 +950,13 @@ int ppp_transposons(ppp_ctx* c, const ppp_interval* intervals, size_t n, ppp_tp_
     return PPP_OK;
 }
 
+int ppp_host_bin_thresholds(float max_freq, float* thresholds) {
+    if (!thresholds || !(max_freq > 1.0f)) return fail(PPP_ERR_ARG, "ppp_host_bin_thresholds: max_freq must be > 1");
+    computeThresholds(max_freq, thresholds);
+    if (!validateThresholds(max_freq, thresholds)) return fail(PPP_ERR_STATE, "host log10f is not monotone around a bin threshold");
+    return PPP_OK;
+}
+
 int ppp_timings_get(ppp_ctx* c, ppp_timings* out) {
     if (!c || !out) return fail(PPP_ERR_ARG, "null argument");
     CK(cudaSetDevice(c->device));

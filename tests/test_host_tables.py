@@ -1,0 +1,81 @@
+"""The height-score bin thresholds (host libm, no device): the table the binning kernel searches must reproduce
+pingpongpro.cpp:591-594 for EVERY float product, i.e. #thresholds <= hs == (int)(0.5 + log10f(hs) / maxHS * 999).
+The literal expression is restated here on top of the C library's log10f (ctypes) and numpy float32 arithmetic."""
+import ctypes
+import ctypes.util
+
+import numpy as np
+import pytest
+
+from pingpongpro_b200 import api
+
+_libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+_libm.log10f.restype = ctypes.c_float
+_libm.log10f.argtypes = [ctypes.c_float]
+
+F = np.float32
+
+
+def log10f(x) -> np.float32:
+    return F(_libm.log10f(ctypes.c_float(float(x))))
+
+
+def max_height_score(max_freq: float) -> np.float32:
+    return log10f(F(max_freq) * F(max_freq))  # :551
+
+
+def ref_bin(hs, max_hs: np.float32) -> int:
+    t = F(F(log10f(hs) / max_hs) * F(999.0))  # :593, float throughout
+    return int(0.5 + float(t))                # :594, the 0.5 is a double
+
+
+def below(x: np.float32) -> np.float32:
+    return np.nextafter(F(x), F(0))
+
+
+MAX_FREQS = [2, 3, 5, 17, 100, 622, 4096, 12345, 250000, 1e6, 9999999, 16777215, 16777216]
+
+
+@pytest.mark.parametrize("max_freq", MAX_FREQS)
+def test_every_threshold_is_the_first_float_of_its_bin(max_freq):
+    thr = api.bin_thresholds(max_freq)
+    max_hs = max_height_score(max_freq)
+    top = F(max_freq) * F(max_freq)
+    assert ref_bin(top, max_hs) == 999  # the tallest product sits in the last bin
+    assert np.all(np.isfinite(thr)) and np.all(np.diff(thr) >= 0) and thr[0] > 1 and thr[-1] <= top
+    for b in range(1, 1000):
+        t = thr[b - 1]
+        assert ref_bin(t, max_hs) >= b, (max_freq, b)
+        if b == 1 or thr[b - 2] < t:
+            assert ref_bin(below(t), max_hs) < b, (max_freq, b)
+
+
+@pytest.mark.parametrize("max_freq", [5, 622, 12345, 1e6, 16777216])
+def test_threshold_count_equals_the_reference_bin_for_products(max_freq):
+    """The device computes the bin as the number of thresholds <= hs: random products, the floats around every
+    threshold, and the extremes."""
+    thr = api.bin_thresholds(max_freq)
+    max_hs = max_height_score(max_freq)
+    rng = np.random.default_rng(int(max_freq))
+    a = np.floor(10 ** rng.uniform(0, np.log10(max_freq), 3000)).astype(np.float32)
+    b = np.floor(10 ** rng.uniform(0, np.log10(max_freq), 3000)).astype(np.float32)
+    hs = np.concatenate([a * b, [F(1), F(max_freq), F(max_freq) * F(max_freq)],
+                         thr[::7], np.nextafter(thr[::7], F(0)), np.nextafter(thr[::7], F(np.inf))]).astype(np.float32)
+    hs = hs[(hs >= 1) & (hs <= F(max_freq) * F(max_freq))]
+    got = np.searchsorted(thr, hs, side="right")
+    want = np.array([ref_bin(x, max_hs) for x in hs])
+    assert np.array_equal(got, want)
+
+
+def test_many_maximum_frequencies_validate():
+    """ppp_host_bin_thresholds re-checks the floats around every step with the literal expression and fails otherwise."""
+    rng = np.random.default_rng(11)
+    for mf in np.floor(10 ** rng.uniform(0.31, 7.2247, 300)):
+        thr = api.bin_thresholds(float(mf))
+        assert thr.shape == (999,) and thr[-1] <= F(mf) * F(mf)
+
+
+def test_rejects_degenerate_maximum():
+    for bad in (1.0, 0.0, -3.0, float("nan")):
+        with pytest.raises(api.PppError):
+            api.bin_thresholds(bad)
