@@ -139,6 +139,17 @@ PPP_API int ppp_set_rank(ppp_ctx* ctx, int rank, int world);
 PPP_API int ppp_nccl_unique_id(void* id);
 PPP_API int ppp_nccl_attach(ppp_ctx* ctx, const void* id, int rank, int world);
 
+/* Built-in collective for the contexts of ONE process (e.g. one host driver feeding the GPUs of a box, one thread per
+ * context): the all-reduces go through host memory (they move kilobytes, twice per run).  Create the group, attach
+ * every context with its rank (ascending range order; implies ppp_set_rank), then call ppp_height_hist / ppp_scan of
+ * all contexts CONCURRENTLY from one thread each -- they meet inside the collective.  ppp_group_abort releases ranks
+ * that wait for one that failed elsewhere (their calls return an error).  Destroy the group after its contexts. */
+typedef struct ppp_group ppp_group;
+PPP_API int ppp_group_create(int n_ranks, ppp_group** group);
+PPP_API int ppp_group_attach(ppp_ctx* ctx, ppp_group* group, int rank);
+PPP_API void ppp_group_abort(ppp_group* group);
+PPP_API void ppp_group_destroy(ppp_group* group);
+
 /* Pinned host memory for the double-buffered uploads. */
 PPP_API int ppp_pinned_alloc(size_t bytes, void** ptr);
 PPP_API int ppp_pinned_free(void* ptr);
@@ -195,6 +206,13 @@ PPP_API int ppp_pairs_download(ppp_ctx* ctx, ppp_pair* out, size_t capacity, siz
  * returned in the reference's order (contig, start, end; ties in input order, :1174) together with the
  * permutation `order[i]` = input index of result i (optional). */
 PPP_API int ppp_transposons(ppp_ctx* ctx, const ppp_interval* intervals, size_t n, ppp_tp_result* results, uint32_t* order);
+
+/* The same for a range-sharded genome driven by ONE host thread: `ctxs` are the n_ctx contexts of the shards in
+ * ascending range order (on one or several devices), each after its ppp_score.  Transposons that straddle a range
+ * boundary are scored as in an unsharded run: the sequential single-precision sums of :1227-1234 continue from context
+ * to context in position order, and the iterator history of :1215-1222 is replayed on the whole lists.
+ * (ppp_transposons on a single shard only sees that shard's signatures.) */
+PPP_API int ppp_transposons_sharded(ppp_ctx* const* ctxs, int n_ctx, const ppp_interval* intervals, size_t n, ppp_tp_result* results, uint32_t* order);
 
 /* Test hook, host only (no device needed): the height-score bin thresholds the binning kernel works with.
  * thresholds[b-1] (b = 1..999) = smallest float product hs = freq[h+] * freq[h-] whose bin

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "host_tables.h"
+#include "local_group.h"
 #include "nccl_loader.h"
 #include "ppp_b200.h"
 #include "transposons.cuh"
@@ -139,6 +140,7 @@ struct ppp_ctx {
     ppp_allreduce_fn allreduce = nullptr;
     void* allreduceUser = nullptr;
     void* ncclComm = nullptr;  // communicator of the built-in collective (ppp_nccl_attach)
+    struct GroupMember* groupMember = nullptr;  // membership of an in-process group (ppp_group_attach)
     int rank = 0, world = 0;   // known (ppp_set_rank / ppp_nccl_attach): tall stacks are exchanged as compact lists
     uint32_t* dGather = nullptr;  // [world][kTallHeader + tallCap], see launch_tall_apply
     uint32_t tallCap = 0;
@@ -343,6 +345,25 @@ int ncclHook(void* user, void* buf, size_t count, int dtype, int op, void* strea
 
 }  // namespace
 
+// ---- built-in collective for contexts of ONE process: all-reduce through host memory (local_group.cpp) ----
+struct ppp_group {
+    LocalGroup g;
+    explicit ppp_group(int n) : g(n) {}
+};
+struct GroupMember {
+    ppp_group* group;
+    int rank;
+};
+
+namespace {
+
+int groupHook(void* user, void* buf, size_t count, int dtype, int op, void* stream) {
+    GroupMember* m = static_cast<GroupMember*>(user);
+    return m->group->g.allReduce(m->rank, buf, count, dtype, op, static_cast<cudaStream_t>(stream));
+}
+
+}  // namespace
+
 extern "C" {
 
 const char* ppp_last_error(void) { return g_err.c_str(); }
@@ -487,6 +508,7 @@ void ppp_destroy(ppp_ctx* c) {
         if (c->foldStream[k]) cudaStreamSynchronize(c->foldStream[k]);
     foldBuildTimers(c);
     if (c->ncclComm) nccl().commDestroy(c->ncclComm);
+    delete c->groupMember;
     if (c->dGather) cudaFree(c->dGather);
     if (c->dOverflow) cudaFree(c->dOverflow);
     void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
@@ -578,6 +600,28 @@ int ppp_nccl_attach(ppp_ctx* c, const void* id, int rank, int world) {
     c->allreduceUser = c;
     return ppp_set_rank(c, rank, world);
 }
+
+int ppp_group_create(int n_ranks, ppp_group** out) {
+    if (!out || n_ranks < 1) return fail(PPP_ERR_ARG, "ppp_group_create: %d ranks", n_ranks);
+    *out = new ppp_group(n_ranks);
+    return PPP_OK;
+}
+
+int ppp_group_attach(ppp_ctx* c, ppp_group* g, int rank) {
+    if (!c || !g) return fail(PPP_ERR_ARG, "null argument");
+    if (rank < 0 || rank >= g->g.size()) return fail(PPP_ERR_ARG, "rank %d of %d", rank, g->g.size());
+    if (c->groupMember || c->ncclComm) return fail(PPP_ERR_STATE, "a collective is already attached");
+    c->groupMember = new GroupMember{g, rank};
+    c->allreduce = groupHook;
+    c->allreduceUser = c->groupMember;
+    return ppp_set_rank(c, rank, g->g.size());
+}
+
+void ppp_group_abort(ppp_group* g) {
+    if (g) g->g.abort();
+}
+
+void ppp_group_destroy(ppp_group* g) { delete g; }
 
 int ppp_reads_submit_device(ppp_ctx* c, int32_t contig, const ppp_read* dReads, size_t n) {
     if (!c) return fail(PPP_ERR_ARG, "null context");
@@ -947,6 +991,46 @@ int ppp_transposons(ppp_ctx* c, const ppp_interval* intervals, size_t n, ppp_tp_
     if (!err.empty()) return fail(PPP_ERR_ARG, "%s", err.c_str());
     if ((rc = timerStop(c, c->tTransposon))) return rc;
     CK(cudaStreamSynchronize(c->stream));
+    return PPP_OK;
+}
+
+int ppp_transposons_sharded(ppp_ctx* const* ctxs, int n_ctx, const ppp_interval* intervals, size_t n, ppp_tp_result* results, uint32_t* order) {
+    if (!ctxs || n_ctx <= 0) return fail(PPP_ERR_ARG, "no contexts");
+    if (n && (!intervals || !results)) return fail(PPP_ERR_ARG, "null argument");
+    std::vector<TransposonJob> jobs(n_ctx);
+    std::vector<int> devices(n_ctx);
+    bool havePrev = false;
+    uint64_t prevKey = 0;
+    for (int k = 0; k < n_ctx; ++k) {
+        ppp_ctx* c = ctxs[k];
+        if (!c) return fail(PPP_ERR_ARG, "null context");
+        if (!c->haveScore) return fail(PPP_ERR_STATE, "call ppp_score on every context before ppp_transposons_sharded");
+        if (c->contigLen != ctxs[0]->contigLen || c->W != ctxs[0]->W || c->minOv != ctxs[0]->minOv || c->ppOv != ctxs[0]->ppOv)
+            return fail(PPP_ERR_ARG, "contexts %d and 0 do not describe the same genome and overlap range", k);
+        if (!c->ownedSlots.empty()) {  // ranges must ascend: the sums are chained in position order
+            const Slot& f = c->ownedSlots.front();
+            uint64_t key = ((uint64_t)f.contig << 32) | f.first;
+            if (havePrev && key <= prevKey) return fail(PPP_ERR_ARG, "contexts must be passed in ascending range order");
+            const Slot& l = c->ownedSlots.back();
+            prevKey = ((uint64_t)l.contig << 32) | l.first;
+            havePrev = true;
+        }
+        TransposonJob& job = jobs[k];
+        job.pairs = c->dPairs;
+        job.pairFdr = c->dPairFdr;
+        job.nPairs = c->nPairs;
+        job.W = c->W;
+        job.ppIdx = c->ppOv - c->minOv;
+        job.slots = &c->slotOfContig;
+        job.stream = c->stream;
+        job.launches = &c->launches;
+        devices[k] = c->device;
+    }
+    std::string err;
+    cudaError_t e = n_ctx == 1 ? (cudaSetDevice(devices[0]), run_transposons(jobs[0], intervals, n, results, order, err))
+                               : run_transposons_sharded(jobs.data(), devices.data(), n_ctx, intervals, n, results, order, err);
+    if (e != cudaSuccess) return fail(PPP_ERR_CUDA, "transposons: %s %s", cudaGetErrorString(e), err.c_str());
+    if (!err.empty()) return fail(PPP_ERR_ARG, "%s", err.c_str());
     return PPP_OK;
 }
 

@@ -139,6 +139,28 @@ __global__ void k_tp_sums(uint32_t nTp, int W, int ppIdx, const uint32_t* __rest
     if ((int)o == ppIdx) { rPlus[t] = rp; rMinus[t] = rm; }
 }
 
+// Range sharding: the signatures of one (transposon, overlap) may be spread over several contexts (position ranges in
+// ascending order).  The sums are sequential single-precision additions in position order, so the contexts fold one
+// after the other, each continuing from the values the previous one left in hist / rPlus / rMinus (zero for the first).
+__global__ void k_tp_sums_chain(uint32_t nTp, int W, int ppIdx, const uint32_t* __restrict__ bounds, const uint8_t* __restrict__ skip, const float* __restrict__ sScore,
+                                const float* __restrict__ sRp, const float* __restrict__ sRm, float* __restrict__ hist, float* __restrict__ rPlus,
+                                float* __restrict__ rMinus) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nTp * (uint32_t)W) return;
+    uint32_t t = g / (uint32_t)W, o = g % (uint32_t)W;
+    const uint32_t* b = bounds + (size_t)g * 4;
+    if (skip[g] || b[2] >= b[3]) return;  // nothing of this list lives here: the running values pass through
+    const bool pp = (int)o == ppIdx;
+    float sum = hist[(size_t)t * 32 + o], rp = 0.f, rm = 0.f;
+    if (pp) { rp = rPlus[t]; rm = rMinus[t]; }
+    for (uint32_t i = b[2]; i < b[3]; ++i) {
+        sum = __fadd_rn(sum, sScore[i]);                                          // :1227
+        if (pp) { rp = __fadd_rn(rp, sRp[i]); rm = __fadd_rn(rm, sRm[i]); }       // :1230-1234
+    }
+    hist[(size_t)t * 32 + o] = sum;                                               // :1240
+    if (pp) { rPlus[t] = rp; rMinus[t] = rm; }
+}
+
 __global__ void k_tp_stats(uint32_t nTp, int W, int ppIdx, double coeff, const float* __restrict__ hist, double* __restrict__ zOut, double* __restrict__ pOut) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nTp) return;
@@ -188,12 +210,12 @@ struct DevBuf {
         if (e__ != cudaSuccess) return e__; \
     } while (0)
 
-cudaError_t run_transposons(const TransposonJob& job, const ppp_interval* intervals, size_t n, ppp_tp_result* results, uint32_t* order, std::string& err) {
-    if (n == 0) return cudaSuccess;
-    if (n >= 0x7fffffffull / 32) { err = "too many intervals"; return cudaSuccess; }
-    const int W = job.W;
-    // reference order: contig (std::map key), then start, end (:206-212), ties in input order (stable list::sort, :1174)
-    std::vector<uint32_t> perm(n);
+namespace {
+
+// reference order: contig (std::map key), then start, end (:206-212), ties in input order (stable list::sort, :1174);
+// groupStart = first index of every contig group (+ n)
+void sortIntervals(const ppp_interval* intervals, size_t n, std::vector<uint32_t>& perm, std::vector<uint32_t>& groupStart) {
+    perm.resize(n);
     for (size_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
     std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) {
         const ppp_interval &x = intervals[a], &y = intervals[b];
@@ -201,22 +223,74 @@ cudaError_t run_transposons(const TransposonJob& job, const ppp_interval* interv
         if (x.start != y.start) return x.start < y.start;
         return x.end < y.end;
     });
-    std::vector<TpDev> tp(n);
-    std::vector<uint32_t> groupStart;
+    groupStart.clear();
+    for (size_t k = 0; k < n; ++k)
+        if (k == 0 || intervals[perm[k - 1]].contig != intervals[perm[k]].contig) groupStart.push_back((uint32_t)k);
+    groupStart.push_back((uint32_t)n);
+}
+
+// The sorted intervals in the coordinates of one context's slots.
+void localIntervals(const std::vector<Slot>& slots, const ppp_interval* intervals, const std::vector<uint32_t>& perm, std::vector<TpDev>& tp) {
+    const size_t n = perm.size();
+    tp.resize(n);
     for (size_t k = 0; k < n; ++k) {
         const ppp_interval& iv = intervals[perm[k]];
-        if (k == 0 || intervals[perm[k - 1]].contig != iv.contig) groupStart.push_back((uint32_t)k);
         TpDev d;
         d.start = iv.start;
         d.end = iv.end;
         d.off = d.first = d.cLo = d.cHi = 0;
-        if (iv.contig < job.slots->size()) {  // contigs unknown to the alignment header have no signatures (:1101-1106)
-            const Slot& s = (*job.slots)[iv.contig];
+        if (iv.contig < slots.size()) {  // contigs unknown to the alignment header have no signatures (:1101-1106)
+            const Slot& s = slots[iv.contig];
             if (s.lenMinus) { d.off = s.off; d.first = s.first; d.cLo = s.off; d.cHi = s.off + s.lenPlus; }
         }
         tp[k] = d;
     }
-    groupStart.push_back((uint32_t)n);
+}
+
+// Host tail: copies the sums and statistics into results[] (sorted order) and computes the q-values (:1276-1312).
+void finishResults(size_t n, int ppIdx, const std::vector<float>& hist, const std::vector<float>& rp, const std::vector<float>& rm, const std::vector<double>& z,
+                   const std::vector<double>& p, const std::vector<uint32_t>& perm, ppp_tp_result* results, uint32_t* order) {
+    for (size_t k = 0; k < n; ++k) {
+        ppp_tp_result& r = results[k];
+        for (int o = 0; o < 32; ++o) r.histogram[o] = hist[k * 32 + o];
+        r.reads_plus = rp[k];
+        r.reads_minus = rm[k];
+        r.z = z[k];
+        r.p = p[k];
+        r.p_value = (float)p[k];  // :1271
+        r.q_value = 1.0f;         // :187
+        if (order) order[k] = perm[k];
+    }
+    // q-values, :1276-1312: stable sort by p ascending (:1281), walked from the largest p with i = 1, 2, ...
+    std::vector<uint32_t> byP(n);
+    for (size_t k = 0; k < n; ++k) byP[k] = (uint32_t)k;
+    std::stable_sort(byP.begin(), byP.end(), [&](uint32_t a, uint32_t b) { return results[a].p_value < results[b].p_value; });
+    unsigned i = 1;
+    float prevP = 1, prevQ = 1;
+    for (size_t k = n; k-- > 0;) {
+        ppp_tp_result& r = results[byP[k]];
+        if (r.histogram[ppIdx] / (r.reads_plus + r.reads_minus) < 0.2) r.q_value = 1;  // :1289-1291
+        else if (r.p_value == prevP) r.q_value = prevQ;                                // :1293-1298
+        else {
+            r.q_value = r.p_value * (float)n / (float)i;                               // :1302
+            if (r.q_value > 1) r.q_value = 1;
+            prevP = r.p_value;
+            prevQ = r.q_value;
+        }
+        i++;
+    }
+}
+
+}  // namespace
+
+cudaError_t run_transposons(const TransposonJob& job, const ppp_interval* intervals, size_t n, ppp_tp_result* results, uint32_t* order, std::string& err) {
+    if (n == 0) return cudaSuccess;
+    if (n >= 0x7fffffffull / 32) { err = "too many intervals"; return cudaSuccess; }
+    const int W = job.W;
+    std::vector<uint32_t> perm, groupStart;
+    sortIntervals(intervals, n, perm, groupStart);
+    std::vector<TpDev> tp;
+    localIntervals(*job.slots, intervals, perm, tp);
     const uint32_t nGroups = (uint32_t)groupStart.size() - 1;
     const uint32_t nPairs = (uint32_t)job.nPairs;
     const uint32_t nBlocks = std::max<uint32_t>(1, (nPairs + kPartThreads - 1) / kPartThreads);
@@ -275,34 +349,166 @@ cudaError_t run_transposons(const TransposonJob& job, const ppp_interval* interv
     TCK(cudaMemcpyAsync(z.data(), bZ.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     TCK(cudaMemcpyAsync(p.data(), bP.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     TCK(cudaStreamSynchronize(s));
-    for (size_t k = 0; k < n; ++k) {
-        ppp_tp_result& r = results[k];
-        for (int o = 0; o < 32; ++o) r.histogram[o] = hist[k * 32 + o];
-        r.reads_plus = rp[k];
-        r.reads_minus = rm[k];
-        r.z = z[k];
-        r.p = p[k];
-        r.p_value = (float)p[k];  // :1271
-        r.q_value = 1.0f;         // :187
-        if (order) order[k] = perm[k];
-    }
-    // q-values, :1276-1312: stable sort by p ascending (:1281), walked from the largest p with i = 1, 2, ...
-    std::vector<uint32_t> byP(n);
-    for (size_t k = 0; k < n; ++k) byP[k] = (uint32_t)k;
-    std::stable_sort(byP.begin(), byP.end(), [&](uint32_t a, uint32_t b) { return results[a].p_value < results[b].p_value; });
-    unsigned i = 1;
-    float prevP = 1, prevQ = 1;
-    for (size_t k = n; k-- > 0;) {
-        ppp_tp_result& r = results[byP[k]];
-        if (r.histogram[job.ppIdx] / (r.reads_plus + r.reads_minus) < 0.2) r.q_value = 1;  // :1289-1291
-        else if (r.p_value == prevP) r.q_value = prevQ;                                    // :1293-1298
-        else {
-            r.q_value = r.p_value * (float)n / (float)i;                                   // :1302
-            if (r.q_value > 1) r.q_value = 1;
-            prevP = r.p_value;
-            prevQ = r.q_value;
+    finishResults(n, job.ppIdx, hist, rp, rm, z, p, perm, results, order);
+    return cudaSuccess;
+}
+
+namespace {
+
+// What one context keeps on its device between the phases of the sharded run.
+struct ShardState {
+    DevBuf bHist, bScratch, bPos, bScore, bRp, bRm, bTp, bBounds, bSkip, bOutHist, bOutRp, bOutRm;
+    std::vector<uint32_t> bounds;  // host copy of k_tp_bounds' output
+};
+
+}  // namespace
+
+// The same over the contexts of a range-sharded genome (jobs[] in ascending range order, one host thread, contexts on
+// one or several devices).  A transposon that straddles a range boundary -- or lies in another range altogether -- is
+// handled exactly like in the single-context run:
+//   1. every context partitions ITS signatures by overlap and finds, per (transposon, overlap), its local list and range;
+//   2. the iterator history of step 3 above depends only on the length of the whole list (sum of the local lengths) and
+//      on whether a transposon consumed it to the end (true iff it did so in every context): those two facts are
+//      combined on the host and replayed by k_tp_skip on the first context's device;
+//   3. the sums are chained: context after context continues the sequential single-precision additions from the
+//      values of its predecessor (k_tp_sums_chain), so the additions happen in global position order;
+//   4. mean / sigma / z / p on the last context's device, q-values on the host.
+cudaError_t run_transposons_sharded(const TransposonJob* jobs, const int* devices, int nShards, const ppp_interval* intervals, size_t n, ppp_tp_result* results,
+                                    uint32_t* order, std::string& err) {
+    if (nShards <= 0) { err = "no contexts"; return cudaSuccess; }
+    if (n == 0) return cudaSuccess;
+    if (n >= 0x7fffffffull / 32) { err = "too many intervals"; return cudaSuccess; }
+    const int W = jobs[0].W, ppIdx = jobs[0].ppIdx;
+    for (int k = 1; k < nShards; ++k)
+        if (jobs[k].W != W || jobs[k].ppIdx != ppIdx) { err = "contexts differ in their overlap range"; return cudaSuccess; }
+    std::vector<uint32_t> perm, groupStart;
+    sortIntervals(intervals, n, perm, groupStart);
+    const uint32_t nGroups = (uint32_t)groupStart.size() - 1;
+    const uint32_t nTp = (uint32_t)n;
+    const size_t nCells = n * (size_t)W;
+    const unsigned th = 128;
+    std::vector<ShardState> st(nShards);
+    std::vector<TpDev> tp;
+
+    // 1. local partitions and bounds
+    for (int k = 0; k < nShards; ++k) {
+        const TransposonJob& job = jobs[k];
+        ShardState& S = st[k];
+        TCK(cudaSetDevice(devices[k]));
+        localIntervals(*job.slots, intervals, perm, tp);
+        const uint32_t nPairs = (uint32_t)job.nPairs;
+        const uint32_t nBlocks = std::max<uint32_t>(1, (nPairs + kPartThreads - 1) / kPartThreads);
+        const size_t histWords = (size_t)32 * nBlocks;
+        const size_t scratchWords = exclusive_scan_scratch_words(histWords);
+        TCK(S.bHist.alloc(histWords * 4));
+        TCK(S.bScratch.alloc(scratchWords * 4));
+        TCK(S.bPos.alloc((size_t)nPairs * 4));
+        TCK(S.bScore.alloc((size_t)nPairs * 4));
+        TCK(S.bRp.alloc((size_t)nPairs * 4));
+        TCK(S.bRm.alloc((size_t)nPairs * 4));
+        TCK(S.bTp.alloc(n * sizeof(TpDev)));
+        TCK(S.bBounds.alloc(nCells * 4 * sizeof(uint32_t)));
+        TCK(S.bSkip.alloc(nCells));
+        TCK(S.bOutHist.alloc(n * 32 * sizeof(float)));
+        TCK(S.bOutRp.alloc(n * sizeof(float)));
+        TCK(S.bOutRm.alloc(n * sizeof(float)));
+        cudaStream_t s = job.stream;
+        TCK(cudaMemcpyAsync(S.bTp.p, tp.data(), n * sizeof(TpDev), cudaMemcpyHostToDevice, s));
+        TCK(cudaMemsetAsync(S.bHist.p, 0, histWords * 4, s));
+        if (nPairs) {
+            k_ov_count<<<nBlocks, kPartThreads, 0, s>>>(job.pairs, nPairs, S.bHist.as<uint32_t>(), nBlocks);
+            *job.launches += 1;
         }
-        i++;
+        TCK(exclusive_scan_u32(S.bHist.as<uint32_t>(), S.bHist.as<uint32_t>(), histWords, S.bScratch.as<uint32_t>(), scratchWords, s, job.launches));
+        if (nPairs) {
+            k_ov_scatter<<<nBlocks, kPartThreads, 0, s>>>(job.pairs, job.pairFdr, nPairs, S.bHist.as<uint32_t>(), nBlocks, S.bPos.as<uint32_t>(), S.bScore.as<float>(),
+                                                          S.bRp.as<float>(), S.bRm.as<float>());
+            *job.launches += 1;
+        }
+        k_tp_bounds<<<(nTp * W + th - 1) / th, th, 0, s>>>(S.bTp.as<TpDev>(), nTp, W, S.bHist.as<uint32_t>(), nBlocks, nPairs, S.bPos.as<uint32_t>(), S.bBounds.as<uint32_t>());
+        *job.launches += 1;
+        TCK(cudaGetLastError());
+        S.bounds.resize(nCells * 4);
+        TCK(cudaMemcpyAsync(S.bounds.data(), S.bBounds.p, nCells * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));  // (pageable: the copy is synchronous for the host)
+        TCK(cudaStreamSynchronize(s));  // tp is refilled for the next context
+    }
+
+    // 2. whole-list facts -> iterator history, replayed on the first context's device
+    std::vector<uint32_t> whole(nCells * 4);
+    for (size_t g = 0; g < nCells; ++g) {
+        uint64_t len = 0;
+        bool consumed = true;
+        for (int k = 0; k < nShards; ++k) {
+            const uint32_t* b = st[k].bounds.data() + g * 4;
+            len += b[1] - b[0];
+            consumed = consumed && b[3] == b[1];
+        }
+        if (len > 0xfffffffeull) { err = "more than 2^32 signatures in one list"; return cudaSuccess; }
+        uint32_t* w = whole.data() + g * 4;
+        w[0] = 0;
+        w[1] = (uint32_t)len;
+        w[2] = 0;
+        w[3] = consumed ? (uint32_t)len : 0xffffffffu;  // k_tp_skip only asks whether [3] == [1]
+    }
+    std::vector<uint8_t> skip(nCells);
+    {
+        TCK(cudaSetDevice(devices[0]));
+        cudaStream_t s = jobs[0].stream;
+        DevBuf bWhole, bGroups;
+        TCK(bWhole.alloc(nCells * 4 * sizeof(uint32_t)));
+        TCK(bGroups.alloc(groupStart.size() * 4));
+        TCK(cudaMemcpyAsync(bWhole.p, whole.data(), nCells * 4 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        TCK(cudaMemcpyAsync(bGroups.p, groupStart.data(), groupStart.size() * 4, cudaMemcpyHostToDevice, s));
+        k_tp_skip<<<(nGroups * W + th - 1) / th, th, 0, s>>>(st[0].bTp.as<TpDev>(), bGroups.as<uint32_t>(), nGroups, W, bWhole.as<uint32_t>(), st[0].bSkip.as<uint8_t>());
+        *jobs[0].launches += 1;
+        TCK(cudaGetLastError());
+        TCK(cudaMemcpyAsync(skip.data(), st[0].bSkip.p, nCells, cudaMemcpyDeviceToHost, s));
+        TCK(cudaStreamSynchronize(s));
+    }
+
+    // 3. chained sums (running values travel through the host; kilobytes to a few megabytes)
+    std::vector<float> hist(n * 32, 0.f), rp(n, 0.f), rm(n, 0.f);
+    for (int k = 0; k < nShards; ++k) {
+        ShardState& S = st[k];
+        TCK(cudaSetDevice(devices[k]));
+        cudaStream_t s = jobs[k].stream;
+        if (k > 0) TCK(cudaMemcpyAsync(S.bSkip.p, skip.data(), nCells, cudaMemcpyHostToDevice, s));
+        TCK(cudaMemcpyAsync(S.bOutHist.p, hist.data(), n * 32 * sizeof(float), cudaMemcpyHostToDevice, s));
+        TCK(cudaMemcpyAsync(S.bOutRp.p, rp.data(), n * sizeof(float), cudaMemcpyHostToDevice, s));
+        TCK(cudaMemcpyAsync(S.bOutRm.p, rm.data(), n * sizeof(float), cudaMemcpyHostToDevice, s));
+        k_tp_sums_chain<<<(nTp * W + th - 1) / th, th, 0, s>>>(nTp, W, ppIdx, S.bBounds.as<uint32_t>(), S.bSkip.as<uint8_t>(), S.bScore.as<float>(), S.bRp.as<float>(),
+                                                               S.bRm.as<float>(), S.bOutHist.as<float>(), S.bOutRp.as<float>(), S.bOutRm.as<float>());
+        *jobs[k].launches += 1;
+        TCK(cudaGetLastError());
+        if (k + 1 < nShards) {
+            TCK(cudaMemcpyAsync(hist.data(), S.bOutHist.p, n * 32 * sizeof(float), cudaMemcpyDeviceToHost, s));
+            TCK(cudaMemcpyAsync(rp.data(), S.bOutRp.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+            TCK(cudaMemcpyAsync(rm.data(), S.bOutRm.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+            TCK(cudaStreamSynchronize(s));
+        }
+    }
+
+    // 4. statistics where the final sums are
+    {
+        ShardState& S = st[nShards - 1];
+        TCK(cudaSetDevice(devices[nShards - 1]));
+        cudaStream_t s = jobs[nShards - 1].stream;
+        DevBuf bZ, bP;
+        TCK(bZ.alloc(n * sizeof(double)));
+        TCK(bP.alloc(n * sizeof(double)));
+        const double pi = 3.14159265358979323846;  // :50
+        const double coeff = 0.01 * 1 / sqrt(2 * pi);
+        k_tp_stats<<<(nTp + th - 1) / th, th, 0, s>>>(nTp, W, ppIdx, coeff, S.bOutHist.as<float>(), bZ.as<double>(), bP.as<double>());
+        *jobs[nShards - 1].launches += 1;
+        TCK(cudaGetLastError());
+        std::vector<double> z(n), p(n);
+        TCK(cudaMemcpyAsync(hist.data(), S.bOutHist.p, n * 32 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        TCK(cudaMemcpyAsync(rp.data(), S.bOutRp.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        TCK(cudaMemcpyAsync(rm.data(), S.bOutRm.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        TCK(cudaMemcpyAsync(z.data(), bZ.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        TCK(cudaMemcpyAsync(p.data(), bP.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        TCK(cudaStreamSynchronize(s));
+        finishResults(n, ppIdx, hist, rp, rm, z, p, perm, results, order);
     }
     return cudaSuccess;
 }

@@ -22,4 +22,9 @@ struct TransposonJob {
 // input index of each result.  `err` is set (and cudaSuccess returned) for argument errors.
 cudaError_t run_transposons(const TransposonJob& job, const ppp_interval* intervals, size_t n, ppp_tp_result* results, uint32_t* order, std::string& err);
 
+// The same over the contexts of a range-sharded genome: jobs[k] / devices[k] in ascending range order.  Transposons that
+// straddle a range boundary get the sums (and the iterator history) of the unsharded run.
+cudaError_t run_transposons_sharded(const TransposonJob* jobs, const int* devices, int nShards, const ppp_interval* intervals, size_t n, ppp_tp_result* results,
+                                    uint32_t* order, std::string& err);
+
 }  // namespace pppk

@@ -72,6 +72,7 @@ void printHelp(std::ostream& os) {
           "B200 BUILD\n"
           "    --max-overlap NT, --min-overlap NT\n          Background overlap range (compile-time constants 3 and 23 in the reference).\n"
           "    --device ORDINAL\n          CUDA device to run on. Default: 0.\n"
+          "    --gpus N\n          Cut the genome into N position ranges, one per GPU starting at --device. Default: 1.\n"
           "    --threads N\n          Worker threads that inflate BGZF blocks of BAM input. Default: all hardware threads.\n\n"
           "VERSION\n    pingpongpro version: 1.0 (B200)\n    Last update Apr 2014\n";
 }
@@ -84,7 +85,7 @@ ParseResult parseCommandLine(AppOptions& o, int argc, char const** argv) {
         {"b", "browserTracks", false}, {"s", "min-stack-height", true}, {"i", "input", true}, {"l", "min-alignment-length", true},
         {"L", "max-alignment-length", true}, {"m", "multi-hits", true}, {"o", "output", true}, {"p", "plot", false},
         {"t", "transposons", true}, {"T", "predict-transposons", true}, {"v", "verbose", false},
-        {"", "max-overlap", true}, {"", "min-overlap", true}, {"", "device", true}, {"", "threads", true},
+        {"", "max-overlap", true}, {"", "min-overlap", true}, {"", "device", true}, {"", "gpus", true}, {"", "threads", true},
     };
     bool predictSet = false;
     std::string multiHits = "weighted";
@@ -124,6 +125,7 @@ ParseResult parseCommandLine(AppOptions& o, int argc, char const** argv) {
         else if (ln == "max-overlap") { if (!parseInt(value, 0, u, "max-overlap")) return PARSE_ERROR; o.maxOverlap = (int)u; }
         else if (ln == "min-overlap") { if (!parseInt(value, 0, u, "min-overlap")) return PARSE_ERROR; o.minOverlap = (int)u; }
         else if (ln == "device") { if (!parseInt(value, 0, u, "device")) return PARSE_ERROR; o.device = (int)u; }
+        else if (ln == "gpus") { if (!parseInt(value, 1, u, "gpus")) return PARSE_ERROR; o.gpus = (int)u; }
         else if (ln == "threads") { if (!parseInt(value, 0, u, "threads")) return PARSE_ERROR; o.threads = (int)u; }
         else if (ln == "input") {
             if (!hasExtension(value, {".bam", ".sam"})) {

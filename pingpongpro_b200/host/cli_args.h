@@ -21,6 +21,7 @@ struct AppOptions {
     // extensions of the B200 build (not in the reference; its values are compile-time constants :108-113)
     int minOverlap = 3, maxOverlap = 23;        // --min-overlap / --max-overlap
     int device = 0;                             // --device
+    int gpus = 1;                               // --gpus: position-range shards, one CUDA context each
     int threads = 0;                            // --threads: BGZF inflate workers (0 = all hardware threads)
 };
 

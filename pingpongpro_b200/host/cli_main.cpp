@@ -96,6 +96,14 @@ struct Uploader {
         for (size_t i = 0; i < n; ++i) v[old + i] = e[i].read;
         return v.size() < kBatch || !ctx || flush(contig);  // without a context yet, reads simply accumulate
     }
+    // the same for a range shard: keeps the reads whose key lies in [lo, hi) of their contig (the context's own range plus
+    // its halo -- a superset is fine, the context ignores what it does not own)
+    bool addRunRouted(size_t contig, const ExtractedRead* e, size_t n, uint32_t lo, uint32_t hi) {
+        std::vector<ppp_read>& v = pending[contig];
+        for (size_t i = 0; i < n; ++i)
+            if (e[i].read.key >= lo && e[i].read.key < hi) v.push_back(e[i].read);
+        return v.size() < kBatch || !ctx || flush(contig);
+    }
     bool flushAll() {
         for (size_t c = 0; c < pending.size(); ++c)
             if (!pending[c].empty() && !flush(c)) return false;
@@ -107,7 +115,81 @@ struct Uploader {
     }
 };
 
-std::vector<ScoredTransposon> scoreTransposons(ppp_ctx* ctx, const TransposonsPerGenome& tp, bool& ok) {
+// One position range of the genome on one GPU (--gpus N; a single shard without a range otherwise).
+struct Shard {
+    ppp_ctx* ctx = nullptr;
+    Uploader up;
+    uint64_t rangeBegin = 0, rangeEnd = 0;
+    std::vector<uint32_t> lo, hi;  // per contig: keys worth sending to this shard (own range + minus-strand halo)
+    std::string error;             // ppp_last_error() is per thread: kept by the thread that saw it
+};
+
+// Keys of every contig that a shard accepts (ppp_config.range_begin / range_end, ppp_b200.h): its own range, up to
+// 64 keys beyond the contig when it holds the contig's last base, plus max_overlap keys of halo.
+void shardKeyRanges(Shard& sh, const std::vector<uint64_t>& lengths, int maxOverlap) {
+    sh.lo.assign(lengths.size(), 0);
+    sh.hi.assign(lengths.size(), 0);
+    uint64_t cum = 0;
+    for (size_t c = 0; c < lengths.size(); ++c) {
+        const uint64_t L = lengths[c];
+        const uint64_t lo = sh.rangeBegin > cum ? sh.rangeBegin - cum : 0;
+        const bool holdsEnd = sh.rangeEnd >= cum + L;  // ... and with it every key beyond the contig (the context reports those)
+        const uint64_t hi = holdsEnd ? 0xffffffffull : (sh.rangeEnd > cum ? sh.rangeEnd - cum : 0);
+        if (L != 0 && lo < L && hi > lo) {
+            sh.lo[c] = (uint32_t)lo;
+            sh.hi[c] = (uint32_t)std::min<uint64_t>(hi + (uint64_t)maxOverlap + 1, 0xffffffffull);
+        }
+        cum += L;
+    }
+}
+
+int shardError(const std::vector<Shard>& shards) {
+    for (size_t k = 0; k < shards.size(); ++k)
+        if (!shards[k].error.empty()) std::cerr << "pingpongpro: " << shards[k].error << (shards.size() > 1 ? " (shard " + std::to_string(k) + ")" : std::string()) << std::endl;
+    return 1;
+}
+
+// ppp_height_hist + ppp_scan of every shard; with several shards one thread each, because the calls meet inside the
+// group's all-reduces (height histogram, grouped counts).
+bool histAndScan(std::vector<Shard>& shards, ppp_group* group) {
+    auto one = [&](Shard& sh) {
+        if (ppp_height_hist(sh.ctx, nullptr, nullptr) != PPP_OK) { sh.error = std::string("height histogram failed: ") + ppp_last_error(); return false; }
+        if (ppp_scan(sh.ctx, nullptr, nullptr) != PPP_OK) { sh.error = std::string("overlap scan failed: ") + ppp_last_error(); return false; }
+        return true;
+    };
+    if (shards.size() == 1) return one(shards[0]);
+    std::vector<std::thread> th;
+    std::vector<char> ok(shards.size(), 0);
+    for (size_t k = 0; k < shards.size(); ++k)
+        th.emplace_back([&, k] {
+            ok[k] = one(shards[k]) ? 1 : 0;
+            if (!ok[k]) ppp_group_abort(group);  // the other ranks must not wait for this one
+        });
+    for (std::thread& t : th) t.join();
+    for (char c : ok)
+        if (!c) return false;
+    return true;
+}
+
+// ppp_score of every shard (no collective inside); the loci of the shards concatenate in rank order = (contig, position).
+bool scoreAll(std::vector<Shard>& shards, uint32_t minStackHeight, uint32_t* nBins, float* cells, std::vector<ppp_locus>& joined, const ppp_locus*& loci, size_t& nLoci) {
+    joined.clear();
+    for (size_t k = 0; k < shards.size(); ++k) {
+        const ppp_locus* l = nullptr;
+        size_t n = 0;
+        if (ppp_score(shards[k].ctx, minStackHeight, k == 0 ? nBins : nullptr, nullptr, k == 0 ? cells : nullptr, nullptr, &l, &n) != PPP_OK) {
+            shards[k].error = std::string("scoring failed: ") + ppp_last_error();
+            return false;
+        }
+        if (shards.size() == 1) { loci = l; nLoci = n; return true; }
+        joined.insert(joined.end(), l, l + n);
+    }
+    loci = joined.data();
+    nLoci = joined.size();
+    return true;
+}
+
+std::vector<ScoredTransposon> scoreTransposons(std::vector<Shard>& shards, const TransposonsPerGenome& tp, bool& ok) {
     std::vector<ScoredTransposon> rows;
     std::vector<ppp_interval> iv;
     for (const auto& kv : tp)
@@ -121,7 +203,12 @@ std::vector<ScoredTransposon> scoreTransposons(ppp_ctx* ctx, const TransposonsPe
         }
     std::vector<ppp_tp_result> res(iv.size());
     std::vector<uint32_t> order(iv.size());
-    ok = iv.empty() || ppp_transposons(ctx, iv.data(), iv.size(), res.data(), order.data()) == PPP_OK;
+    if (shards.size() == 1) ok = iv.empty() || ppp_transposons(shards[0].ctx, iv.data(), iv.size(), res.data(), order.data()) == PPP_OK;
+    else {
+        std::vector<ppp_ctx*> ctxs;
+        for (Shard& sh : shards) ctxs.push_back(sh.ctx);
+        ok = iv.empty() || ppp_transposons_sharded(ctxs.data(), (int)ctxs.size(), iv.data(), iv.size(), res.data(), order.data()) == PPP_OK;
+    }
     if (ok)
         for (size_t k = 0; k < rows.size(); ++k) rows[order[k]].r = res[k];  // results come back in (contig, start, end) order = our order
     return rows;
@@ -149,8 +236,11 @@ static int run(int argc, char const** argv) {
 
     std::vector<std::string> names;   // bamNameStore
     std::vector<uint64_t> lengths;
-    ppp_ctx* ctx = nullptr;
-    Uploader up;
+    // --gpus N: the genome is cut into N position ranges, one context (GPU) each; SURVEY §8(e)
+    const int nShards = options.gpus > 1 ? options.gpus : 1;
+    std::vector<Shard> shards(nShards);
+    ppp_group* group = nullptr;
+    bool haveContexts = false;
     double totalReadCount = 0;
     const int W = options.maxOverlap - options.minOverlap + 1, ppIdx = 10 - options.minOverlap;
 
@@ -162,27 +252,50 @@ static int run(int argc, char const** argv) {
             std::cerr << "Failed to open input file: " << path << std::endl;  // :1485
             return 1;
         }
-        if (!ctx) {
+        if (!haveContexts) {
             names = reader.names();
             lengths = reader.lengths();
             if (lengths.empty()) lengths.push_back(0);
             mark("header read");
-            up.prepare(lengths.size());
             // CUDA start-up (cuInit + context creation, 0.4-0.8 s on the measured boxes) is a fixed cost.  Letting the
             // decode workers run ahead meanwhile (on a helper thread, or simply by starting them first) was measured
             // twice and does not pay: with all cores busy the driver's start-up takes 1.1-1.4 s instead of 0.5 s.
-            ppp_config cfg;
-            memset(&cfg, 0, sizeof cfg);
-            cfg.device = options.device;
-            cfg.n_contigs = (uint32_t)lengths.size();
-            cfg.contig_lengths = lengths.data();
-            cfg.min_overlap = options.minOverlap;
-            cfg.max_overlap = options.maxOverlap;
-            cfg.pingpong_overlap = 10;
-            cfg.multi_hits = options.countMultiHits;
-            if (ppp_init(&cfg, &ctx) != PPP_OK) return gpuError("cannot initialise the CUDA context");
+            uint64_t total = 0;
+            for (uint64_t L : lengths) total += L;
+            int nDevices = 1;
+            if (nShards > 1) {
+                if (ppp_device_count(&nDevices) != PPP_OK || nDevices < 1) return gpuError("cannot initialise the CUDA context");
+                if (ppp_group_create(nShards, &group) != PPP_OK) return gpuError("cannot create the context group");
+            }
+            for (int k = 0; k < nShards; ++k) {
+                Shard& sh = shards[k];
+                sh.up.prepare(lengths.size());
+                ppp_config cfg;
+                memset(&cfg, 0, sizeof cfg);
+                cfg.device = nShards > 1 ? (options.device + k) % nDevices : options.device;  // more shards than GPUs: they share
+                cfg.n_contigs = (uint32_t)lengths.size();
+                cfg.contig_lengths = lengths.data();
+                cfg.min_overlap = options.minOverlap;
+                cfg.max_overlap = options.maxOverlap;
+                cfg.pingpong_overlap = 10;
+                cfg.multi_hits = options.countMultiHits;
+                if (nShards > 1) {
+                    sh.rangeBegin = total * (uint64_t)k / (uint64_t)nShards;
+                    sh.rangeEnd = total * (uint64_t)(k + 1) / (uint64_t)nShards;
+                    if (sh.rangeEnd == sh.rangeBegin) {
+                        std::cerr << "pingpongpro: --gpus " << nShards << " leaves a GPU without a single position of this genome" << std::endl;
+                        return 1;
+                    }
+                    cfg.range_begin = sh.rangeBegin;
+                    cfg.range_end = sh.rangeEnd;
+                    shardKeyRanges(sh, lengths, options.maxOverlap);
+                }
+                if (ppp_init(&cfg, &sh.ctx) != PPP_OK) return gpuError("cannot initialise the CUDA context");
+                if (group && ppp_group_attach(sh.ctx, group, k) != PPP_OK) return gpuError("cannot attach the context to its group");
+                if (!sh.up.attach(sh.ctx)) return gpuError("cannot allocate pinned upload buffers");
+            }
+            haveContexts = true;
             mark("ppp_init done");
-            if (!up.attach(ctx)) return gpuError("cannot allocate pinned upload buffers");
         }
         ExtractOptions eo;
         eo.minLen = options.minAlignmentLength;
@@ -202,8 +315,13 @@ static int run(int argc, char const** argv) {
                 const int32_t contig = e[k].contig;
                 size_t j = k;
                 for (; j < m && e[j].contig == contig; ++j) totalReadCount += (double)e[j].weight;  // :488, file order
-                if ((size_t)contig >= up.pending.size()) foreignContig = true;  // header differs: reported below
-                else if (!up.addRun((size_t)contig, e + k, j - k)) return gpuError("upload failed");
+                if ((size_t)contig >= lengths.size()) foreignContig = true;  // header differs: reported below
+                else if (nShards == 1) {
+                    if (!shards[0].up.addRun((size_t)contig, e + k, j - k)) return gpuError("upload failed");
+                } else {
+                    for (Shard& sh : shards)
+                        if (sh.hi[contig] && !sh.up.addRunRouted((size_t)contig, e + k, j - k, sh.lo[contig], sh.hi[contig])) return gpuError("upload failed");
+                }
                 k = j;
             }
             if (err) {
@@ -224,8 +342,10 @@ static int run(int argc, char const** argv) {
         stopwatch(options.verbosity);
     }
     mark("decode done");
-    if (!up.flushAll()) return gpuError("upload failed");
-    if (ppp_stacks_finish(ctx) != PPP_OK) return gpuError("stack build failed");
+    for (Shard& sh : shards)
+        if (!sh.up.flushAll()) return gpuError("upload failed");
+    for (Shard& sh : shards)
+        if (ppp_stacks_finish(sh.ctx) != PPP_OK) return gpuError("stack build failed");
     mark("stacks finished");
 
     TransposonsPerGenome transposons;
@@ -252,8 +372,7 @@ static int run(int argc, char const** argv) {
     }
 
     stopwatch("Binning stacks", options.verbosity);
-    if (ppp_height_hist(ctx, nullptr, nullptr) != PPP_OK) return gpuError("height histogram failed");
-    if (ppp_scan(ctx, nullptr, nullptr) != PPP_OK) return gpuError("overlap scan failed");
+    if (!histAndScan(shards, group)) return shardError(shards);
     stopwatch(options.verbosity);
 
     stopwatch("Calculating FDR for putative ping-pong signatures", options.verbosity);
@@ -261,8 +380,8 @@ static int run(int argc, char const** argv) {
     std::vector<float> cells((size_t)W * PPP_HEIGHT_SCORE_BINS * 4);
     const ppp_locus* loci = nullptr;
     size_t nLoci = 0;
-    if (ppp_score(ctx, options.minStackHeight, &nBins, nullptr, options.plot ? cells.data() : nullptr, nullptr, &loci, &nLoci) != PPP_OK)
-        return gpuError("scoring failed");
+    std::vector<ppp_locus> joined;  // several shards: their loci, concatenated
+    if (!scoreAll(shards, options.minStackHeight, &nBins, options.plot ? cells.data() : nullptr, joined, loci, nLoci)) return shardError(shards);
     stopwatch(options.verbosity);
 
     if (options.plot) {  // generateGroupedStackCountsPlot, :944-981
@@ -295,7 +414,7 @@ static int run(int argc, char const** argv) {
     if (!options.transposonFiles.empty()) {
         stopwatch("Checking input transposons for ping-pong activity", options.verbosity);
         bool ok = true;
-        std::vector<ScoredTransposon> rows = scoreTransposons(ctx, transposons, ok);
+        std::vector<ScoredTransposon> rows = scoreTransposons(shards, transposons, ok);
         if (!ok) return gpuError("transposon scoring failed");
         stopwatch(options.verbosity);
         stopwatch("Writing input transposons to file", options.verbosity);
@@ -311,7 +430,7 @@ static int run(int argc, char const** argv) {
     if (options.predictTransposonsRange > 0) {
         stopwatch("Predicting transposons based on ping-pong activity", options.verbosity);
         // prediction walks ALL overlap-10 signatures, whatever -s says (:1327)
-        if (options.minStackHeight != 0 && ppp_score(ctx, 0, nullptr, nullptr, nullptr, nullptr, &loci, &nLoci) != PPP_OK) return gpuError("scoring failed");
+        if (options.minStackHeight != 0 && !scoreAll(shards, 0, nullptr, nullptr, joined, loci, nLoci)) return shardError(shards);
         std::map<unsigned, std::vector<unsigned> > positions;
         for (size_t i = 0; i < nLoci; ++i) positions[loci[i].contig].push_back(loci[i].position);
         // findSuppressedTransposons has indexed the signature map with every annotated contig (:1203-1206), which
@@ -321,7 +440,7 @@ static int run(int argc, char const** argv) {
         TransposonsPerGenome putative;
         predictTransposons(positions, names, options.predictTransposonsRange, putative);
         bool ok = true;
-        std::vector<ScoredTransposon> rows = scoreTransposons(ctx, putative, ok);
+        std::vector<ScoredTransposon> rows = scoreTransposons(shards, putative, ok);
         if (!ok) return gpuError("transposon scoring failed");
         stopwatch(options.verbosity);
         stopwatch("Writing predicted transposons to file", options.verbosity);
