@@ -727,7 +727,9 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
     invalidateResults(c);
     Trace tr("height_hist");
     // signatures are ~0.1-0.3 per read on real densities; a scan that overflows the store reports the exact count and is re-run once
-    uint64_t want = c->cfgPairCapacity ? c->cfgPairCapacity : std::max<uint64_t>((uint64_t)1 << 20, c->readsSubmitted / 3);
+    // (a shard sizes the store for one signature per read: a re-run repeats the collectives, which every rank would have
+    // to agree on -- a lone re-run is caught as a size mismatch by the in-process group, and must simply not happen)
+    uint64_t want = c->cfgPairCapacity ? c->cfgPairCapacity : std::max<uint64_t>((uint64_t)1 << 20, c->allreduce ? c->readsSubmitted : c->readsSubmitted / 3);
     if (want < c->pairCapacity) want = c->pairCapacity;
     int rc = ensurePairCapacity(c, want);
     if (rc) return rc;
