@@ -233,3 +233,27 @@ def test_malformed_sam_record_fails_at_the_same_place(tmp_path, threads):
     p.write_text("@SQ\tSN:c1\tLN:5000\n" + good * 2 + "r\t0\tc1\t5\t255\t25Q\t*\t0\t0\tACGT\tIIII\n")  # bad CIGAR operation
     with pytest.raises(ValueError, match="Failed to read record"):
         host.decode_file(str(p), threads=threads)
+
+
+def test_sam_mapped_file_equals_streamed_input(tmp_path, monkeypatch):
+    """Batch mode parses a regular SAM file through a memory mapping (jobs are windows of the file) and anything else
+    (or any file with PPP_NO_MMAP=1) through buffered reads: same records either way, including a line
+    longer than one 2 MB job (a tag of 5 MB), CRLF, blank lines and a last line without a line feed."""
+    long_tag = "XX:Z:" + "A" * (5 << 20)
+    head, rest = SAM_EDGE.split("r1", 1)
+    text = head + "r0\t0\tc1\t150\t255\t25M\t*\t0\t0\tACGTACGTAAACGTACGTACGTACG\t*\t" + long_tag + "\tNH:i:3\nr1" + rest
+    big = tmp_path / "big.sam"
+    subprocess.check_call([os.path.join(_build.BIN, "ppp_synth"), "--genome", "tiny", "--reads", "60000", "--seed", "10", "--out", str(big)])
+    body = "".join(l for l in big.read_text().splitlines(keepends=True) if not l.startswith("@"))
+    hdr = "".join(l for l in big.read_text().splitlines(keepends=True) if l.startswith("@"))
+    cases = {"edge_long.sam": text, "big_noeol.sam": hdr + body.rstrip("\n"), "header_only.sam": hdr, "one.sam": hdr + body.splitlines(keepends=True)[0]}
+    for name, content in cases.items():
+        p = tmp_path / name
+        p.write_bytes(content.encode())
+        seq = host.decode_file(str(p), threads=1)
+        mapped = host.decode_file(str(p), threads=4)
+        monkeypatch.setenv("PPP_NO_MMAP", "1")
+        streamed = host.decode_file(str(p), threads=4)
+        monkeypatch.delenv("PPP_NO_MMAP")
+        _decoded_equal(seq, mapped)
+        _decoded_equal(seq, streamed)
