@@ -36,6 +36,9 @@ PPP_API double ppp_fe_total_weight(const ppp_fe* fe);
 /* Records seen in the file / records kept after the filters of :415, :426, :458. */
 PPP_API uint64_t ppp_fe_n_records(const ppp_fe* fe);
 PPP_API uint64_t ppp_fe_n_kept(const ppp_fe* fe);
+/* Test hook (threads > 1, BAM): runs of BGZF blocks whose guessed first record boundary was rejected by the in-order
+ * check and which were therefore decoded again from the true boundary (host/aln_reader.h). */
+PPP_API uint64_t ppp_fe_rejected_guesses(const ppp_fe* fe);
 
 /* Transposon annotation input, replaces readTransposonsFromFile (pingpongpro.cpp:993-1175) incl. the format
  * detection of main() (:1543-1554).  Files are read in order; contig names that `contig_names` lacks are

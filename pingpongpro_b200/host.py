@@ -66,6 +66,8 @@ def host_lib() -> C.CDLL:
         L.ppp_fe_total_weight.restype = C.c_double
         L.ppp_fe_n_records.argtypes = [C.c_void_p]
         L.ppp_fe_n_records.restype = C.c_uint64
+        L.ppp_fe_rejected_guesses.argtypes = [C.c_void_p]
+        L.ppp_fe_rejected_guesses.restype = C.c_uint64
         L.ppp_fe_n_kept.argtypes = [C.c_void_p]
         L.ppp_fe_n_kept.restype = C.c_uint64
         L.ppp_annot_read.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_void_p)]
@@ -138,6 +140,7 @@ class DecodedFile:
         self.total_weight = total_weight
         self.n_records = n_records
         self.n_kept = n_kept
+        self.rejected_guesses = 0  # BAM, threads > 1: runs of blocks decoded again because the guessed record boundary was wrong
 
 
 def decode_file(path: str, min_len: int = 24, max_len: int = 32, mode: str = "weighted", threads: int = 1) -> DecodedFile:
@@ -160,7 +163,9 @@ def decode_file(path: str, min_len: int = 24, max_len: int = 32, mode: str = "we
                 reads.append(np.frombuffer(buf, dtype=READ_DTYPE).copy())
             else:
                 reads.append(np.empty(0, dtype=READ_DTYPE))
-        return DecodedFile(names, lengths, reads, float(L.ppp_fe_total_weight(h)), int(L.ppp_fe_n_records(h)), int(L.ppp_fe_n_kept(h)))
+        d = DecodedFile(names, lengths, reads, float(L.ppp_fe_total_weight(h)), int(L.ppp_fe_n_records(h)), int(L.ppp_fe_n_kept(h)))
+        d.rejected_guesses = int(L.ppp_fe_rejected_guesses(h))
+        return d
     finally:
         L.ppp_fe_free(h)
 

@@ -25,6 +25,96 @@ struct AlnReader::NameMap {
 static const size_t kRawChunk = 4u << 20;
 
 // ---------------------------------------------------------------------------
+// BAM record decoding (shared by the sequential walk and the batch workers)
+// ---------------------------------------------------------------------------
+static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type);
+
+static size_t bamTypeSize(char t) {
+    switch (t) {
+        case 'A': case 'c': case 'C': return 1;
+        case 's': case 'S': return 2;
+        case 'i': case 'I': case 'f': return 4;
+        default: return 0;
+    }
+}
+
+static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type) {
+    size_t sz = bamTypeSize(type);
+    if (sz) { if (n < sz) return false; used = sz; return true; }
+    if (type == 'Z' || type == 'H') {
+        const void* z = memchr(p, 0, n);
+        if (!z) return false;
+        used = (size_t)((const uint8_t*)z - p) + 1;
+        return true;
+    }
+    if (type == 'B') {
+        if (n < 5) return false;
+        size_t es = bamTypeSize((char)p[0]);
+        uint32_t cnt;
+        memcpy(&cnt, p + 1, 4);
+        if (!es || n < 5 + es * (size_t)cnt) return false;
+        used = 5 + es * (size_t)cnt;
+        return true;
+    }
+    return false;
+}
+
+// `p` points behind the block_size word of one record of `blockSize` bytes.  False: malformed.
+static bool parseBamRecord(const uint8_t* p, uint32_t blockSize, std::vector<uint32_t>& cigarScratch, AlnView& out) {
+    if (blockSize < 32) return false;
+    int32_t refID, pos;
+    memcpy(&refID, p, 4);
+    memcpy(&pos, p + 4, 4);
+    uint32_t lReadName = p[8];
+    uint16_t nCigar, flag;
+    memcpy(&nCigar, p + 12, 2);
+    memcpy(&flag, p + 14, 2);
+    uint32_t lSeq;
+    memcpy(&lSeq, p + 16, 4);
+    size_t off = 32 + lReadName;
+    size_t need = off + 4 * (size_t)nCigar + ((size_t)lSeq + 1) / 2 + lSeq;
+    if (need > blockSize) return false;
+    out.rID = refID;
+    out.beginPos = pos;
+    out.flag = flag;
+    cigarScratch.resize(nCigar);
+    if (nCigar) memcpy(cigarScratch.data(), p + off, 4 * (size_t)nCigar);  // unaligned source
+    out.cigar = cigarScratch.data();
+    out.nCigar = nCigar;
+    off += 4 * (size_t)nCigar;
+    out.seqText = nullptr;
+    out.seq4 = p + off;
+    out.lSeq = lSeq;
+    off += ((size_t)lSeq + 1) / 2 + lSeq;
+    // tags
+    out.hasNH = false;
+    out.nh = 1;
+    const uint8_t* t = p + off;
+    size_t n = blockSize - off;
+    while (n >= 3) {
+        char type = (char)t[2];
+        size_t used = 0;
+        if (!skipBamTag(t + 3, n - 3, used, type)) break;
+        if (t[0] == 'N' && t[1] == 'H') {
+            const uint8_t* v = t + 3;
+            switch (type) {
+                case 'c': out.hasNH = true; out.nh = (uint32_t)(int32_t)(int8_t)v[0]; break;
+                case 'C': out.hasNH = true; out.nh = v[0]; break;
+                case 's': { int16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = (uint32_t)(int32_t)x; break; }
+                case 'S': { uint16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = x; break; }
+                case 'i': { int32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = (uint32_t)x; break; }
+                case 'I': { uint32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = x; break; }
+                default: break;
+            }
+            break;
+        }
+        t += 3 + used;
+        n -= 3 + used;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
 // parallel BGZF inflate: one reader thread cuts the file into jobs of whole blocks, a pool inflates them, the
 // consumer takes the jobs back in file order.  BGZF blocks are independent deflate streams, so this is exact.
 // ---------------------------------------------------------------------------
@@ -37,10 +127,24 @@ struct AlnReader::Pipeline {
         size_t rawCap = 0, outCap = 0, outLen = 0;
         std::vector<Block> blocks;
         bool done = false, bad = false;
+        // batch mode: what the inflating worker decoded itself -- the records in out[specStart, tailOff), their kept
+        // bytes in recOut[kHeadroom, ...)
+        std::vector<uint8_t> recOut;
+        uint64_t nParsed = 0;
+        size_t specStart = 0, tailOff = 0;
+        bool parsed = false;    // a start was guessed and the records behind it were decoded
+        bool parseBad = false;  // ... up to a malformed one at tailOff
         void needRaw(size_t n) { if (rawCap < n) { raw.reset(new uint8_t[n]); rawCap = n; } }
         void needOut(size_t n) { if (outCap < n) { out.reset(new uint8_t[n]); outCap = n; } }
     };
     FILE* fp;
+    // batch mode (AlnReader::startBatches): the worker that inflated a job also decodes its records, block by block,
+    // while they are in its cache -- see findRecordStart and AlnReader::BamBatcher
+    static constexpr size_t kHeadroom = 1024;  // bytes left free in front of Job::recOut for the consumer's stitched records
+    AlnReader::RecordFn fn = nullptr;
+    void* user = nullptr;
+    int32_t nRef = 0;
+    bool noGuess = false;  // test knob (PPP_BAM_NO_GUESS): every job goes through the consumer's own decoding
     std::mutex mu;
     std::condition_variable cvWork, cvDone, cvSpace;
     std::deque<std::shared_ptr<Job> > todo, ordered;  // ordered: every job in file order until consumed
@@ -64,12 +168,17 @@ struct AlnReader::Pipeline {
         j->outLen = 0;
         j->blocks.clear();
         j->done = j->bad = false;
+        j->recOut.clear();
+        j->nParsed = 0;
+        j->specStart = j->tailOff = 0;
+        j->parsed = j->parseBad = false;
         std::lock_guard<std::mutex> l(mu);
         if (pool.size() < 256) pool.push_back(std::move(j));
         j.reset();
     }
 
-    Pipeline(FILE* f, int threads) : fp(f), maxOutstanding((size_t)threads * 3 + 2) {
+    Pipeline(FILE* f, int threads, AlnReader::RecordFn fn_ = nullptr, void* user_ = nullptr, int32_t nRef_ = 0)
+        : fp(f), fn(fn_), user(user_), nRef(nRef_), noGuess(getenv("PPP_BAM_NO_GUESS") != nullptr), maxOutstanding((size_t)threads * 3 + 2) {
         reader = std::thread([this] { readLoop(); });
         for (int i = 0; i < threads; ++i) workers.emplace_back([this] { workLoop(); });
     }
@@ -141,6 +250,92 @@ struct AlnReader::Pipeline {
             }
         }
     }
+    // ---- batch mode: record decoding inside the inflate worker ----
+    struct RecordWalk {
+        enum State { kSearching, kWalking, kGaveUp } state = kSearching;
+        size_t start = 0, pos = 0;
+        std::vector<uint32_t> cigarScratch;
+        AlnView view;
+    };
+    // Does a BAM record that is consistent with itself and with the header start at data[q]?  (block_size, refID,
+    // next_refID within the reference table, the variable-length fields inside the block, a NUL behind the read name.)
+    // `known` = bytes available.  1 = yes, 0 = no, -1 = the fixed part is not fully available.
+    int plausibleRecord(const uint8_t* data, size_t q, size_t known) const {
+        if (known - q < 36) return -1;
+        uint32_t bs, lSeq;
+        int32_t refID, pos, nextRef;
+        uint16_t nCigar;
+        memcpy(&bs, data + q, 4);
+        memcpy(&refID, data + q + 4, 4);
+        memcpy(&pos, data + q + 8, 4);
+        const uint32_t lName = data[q + 12];
+        memcpy(&nCigar, data + q + 16, 2);
+        memcpy(&lSeq, data + q + 20, 4);
+        memcpy(&nextRef, data + q + 24, 4);
+        if (bs < 32 || bs > (1u << 24) || refID < -1 || refID >= nRef || nextRef < -1 || nextRef >= nRef || pos < -1 || lName == 0 || lSeq > (1u << 24)) return 0;
+        if (32 + (size_t)lName + 4 * (size_t)nCigar + ((size_t)lSeq + 1) / 2 + lSeq > bs) return 0;
+        const size_t nul = q + 4 + 32 + lName - 1;
+        if (nul < known && data[nul] != 0) return 0;
+        return 1;
+    }
+    // A guess at the first record boundary in a job's output: the first offset (among the first 64 KB) from which eight
+    // consecutive plausible records follow, or as many as the known bytes hold (at least three, unless the job ends).
+    // >= 0: offset; -1: more bytes are needed to decide; -2: none.
+    // The guess is only ever USED after the in-order consumer has verified it against the true boundary.
+    long findRecordStart(const uint8_t* data, size_t known, size_t total) const {
+        const size_t limit = std::min<size_t>(known, 65536);
+        for (size_t p = 0; p < limit; ++p) {
+            size_t q = p;
+            int count = 0;
+            for (;;) {
+                int r = plausibleRecord(data, q, known);
+                if (r == 0) { count = -1; break; }
+                if (r < 0) break;  // ran out of known bytes
+                uint32_t bs;
+                memcpy(&bs, data + q, 4);
+                q += 4 + (size_t)bs;
+                if (++count == 8) break;
+                if (q >= known) break;
+            }
+            if (count < 0) continue;
+            if (count >= 8 || count >= 3 || (known == total && count >= 1)) return (long)p;
+            if (known < total) return -1;  // plausible so far, too short to tell
+        }
+        if (known < 65536 && known < total) return -1;
+        return -2;
+    }
+    // Decodes the records that are complete within out[0, known).
+    void decodeAvailable(Job& job, RecordWalk& w, size_t known) {
+        const uint8_t* data = job.out.get();
+        if (w.state == RecordWalk::kSearching) {
+            long s = findRecordStart(data, known, job.outLen);
+            if (s == -1) return;
+            if (s < 0) { w.state = RecordWalk::kGaveUp; return; }
+            w.state = RecordWalk::kWalking;
+            w.start = w.pos = (size_t)s;
+        }
+        if (w.state != RecordWalk::kWalking || job.parseBad) return;
+        while (known - w.pos >= 4) {
+            uint32_t bs;
+            memcpy(&bs, data + w.pos, 4);
+            if (known - w.pos - 4 < (size_t)bs) break;
+            if (!parseBamRecord(data + w.pos + 4, bs, w.cigarScratch, w.view)) { job.parseBad = true; break; }
+            fn(user, w.view, job.recOut);
+            ++job.nParsed;
+            w.pos += 4 + (size_t)bs;
+        }
+    }
+    // Next job in file order (inflated, and in batch mode decoded); null at the end of the file or after requestStop.
+    // The caller hands it back with recycle().
+    std::shared_ptr<Job> nextJob() {
+        std::unique_lock<std::mutex> l(mu);
+        cvDone.wait(l, [this] { return stop || (!ordered.empty() && ordered.front()->done) || (ordered.empty() && eof); });
+        if (stop || ordered.empty()) return nullptr;
+        std::shared_ptr<Job> j = ordered.front();
+        ordered.pop_front();
+        cvSpace.notify_one();
+        return j;
+    }
     void workLoop() {
         for (;;) {
             std::shared_ptr<Job> job;
@@ -155,25 +350,34 @@ struct AlnReader::Pipeline {
             bool bad = false;
             z_stream zs;
             bool zsLive = false;
+            RecordWalk walk;
+            if (fn && !noGuess) job->recOut.resize(kHeadroom);
             for (const Block& b : job->blocks) {
                 if (bad) break;
                 if (b.isize == 0) continue;
                 // own decoder first; zlib takes over (and judges the block) whenever that one declines
-                if (fast_inflate(job->raw.get() + b.off, b.clen, job->out.get() + b.outOff, b.isize)) continue;
-                if (!zsLive) {
-                    memset(&zs, 0, sizeof zs);
-                    if (inflateInit2(&zs, -15) != Z_OK) { bad = true; break; }
-                    zsLive = true;
+                if (!fast_inflate(job->raw.get() + b.off, b.clen, job->out.get() + b.outOff, b.isize)) {
+                    if (!zsLive) {
+                        memset(&zs, 0, sizeof zs);
+                        if (inflateInit2(&zs, -15) != Z_OK) { bad = true; break; }
+                        zsLive = true;
+                    }
+                    inflateReset(&zs);
+                    zs.next_in = job->raw.get() + b.off;
+                    zs.avail_in = (uInt)b.clen;
+                    zs.next_out = job->out.get() + b.outOff;
+                    zs.avail_out = b.isize;
+                    int rc = inflate(&zs, Z_FINISH);
+                    if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = true; break; }
                 }
-                inflateReset(&zs);
-                zs.next_in = job->raw.get() + b.off;
-                zs.avail_in = (uInt)b.clen;
-                zs.next_out = job->out.get() + b.outOff;
-                zs.avail_out = b.isize;
-                int rc = inflate(&zs, Z_FINISH);
-                if (rc != Z_STREAM_END || zs.avail_out != 0) bad = true;
+                if (fn && !noGuess) decodeAvailable(*job, walk, b.outOff + b.isize);  // the block just written is still in this core's cache
             }
             if (zsLive) inflateEnd(&zs);
+            if (fn && !noGuess && !bad && walk.state == RecordWalk::kWalking) {
+                job->parsed = true;
+                job->specStart = walk.start;
+                job->tailOff = walk.pos;
+            }
             {
                 std::lock_guard<std::mutex> l(mu);
                 job->bad = job->bad || bad;
@@ -374,6 +578,7 @@ struct AlnReader::SamPipeline {
     // consumed jobs are reused: their buffers keep their capacity, so the steady state allocates nothing (fresh
     // multi-megabyte allocations mean mmap / page faults / munmap, which serialise the threads on the address space)
     std::vector<std::shared_ptr<Job> > pool;
+    std::shared_ptr<Job> held;  // batch mode: the job whose output the caller is looking at
     std::shared_ptr<Job> obtain() {
         std::lock_guard<std::mutex> l(mu);
         if (pool.empty()) return std::make_shared<Job>();
@@ -551,256 +756,114 @@ struct AlnReader::SamPipeline {
 };
 
 // ---------------------------------------------------------------------------
-// BAM record decoding (shared by the sequential walk and the batch workers)
-// ---------------------------------------------------------------------------
-static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type);
-
-static size_t bamTypeSize(char t) {
-    switch (t) {
-        case 'A': case 'c': case 'C': return 1;
-        case 's': case 'S': return 2;
-        case 'i': case 'I': case 'f': return 4;
-        default: return 0;
-    }
-}
-
-static bool skipBamTag(const uint8_t* p, size_t n, size_t& used, char type) {
-    size_t sz = bamTypeSize(type);
-    if (sz) { if (n < sz) return false; used = sz; return true; }
-    if (type == 'Z' || type == 'H') {
-        const void* z = memchr(p, 0, n);
-        if (!z) return false;
-        used = (size_t)((const uint8_t*)z - p) + 1;
-        return true;
-    }
-    if (type == 'B') {
-        if (n < 5) return false;
-        size_t es = bamTypeSize((char)p[0]);
-        uint32_t cnt;
-        memcpy(&cnt, p + 1, 4);
-        if (!es || n < 5 + es * (size_t)cnt) return false;
-        used = 5 + es * (size_t)cnt;
-        return true;
-    }
-    return false;
-}
-
-// `p` points behind the block_size word of one record of `blockSize` bytes.  False: malformed.
-static bool parseBamRecord(const uint8_t* p, uint32_t blockSize, std::vector<uint32_t>& cigarScratch, AlnView& out) {
-    if (blockSize < 32) return false;
-    int32_t refID, pos;
-    memcpy(&refID, p, 4);
-    memcpy(&pos, p + 4, 4);
-    uint32_t lReadName = p[8];
-    uint16_t nCigar, flag;
-    memcpy(&nCigar, p + 12, 2);
-    memcpy(&flag, p + 14, 2);
-    uint32_t lSeq;
-    memcpy(&lSeq, p + 16, 4);
-    size_t off = 32 + lReadName;
-    size_t need = off + 4 * (size_t)nCigar + ((size_t)lSeq + 1) / 2 + lSeq;
-    if (need > blockSize) return false;
-    out.rID = refID;
-    out.beginPos = pos;
-    out.flag = flag;
-    cigarScratch.resize(nCigar);
-    if (nCigar) memcpy(cigarScratch.data(), p + off, 4 * (size_t)nCigar);  // unaligned source
-    out.cigar = cigarScratch.data();
-    out.nCigar = nCigar;
-    off += 4 * (size_t)nCigar;
-    out.seqText = nullptr;
-    out.seq4 = p + off;
-    out.lSeq = lSeq;
-    off += ((size_t)lSeq + 1) / 2 + lSeq;
-    // tags
-    out.hasNH = false;
-    out.nh = 1;
-    const uint8_t* t = p + off;
-    size_t n = blockSize - off;
-    while (n >= 3) {
-        char type = (char)t[2];
-        size_t used = 0;
-        if (!skipBamTag(t + 3, n - 3, used, type)) break;
-        if (t[0] == 'N' && t[1] == 'H') {
-            const uint8_t* v = t + 3;
-            switch (type) {
-                case 'c': out.hasNH = true; out.nh = (uint32_t)(int32_t)(int8_t)v[0]; break;
-                case 'C': out.hasNH = true; out.nh = v[0]; break;
-                case 's': { int16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = (uint32_t)(int32_t)x; break; }
-                case 'S': { uint16_t x; memcpy(&x, v, 2); out.hasNH = true; out.nh = x; break; }
-                case 'i': { int32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = (uint32_t)x; break; }
-                case 'I': { uint32_t x; memcpy(&x, v, 4); out.hasNH = true; out.nh = x; break; }
-                default: break;
-            }
-            break;
-        }
-        t += 3 + used;
-        n -= 3 + used;
-    }
-    return true;
-}
-
-// ---------------------------------------------------------------------------
-// BAM batch mode, the third stage behind the parallel inflate: ONE thread walks the record boundaries of the inflated
-// chunks (4 bytes per record; a record that straddles two chunks is stitched into a side buffer), the workers decode
-// the records of a chunk and apply the record function, the consumer receives the outputs in file order.
+// BAM batch mode, consumer side.  The worker that inflated a job has already decoded the records that lie wholly
+// inside it, starting at a boundary it GUESSED (Pipeline::findRecordStart); this stage, which sees the jobs in file
+// order, knows the true boundary -- it owns the bytes of the record that the previous job left unfinished -- and
+//   * accepts the guess when those bytes plus the job's bytes in front of the guess are a whole number of records
+//     (walking from a true boundary and landing on the guess proves that the guess is one), decoding just these few
+//     stitched records itself, or
+//   * otherwise decodes the whole job again from the true boundary (never observed on real files; the tests force it).
+// Either way the records and their order are exactly those of the sequential walk.
 // ---------------------------------------------------------------------------
 struct AlnReader::BamBatcher {
     typedef AlnReader::RecordFn RecordFn;
-    struct Batch {
-        std::shared_ptr<Pipeline::Job> chunk;  // keeps the inflated bytes alive
-        std::vector<uint8_t> stitched;         // records that began in an earlier chunk (block_size word included)
-        std::vector<uint32_t> stitchedOff, chunkOff;  // offsets of the block_size words, file order: stitched first
-        std::vector<uint8_t> out;
-        uint64_t nRecords = 0;
-        bool bad = false, done = false;
-    };
     Pipeline* src;
     RecordFn fn;
     void* user;
-    std::vector<uint8_t> carry;  // bytes the sequential header parser had read ahead, then incomplete records
-    std::mutex mu;
-    std::condition_variable cvWork, cvDone, cvSpace;
-    std::deque<std::shared_ptr<Batch> > todo, ordered;
-    bool eof = false, stop = false;
-    size_t maxOutstanding;
-    std::thread walker;
-    std::vector<std::thread> workers;
+    std::vector<uint8_t> carry;  // starts at a true record boundary: bytes the header parser had read ahead, then unfinished records
+    std::shared_ptr<Pipeline::Job> held;  // the job whose output the caller is looking at
+    std::vector<uint8_t> stitchedOut, redoOut;
+    std::vector<uint32_t> cigarScratch;
+    bool finished = false;
+    uint64_t nGuessesRejected = 0;
 
-    BamBatcher(Pipeline* p, int threads, RecordFn f, void* u, const uint8_t* initial, size_t nInitial)
-        : src(p), fn(f), user(u), carry(initial, initial + nInitial), maxOutstanding((size_t)threads * 3 + 2) {
-        walker = std::thread([this] { walkLoop(); });
-        for (int i = 0; i < threads; ++i) workers.emplace_back([this] { workLoop(); });
-    }
-    ~BamBatcher() {
-        {
-            std::lock_guard<std::mutex> l(mu);
-            stop = true;
+    BamBatcher(Pipeline* p, RecordFn f, void* u, const uint8_t* initial, size_t nInitial) : src(p), fn(f), user(u), carry(initial, initial + nInitial) {}
+
+    // Decodes the whole records at the front of `carry` into `out` and removes them.  False: a malformed record.
+    bool drainCarry(std::vector<uint8_t>& out, uint64_t& nRecords) {
+        AlnView v;
+        size_t q = 0;
+        bool ok = true;
+        while (carry.size() - q >= 4) {
+            uint32_t bs;
+            memcpy(&bs, carry.data() + q, 4);
+            if (carry.size() - q - 4 < (size_t)bs) break;
+            if (!parseBamRecord(carry.data() + q + 4, bs, cigarScratch, v)) { ok = false; break; }
+            fn(user, v, out);
+            ++nRecords;
+            q += 4 + (size_t)bs;
         }
-        cvWork.notify_all();
-        cvSpace.notify_all();
-        cvDone.notify_all();
-        // the walker may be waiting inside src->next(): stopping the source first releases it
-        src->requestStop();
-        walker.join();
-        for (auto& w : workers) w.join();
+        carry.erase(carry.begin(), carry.begin() + q);
+        return ok;
     }
-    bool push(std::shared_ptr<Batch> b) {
-        std::unique_lock<std::mutex> l(mu);
-        cvSpace.wait(l, [this] { return stop || ordered.size() < maxOutstanding; });
-        if (stop) return false;
-        ordered.push_back(b);
-        todo.push_back(b);
-        cvWork.notify_one();
+    // True when carry + data[0, guess) is a whole number of records (then `guess` is a record boundary).
+    bool guessHolds(const uint8_t* data, size_t guess) const {
+        // the records in question: all of carry, continued by the first `guess` bytes of the job
+        const size_t total = carry.size() + guess;
+        auto byteAt = [&](size_t i) { return i < carry.size() ? carry[i] : data[i - carry.size()]; };
+        size_t q = 0;
+        while (q < total) {
+            if (total - q < 4) return false;
+            const uint32_t bs = (uint32_t)byteAt(q) | ((uint32_t)byteAt(q + 1) << 8) | ((uint32_t)byteAt(q + 2) << 16) | ((uint32_t)byteAt(q + 3) << 24);
+            if (total - q - 4 < (size_t)bs) return false;
+            q += 4 + (size_t)bs;
+        }
         return true;
     }
-    void finish(bool bad) {
-        if (bad) {
-            auto b = std::make_shared<Batch>();
-            b->bad = true;
-            b->done = true;
-            std::lock_guard<std::mutex> l(mu);
-            ordered.push_back(b);
+    // Next job's records in file order.  False at the end of the input.
+    bool next(const uint8_t*& out, size_t& outLen, uint64_t& nRecords, bool& bad) {
+        out = nullptr;
+        outLen = 0;
+        nRecords = 0;
+        bad = false;
+        if (held) { src->recycle(held); }
+        if (finished) return false;
+        std::shared_ptr<Pipeline::Job> j = src->nextJob();
+        if (!j) {
+            finished = true;
+            if (carry.empty()) return false;
+            bad = true;  // a truncated record at the end is malformed
+            return true;
         }
-        std::lock_guard<std::mutex> l(mu);
-        eof = true;
-        cvDone.notify_all();
-        cvWork.notify_all();
-    }
-    void walkLoop() {
-        for (;;) {
-            const uint8_t* data = nullptr;
-            size_t len = 0;
-            bool bad = false;
-            std::shared_ptr<Pipeline::Job> chunk;
-            if (!src->next(data, len, bad, &chunk)) { finish(!carry.empty()); return; }  // a truncated record at the end is malformed
-            if (bad) { finish(true); return; }
-            auto b = std::make_shared<Batch>();
-            b->chunk = chunk;
-            size_t p = 0;
-            // records that began earlier (the carry may hold several: the header parser reads whole blocks ahead)
-            size_t cpos = 0;
-            while (cpos < carry.size()) {
-                size_t have = carry.size() - cpos;
-                size_t want = 4;
-                if (have >= 4) {
-                    uint32_t bs;
-                    memcpy(&bs, carry.data() + cpos, 4);
-                    want = (size_t)bs + 4;
+        held = j;
+        if (j->bad) { bad = true; finished = true; return true; }
+        const uint8_t* data = j->out.get();
+        const size_t len = j->outLen;
+        if (j->parsed && guessHolds(data, j->specStart)) {
+            stitchedOut.clear();
+            if (j->specStart || !carry.empty()) {
+                carry.insert(carry.end(), data, data + j->specStart);
+                if (!drainCarry(stitchedOut, nRecords)) { bad = true; finished = true; }
+            }
+            if (!bad) {
+                // the worker left room in front of its output for the few stitched records
+                std::vector<uint8_t>& ro = j->recOut;
+                size_t begin = Pipeline::kHeadroom;
+                if (stitchedOut.size() <= begin) {
+                    begin -= stitchedOut.size();
+                    if (!stitchedOut.empty()) memcpy(ro.data() + begin, stitchedOut.data(), stitchedOut.size());
+                } else {
+                    ro.insert(ro.begin() + (ptrdiff_t)begin, stitchedOut.begin(), stitchedOut.end());
                 }
-                if (have >= want && want > 4) {
-                    b->stitchedOff.push_back((uint32_t)b->stitched.size());
-                    b->stitched.insert(b->stitched.end(), carry.begin() + cpos, carry.begin() + cpos + want);
-                    cpos += want;
-                    continue;
-                }
-                if (have >= 4 && want == 4) { b->stitchedOff.push_back((uint32_t)b->stitched.size()); b->stitched.insert(b->stitched.end(), carry.begin() + cpos, carry.begin() + cpos + 4); cpos += 4; continue; }  // block_size 0: the decoder rejects it
-                if (p >= len) break;  // chunk exhausted, record still incomplete
-                size_t take = std::min(want - have, len - p);
-                carry.insert(carry.end(), data + p, data + p + take);
-                p += take;
-            }
-            if (cpos) carry.erase(carry.begin(), carry.begin() + cpos);
-            // whole records inside this chunk
-            // (this loop is the one serial stage of the BAM path; the chunk was written by another core, so the lines
-            // ahead are requested early -- 27 -> 9 ns per record)
-            b->chunkOff.reserve(len / 64);
-            while (carry.empty() && len - p >= 4) {
-                __builtin_prefetch(data + p + 2048);
-                __builtin_prefetch(data + p + 2112);
-                uint32_t bs;
-                memcpy(&bs, data + p, 4);
-                if (len - p < (size_t)bs + 4) break;
-                b->chunkOff.push_back((uint32_t)p);
-                p += (size_t)bs + 4;
-            }
-            if (carry.empty() && p < len) carry.assign(data + p, data + len);
-            if (!push(b)) return;
-        }
-    }
-    void workLoop() {
-        std::vector<uint32_t> cigarScratch;
-        AlnView v;
-        for (;;) {
-            std::shared_ptr<Batch> b;
-            {
-                std::unique_lock<std::mutex> l(mu);
-                cvWork.wait(l, [this] { return stop || !todo.empty() || eof; });
-                if (stop) return;
-                if (todo.empty()) { if (eof) return; continue; }
-                b = todo.front();
-                todo.pop_front();
-            }
-            b->out.reserve((b->stitchedOff.size() + b->chunkOff.size()) * 12);
-            auto one = [&](const uint8_t* rec) {
-                uint32_t bs;
-                memcpy(&bs, rec, 4);
-                if (!parseBamRecord(rec + 4, bs, cigarScratch, v)) return false;
-                fn(user, v, b->out);
-                ++b->nRecords;
+                out = ro.data() + begin;
+                outLen = ro.size() - begin;
+                nRecords += j->nParsed;
+                carry.assign(data + j->tailOff, data + len);
+                if (j->parseBad) { bad = true; finished = true; }
                 return true;
-            };
-            bool ok = true;
-            for (size_t k = 0; ok && k < b->stitchedOff.size(); ++k) ok = one(b->stitched.data() + b->stitchedOff[k]);
-            const uint8_t* base = b->chunk ? b->chunk->out.get() : nullptr;
-            for (size_t k = 0; ok && k < b->chunkOff.size(); ++k) ok = one(base + b->chunkOff[k]);
-            {
-                std::lock_guard<std::mutex> l(mu);
-                b->bad = !ok;
-                b->done = true;
             }
-            src->recycle(b->chunk);  // the inflated bytes are no longer needed: only the extracted output waits for the consumer
-            cvDone.notify_all();
+            out = stitchedOut.data();
+            outLen = stitchedOut.size();
+            return true;
         }
-    }
-    std::shared_ptr<Batch> next() {
-        std::unique_lock<std::mutex> l(mu);
-        cvDone.wait(l, [this] { return (!ordered.empty() && ordered.front()->done) || (ordered.empty() && eof); });
-        if (ordered.empty()) return nullptr;
-        std::shared_ptr<Batch> b = ordered.front();
-        ordered.pop_front();
-        cvSpace.notify_one();
-        return b;
+        // no usable guess: everything from the true boundary, here
+        if (j->parsed) ++nGuessesRejected;
+        redoOut.clear();
+        carry.insert(carry.end(), data, data + len);
+        if (!drainCarry(redoOut, nRecords)) { bad = true; finished = true; }
+        out = redoOut.data();
+        outLen = redoOut.size();
+        return true;
     }
 };
 
@@ -1079,28 +1142,28 @@ void AlnReader::startBatches(int threads, RecordFn fn, void* user) {
     batchFn_ = fn;
     batchUser_ = user;
     if (isBam_) {
-        pipe_ = new Pipeline(fp_, threads);
-        bamBatch_ = new BamBatcher(pipe_, threads, fn, user, buf_.data() + cur_, end_ - cur_);
+        pipe_ = new Pipeline(fp_, threads, fn, user, (int32_t)names_.size());
+        bamBatch_ = new BamBatcher(pipe_, fn, user, buf_.data() + cur_, end_ - cur_);
     } else {
         samPipe_ = new SamPipeline(fp_, threads, buf_.data() + cur_, end_ - cur_, nameMap_->m, fn, user);
     }
     cur_ = end_ = 0;
 }
 
-bool AlnReader::nextBatch(std::vector<uint8_t>& out, uint64_t& nRecords, int& error) {
-    out.clear();
+bool AlnReader::nextBatch(const uint8_t*& out, size_t& outLen, uint64_t& nRecords, int& error) {
+    out = nullptr;
+    outLen = 0;
     nRecords = 0;
     error = 0;
     if (batchFailed_ || !batchFn_) return false;
     if (bamBatch_) {
-        std::shared_ptr<BamBatcher::Batch> b = bamBatch_->next();
-        if (!b) return false;
-        out.swap(b->out);
-        nRecords = b->nRecords;
+        bool bad = false;
+        if (!bamBatch_->next(out, outLen, nRecords, bad)) return false;
         nRecords_ += nRecords;
-        if (b->bad) { error = 1; batchFailed_ = true; }
+        if (bad) { error = 1; batchFailed_ = true; }
         return true;
     }
+    if (samPipe_->held) samPipe_->recycle(samPipe_->held);  // the caller is done with the previous job's output
     std::shared_ptr<SamPipeline::Job> j = samPipe_->next();
     if (!j) return false;
     if (j->unknownName) {  // a contig that is missing from the header: this job is redone here, where the name store may grow
@@ -1113,13 +1176,16 @@ bool AlnReader::nextBatch(std::vector<uint8_t>& out, uint64_t& nRecords, int& er
             batchFn_(batchUser_, v, j->out);
         }
     }
-    out.swap(j->out);  // (the caller's previous buffer goes back into the pool with the job)
+    out = j->out.data();
+    outLen = j->out.size();
     nRecords = j->recs.size();
     nRecords_ += nRecords;
     if (j->bad) { error = 1; batchFailed_ = true; }
-    samPipe_->recycle(j);
+    samPipe_->held = j;
     return true;
 }
+
+uint64_t AlnReader::rejectedBoundaryGuesses() const { return bamBatch_ ? bamBatch_->nGuessesRejected : 0; }
 
 int AlnReader::next(AlnView& out) {
     if (!good_) return 1;

@@ -71,6 +71,9 @@ public:
 
     // Records decoded so far.
     uint64_t recordCount() const { return nRecords_; }
+    // Batch mode, BAM: runs of blocks whose guessed first record boundary the in-order check rejected (they were decoded
+    // again from the true boundary).  0 on every real file seen so far; the tests provoke it.
+    uint64_t rejectedBoundaryGuesses() const;
 
     // BAM only: inflate BGZF blocks on `n` worker threads (read-ahead, in order) while next() keeps walking the records
     // on the calling thread.  Call after open(); n <= 1 keeps the sequential path.
@@ -78,14 +81,15 @@ public:
 
     // Batch mode: the per-record work runs on the worker threads as well.  `fn` is called for every record (on any
     // thread, concurrently; it appends what it wants to keep to `out`), and nextBatch() hands the bytes produced for
-    // consecutive records back in file order.  BAM: blocks are inflated in parallel, one thread walks the record
-    // boundaries, the workers decode the records.  SAM: the workers parse whole lines.  Use either atEnd()/next() or
-    // startBatches()/nextBatch() on one file, not both.
+    // consecutive records back in file order.  BAM: the worker that inflates a run of blocks also decodes the records
+    // inside it, from a record boundary it guesses; the calling thread, which sees the runs in order, verifies every
+    // guess against the true boundary and decodes the few records that straddle two runs.  SAM: the workers parse whole
+    // lines.  Use either atEnd()/next() or startBatches()/nextBatch() on one file, not both.
     typedef void (*RecordFn)(void* user, const AlnView& v, std::vector<uint8_t>& out);
     void startBatches(int threads, RecordFn fn, void* user);
-    // False at the end of the input.  error != 0: a malformed record follows the records of this batch
-    // ("Failed to read record"); the call after that returns false.
-    bool nextBatch(std::vector<uint8_t>& out, uint64_t& nRecords, int& error);
+    // False at the end of the input.  out[0, outLen) stays valid until the next call.  error != 0: a malformed record
+    // follows the records of this batch ("Failed to read record"); the call after that returns false.
+    bool nextBatch(const uint8_t*& out, size_t& outLen, uint64_t& nRecords, int& error);
 
 private:
     bool fill();                  // refill raw buffer (decompressing BGZF blocks for BAM)
@@ -117,7 +121,7 @@ private:
     struct SamPipeline;
     SamPipeline* samPipe_ = nullptr;  // parallel SAM line parsing (startBatches)
     struct BamBatcher;
-    BamBatcher* bamBatch_ = nullptr;  // record boundary walk + parallel record decoding (startBatches)
+    BamBatcher* bamBatch_ = nullptr;  // in-order verification of the workers' record decoding (startBatches)
     RecordFn batchFn_ = nullptr;
     void* batchUser_ = nullptr;
     bool batchFailed_ = false;

@@ -306,12 +306,13 @@ static int run(int argc, char const** argv) {
         // reads in file order (the order of the float additions of -m weighted, :487) and feeds the uploads
         int nt = options.threads > 0 ? options.threads : (int)std::thread::hardware_concurrency();
         reader.startBatches(nt > 2 ? nt - 2 : 1, extract_record_fn, &eo);
-        std::vector<uint8_t> bytes;
+        const uint8_t* bytes;
+        size_t nBytes;
         uint64_t nRecords;
         int err;
-        while (reader.nextBatch(bytes, nRecords, err)) {
-            const ExtractedRead* e = reinterpret_cast<const ExtractedRead*>(bytes.data());
-            for (size_t k = 0, m = bytes.size() / sizeof(ExtractedRead); k < m;) {  // runs of one contig are appended in bulk
+        while (reader.nextBatch(bytes, nBytes, nRecords, err)) {
+            const ExtractedRead* e = reinterpret_cast<const ExtractedRead*>(bytes);
+            for (size_t k = 0, m = nBytes / sizeof(ExtractedRead); k < m;) {  // runs of one contig are appended in bulk
                 const int32_t contig = e[k].contig;
                 size_t j = k;
                 for (; j < m && e[j].contig == contig; ++j) totalReadCount += (double)e[j].weight;  // :488, file order

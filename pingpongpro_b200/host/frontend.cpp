@@ -26,13 +26,14 @@ int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int
     if (threads > 1) {
         ExtractOptions opts = o;
         rd.startBatches(threads, extract_record_fn, &opts);
-        std::vector<uint8_t> bytes;
+        const uint8_t* bytes;
+        size_t nBytes;
         uint64_t n;
         int err;
-        while (rd.nextBatch(bytes, n, err)) {
+        while (rd.nextBatch(bytes, nBytes, n, err)) {
             out.nRecords += n;
-            const ExtractedRead* e = reinterpret_cast<const ExtractedRead*>(bytes.data());
-            for (size_t k = 0, m = bytes.size() / sizeof(ExtractedRead); k < m; ++k) {
+            const ExtractedRead* e = reinterpret_cast<const ExtractedRead*>(bytes);
+            for (size_t k = 0, m = nBytes / sizeof(ExtractedRead); k < m; ++k) {
                 if ((size_t)e[k].contig >= out.reads.size()) {  // contig that is missing from the header
                     out.names = rd.names();
                     out.lengths = rd.lengths();
@@ -45,6 +46,7 @@ int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int
             }
             if (err) return 2;
         }
+        out.nRejectedGuesses = rd.rejectedBoundaryGuesses();
         return rd.good() ? 0 : 2;
     }
     AlnView v;
@@ -103,6 +105,7 @@ const ppp_read* ppp_fe_reads(const ppp_fe* fe, int c) { return fe->f.reads[c].da
 double ppp_fe_total_weight(const ppp_fe* fe) { return fe->f.totalWeight; }
 uint64_t ppp_fe_n_records(const ppp_fe* fe) { return fe->f.nRecords; }
 uint64_t ppp_fe_n_kept(const ppp_fe* fe) { return fe->f.nKept; }
+uint64_t ppp_fe_rejected_guesses(const ppp_fe* fe) { return fe->f.nRejectedGuesses; }
 
 struct ppp_annot_impl {
     std::vector<std::string> names;

@@ -74,6 +74,7 @@ struct DecodedFile {
     std::vector<std::vector<ppp_read> > reads;
     double totalWeight = 0;  // :488
     uint64_t nRecords = 0, nKept = 0;
+    uint64_t nRejectedGuesses = 0;  // AlnReader::rejectedBoundaryGuesses()
 };
 
 // 0 = ok, 1 = cannot open, 2 = malformed record.

@@ -142,12 +142,12 @@ def _bgzf_payload(path):
     return b"".join(out)
 
 
-def _bgzf_write(path, payload, block_bytes):
+def _bgzf_write(path, payload, block_bytes, level=6):
     import zlib
     with open(path, "wb") as f:
         for o in list(range(0, len(payload), block_bytes)) + [None]:
             chunk = b"" if o is None else payload[o:o + block_bytes]  # None: the empty end-of-file block
-            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            c = zlib.compressobj(level, zlib.DEFLATED, -15)
             body = c.compress(chunk) + c.flush()
             f.write(bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0]) + (len(body) + 25).to_bytes(2, "little") + body
                     + zlib.crc32(chunk).to_bytes(4, "little") + len(chunk).to_bytes(4, "little"))
@@ -257,3 +257,50 @@ def test_sam_mapped_file_equals_streamed_input(tmp_path, monkeypatch):
         monkeypatch.delenv("PPP_NO_MMAP")
         _decoded_equal(seq, mapped)
         _decoded_equal(seq, streamed)
+
+
+def _bam_record(ref_id, pos, name, cigar_len, seq_len, tags=b""):
+    import struct
+    cigar = struct.pack("<I", cigar_len << 4)  # <n>M
+    body = (struct.pack("<iiBBHHHIiii", ref_id, pos, len(name) + 1, 255, 4681, 1, 0, seq_len, -1, -1, 0) + name + b"\0" + cigar
+            + bytes([0x12] * ((seq_len + 1) // 2)) + bytes([30] * seq_len) + tags)   # 0x12 = "AC"
+    return struct.pack("<I", len(body)) + body
+
+
+def test_bam_boundary_guesses_are_verified(tmp_path, monkeypatch):
+    """Batch mode lets every worker start decoding its run of blocks at a GUESSED record boundary; the in-order stage
+    accepts a guess only if walking from the true boundary lands on it.  A 3 MB uint8-array tag filled with byte
+    sequences that look exactly like (kept) BAM records, written as stored blocks so that runs begin inside it, makes
+    the guesses wrong: those runs are decoded again from the true boundary and the result still equals the sequential
+    walk -- and no decoy becomes a read."""
+    import struct
+    src = str(tmp_path / "src.bam")
+    subprocess.check_call([os.path.join(_build.BIN, "ppp_synth"), "--genome", "tiny", "--reads", "30000", "--seed", "35", "--out", src])
+    payload = _bgzf_payload(src)
+    l_text = struct.unpack_from("<I", payload, 4)[0]
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<I", payload, p)[0]
+    p += 4
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<I", payload, p)[0]
+        p += 4 + l_name + 4
+    # walk 10 000 records in
+    q = p
+    for _ in range(10000):
+        q += 4 + struct.unpack_from("<I", payload, q)[0]
+    decoy = _bam_record(0, 777, b"x", 25, 25)
+    fill = decoy * ((3 << 20) // len(decoy))
+    carrier = _bam_record(0, 1234, b"carrier", 26, 26, b"XBBC" + struct.pack("<I", len(fill)) + fill + b"NHC\x02")
+    doctored = payload[:q] + carrier + payload[q:]
+    f = str(tmp_path / "decoy.bam")
+    _bgzf_write(f, doctored, 65280, level=0)  # stored blocks: a run of blocks (1 MB of file) is 1 MB of records
+    seq = host.decode_file(f, threads=1)
+    base = host.decode_file(src, threads=1)
+    assert seq.n_records == base.n_records + 1 and seq.n_kept == base.n_kept + 1  # the carrier itself is a 26-nt read
+    for t in (2, 5):
+        par = host.decode_file(f, threads=t)
+        _decoded_equal(seq, par)
+        assert par.rejected_guesses >= 2  # the runs that began inside the tag
+    assert host.decode_file(src, threads=4).rejected_guesses == 0
+    monkeypatch.setenv("PPP_BAM_NO_GUESS", "1")  # every run decoded by the in-order stage: same records
+    _decoded_equal(seq, host.decode_file(f, threads=3))
