@@ -3,6 +3,9 @@
 
 #include "fast_inflate.h"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <zlib.h>
@@ -421,6 +424,30 @@ struct AlnReader::Pipeline {
 // ---------------------------------------------------------------------------
 // SAM line parser and its worker-thread pipeline
 // ---------------------------------------------------------------------------
+// Offsets of the tabs of s[0, n) in pos[0, cap); returns how many were stored (cap: there may be more).
+static const int kMaxTabs = 48;
+static inline int findTabs(const char* s, size_t n, uint32_t* pos, int cap) {
+    int k = 0;
+    size_t i = 0;
+#if defined(__SSE2__)
+    const __m128i tab = _mm_set1_epi8('\t');
+    for (; i + 16 <= n; i += 16) {
+        unsigned m = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i)), tab));
+        while (m) {
+            if (k == cap) return k;
+            pos[k++] = (uint32_t)i + (uint32_t)__builtin_ctz(m);
+            m &= m - 1;
+        }
+    }
+#endif
+    for (; i < n; ++i)
+        if (s[i] == '\t') {
+            if (k == cap) return k;
+            pos[k++] = (uint32_t)i;
+        }
+    return k;
+}
+
 static inline bool parseU32(const char* s, size_t n, uint32_t& v) {
     if (n == 0) return false;
     uint64_t x = 0;
@@ -448,23 +475,19 @@ struct SamFields {
     uint32_t flag, cigarOff, nCigar, seqOff, lSeq, nh, nameOff, nameLen;
     bool hasNH;
 };
-static int parseSamLine(const char* line, size_t len, const std::unordered_map<std::string, int32_t>& names, std::string& lastName, int32_t& lastId,
+static int parseSamLine(const char* line, size_t len, const std::unordered_map<std::string, int32_t>& names, SamNameCache& cache,
                         std::vector<uint32_t>& cigars, SamFields& out) {
-    // split the 11 mandatory fields
-    const char* f[12];
-    size_t fl[12];
-    int nf = 0;
-    size_t i = 0;
-    while (nf < 11) {
-        const char* t = (const char*)memchr(line + i, '\t', len - i);
-        size_t j = t ? (size_t)(t - line) : len;
-        f[nf] = line + i;
-        fl[nf] = j - i;
-        ++nf;
-        if (j >= len) { i = len; break; }
-        i = j + 1;
+    // every tab of the line in one pass (a memchr call per field costs more than the whole rest of the parser)
+    uint32_t tabs[kMaxTabs];
+    const int nTabs = findTabs(line, len, tabs, kMaxTabs);
+    if (nTabs < 10) return 1;  // fewer than the 11 mandatory fields
+    const char* f[11];
+    size_t fl[11];
+    for (int k = 0; k < 11; ++k) {
+        const size_t b = k ? (size_t)tabs[k - 1] + 1 : 0, e = k < nTabs ? (size_t)tabs[k] : len;
+        f[k] = line + b;
+        fl[k] = e - b;
     }
-    if (nf < 11) return 1;
     uint32_t flag, pos;
     if (!parseU32(f[1], fl[1], flag) || !parseU32(f[3], fl[3], pos)) return 1;
     out.flag = flag;
@@ -474,12 +497,27 @@ static int parseSamLine(const char* line, size_t len, const std::unordered_map<s
     int rc = 0;
     if (fl[2] == 1 && f[2][0] == '*') {
         out.rID = -1;
-    } else if (lastId >= 0 && lastName.size() == fl[2] && memcmp(lastName.data(), f[2], fl[2]) == 0) {
-        out.rID = lastId;  // sorted input: long runs of one contig
     } else {
-        auto it = names.find(std::string(f[2], fl[2]));
-        if (it == names.end()) { out.rID = -2; rc = 2; }
-        else { out.rID = it->second; lastName.assign(f[2], fl[2]); lastId = it->second; }
+        // the last (up to) eight bytes of the name; RNAME is the third field, so bytes in front of it exist -- eight of
+        // them unless the line is degenerate, which takes the general map
+        const size_t nameEnd = (size_t)(f[2] - line) + fl[2];
+        SamNameCache::Entry* slot = nullptr;
+        uint64_t tail = 0;
+        if (nameEnd >= 8 && fl[2] != 0) {
+            memcpy(&tail, line + nameEnd - 8, 8);
+            if (fl[2] < 8) tail >>= 8 * (8 - fl[2]);  // (little endian: the name's bytes are the high ones)
+            slot = &cache.slot[((tail ^ fl[2]) * 0x9E3779B97F4A7C15ull) >> 58];
+        }
+        if (slot && slot->id >= 0 && slot->tail == tail && slot->len == fl[2] && (fl[2] <= 8 || memcmp(slot->name.data(), f[2], fl[2]) == 0)) {
+            out.rID = slot->id;
+        } else {
+            auto it = names.find(std::string(f[2], fl[2]));
+            if (it == names.end()) { out.rID = -2; rc = 2; }
+            else {
+                out.rID = it->second;
+                if (slot) { slot->tail = tail; slot->len = (uint32_t)fl[2]; slot->id = it->second; slot->name.assign(f[2], fl[2]); }
+            }
+        }
     }
     // CIGAR
     out.cigarOff = (uint32_t)cigars.size();
@@ -503,24 +541,34 @@ static int parseSamLine(const char* line, size_t len, const std::unordered_map<s
     // SEQ
     out.seqOff = (uint32_t)(f[9] - line);
     out.lSeq = (fl[9] == 1 && f[9][0] == '*') ? 0u : (uint32_t)fl[9];
-    // optional fields: look for NH:i:<n>
+    // optional fields: the first one that reads NH:i:<something> decides (:440-444)
     out.hasNH = false;
     out.nh = 1;
-    while (i < len) {
-        const char* t = (const char*)memchr(line + i, '\t', len - i);
-        size_t j = t ? (size_t)(t - line) : len;
-        if (j - i >= 6 && line[i] == 'N' && line[i + 1] == 'H' && line[i + 2] == ':' && line[i + 3] == 'i' && line[i + 4] == ':') {
-            const char* sv = line + i + 5;
-            size_t n = j - i - 5;
-            bool neg = (n && sv[0] == '-');
-            uint32_t v;
-            if (parseU32(sv + (neg ? 1 : 0), n - (neg ? 1 : 0), v)) {
-                out.hasNH = true;
-                out.nh = neg ? (uint32_t)(-(int64_t)v) : v;
-            }
-            break;
+    auto tryField = [&](size_t b, size_t e) {  // true: this was the NH field
+        if (e - b < 6 || memcmp(line + b, "NH:i:", 5) != 0) return false;
+        const char* sv = line + b + 5;
+        size_t n = e - b - 5;
+        bool neg = sv[0] == '-';
+        uint32_t v;
+        if (parseU32(sv + (neg ? 1 : 0), n - (neg ? 1 : 0), v)) {
+            out.hasNH = true;
+            out.nh = neg ? (uint32_t)(-(int64_t)v) : v;
         }
-        i = j + 1;
+        return true;
+    };
+    int k = 11;
+    for (; k <= nTabs; ++k) {  // field k lies between tab k-1 and tab k (or the end of the line)
+        const size_t b = (size_t)tabs[k - 1] + 1, e = k < nTabs ? (size_t)tabs[k] : len;
+        if (b >= len || tryField(b, e)) return rc;
+    }
+    if (nTabs == kMaxTabs) {  // more tabs than the table holds: the rest the slow way
+        size_t i = (size_t)tabs[kMaxTabs - 1] + 1;
+        while (i < len) {
+            const char* t = (const char*)memchr(line + i, '\t', len - i);
+            size_t j = t ? (size_t)(t - line) : len;
+            if (tryField(i, j)) break;
+            i = j + 1;
+        }
     }
     return rc;
 }
@@ -699,8 +747,7 @@ struct AlnReader::SamPipeline {
         finishInput();
     }
     void workLoop() {
-        std::string lastName;
-        int32_t lastId = -1;
+        SamNameCache cache;
         for (;;) {
             std::shared_ptr<Job> job;
             {
@@ -723,7 +770,7 @@ struct AlnReader::SamPipeline {
                 Rec r;
                 r.lineOff = (uint32_t)p;
                 r.lineLen = (uint32_t)len;
-                int rc = parseSamLine(t + p, len, names, lastName, lastId, job->cigars, r.f);
+                int rc = parseSamLine(t + p, len, names, cache, job->cigars, r.f);
                 if (rc == 1) { job->bad = true; break; }
                 job->recs.push_back(r);
                 if (rc == 2) job->unknownName = true;
@@ -885,8 +932,7 @@ void AlnReader::close() {
     delete samPipe_;
     samPipe_ = nullptr;
     extraNames_.clear();
-    lastName_.clear();
-    lastId_ = -1;
+    nameCache_.clear();
     if (fp_) fclose(fp_);
     fp_ = nullptr;
     delete nameMap_;
@@ -1100,7 +1146,7 @@ int AlnReader::nextSam(AlnView& out) {
     size_t len;
     if (atEnd() || !getLine(line, len) || len == 0) return 1;
     cigarScratch_.clear();
-    if (parseSamLine(line, len, nameMap_->m, lastName_, lastId_, cigarScratch_, fld) == 1) return 1;
+    if (parseSamLine(line, len, nameMap_->m, nameCache_, cigarScratch_, fld) == 1) return 1;
     if (fld.rID == -2) fld.rID = internExtraName(std::string(line + fld.nameOff, fld.nameLen));
     fillView(out, fld, line, cigarScratch_.data());
     ++nRecords_;

@@ -44,6 +44,21 @@ struct AlnView {
     }
 };
 
+// SAM: a small direct-mapped cache in front of the RNAME -> rID hash map (one per parsing thread).  Sorted input repeats one
+// name for millions of lines, unsorted input cycles through a handful; either way the std::string construction and the
+// hashing of the general map (60 ns per line) are avoided.  Keyed by the last (up to) eight bytes of the name and its length.
+struct SamNameCache {
+    struct Entry {
+        uint64_t tail = 0;
+        uint32_t len = 0;
+        int32_t id = -1;
+        std::string name;  // compared in full only for names longer than eight bytes
+    };
+    static const int kSlots = 64;
+    Entry slot[kSlots];
+    void clear() { for (Entry& e : slot) e = Entry(); }
+};
+
 class AlnReader {
 public:
     AlnReader();
@@ -126,8 +141,7 @@ private:
     void* batchUser_ = nullptr;
     bool batchFailed_ = false;
     std::unordered_map<std::string, int32_t> extraNames_;  // SAM contigs that are missing from the header, in order of appearance
-    std::string lastName_;        // SAM: the previous record's RNAME (sorted input repeats it)
-    int32_t lastId_ = -1;
+    SamNameCache nameCache_;      // SAM: RNAME -> rID of the records seen lately
 };
 
 }  // namespace ppp

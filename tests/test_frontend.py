@@ -304,3 +304,31 @@ def test_bam_boundary_guesses_are_verified(tmp_path, monkeypatch):
     assert host.decode_file(src, threads=4).rejected_guesses == 0
     monkeypatch.setenv("PPP_BAM_NO_GUESS", "1")  # every run decoded by the in-order stage: same records
     _decoded_equal(seq, host.decode_file(f, threads=3))
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_sam_many_optional_fields_and_lookalike_contig_names(tmp_path, threads):
+    """The line parser finds all tabs in one pass (a table of 48, the rest the slow way) and resolves RNAME through a
+    small cache keyed by the name's last eight bytes and length: NH behind 70 other tags, an empty NH:i: field that does
+    not count (:440-444 needs a value), and contig names that share length and their last eight bytes."""
+    seq25 = "ACGTACGTAAACGTACGTACGTACG"
+    names = ["AAAAscaffold_1", "BBBBscaffold_1", "c", "scaffold_1", "Xscaffold_1"]
+    hdr = "".join(f"@SQ\tSN:{n}\tLN:9000\n" for n in names)
+    many = "\t".join(f"X{chr(65 + k % 26)}:i:{k}" for k in range(70))
+    lines = []
+    for k in range(400):
+        n = names[(k * 7) % len(names)]
+        tags = [f"{many}\tNH:i:{2 + k % 3}", "NH:i:\tNH:i:5", f"XA:Z:NH:i:9\tNH:i:{1 + k % 2}", "NH:i:-", ""][k % 5]
+        lines.append(f"r{k}\t{16 * (k % 2)}\t{n}\t{100 + k}\t255\t25M\t*\t0\t0\t{seq25}\t*" + ("\t" + tags if tags else "") + "\n")
+    p = tmp_path / "tags.sam"
+    p.write_text(hdr + "".join(lines))
+    d = host.decode_file(str(p), threads=threads)
+    assert d.names == names and d.n_records == 400 and d.n_kept == 400
+    per_contig = [0] * len(names)
+    for k in range(400):
+        c = (k * 7) % len(names)
+        r = d.reads[c][per_contig[c]]
+        per_contig[c] += 1
+        want_nh = [2 + k % 3, 5, 1 + k % 2, 1, 1][k % 5]
+        assert (int(r["meta"]) >> 2) == want_nh, k
+        assert int(r["key"]) == (99 + k + 25 if k % 2 else 99 + k), k
