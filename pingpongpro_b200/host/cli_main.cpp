@@ -247,6 +247,10 @@ static int run(int argc, char const** argv) {
     if (options.verbosity >= 3) std::cerr << "Counting reads in SAM/BAM files" << std::endl;
     for (const std::string& path : options.inputFiles) {
         stopwatch(std::string("  ") + path, options.verbosity);
+        ExtractOptions eo;  // read by the reader's worker threads: declared before the reader, so that it outlives them on every return path
+        eo.minLen = options.minAlignmentLength;
+        eo.maxLen = options.maxAlignmentLength;
+        eo.mode = options.countMultiHits;
         AlnReader reader;
         if (!reader.open(path.c_str())) {
             std::cerr << "Failed to open input file: " << path << std::endl;  // :1485
@@ -297,10 +301,6 @@ static int run(int argc, char const** argv) {
             haveContexts = true;
             mark("ppp_init done");
         }
-        ExtractOptions eo;
-        eo.minLen = options.minAlignmentLength;
-        eo.maxLen = options.maxAlignmentLength;
-        eo.mode = options.countMultiHits;
         bool foreignContig = false;
         // inflate / line parsing, record decoding and extraction run on worker threads; this thread appends the kept
         // reads in file order (the order of the float additions of -m weighted, :487) and feeds the uploads

@@ -18,13 +18,13 @@ void extract_record_fn(void* user, const AlnView& v, std::vector<uint8_t>& out) 
 }
 
 int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int threads) {
+    ExtractOptions opts = o;  // read by the reader's worker threads: declared before the reader, so that it outlives them on every return path
     AlnReader rd;
     if (!rd.open(path)) return 1;
     out.names = rd.names();
     out.lengths = rd.lengths();
     out.reads.assign(out.names.size(), std::vector<ppp_read>());
     if (threads > 1) {
-        ExtractOptions opts = o;
         rd.startBatches(threads, extract_record_fn, &opts);
         const uint8_t* bytes;
         size_t nBytes;

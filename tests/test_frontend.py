@@ -332,3 +332,58 @@ def test_sam_many_optional_fields_and_lookalike_contig_names(tmp_path, threads):
         want_nh = [2 + k % 3, 5, 1 + k % 2, 1, 1][k % 5]
         assert (int(r["meta"]) >> 2) == want_nh, k
         assert int(r["key"]) == (99 + k + 25 if k % 2 else 99 + k), k
+
+
+def test_corrupted_bam_sequential_and_batch_modes_agree(tmp_path):
+    """Mutation fuzz: bit flips, random bytes, corrupted block_size words and deleted spans in the record stream.  The
+    batch mode (boundary guesses + in-order verification) must do what the sequential walk does -- the same records when
+    the file still decodes, a read error when it does not; never a crash.  (tools/fuzz_bam.py runs the same under
+    ASan / UBSan with more iterations.)"""
+    import random
+    import struct
+    src = str(tmp_path / "src.bam")
+    subprocess.check_call([os.path.join(_build.BIN, "ppp_synth"), "--genome", "tiny", "--reads", "20000", "--seed", "5", "--out", src])
+    payload = _bgzf_payload(src)
+    l_text = struct.unpack_from("<I", payload, 4)[0]
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<I", payload, p)[0]
+    p += 4
+    for _ in range(n_ref):
+        p += 4 + struct.unpack_from("<I", payload, p)[0] + 4
+    starts = [p]
+    while starts[-1] + 4 <= len(payload):
+        nxt = starts[-1] + 4 + struct.unpack_from("<I", payload, starts[-1])[0]
+        if nxt + 4 > len(payload):
+            break
+        starts.append(nxt)
+    rng = random.Random(2024)
+    outcomes = {"ok": 0, "error": 0}
+    for it in range(36):
+        m = bytearray(payload)
+        kind = it % 4
+        for _ in range(rng.randrange(1, 4)):
+            pos = rng.randrange(p, len(m))
+            if kind == 0:
+                m[pos] ^= 1 << rng.randrange(8)
+            elif kind == 1:
+                m[pos] = rng.randrange(256)
+            elif kind == 2:
+                q = rng.choice(starts)
+                old = struct.unpack_from("<I", payload, q)[0]
+                struct.pack_into("<I", m, q, rng.choice([0, 31, 33, 90, 5000, 70000, 1 << 20, 0xFFFFFFFF, old - 1, old + 1, old + 16]) & 0xFFFFFFFF)
+            else:
+                a = rng.randrange(p, len(m) - 300)
+                del m[a:a + rng.randrange(1, 300)]
+        f = str(tmp_path / "m.bam")
+        _bgzf_write(f, bytes(m), rng.choice([601, 7919, 65280]), level=rng.choice([0, 1]))
+        results = []
+        for t in (1, 3):
+            try:
+                results.append(host.decode_file(f, threads=t))
+            except ValueError:
+                results.append(None)
+        assert (results[0] is None) == (results[1] is None), it
+        if results[0] is not None:
+            _decoded_equal(results[0], results[1])
+        outcomes["ok" if results[0] is not None else "error"] += 1
+    assert outcomes["ok"] >= 5 and outcomes["error"] >= 5  # both behaviours were exercised
