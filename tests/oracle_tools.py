@@ -31,7 +31,7 @@ def have_ref(max_overlap: int = 23) -> bool:
 
 
 def _lib() -> C.CDLL:
-    path = os.path.join(ORACLE_DIR, "_build", "libppp_oracle.so")
+    path = os.environ.get("PPP_ORACLE_LIB") or os.path.join(ORACLE_DIR, "_build", "libppp_oracle.so")  # (override: a sanitizer build)
     if not os.path.exists(path):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
     L = C.CDLL(path)
