@@ -9,6 +9,11 @@
 //   ppp_harness dump OUT.bin [-m weighted|discard|unique] [-l MIN] [-L MAX] [-t ANNOT]... -i FILE...
 //   ppp_harness time --genome G --reads N --seed S [--nh1] [--gpos LO:HI] [-m MODE]
 //                    [--steps K] [--warmup W] [--from-packed]
+//   ppp_harness digest --genome G --reads N --seed S [--nh1] [-m MODE] [-t ANNOT]... [-s S1,S2,...]
+//                    [--pq OUT.f32]
+//       full-size runs (BASELINE.json configs 2-5): the synthetic records are generated on the fly and fed to
+//       the reference's own functions; SHA-256 digests of every intermediate go to stdout as one JSON object
+//       (byte layouts in tests/fullsize_digest.py, which hashes the CUDA path's results the same way).
 //
 // Dump format (little endian): repeated sections  { char tag[4]; uint64 count; payload }.
 #define main reference_main
@@ -17,8 +22,10 @@
 
 #include <chrono>
 #include <cstdio>
+#include <set>
 #include <thread>
 
+#include "sha256.h"
 #include "synth_core.h"
 
 namespace {
@@ -248,9 +255,262 @@ int runTime(int argc, char** argv) {
     return 0;
 }
 
+// ---- digest mode ------------------------------------------------------------------------------------
+// Records of the synthetic model, generated in parallel one batch at a time and served in index (= file) order.
+struct SynthFeed {
+    const ppp_synth::Model* m;
+    uint64_t next = 0, end = 0;
+    struct Lite {
+        int32_t rID, beginPos;
+        uint8_t minus, clipLead, clipTrail, len, nh;
+        char seq[35];
+    };
+    std::vector<Lite> batch;
+    size_t pos = 0;
+    void refill() {
+        const uint64_t kBatch = 1u << 22;
+        uint64_t n = std::min<uint64_t>(kBatch, end - next);
+        batch.resize(n);
+        pos = 0;
+        unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; ++t)
+            pool.emplace_back([&, t]() {
+                for (uint64_t k = n * t / nt; k < n * (t + 1) / nt; ++k) {
+                    ppp_synth::Read r;
+                    m->read(next + k, r);
+                    Lite& l = batch[k];
+                    l.rID = r.contig; l.beginPos = r.beginPos; l.minus = r.minus; l.clipLead = r.clipLead; l.clipTrail = r.clipTrail; l.len = r.len; l.nh = r.nh;
+                    m->seq(next + k, r, l.seq);
+                }
+            });
+        for (auto& th : pool) th.join();
+        next += n;
+    }
+    static bool pull(seqan::shim::MemRecord& mr, void* user) {
+        SynthFeed* f = static_cast<SynthFeed*>(user);
+        if (f->pos >= f->batch.size()) {
+            if (f->next >= f->end) return false;
+            f->refill();
+        }
+        const Lite& l = f->batch[f->pos++];
+        mr.rID = l.rID;
+        mr.beginPos = l.beginPos;            // -1 when unmapped (flag 4): skipped at pingpongpro.cpp:415
+        mr.flag = l.beginPos < 0 ? 4u : (l.minus ? 16u : 0u);
+        mr.cigar.clear();
+        if (l.clipLead) mr.cigar.push_back(seqan::CigarElement{'S', l.clipLead});
+        mr.cigar.push_back(seqan::CigarElement{'M', (unsigned)l.len - l.clipLead - l.clipTrail});
+        if (l.clipTrail) mr.cigar.push_back(seqan::CigarElement{'S', l.clipTrail});
+        mr.seq.assign(l.seq, l.len);
+        mr.hasNH = true;
+        mr.nh = l.nh;
+        return true;
+    }
+};
+
+int runDigest(int argc, char** argv) {
+    std::string genome = "dm6", mode = "weighted", pqPath;
+    uint64_t nReads = 1000000, seed = 2;
+    bool nh1 = false;
+    unsigned minLen = 24, maxLen = 32;
+    std::vector<std::string> annots;
+    std::vector<unsigned> minHeights(1, 0u);
+    for (int i = 2; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "--genome") genome = argv[++i];
+        else if (a == "--reads") nReads = strtoull(argv[++i], 0, 10);
+        else if (a == "--seed") seed = strtoull(argv[++i], 0, 10);
+        else if (a == "--nh1") nh1 = true;
+        else if (a == "-m") mode = argv[++i];
+        else if (a == "-t") annots.push_back(argv[++i]);
+        else if (a == "--pq") pqPath = argv[++i];
+        else if (a == "-s") {
+            minHeights.clear();
+            std::string v = argv[++i];
+            for (size_t p = 0; p < v.size();) { size_t c = v.find(',', p); if (c == std::string::npos) c = v.size(); minHeights.push_back(atoi(v.substr(p, c - p).c_str())); p = c + 1; }
+        } else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    std::vector<std::string> names;
+    std::vector<uint64_t> lens;
+    if (!ppp_synth::preset(genome, names, lens)) return 2;
+    ppp_synth::Model m;
+    m.init(names, lens, seed, nReads);
+    m.nh1 = nh1;
+    seqan::shim::memNames() = names;
+    SynthFeed feed;
+    feed.m = &m;
+    feed.end = nReads;
+    seqan::shim::genSource().fn = &SynthFeed::pull;
+    seqan::shim::genSource().user = &feed;
+
+    double t0 = now();
+    TReadStacksPerGenome readStacks;
+    TNameStore nameStoreCopy;
+    double total = 0;
+    {
+        BamStream bam("@gen");
+        if (countReadsInBamFile(bam, readStacks, minLen, maxLen, parseMode(mode), total) != 0) return 1;
+        nameStoreCopy = nameStore(bam.bamIOContext);
+    }
+    double t1 = now();
+    fprintf(stderr, "[digest] countReadsInBamFile %.1f s\n", t1 - t0);
+
+    printf("{\"genome\": \"%s\", \"reads\": %llu, \"seed\": %llu, \"mode\": \"%s\", \"nh1\": %s, \"min_overlap\": %d, \"max_overlap\": %d",
+           genome.c_str(), (unsigned long long)nReads, (unsigned long long)seed, mode.c_str(), nh1 ? "true" : "false", MIN_ARBITRARY_OVERLAP, MAX_ARBITRARY_OVERLAP);
+    {   // stacks: {u32 strand, u32 contig, u32 key, f32 reads, u32 a10} in (strand, contig, key) order
+        ppp_sha::Sha256 h;
+        uint64_t n = 0;
+        for (unsigned s = 0; s < 2; ++s)
+            for (TReadStacksPerStrand::iterator c = readStacks[s].begin(); c != readStacks[s].end(); ++c)
+                for (TReadStacksPerContig::iterator p = c->second.begin(); p != c->second.end(); ++p, ++n) {
+                    h.put((uint32_t)s); h.put((uint32_t)c->first); h.put((uint32_t)p->first); h.put((float)p->second.reads); h.put((uint32_t)(p->second.AAtPosition10 ? 1 : 0));
+                }
+        printf(", \"n_stacks\": %llu, \"stacks\": \"%s\", \"total_weight\": %.17g", (unsigned long long)n, h.hex().c_str(), total);
+    }
+
+    TTransposonsPerGenome transposons;
+    for (size_t k = 0; k < annots.size(); ++k) {
+        ifstream fs(annots[k].c_str());
+        if (fs.fail()) { fprintf(stderr, "Failed to open transposon file \"%s\".\n", annots[k].c_str()); return 1; }
+        TFileFormat ff = fileFormatTSV;
+        if (_compareExtension(annots[k].c_str(), ".bed")) ff = fileFormatBED;
+        else if (_compareExtension(annots[k].c_str(), ".csv")) ff = fileFormatCSV;
+        else if (_compareExtension(annots[k].c_str(), ".gff")) ff = fileFormatGFF;
+        else if (_compareExtension(annots[k].c_str(), ".gtf")) ff = fileFormatGTF;
+        readTransposonsFromFile(fs, ff, transposons, nameStoreCopy);
+    }
+
+    THeightScoreMap heightScoreMap;
+    mapHeightsToScores(readStacks, heightScoreMap);
+    double t2 = now();
+    fprintf(stderr, "[digest] mapHeightsToScores %.1f s\n", t2 - t1);
+    {   // {u32 height, f32 frequency} ascending; how many counters reached the 2^24 ceiling of a float counter (:508)
+        ppp_sha::Sha256 h;
+        uint64_t saturated = 0;
+        float maxFreq = 0;
+        for (THeightScoreMap::iterator x = heightScoreMap.begin(); x != heightScoreMap.end(); ++x) {
+            h.put((uint32_t)x->first); h.put((float)x->second);
+            if (x->second >= 16777216.0f) ++saturated;
+            if (x->second > maxFreq) maxFreq = x->second;
+        }
+        printf(", \"n_heights\": %zu, \"freq\": \"%s\", \"freq_saturated\": %llu, \"max_freq\": %.9g, \"max_height\": %u", heightScoreMap.size(), h.hex().c_str(),
+               (unsigned long long)saturated, maxFreq, heightScoreMap.empty() ? 0u : (unsigned)heightScoreMap.rbegin()->first);
+    }
+
+    TGroupedStackCountsByOverlap grouped;
+    TPingPongSignaturesByOverlap sigs;
+    countStacksByGroup(readStacks, heightScoreMap, grouped, sigs);
+    double t3 = now();
+    fprintf(stderr, "[digest] countStacksByGroup %.1f s\n", t3 - t2);
+    for (unsigned s = 0; s < 2; ++s) TReadStacksPerStrand().swap(readStacks[s]);  // the stacks are not read again (memory for the signature lists)
+    auto digestGrouped = [&](const char* key) {
+        ppp_sha::Sha256 h;
+        uint64_t bins = grouped.begin()->size(), saturated = 0;
+        for (unsigned ov = 0; ov < grouped.size(); ++ov)
+            for (unsigned b = 0; b < bins; ++b)
+                for (unsigned i = 0; i < 2; ++i)
+                    for (unsigned j = 0; j < 2; ++j) { h.put((float)grouped[ov][b][i][j]); if (grouped[ov][b][i][j] >= 16777216.0f) ++saturated; }
+        printf(", \"%s_bins\": %llu, \"%s\": \"%s\", \"%s_cells_at_or_above_2p24\": %llu", key, (unsigned long long)bins, key, h.hex().c_str(), key, (unsigned long long)saturated);
+    };
+    digestGrouped("grouped_pre");
+    // height-score bins before the collapse, per (overlap, contig) in list order
+    std::vector<std::map<unsigned, std::vector<uint16_t> > > binPre(sigs.size());
+    for (unsigned ov = 0; ov < sigs.size(); ++ov)
+        for (TPingPongSignaturesPerGenome::iterator c = sigs[ov].begin(); c != sigs[ov].end(); ++c) {
+            std::vector<uint16_t>& v = binPre[ov][c->first];
+            v.reserve(c->second.size());
+            for (TPingPongSignaturesPerContig::iterator s = c->second.begin(); s != c->second.end(); ++s) v.push_back((uint16_t)s->heightScoreBin);
+        }
+    collapseBins(grouped, sigs);
+    digestGrouped("grouped_post");
+    calculateFDRs(grouped, sigs);
+    double t4 = now();
+    fprintf(stderr, "[digest] collapseBins + calculateFDRs %.1f s\n", t4 - t3);
+    {   // signatures in (contig, position, overlap) order, the layout of ppp_pair (include/ppp_b200.h):
+        // {u32 contig, position, overlap, bin before collapse, collapsed bin, local bin, bias bin; f32 r+, r-, fdr}
+        ppp_sha::Sha256 h;
+        uint64_t n = 0;
+        std::set<unsigned> contigs;
+        for (unsigned ov = 0; ov < sigs.size(); ++ov)
+            for (TPingPongSignaturesPerGenome::iterator c = sigs[ov].begin(); c != sigs[ov].end(); ++c) contigs.insert(c->first);
+        for (std::set<unsigned>::iterator ci = contigs.begin(); ci != contigs.end(); ++ci) {
+            const unsigned nOv = sigs.size();
+            std::vector<TPingPongSignaturesPerContig::iterator> it(nOv), en(nOv);
+            std::vector<const std::vector<uint16_t>*> pre(nOv, nullptr);
+            std::vector<size_t> idx(nOv, 0);
+            TPingPongSignaturesPerContig empty;
+            for (unsigned ov = 0; ov < nOv; ++ov) {
+                TPingPongSignaturesPerGenome::iterator f = sigs[ov].find(*ci);
+                if (f == sigs[ov].end()) { it[ov] = en[ov] = empty.end(); continue; }
+                it[ov] = f->second.begin();
+                en[ov] = f->second.end();
+                pre[ov] = &binPre[ov][*ci];
+            }
+            for (;;) {
+                unsigned best = 0xffffffffu;
+                for (unsigned ov = 0; ov < nOv; ++ov)
+                    if (it[ov] != en[ov] && it[ov]->position < best) best = it[ov]->position;
+                if (best == 0xffffffffu) {
+                    bool any = false;
+                    for (unsigned ov = 0; ov < nOv; ++ov) any = any || it[ov] != en[ov];
+                    if (!any) break;
+                }
+                for (unsigned ov = 0; ov < nOv; ++ov)
+                    while (it[ov] != en[ov] && it[ov]->position == best) {
+                        h.put((uint32_t)*ci); h.put((uint32_t)it[ov]->position); h.put((uint32_t)(ov + MIN_ARBITRARY_OVERLAP)); h.put((uint32_t)(*pre[ov])[idx[ov]++]);
+                        h.put((uint32_t)it[ov]->heightScoreBin); h.put((uint32_t)it[ov]->localHeightScoreBin); h.put((uint32_t)it[ov]->baseBiasBin);
+                        h.put((float)it[ov]->readsOnPlusStrand); h.put((float)it[ov]->readsOnMinusStrand); h.put((float)it[ov]->fdr);
+                        ++it[ov];
+                        ++n;
+                    }
+            }
+        }
+        printf(", \"n_signatures\": %llu, \"signatures\": \"%s\"", (unsigned long long)n, h.hex().c_str());
+    }
+    {   // reported loci per -s (the filter of pingpongpro.cpp:903), the layout of ppp_locus: {u32 contig, position; f32 fdr, r+, r-}
+        TPingPongSignaturesPerGenome& pp = sigs[PING_PONG_OVERLAP - MIN_ARBITRARY_OVERLAP];
+        printf(", \"loci\": {");
+        for (size_t k = 0; k < minHeights.size(); ++k) {
+            const unsigned int minStackHeight = minHeights[k];
+            ppp_sha::Sha256 h;
+            uint64_t n = 0;
+            for (TPingPongSignaturesPerGenome::iterator contig = pp.begin(); contig != pp.end(); ++contig)
+                for (TPingPongSignaturesPerContig::iterator s = contig->second.begin(); s != contig->second.end(); ++s)
+                    if ((s->readsOnPlusStrand >= minStackHeight) && (s->readsOnMinusStrand >= minStackHeight)) {
+                        h.put((uint32_t)contig->first); h.put((uint32_t)s->position); h.put((float)s->fdr); h.put((float)s->readsOnPlusStrand); h.put((float)s->readsOnMinusStrand);
+                        ++n;
+                    }
+            printf("%s\"%u\": {\"n\": %llu, \"sha256\": \"%s\"}", k ? ", " : "", minStackHeight, (unsigned long long)n, h.hex().c_str());
+        }
+        printf("}");
+    }
+    if (!annots.empty()) {
+        findSuppressedTransposons(sigs, transposons);
+        // per transposon in the reference's order (contig map, list sorted by start / end):
+        //   sums    {u32 contig, strand, start, end; f32 R+, R-, hist[W]}   -- bit-exact contract
+        //   pq      {f32 p, f32 q}                                          -- fp64 integral narrowed to float
+        ppp_sha::Sha256 hs, hp;
+        uint64_t n = 0;
+        FILE* pq = pqPath.empty() ? nullptr : fopen(pqPath.c_str(), "wb");
+        for (TTransposonsPerGenome::iterator c = transposons.begin(); c != transposons.end(); ++c)
+            for (TTransposonsPerContig::iterator x = c->second.begin(); x != c->second.end(); ++x, ++n) {
+                hs.put((uint32_t)c->first); hs.put((uint32_t)x->strand); hs.put((uint32_t)x->start); hs.put((uint32_t)x->end);
+                hs.put((float)x->readsOnPlusStrand); hs.put((float)x->readsOnMinusStrand);
+                for (unsigned k = 0; k < W; ++k) hs.put((float)(k < x->histogram.size() ? x->histogram[k] : 0.0f));
+                hp.put((float)x->pValue); hp.put((float)x->qValue);
+                if (pq) { float v[2] = {x->pValue, x->qValue}; fwrite(v, 4, 2, pq); }
+            }
+        if (pq) fclose(pq);
+        printf(", \"n_transposons\": %llu, \"transposon_sums\": \"%s\", \"transposon_pq\": \"%s\"", (unsigned long long)n, hs.hex().c_str(), hp.hex().c_str());
+    }
+    printf(", \"seconds\": {\"count\": %.1f, \"heights\": %.1f, \"group\": %.1f, \"collapse_fdr\": %.1f}}\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "digest") return runDigest(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "dump") return runDump(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "time") return runTime(argc, argv);
     fprintf(stderr, "usage: ppp_harness dump OUT.bin [...] -i FILE... | ppp_harness time --genome G --reads N ...\n");

@@ -11,7 +11,8 @@
 //
 // An extra, non-SeqAn entry exists for the timing harness: a BamStream opened on the
 // pseudo path "@mem" serves records from seqan::shim::memRecords() instead of a file,
-// which lets the reference's countReadsInBamFile be timed without text parsing.
+// which lets the reference's countReadsInBamFile be timed without text parsing; "@gen"
+// pulls them from a callback instead (full-size digests: 500 M records never fit in memory).
 #pragma once
 
 #include <sys/stat.h>
@@ -117,6 +118,13 @@ struct MemRecord {
     unsigned nh;
 };
 inline std::vector<MemRecord>& memRecords() { static std::vector<MemRecord> r; return r; }
+// "@gen": fills `rec` with the next record and returns true, or returns false at the end of the stream
+typedef bool (*GenFn)(MemRecord& rec, void* user);
+struct GenSource {
+    GenFn fn = nullptr;
+    void* user = nullptr;
+};
+inline GenSource& genSource() { static GenSource g; return g; }
 inline std::vector<std::string>& memNames() { static std::vector<std::string> n; return n; }
 }  // namespace shim
 
@@ -128,9 +136,15 @@ struct BamStream {
     BamIOContext bamIOContext;
     ppp::AlnReader reader;
     bool ok = false;
-    bool mem = false;
+    bool mem = false, gen = false, genHave = false;
     size_t memPos = 0;
+    shim::MemRecord genRec;
     explicit BamStream(const char* path) {
+        if (strcmp(path, "@gen") == 0) {
+            gen = ok = true;
+            for (const std::string& n : shim::memNames()) bamIOContext.names.v.push_back(CharString(n));
+            return;
+        }
         if (strcmp(path, "@mem") == 0) {
             mem = ok = true;
             for (const std::string& n : shim::memNames()) bamIOContext.names.v.push_back(CharString(n));
@@ -143,15 +157,23 @@ struct BamStream {
 };
 
 inline bool isGood(BamStream& s) { return s.ok; }
-inline bool atEnd(BamStream& s) { return s.mem ? s.memPos >= shim::memRecords().size() : s.reader.atEnd(); }
-inline void close(BamStream& s) { if (!s.mem) s.reader.close(); }
+inline bool atEnd(BamStream& s) {
+    if (s.gen) {
+        if (!s.genHave) s.genHave = shim::genSource().fn(s.genRec, shim::genSource().user);
+        return !s.genHave;
+    }
+    return s.mem ? s.memPos >= shim::memRecords().size() : s.reader.atEnd();
+}
+inline void close(BamStream& s) { if (!s.mem && !s.gen) s.reader.close(); }
 inline StringSet<CharString>& nameStore(BamIOContext& c) {
     return c.names;
 }
 
 inline int readRecord(BamAlignmentRecord& rec, BamStream& s) {
-    if (s.mem) {
-        const shim::MemRecord& m = shim::memRecords()[s.memPos++];
+    if (s.mem || s.gen) {
+        if (s.gen && !s.genHave && atEnd(s)) return 1;
+        const shim::MemRecord& m = s.gen ? s.genRec : shim::memRecords()[s.memPos++];
+        s.genHave = false;
         rec.rID = m.rID;
         rec.beginPos = m.beginPos;
         rec.flag = m.flag;

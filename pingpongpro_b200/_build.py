@@ -103,7 +103,7 @@ def build_oracle() -> None:
     _run(["make", "-s", "-C", odir, "port"])
     ref_src = os.environ.get("PPP_REFERENCE_SOURCE", "/root/reference/pingpongpro.cpp")
     harness = os.path.join(odir, "_ref", "ppp_harness")
-    deps = [os.path.join(odir, "harness.cpp"), os.path.join(odir, "seqan_shim", "seqan", "shim_impl.h"),
+    deps = [os.path.join(odir, "harness.cpp"), os.path.join(odir, "sha256.h"), os.path.join(odir, "seqan_shim", "seqan", "shim_impl.h"),
             os.path.join(HOST, "aln_reader.cpp"), os.path.join(HOST, "aln_reader.h"), os.path.join(HOST, "fast_inflate.cpp"), os.path.join(TOOLS, "synth_core.h")]
     if os.path.exists(ref_src) and _newer(harness, deps):
         _run(["make", "-s", "-C", odir, "ref", f"REF={ref_src}"])
