@@ -6,6 +6,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -57,15 +58,19 @@ struct Timer {
 };
 
 struct PinnedScalars {
-    uint32_t maxHeight;
-    uint32_t nBins;
-    uint32_t tallOverflow;
-    uint32_t pad;
-    unsigned long long cursor;
+    // mirror of the tail of PassState (one copy): totals[2], maxCount, maxHeight, ticket, overflow, pad
+    unsigned long long totals[2];
     unsigned long long maxCount;
+    uint32_t maxHeight, ticket, tallOverflow, pad;
+    // mirror of ScoreState
     unsigned long long nLoci;
+    uint32_t scoreTicket, scorePad;
+    uint32_t nBins;
+    uint32_t rerun;                    // multi-GPU: ranks whose signature store overflowed in this pass (all-reduced)
+    uint32_t stackTotals[2];           // stacks per strand (ppp_stacks_finish)
     unsigned long long counters[2];
 };
+static_assert(offsetof(PassState, maxHeight) - offsetof(PassState, totals) == 24, "PassState tail layout");
 
 }  // namespace
 
@@ -103,39 +108,54 @@ struct ppp_ctx {
     bool sortUsed[kStages] = {};
     unsigned batchCount = 0;
 
+    // compact stack store (compact.cu), rebuilt by ppp_stacks_finish
+    uint32_t* dCmp = nullptr;            // plus-strand words, then minus-strand words
+    size_t cmpCapacity = 0;
+    uint32_t *dTileCntP = nullptr, *dTileCntM = nullptr, *dTileOffP = nullptr, *dTileOffM = nullptr;  // [nTiles + 1] each
+    uint64_t nStacksP = 0, nStacksM = 0;
+
     // scan state
-    unsigned long long* dFreqLow = nullptr;
+    PassState* dState = nullptr;             // + the look-back states of the tiles (one allocation, one memset per pass)
+    unsigned long long* dTileState = nullptr;
     uint32_t* dFreqTail = nullptr;
     float* dLut = nullptr;
-    uint32_t* dMaxHeight = nullptr;
-    unsigned long long* dMaxCount = nullptr;
-    unsigned long long* dCursor = nullptr;
-    unsigned long long* dNLoci = nullptr;
     uint32_t prevMaxHeight = 0;
-    PairRec *dPairsRaw = nullptr, *dPairs = nullptr;
-    float* dPairFdr = nullptr;
+    // signature records (structure of arrays, (position, overlap) order) and the overlap-`pingpong` stream
+    uint32_t* dRecPos = nullptr;
+    float *dRecRp = nullptr, *dRecRm = nullptr;
+    uint8_t* dRecMisc = nullptr;
+    uint16_t* dRecBin = nullptr;
+    PairRec* dPP = nullptr;
     LocusOut* dLoci = nullptr;
-    uint64_t pairCapacity = 0, cfgPairCapacity = 0;
-    uint32_t *dTileCnt = nullptr, *dTileBase = nullptr, *dTileDst = nullptr, *dScanScratch = nullptr, *dBlockCnt = nullptr;
-    size_t scanScratchWords = 0, blockCntWords = 0;
-    uint32_t* dGrouped = nullptr;
+    ScoreState* dScoreState = nullptr;       // + the look-back states of k_score's tiles
+    unsigned long long* dScoreTiles = nullptr;
+    size_t scoreTileWords = 0;
+    uint64_t pairCapacity = 0, ppCapacity = 0, cfgPairCapacity = 0;
+    // array-of-structures view of the records + per-record FDRs, materialised on demand (pairs_download, transposons)
+    PairRec* dPairs = nullptr;
+    float* dPairFdr = nullptr;
+    uint64_t viewCapacity = 0;
+    bool viewValid = false, viewHasFdr = false;
+    uint32_t* dScanScratch = nullptr;
+    size_t scanScratchWords = 0;
+    uint32_t* dGrouped = nullptr;            // [W * 1000 * 4] + 1 word: ranks that must re-run the pass
     float *dThresholds = nullptr, *hThresholds = nullptr;
     float *dCells = nullptr, *dFdr = nullptr;
     uint16_t* dBinMap = nullptr;
     uint16_t* dGroupStart = nullptr;
     unsigned long long* dCellSums = nullptr;
     uint32_t* dNBins = nullptr;
-    uint32_t* dTileCursor = nullptr;
     double *dXs = nullptr, *dWs = nullptr;
     int nSteps = 0;
     PinnedScalars* hs = nullptr;
     std::vector<uint64_t> hFreq;
     ppp_locus* hLoci = nullptr;
     size_t hLociCap = 0;
-    uint64_t nPairs = 0;
+    uint64_t nPairs = 0, nPP = 0;
     uint32_t maxHeight = 0;
     float binScale = 0.f;  // 999 / maxHeightScore: only seeds the device's bin proposal
     bool finished = false, haveHist = false, haveScan = false, haveScore = false;
+    bool localOverflow = false;  // this context's signature store was too small in the last scan pass
 
     ppp_allreduce_fn allreduce = nullptr;
     void* allreduceUser = nullptr;
@@ -144,7 +164,6 @@ struct ppp_ctx {
     int rank = 0, world = 0;   // known (ppp_set_rank / ppp_nccl_attach): tall stacks are exchanged as compact lists
     uint32_t* dGather = nullptr;  // [world][kTallHeader + tallCap], see launch_tall_apply
     uint32_t tallCap = 0;
-    uint32_t* dOverflow = nullptr;
     float thresholdFreq = 0.f;  // the maximum frequency hThresholds was built for (0: none)
     bool denseTail = false;    // a list overflowed once: this context reduces the dense tables from then on
 
@@ -215,21 +234,58 @@ int buildLayout(ppp_ctx* c, const ppp_config* cfg) {
 }
 
 int ensurePairCapacity(ppp_ctx* c, uint64_t want) {
-    if (want <= c->pairCapacity && c->dPairsRaw) return PPP_OK;
-    if (want >= 0xfffffff0ull) return fail(PPP_ERR_NOMEM, "signature store would exceed 2^32 records");
-    if (c->dPairsRaw) { cudaFree(c->dPairsRaw); cudaFree(c->dPairs); cudaFree(c->dPairFdr); cudaFree(c->dLoci); cudaFree(c->dBlockCnt); }
-    c->dPairsRaw = c->dPairs = nullptr;
-    c->dPairFdr = nullptr;
+    if (want <= c->pairCapacity && c->dRecPos) return PPP_OK;
+    if (want >= kMaxPairCapacity) return fail(PPP_ERR_NOMEM, "signature store would exceed 2^32 records");
+    void* old[] = {c->dRecPos, c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dPP, c->dLoci, c->dScoreState};
+    for (void* q : old)
+        if (q) cudaFree(q);
+    c->dRecPos = nullptr;
+    c->dRecRp = c->dRecRm = nullptr;
+    c->dRecMisc = nullptr;
+    c->dRecBin = nullptr;
+    c->dPP = nullptr;
     c->dLoci = nullptr;
-    c->dBlockCnt = nullptr;
-    c->pairCapacity = 0;
-    CK(cudaMalloc(&c->dPairsRaw, want * sizeof(PairRec)));
-    CK(cudaMalloc(&c->dPairs, want * sizeof(PairRec)));
-    CK(cudaMalloc(&c->dPairFdr, want * sizeof(float)));
-    CK(cudaMalloc(&c->dLoci, want * sizeof(LocusOut)));
-    c->blockCntWords = want / 256 + 2;
-    CK(cudaMalloc(&c->dBlockCnt, c->blockCntWords * sizeof(uint32_t)));
+    c->dScoreState = nullptr;
+    c->dScoreTiles = nullptr;
+    c->pairCapacity = c->ppCapacity = 0;
+    // every record may be an overlap-`pingpong` record (a library made of nothing but 10-nt pairs), up to the field width of
+    // the look-back state
+    const uint64_t pp = std::min<uint64_t>(want, kMaxLociCapacity);
+    CK(cudaMalloc(&c->dRecPos, want * sizeof(uint32_t)));
+    CK(cudaMalloc(&c->dRecRp, want * sizeof(float)));
+    CK(cudaMalloc(&c->dRecRm, want * sizeof(float)));
+    CK(cudaMalloc(&c->dRecMisc, want + 16));
+    CK(cudaMalloc(&c->dRecBin, want * sizeof(uint16_t) + 16));
+    CK(cudaMalloc(&c->dPP, pp * sizeof(PairRec)));
+    CK(cudaMalloc(&c->dLoci, pp * sizeof(LocusOut)));
+    c->scoreTileWords = score_tiles(pp);
+    CK(cudaMalloc(&c->dScoreState, sizeof(ScoreState) + c->scoreTileWords * sizeof(unsigned long long)));
+    c->dScoreTiles = reinterpret_cast<unsigned long long*>(c->dScoreState + 1);
     c->pairCapacity = want;
+    c->ppCapacity = pp;
+    return PPP_OK;
+}
+
+// Array-of-structures view of the records (+ their FDRs once the table exists) for the consumers outside the scan +
+// score pass: ppp_pairs_download and the transposon kernels.
+int ensurePairView(ppp_ctx* c) {
+    const bool wantFdr = c->haveScore;
+    if (c->viewValid && (c->viewHasFdr || !wantFdr)) return PPP_OK;
+    if (c->viewCapacity < c->nPairs || !c->dPairs) {
+        if (c->dPairs) { cudaFree(c->dPairs); cudaFree(c->dPairFdr); }
+        c->dPairs = nullptr;
+        c->dPairFdr = nullptr;
+        c->viewCapacity = 0;
+        const uint64_t cap = std::max<uint64_t>(c->nPairs, 1);
+        CK(cudaMalloc(&c->dPairs, cap * sizeof(PairRec)));
+        CK(cudaMalloc(&c->dPairFdr, cap * sizeof(float)));
+        c->viewCapacity = cap;
+    }
+    if (!wantFdr) CK(cudaMemsetAsync(c->dPairFdr, 0, std::max<uint64_t>(c->nPairs, 1) * sizeof(float), c->stream));
+    CK(launch_pairs_view(c->dRecPos, c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, (size_t)c->nPairs, wantFdr ? c->dFdr : nullptr, c->dBinMap, c->W, c->dPairs,
+                         c->dPairFdr, c->stream, &c->launches));
+    c->viewValid = true;
+    c->viewHasFdr = wantFdr;
     return PPP_OK;
 }
 
@@ -332,7 +388,7 @@ struct Trace {
     }
 };
 
-void invalidateResults(ppp_ctx* c) { c->haveHist = c->haveScan = c->haveScore = false; }
+void invalidateResults(ppp_ctx* c) { c->haveHist = c->haveScan = c->haveScore = c->viewValid = false; }
 
 // ---- built-in collective: NCCL, bound at run time (nccl_loader.cpp) --------------------------------
 int ncclFail(const char* what, int rc) { return fail(PPP_ERR_CUDA, "%s: %s", what, nccl().getErrorString(rc)); }
@@ -456,28 +512,26 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
         CKI(cudaEventCreateWithFlags(&c->evCopied[k], cudaEventDisableTiming));
         CKI(cudaEventCreateWithFlags(&c->evConsumed[k], cudaEventDisableTiming));
     }
-    CKI(cudaMalloc(&c->dFreqLow, kScanLowBins * sizeof(unsigned long long)));
+    CKI(cudaMalloc(&c->dState, sizeof(PassState) + (size_t)c->nTiles * sizeof(unsigned long long)));
+    c->dTileState = reinterpret_cast<unsigned long long*>(c->dState + 1);
     CKI(cudaMalloc(&c->dFreqTail, (size_t)kFreqCapacity * sizeof(uint32_t)));
     CKI(cudaMemsetAsync(c->dFreqTail, 0, (size_t)kFreqCapacity * sizeof(uint32_t), c->stream));
     CKI(cudaMalloc(&c->dLut, (size_t)kFreqCapacity * sizeof(float)));
-    CKI(cudaMalloc(&c->dMaxHeight, sizeof(uint32_t)));
-    CKI(cudaMalloc(&c->dMaxCount, sizeof(unsigned long long)));
-    CKI(cudaMalloc(&c->dCursor, sizeof(unsigned long long)));
-    CKI(cudaMalloc(&c->dNLoci, sizeof(unsigned long long)));
-    CKI(cudaMalloc(&c->dTileCnt, (size_t)c->nTiles * 4));
-    CKI(cudaMalloc(&c->dTileBase, (size_t)c->nTiles * 4));
-    CKI(cudaMalloc(&c->dTileDst, (size_t)c->nTiles * 4));
-    c->scanScratchWords = exclusive_scan_scratch_words(std::max<size_t>(c->nTiles, (size_t)1 << 24));
+    CKI(cudaMemsetAsync(c->dLut, 0, 4 * sizeof(float), c->stream));  // heights 0..3 are looked up even when they never occur
+    CKI(cudaMalloc(&c->dTileCntP, ((size_t)c->nTiles + 1) * 4));
+    CKI(cudaMalloc(&c->dTileCntM, ((size_t)c->nTiles + 1) * 4));
+    CKI(cudaMalloc(&c->dTileOffP, ((size_t)c->nTiles + 1) * 4));
+    CKI(cudaMalloc(&c->dTileOffM, ((size_t)c->nTiles + 1) * 4));
+    c->scanScratchWords = exclusive_scan_scratch_words((size_t)c->nTiles + 1);
     CKI(cudaMalloc(&c->dScanScratch, c->scanScratchWords * 4));
     size_t tableWords = (size_t)c->W * kBins * 4;
-    CKI(cudaMalloc(&c->dGrouped, tableWords * 4));
+    CKI(cudaMalloc(&c->dGrouped, (tableWords + 1) * 4));
     CKI(cudaMalloc(&c->dCells, tableWords * 4));
     CKI(cudaMalloc(&c->dFdr, tableWords * 4));
     CKI(cudaMalloc(&c->dBinMap, kBins * sizeof(uint16_t)));
     CKI(cudaMalloc(&c->dGroupStart, (kBins + 1) * sizeof(uint16_t)));
     CKI(cudaMalloc(&c->dCellSums, tableWords * sizeof(unsigned long long)));
     CKI(cudaMalloc(&c->dNBins, sizeof(uint32_t)));
-    CKI(cudaMalloc(&c->dTileCursor, sizeof(uint32_t)));
     CKI(cudaMalloc(&c->dThresholds, kBins * sizeof(float)));
     initMark("device tables allocated");
     CKI(cudaMallocHost(&c->hThresholds, kBins * sizeof(float)));
@@ -510,10 +564,9 @@ void ppp_destroy(ppp_ctx* c) {
     if (c->ncclComm) nccl().commDestroy(c->ncclComm);
     delete c->groupMember;
     if (c->dGather) cudaFree(c->dGather);
-    if (c->dOverflow) cudaFree(c->dOverflow);
-    void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dFreqLow, c->dFreqTail, c->dLut, c->dMaxHeight, c->dMaxCount, c->dCursor, c->dNLoci, c->dPairsRaw, c->dPairs,
-                   c->dPairFdr, c->dLoci, c->dTileCnt, c->dTileBase, c->dTileDst, c->dScanScratch, c->dBlockCnt, c->dGrouped, c->dThresholds, c->dCells,
-                   c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dTileCursor};
+    void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dCmp, c->dTileCntP, c->dTileCntM, c->dTileOffP, c->dTileOffM, c->dState, c->dFreqTail, c->dLut,
+                   c->dRecPos, c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dPP, c->dLoci, c->dScoreState, c->dPairs, c->dPairFdr, c->dScanScratch,
+                   c->dGrouped, c->dThresholds, c->dCells, c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums};
     for (void* p : dev)
         if (p) cudaFree(p);
     for (int k = 0; k < kStages; ++k) {
@@ -683,7 +736,31 @@ int ppp_stacks_finish(ppp_ctx* c) {
     CK(cudaStreamSynchronize(c->copyStream));
     CK(cudaStreamSynchronize(c->sortStream));
     for (int k = 0; k < kFoldStreams; ++k) CK(cudaStreamSynchronize(c->foldStream[k]));
+    // the stacks are final: write them down as the compact, position-ordered store the scan reads (compact.cu)
+    Timer t;
+    int rc;
+    if ((rc = timerStart(c, t))) return rc;
+    CK(launch_tile_popc(c->occ, c->G, c->nTiles, c->dTileCntP, c->dTileCntM, c->stream, &c->launches));
+    CK(exclusive_scan_u32(c->dTileCntP, c->dTileOffP, (size_t)c->nTiles + 1, c->dScanScratch, c->scanScratchWords, c->stream, &c->launches));
+    CK(exclusive_scan_u32(c->dTileCntM, c->dTileOffM, (size_t)c->nTiles + 1, c->dScanScratch, c->scanScratchWords, c->stream, &c->launches));
+    CK(cudaMemcpyAsync(&c->hs->stackTotals[0], c->dTileOffP + c->nTiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->hs->stackTotals[1], c->dTileOffM + c->nTiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(c->hs->counters, c->dCounters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->nStacksP = c->hs->stackTotals[0];
+    c->nStacksM = c->hs->stackTotals[1];
+    const size_t need = (size_t)c->nStacksP + (size_t)c->nStacksM + 64;
+    if (need > c->cmpCapacity) {
+        if (c->dCmp) cudaFree(c->dCmp);
+        c->dCmp = nullptr;
+        c->cmpCapacity = 0;
+        const size_t cap = need + need / 8;
+        CK(cudaMalloc(&c->dCmp, cap * sizeof(uint32_t)));
+        c->cmpCapacity = cap;
+    }
+    CK(launch_compact_write(c->H, c->occ, c->G, c->nTiles, c->dTileOffP, c->dTileOffM, c->dCmp, c->dCmp + c->nStacksP, c->stream, &c->launches));
+    if ((rc = timerStop(c, t))) return rc;
+    c->buildTimers.push_back(t);
     CK(cudaStreamSynchronize(c->stream));
     foldBuildTimers(c);
     c->finished = true;
@@ -720,101 +797,105 @@ int ppp_stacks_download(ppp_ctx* c, int32_t contig, int32_t strand, uint64_t beg
     return PPP_OK;
 }
 
-int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
-    if (!c) return fail(PPP_ERR_ARG, "null context");
-    if (!c->finished) return fail(PPP_ERR_STATE, "call ppp_stacks_finish before ppp_height_hist");
-    CK(cudaSetDevice(c->device));
-    invalidateResults(c);
-    Trace tr("height_hist");
-    // signatures are ~0.1-0.3 per read on real densities; a scan that overflows the store reports the exact count and is re-run once
-    // (a shard sizes the store for one signature per read: a re-run repeats the collectives, which every rank would have
-    // to agree on -- a lone re-run is caught as a size mismatch by the in-process group, and must simply not happen)
-    uint64_t want = c->cfgPairCapacity ? c->cfgPairCapacity : std::max<uint64_t>((uint64_t)1 << 20, c->allreduce ? c->readsSubmitted : c->readsSubmitted / 3);
-    if (want < c->pairCapacity) want = c->pairCapacity;
-    int rc = ensurePairCapacity(c, want);
-    if (rc) return rc;
-    for (int attempt = 0;; ++attempt) {
-        CK(cudaMemsetAsync(c->dFreqLow, 0, kScanLowBins * sizeof(unsigned long long), c->stream));
-        if (c->prevMaxHeight >= kScanLowBins)
-            CK(cudaMemsetAsync(c->dFreqTail + kScanLowBins, 0, ((size_t)c->prevMaxHeight - kScanLowBins + 1) * sizeof(uint32_t), c->stream));
-        CK(cudaMemsetAsync(c->dMaxHeight, 0, sizeof(uint32_t), c->stream));
-        CK(cudaMemsetAsync(c->dMaxCount, 0, sizeof(unsigned long long), c->stream));
-        CK(cudaMemsetAsync(c->dCursor, 0, sizeof(unsigned long long), c->stream));
-        ScanParams p;
-        p.H = c->H;
-        p.occ = c->occ;
-        p.G = c->G;
-        p.nTiles = c->nTiles;
-        p.minOv = c->minOv;
-        p.W = c->W;
-        p.haloLo = c->haloLo;
-        p.haloHi = c->haloHi;
-        p.freqLow = c->dFreqLow;
-        p.freqTail = c->dFreqTail;
-        p.maxHeight = c->dMaxHeight;
-        p.pairsRaw = c->dPairsRaw;
-        p.cursor = c->dCursor;
-        p.capacity = c->pairCapacity;
-        p.tileCnt = c->dTileCnt;
-        p.tileBase = c->dTileBase;
-        // multi-GPU with known rank: heights beyond the shared-memory bins go to this rank's slot of the gather buffer
-        const bool gatherTall = c->allreduce && c->world > 1 && !c->denseTail;
-        const size_t slotWords = (size_t)kTallHeader + c->tallCap;
-        p.tallList = nullptr;
-        p.tallCount = nullptr;
-        p.tallCap = 0;
-        if (gatherTall) {
-            if (!c->dGather) {
-                CK(cudaMalloc(&c->dGather, (size_t)c->world * slotWords * sizeof(uint32_t)));
-                CK(cudaMalloc(&c->dOverflow, sizeof(uint32_t)));
-            }
-            CK(cudaMemsetAsync(c->dGather, 0, (size_t)c->world * slotWords * sizeof(uint32_t), c->stream));
-            CK(cudaMemsetAsync(c->dOverflow, 0, sizeof(uint32_t), c->stream));
-            uint32_t* slot = c->dGather + (size_t)c->rank * slotWords;
-            p.tallCount = slot;
-            p.maxHeight = slot + 1;
-            p.freqLow = reinterpret_cast<unsigned long long*>(slot + kTallLow);
-            p.tallList = slot + kTallHeader;
-            p.tallCap = c->tallCap;
-        }
-        c->hs->tallOverflow = 0;
-        if ((rc = timerStart(c, c->tScan))) return rc;
-        CK(launch_scan(p, c->repr, c->stream, &c->launches));
-        if ((rc = timerStop(c, c->tScan))) return rc;
-        if (gatherTall) {
-            // one all-reduce carries every rank's low bins, tall stacks and maximum height; no host round trip in between
-            if ((rc = hookReduce(c, c->dGather, (size_t)c->world * slotWords, 0, 0))) return rc;
-            CK(launch_tall_apply(c->dGather, c->world, c->tallCap, c->dFreqLow, c->dFreqTail, c->dMaxHeight, c->dOverflow, c->stream, &c->launches));
-            CK(cudaMemcpyAsync(&c->hs->tallOverflow, c->dOverflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        } else if (c->allreduce) {
-            // sizes of the table reductions depend on the global maximum height: one extra round trip
-            if ((rc = hookReduce(c, c->dMaxHeight, 1, 0, 1))) return rc;
-            CK(cudaMemcpyAsync(&c->hs->maxHeight, c->dMaxHeight, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            tr.mark("scan + max-height reduce");
-            if ((rc = hookReduce(c, c->dFreqLow, kScanLowBins, 1, 0))) return rc;
-            if (c->hs->maxHeight >= kScanLowBins && (rc = hookReduce(c, c->dFreqTail + kScanLowBins, (size_t)c->hs->maxHeight - kScanLowBins + 1, 0, 0))) return rc;
-            if (tr.on) { CK(cudaStreamSynchronize(c->stream)); tr.mark("histogram reduce"); }
-        }
-        if ((rc = timerStart(c, c->tLut))) return rc;
-        CK(launch_freq_lut(c->dFreqLow, c->dFreqTail, c->dMaxHeight, c->dLut, c->dMaxCount, c->stream, &c->launches));
-        if ((rc = timerStop(c, c->tLut))) return rc;
-        CK(cudaMemcpyAsync(&c->hs->maxHeight, c->dMaxHeight, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(&c->hs->cursor, c->dCursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(&c->hs->maxCount, c->dMaxCount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+}  // extern "C"
+
+namespace {
+
+// One scan pass: state reset, k_scan, exchange of the height histogram, frequency LUT; leaves the pass scalars on their way
+// to the host (no synchronisation).
+int enqueueScanPass(ppp_ctx* c, Trace& tr) {
+    int rc;
+    CK(cudaMemsetAsync(c->dState, 0, sizeof(PassState) + (size_t)c->nTiles * sizeof(unsigned long long), c->stream));
+    if (c->prevMaxHeight >= kScanLowBins)
+        CK(cudaMemsetAsync(c->dFreqTail + kScanLowBins, 0, ((size_t)c->prevMaxHeight - kScanLowBins + 1) * sizeof(uint32_t), c->stream));
+    ScanParams p;
+    p.occ = c->occ;
+    p.cmpP = c->dCmp;
+    p.cmpM = c->dCmp + c->nStacksP;
+    p.tileOffP = c->dTileOffP;
+    p.tileOffM = c->dTileOffM;
+    p.G = c->G;
+    p.nTiles = c->nTiles;
+    p.batchTiles = scan_batch_tiles(c->nTiles);
+    p.minOv = c->minOv;
+    p.W = c->W;
+    p.ppIdx = c->ppOv - c->minOv;
+    p.haloLo = c->haloLo;
+    p.haloHi = c->haloHi;
+    p.state = c->dState;
+    p.tileState = c->dTileState;
+    p.freqLow = c->dState->freqLow;
+    p.freqTail = c->dFreqTail;
+    p.maxHeight = &c->dState->maxHeight;
+    p.recPos = c->dRecPos;
+    p.recRp = c->dRecRp;
+    p.recRm = c->dRecRm;
+    p.recMisc = c->dRecMisc;
+    p.capacity = c->pairCapacity;
+    p.ppRecs = c->dPP;
+    p.ppCapacity = c->ppCapacity;
+    // multi-GPU with known rank: heights beyond the shared-memory bins go to this rank's slot of the gather buffer
+    const bool gatherTall = c->allreduce && c->world > 1 && !c->denseTail;
+    const size_t slotWords = (size_t)kTallHeader + c->tallCap;
+    p.tallList = nullptr;
+    p.tallCount = nullptr;
+    p.tallCap = 0;
+    if (gatherTall) {
+        if (!c->dGather) CK(cudaMalloc(&c->dGather, (size_t)c->world * slotWords * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(c->dGather, 0, (size_t)c->world * slotWords * sizeof(uint32_t), c->stream));
+        uint32_t* slot = c->dGather + (size_t)c->rank * slotWords;
+        p.tallCount = slot;
+        p.maxHeight = slot + 1;
+        p.freqLow = reinterpret_cast<unsigned long long*>(slot + kTallLow);
+        p.tallList = slot + kTallHeader;
+        p.tallCap = c->tallCap;
+    }
+    if ((rc = timerStart(c, c->tScan))) return rc;
+    CK(launch_scan(p, c->repr, c->stream, &c->launches));
+    if ((rc = timerStop(c, c->tScan))) return rc;
+    if (gatherTall) {
+        // one all-reduce carries every rank's low bins, tall stacks and maximum height; no host round trip in between
+        if ((rc = hookReduce(c, c->dGather, (size_t)c->world * slotWords, 0, 0))) return rc;
+        CK(launch_tall_apply(c->dGather, c->world, c->tallCap, c->dState->freqLow, c->dFreqTail, &c->dState->maxHeight, &c->dState->overflow, c->stream, &c->launches));
+    } else if (c->allreduce) {
+        // sizes of the table reductions depend on the global maximum height: one extra round trip
+        if ((rc = hookReduce(c, &c->dState->maxHeight, 1, 0, 1))) return rc;
+        CK(cudaMemcpyAsync(&c->hs->maxHeight, &c->dState->maxHeight, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        tr.mark("histogram reduce + table");
+        tr.mark("scan + max-height reduce");
+        if ((rc = hookReduce(c, c->dState->freqLow, kScanLowBins, 1, 0))) return rc;
+        if (c->hs->maxHeight >= kScanLowBins && (rc = hookReduce(c, c->dFreqTail + kScanLowBins, (size_t)c->hs->maxHeight - kScanLowBins + 1, 0, 0))) return rc;
+        if (tr.on) { CK(cudaStreamSynchronize(c->stream)); tr.mark("histogram reduce"); }
+    }
+    if ((rc = timerStart(c, c->tLut))) return rc;
+    CK(launch_freq_lut(c->dState->freqLow, c->dFreqTail, &c->dState->maxHeight, c->dLut, &c->dState->maxCount, c->stream, &c->launches));
+    if ((rc = timerStop(c, c->tLut))) return rc;
+    CK(cudaMemcpyAsync(c->hs->totals, c->dState->totals, 40, cudaMemcpyDeviceToHost, c->stream));  // totals[2], maxCount, maxHeight, ticket, overflow, pad
+    return PPP_OK;
+}
+
+// Scan pass + what the host must know before the binning kernel: counts, overflow flags, the bin thresholds.
+int scanPass(ppp_ctx* c) {
+    Trace tr("height_hist");
+    int rc;
+    for (int attempt = 0;; ++attempt) {
+        if ((rc = enqueueScanPass(c, tr))) return rc;
+        CK(cudaStreamSynchronize(c->stream));
+        tr.mark("scan + histogram + table");
         c->prevMaxHeight = std::max(c->prevMaxHeight, c->hs->maxHeight);
         if (c->hs->tallOverflow) {  // (the same on every rank: it is read from the reduced buffer) -> dense tables, once and for all
             c->denseTail = true;
             continue;
         }
-        if (c->hs->cursor <= c->pairCapacity) break;
+        c->localOverflow = c->hs->totals[0] > c->pairCapacity || c->hs->totals[1] > c->ppCapacity;
+        if (!c->localOverflow) break;
+        if (c->allreduce) break;  // shards decide together, after the grouped counts were exchanged (ppp_scan)
         if (attempt >= 2) return fail(PPP_ERR_NOMEM, "signature store overflow");
-        if ((rc = ensurePairCapacity(c, c->hs->cursor + c->hs->cursor / 8 + 1024))) return rc;  // rerun with room for every record
+        if ((rc = ensurePairCapacity(c, c->hs->totals[0] + c->hs->totals[0] / 8 + 1024))) return rc;  // rerun with room for every record
     }
     c->maxHeight = c->hs->maxHeight;
-    c->nPairs = c->hs->cursor;
+    c->nPairs = std::min<uint64_t>(c->hs->totals[0], c->pairCapacity);
+    c->nPP = std::min<uint64_t>(c->hs->totals[1], c->ppCapacity);
 
     // bin thresholds from the (global) maximum frequency, with the host libm
     float maxFreq = (float)(c->hs->maxCount < kSaturate ? (uint32_t)c->hs->maxCount : kSaturate);  // :547-550
@@ -828,12 +909,47 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
     }
     CK(cudaMemcpyAsync(c->dThresholds, c->hThresholds, kBins * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     tr.mark("bin thresholds (host)");
+    return PPP_OK;
+}
+
+// Height-score bins + grouped counts of the records of the last scan pass, and their exchange.
+int binPass(ppp_ctx* c) {
+    int rc;
+    const size_t tableWords = (size_t)c->W * kBins * 4;
+    if ((rc = timerStart(c, c->tBin))) return rc;
+    CK(cudaMemsetAsync(c->dGrouped, 0, (tableWords + 1) * 4, c->stream));
+    if (c->localOverflow) CK(cudaMemsetAsync(c->dGrouped + tableWords, 1, 1, c->stream));  // little endian: the word becomes 1
+    if (c->nPairs) CK(launch_bin(c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dState->totals, c->pairCapacity, c->nPairs, c->dLut, c->dThresholds, c->binScale, c->W,
+                                 c->dGrouped, c->stream, &c->launches));
+    if ((rc = timerStop(c, c->tBin))) return rc;
+    // while the binning kernel runs: the monotonicity assumption behind the threshold table is checked on the host
+    if (c->thresholdFreq > 1.0f && !validateThresholds(c->thresholdFreq, c->hThresholds))
+        return fail(PPP_ERR_STATE, "host log10f is not monotone around a bin threshold");
+    return hookReduce(c, c->dGrouped, tableWords + 1, 0, 0);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (!c->finished) return fail(PPP_ERR_STATE, "call ppp_stacks_finish before ppp_height_hist");
+    CK(cudaSetDevice(c->device));
+    invalidateResults(c);
+    // signatures are ~0.1-0.3 per read on real densities; a scan that overflows the store reports the exact count and is re-run
+    // (a shard sizes the store for one signature per read; when that is still too small every rank re-runs, see ppp_scan)
+    uint64_t want = c->cfgPairCapacity ? c->cfgPairCapacity : std::max<uint64_t>((uint64_t)1 << 20, c->allreduce ? c->readsSubmitted : c->readsSubmitted / 3);
+    if (want < c->pairCapacity) want = c->pairCapacity;
+    int rc = ensurePairCapacity(c, want);
+    if (rc) return rc;
+    if ((rc = scanPass(c))) return rc;
 
     if (freq) {
         uint32_t mh = c->maxHeight;
         c->hFreq.assign((size_t)mh + 1, 0);
         std::vector<unsigned long long> low(kScanLowBins);
-        CK(cudaMemcpyAsync(low.data(), c->dFreqLow, kScanLowBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(low.data(), c->dState->freqLow, kScanLowBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         std::vector<uint32_t> tail;
         if (mh >= kScanLowBins) {
             tail.resize((size_t)mh - kScanLowBins + 1);
@@ -853,17 +969,22 @@ int ppp_scan(ppp_ctx* c, uint64_t* grouped, uint64_t* nPairs) {
     if (!c->haveHist) return fail(PPP_ERR_STATE, "call ppp_height_hist before ppp_scan");
     CK(cudaSetDevice(c->device));
     int rc;
-    size_t tableWords = (size_t)c->W * kBins * 4;
-    if ((rc = timerStart(c, c->tBin))) return rc;
-    CK(cudaMemsetAsync(c->dGrouped, 0, tableWords * 4, c->stream));
-    CK(exclusive_scan_u32(c->dTileCnt, c->dTileDst, c->nTiles, c->dScanScratch, c->scanScratchWords, c->stream, &c->launches));
-    CK(launch_bin_group(c->dPairsRaw, c->dPairs, c->dTileCnt, c->dTileBase, c->dTileDst, c->nTiles, c->dLut, c->dThresholds, c->binScale, c->W, c->dGrouped, c->dTileCursor, c->stream,
-                        &c->launches));
-    if ((rc = timerStop(c, c->tBin))) return rc;
-    // while the binning kernel runs: the monotonicity assumption behind the threshold table is checked on the host
-    if (c->thresholdFreq > 1.0f && !validateThresholds(c->thresholdFreq, c->hThresholds))
-        return fail(PPP_ERR_STATE, "host log10f is not monotone around a bin threshold");
-    if ((rc = hookReduce(c, c->dGrouped, tableWords, 0, 0))) return rc;
+    const size_t tableWords = (size_t)c->W * kBins * 4;
+    if ((rc = binPass(c))) return rc;
+    if (c->allreduce) {
+        // A shard whose signature store overflowed cannot re-run alone (the pass contains collectives): the number of such
+        // ranks travels with the grouped counts, and when it is not zero EVERY rank repeats the pass, the overflowed ones
+        // with a larger store.
+        for (int attempt = 0;; ++attempt) {
+            CK(cudaMemcpyAsync(&c->hs->rerun, c->dGrouped + tableWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (!c->hs->rerun) break;
+            if (attempt >= 2) return fail(PPP_ERR_NOMEM, "signature store overflow");
+            if (c->localOverflow && (rc = ensurePairCapacity(c, c->hs->totals[0] + c->hs->totals[0] / 8 + 1024))) return rc;
+            if ((rc = scanPass(c))) return rc;
+            if ((rc = binPass(c))) return rc;
+        }
+    }
     if (grouped) {
         std::vector<uint32_t> g(tableWords);
         CK(cudaMemcpyAsync(g.data(), c->dGrouped, tableWords * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -874,6 +995,7 @@ int ppp_scan(ppp_ctx* c, uint64_t* grouped, uint64_t* nPairs) {
     }
     if (nPairs) *nPairs = c->nPairs;
     c->haveScan = true;
+    c->viewValid = false;
     return PPP_OK;
 }
 
@@ -885,19 +1007,13 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     const int ppIdx = c->ppOv - c->minOv;
     Trace tr("score");
     if ((rc = timerStart(c, c->tScore))) return rc;
-    // which signatures are reported (and where) does not depend on the tables: counted on the sort stream (idle by now)
-    // while collapse and the FDR table run here
-    CK(cudaEventRecord(c->evFork, c->stream));
-    CK(cudaStreamWaitEvent(c->sortStream, c->evFork, 0));
-    CK(launch_score_count(c->dPairs, c->nPairs, ppIdx, minStackHeight, c->dBlockCnt, c->dScanScratch, c->scanScratchWords, c->sortStream, &c->launches));
-    CK(cudaEventRecord(c->evJoin, c->sortStream));
+    CK(cudaMemsetAsync(c->dScoreState, 0, sizeof(ScoreState) + score_tiles(c->nPP) * sizeof(unsigned long long), c->stream));
     CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dCellSums, c->stream, &c->launches));
     CK(launch_fdr_table(c->dCells, c->dNBins, kBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
-    CK(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
-    CK(launch_score_write(c->dPairs, c->nPairs, c->dFdr, c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dPairFdr, c->dLoci,
-                          c->dNLoci, c->dBlockCnt, c->stream, &c->launches));
+    if (c->nPP) CK(launch_score(c->dPP, c->dState->totals, c->ppCapacity, c->nPP, c->dScoreState, c->dScoreTiles, c->dLut, c->dThresholds, c->binScale, c->dFdr,
+                                c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dLoci, c->stream, &c->launches));
     if ((rc = timerStop(c, c->tScore))) return rc;
-    CK(cudaMemcpyAsync(&c->hs->nLoci, c->dNLoci, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->hs->nLoci, c->dScoreState, sizeof(ScoreState), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&c->hs->nBins, c->dNBins, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     tr.mark("binning + reduce + scoring");
@@ -942,6 +1058,8 @@ int ppp_pairs_download(ppp_ctx* c, ppp_pair* out, size_t capacity, size_t* n) {
     if (n) *n = (size_t)c->nPairs;
     if (!out) return PPP_OK;
     if (capacity < c->nPairs) return fail(PPP_ERR_ARG, "capacity %zu < %llu signatures", capacity, (unsigned long long)c->nPairs);
+    int rcView = ensurePairView(c);
+    if (rcView) return rcView;
     std::vector<PairRec> recs((size_t)c->nPairs);
     std::vector<float> fdr((size_t)c->nPairs, 0.f);
     std::vector<uint16_t> binMap(kBins, 0);
@@ -977,6 +1095,7 @@ int ppp_transposons(ppp_ctx* c, const ppp_interval* intervals, size_t n, ppp_tp_
     if (n && (!intervals || !results)) return fail(PPP_ERR_ARG, "null argument");
     CK(cudaSetDevice(c->device));
     int rc;
+    if ((rc = ensurePairView(c))) return rc;
     if ((rc = timerStart(c, c->tTransposon))) return rc;
     TransposonJob job;
     job.pairs = c->dPairs;
@@ -1007,6 +1126,9 @@ int ppp_transposons_sharded(ppp_ctx* const* ctxs, int n_ctx, const ppp_interval*
         ppp_ctx* c = ctxs[k];
         if (!c) return fail(PPP_ERR_ARG, "null context");
         if (!c->haveScore) return fail(PPP_ERR_STATE, "call ppp_score on every context before ppp_transposons_sharded");
+        CK(cudaSetDevice(c->device));
+        int rcView = ensurePairView(c);
+        if (rcView) return rcView;
         if (c->contigLen != ctxs[0]->contigLen || c->W != ctxs[0]->W || c->minOv != ctxs[0]->minOv || c->ppOv != ctxs[0]->ppOv)
             return fail(PPP_ERR_ARG, "contexts %d and 0 do not describe the same genome and overlap range", k);
         if (!c->ownedSlots.empty()) {  // ranges must ascend: the sums are chained in position order

@@ -48,25 +48,60 @@ struct __align__(16) PairRec {
     uint32_t misc;
 };
 
+// Scan-pass state that is zeroed (one memset) at the start of every pass; the look-back states of the tiles follow it
+// in the same allocation.
+struct PassState {
+    unsigned long long freqLow[kScanLowBins];  // height histogram, rounded heights < kScanLowBins
+    unsigned long long totals[2];              // signature records / overlap-`pingpong` records found (may exceed the capacities)
+    unsigned long long maxCount;               // largest height frequency (k_freq_lut)
+    uint32_t maxHeight;
+    uint32_t ticket;                           // next unclaimed tile of k_scan
+    uint32_t overflow;                         // multi-GPU: some rank listed more tall stacks than fit
+    uint32_t pad;
+};
+// State of one k_score launch (zeroed together with the look-back states that follow it).
+struct ScoreState {
+    unsigned long long nLoci;                  // reported loci
+    uint32_t ticket;                           // next unclaimed tile
+    uint32_t pad;
+};
+
+// Look-back state of one tile (decoupled look-back, Merrill & Garland): flag in bits 62..63, the number of
+// overlap-`pingpong` records in bits 34..61, the number of signature records in bits 0..33.
+constexpr int kLbRecBits = 34;
+constexpr unsigned long long kLbRecMask = (1ull << kLbRecBits) - 1;
+constexpr unsigned long long kLbValueMask = (1ull << 62) - 1;
+constexpr unsigned long long kLbAggregate = 1ull << 62, kLbPrefix = 2ull << 62;
+constexpr uint64_t kMaxPairCapacity = 0xfffffff0ull;       // signature records per context
+constexpr uint64_t kMaxLociCapacity = (1ull << 28) - 16;   // overlap-`pingpong` records per context
+
 struct ScanParams {
-    const uint32_t* H;      // both strands
     const uint32_t* occ;    // occupancy bitmap: bit i <-> word i of H (plus strand words [0, G/32), minus [G/32, 2G/32))
+    const uint32_t* cmpP;   // compact plus-strand stack words in position order (launch_compact)
+    const uint32_t* cmpM;   // compact minus-strand stack words
+    const uint32_t* tileOffP;  // [nTiles + 1] index in cmpP of the first stack of every tile
+    const uint32_t* tileOffM;
     uint64_t G;             // words per strand
-    uint32_t nTiles;
-    int minOv, W;
+    uint32_t nTiles, batchTiles;
+    int minOv, W, ppIdx;
     uint32_t haloLo, haloHi;  // minus-strand words in [haloLo, haloHi) are halo copies (not counted)
-    unsigned long long* freqLow;  // [kScanLowBins]
+    PassState* state;
+    unsigned long long* tileState;  // [nTiles]
+    unsigned long long* freqLow;  // [kScanLowBins] (state->freqLow, or this rank's slot of the gather buffer)
     uint32_t* freqTail;           // [kFreqCapacity] (entries >= kScanLowBins used)
     uint32_t* maxHeight;
     // multi-GPU: rounded heights >= kScanLowBins are appended here instead of counted in freqTail (see launch_tall_apply)
     uint32_t* tallList;           // null: count in freqTail
     unsigned int* tallCount;
     uint32_t tallCap;
-    PairRec* pairsRaw;
-    unsigned long long* cursor;   // total records produced (may exceed capacity)
+    // signature records in (position, overlap) order, structure of arrays
+    uint32_t* recPos;             // padded position of the plus stack
+    float* recRp;
+    float* recRm;
+    uint8_t* recMisc;             // bits 0..4 overlap index, bit 5 local bin, bit 6 bias bin
     uint64_t capacity;
-    uint32_t* tileCnt;
-    uint32_t* tileBase;
+    PairRec* ppRecs;           // the overlap-`pingpong` records once more, in position order (K4 reads only these)
+    uint64_t ppCapacity;
 };
 
 // ---- device helpers -------------------------------------------------------------------------
@@ -110,7 +145,13 @@ cudaError_t launch_small_batch(const ppp_read* reads, size_t n, uint32_t* H, uin
                                cudaStream_t s, int* launches);
 cudaError_t launch_stack_fold(const SortedRun& r, uint32_t* H, uint64_t G, uint32_t* occ, size_t capacity, cudaStream_t s, int* launches);
 
+// stacks_finish: dense accumulation arrays -> compact stack store (compact.cu)
+cudaError_t launch_tile_popc(const uint32_t* occ, uint64_t G, uint32_t nTiles, uint32_t* cntP, uint32_t* cntM, cudaStream_t s, int* launches);
+cudaError_t launch_compact_write(const uint32_t* H, const uint32_t* occ, uint64_t G, uint32_t nTiles, const uint32_t* offP, const uint32_t* offM,
+                                 uint32_t* cmpP, uint32_t* cmpM, cudaStream_t s, int* launches);
+
 cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* launches);
+uint32_t scan_batch_tiles(uint32_t nTiles);
 // Multi-GPU exchange of the height histogram in ONE collective.  `gather` holds one slot of kTallHeader + cap words
 // per rank: [count of tall stacks, local maximum height, the rank's low bins (kScanLowBins x u64), tall heights...];
 // every rank fills its own slot of a zeroed buffer and a sum all-reduce turns that into an all-gather.  The kernel
@@ -122,9 +163,11 @@ cudaError_t launch_tall_apply(const uint32_t* gather, int world, uint32_t cap, u
                               uint32_t* overflow, cudaStream_t s, int* launches);
 cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* freqTail, const uint32_t* maxHeight, float* lut,
                             unsigned long long* maxCount, cudaStream_t s, int* launches);
-cudaError_t launch_bin_group(const PairRec* raw, PairRec* ordered, const uint32_t* tileCnt, const uint32_t* tileBase, const uint32_t* tileDst, uint32_t nTiles,
-                             const float* lut, const float* thresholds, float binScale, int W, uint32_t* grouped, uint32_t* tileCursor, cudaStream_t s,
-                             int* launches);
+// `expected`: the host's idea of the number of records (sizes the grid; the kernel reads the exact count from `totals`)
+cudaError_t launch_bin(const float* recRp, const float* recRm, const uint8_t* recMisc, uint16_t* recBin, const unsigned long long* totals, uint64_t capacity,
+                       uint64_t expected, const float* lut, const float* thresholds, float binScale, int W, uint32_t* grouped, cudaStream_t s, int* launches);
+cudaError_t launch_pairs_view(const uint32_t* recPos, const float* recRp, const float* recRm, const uint8_t* recMisc, const uint16_t* recBin, size_t n,
+                              const float* fdrTable, const uint16_t* binMap, int W, PairRec* pairs, float* pairFdr, cudaStream_t s, int* launches);
 cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, uint16_t* groupStart, unsigned long long* sums,
                             cudaStream_t s, int* launches);
 cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, uint32_t maxBins, int W, int ppIdx, const double* xs, const double* ws, int nSteps,
@@ -133,12 +176,12 @@ struct LocusOut {
     uint32_t contig, position;
     float fdr, rp, rm;
 };
-// K4 in two halves: the per-block counts of reported loci (and their prefix sum) do not depend on the FDR table, so the
-// caller runs them beside collapse + FDR table on a second stream; the write needs both.
-cudaError_t launch_score_count(const PairRec* pairs, size_t nPairs, int ppIdx, uint32_t minHeight, uint32_t* blockCnt, uint32_t* scanScratch,
-                               size_t scanScratchWords, cudaStream_t s, int* launches);
-cudaError_t launch_score_write(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
-                               const Slot* slots, uint32_t nSlots, float* pairFdr, LocusOut* loci, unsigned long long* nLoci, const uint32_t* blockCnt,
-                               cudaStream_t s, int* launches);
+// K4, per-locus half (single pass, ordered): see score.cu.  `tileState` holds score_tiles(ppCapacity) words and is zeroed,
+// together with `state`, before every launch.
+cudaError_t launch_score(const PairRec* pp, const unsigned long long* totals, uint64_t ppCapacity, uint64_t expected, ScoreState* state,
+                         unsigned long long* tileState, const float* lut, const float* thresholds, float binScale, const float* fdrTable,
+                         const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight, const Slot* slots, uint32_t nSlots, LocusOut* loci, cudaStream_t s,
+                         int* launches);
+size_t score_tiles(uint64_t records);
 
 }  // namespace pppk

@@ -1,30 +1,30 @@
-// scan.cu -- the streaming pass over the dense stack arrays (K2 + K3 of SURVEY.md §8(a)).
+// scan.cu -- the pass over the stack store (K2 + K3 of SURVEY.md §8(a)).
 //
-// k_scan (fused, occupancy driven): ONE pass that
-//   (K2) builds the height -> frequency histogram of mapHeightsToScores (pingpongpro.cpp:502-509), and
-//   (K3) finds, for every plus stack, the minus stacks at overlaps min..max (:559-577), computes the vicinity
-//        mean / max (:570-578), the local-height bin (:597-599) and the base-bias bin (:602) and appends
-//        one record per (plus stack, minus stack, overlap) (:608).
-// Everything of countStacksByGroup that needs the finished histogram (the height-score bin :589-594 and the
-// grouped counter :605) is deferred to k_bin_group, which touches only the (few) signature records.
+// The stack store the pass reads is COMPACT (compact.cu builds it when the stack builder finishes): per strand the
+// non-empty stack words in position order, an occupancy bitmap (1 bit per position) and the index of every tile's
+// first stack.  Like the reference's std::map walk the work is proportional to the number of stacks, but every byte
+// of it is a coalesced stream: G/4 bytes of bitmap + 4 bytes per stack + the signature records.
 //
-// The dense stack arrays are ~96 % zeros.  A streaming version of this kernel (8 bytes per position, 256-bit loads,
-// shared-memory staging; 0.38 ms on configs[1] = 50 % of the HBM roofline, 70-80 % on the sparser mouse / human
-// sized genomes -- profiles/README.md) spent ~1500 instructions per 64 words mostly discovering that.  This version
-// reads the OCCUPANCY BITMAPS that the stack builder maintains (1 bit per word: G/4 bytes instead of 8 G) and gathers
-// only the words that exist, so the work is proportional to the number of stacks, like the reference's std::map walk
-// -- but over 8192 positions per CTA iteration in parallel:
-//   * a thread owns 32 consecutive positions = one bitmap word per strand (prefetched one tile ahead);
-//   * histogram: loop over the set bits, gather the word (one 32-byte sector), classify (height 1 in a register,
-//     heights 0..3 in packed byte counters, bins < 512 in shared memory, the tall tail by red.add to a global table);
-//   * the window test of a plus stack is one 64-bit funnel shift over two minus-strand bitmap words in shared memory;
-//   * all per-signature work is dense: block scan of (records, candidates), candidate list in shared memory, one
-//     thread per CANDIDATE gathers the present window words, evaluates the float expressions in the reference's
-//     order and writes its records.  The records of a tile are written contiguously (one atomicAdd on a global
-//     cursor) in (position, overlap) order; k_bin_group later copies the runs into global position order.
+// k_scan (fused): ONE pass that
+//   (K2) builds the height -> frequency histogram of mapHeightsToScores (pingpongpro.cpp:502-509): the compact words of
+//        a tile are read densely, 256 consecutive words per step, whatever their positions;
+//   (K3) finds, for every plus stack, the minus stacks at overlaps min..max (:559-577): the window test is one funnel
+//        shift over two minus-strand bitmap words in shared memory, the rank of a position inside the tile (prefix
+//        popcount) is the index of its word in the compact array, and the present stacks of a window are CONSECUTIVE
+//        compact words; then the vicinity mean / max (:570-578), the local-height bin (:597-599), the base-bias bin
+//        (:602) and one record per (plus stack, minus stack, overlap) (:608).
+// Records leave the kernel in global (position, overlap) order, straight into their final place: tiles are claimed in
+// order from a ticket counter, publish how many records they hold and find their first index by decoupled look-back
+// (Merrill & Garland) over the tiles before them.  The overlap-`pingpong` records are written a second time into a
+// stream of their own (16 B each) -- the scoring kernel (score.cu) reads nothing else.
+// Everything of countStacksByGroup that needs the finished histogram (the height-score bin :589-594 and the grouped
+// counter :605) is deferred to k_bin, which reads 9 bytes and writes 2 bytes per record.
 //
-// Bound: DRAM sector gathers (32 B per touched sector) + latency.  Algorithmic bytes in SURVEY §8(d)'s dense
-// accounting stay 8 * G + 16 * P per launch; the traffic actually moved is G/4 + 32 B per occupied sector + 16 * P.
+// Bound: HBM streaming.  Algorithmic bytes per launch: G/4 (bitmaps) + 4 S (stack words) + 13 P (records) + 16 P10
+// (overlap-`pingpong` stream) + 8 per tile (compact offsets); k_bin 11 P.  (SURVEY §8(d)'s dense accounting of the same
+// work is 16 G + 36 P.)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pppk {
@@ -32,10 +32,12 @@ namespace pppk {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
 constexpr int kPerThread = 32;                 // consecutive positions owned by one thread = one occupancy word per strand
-constexpr int kTile = kScanTile;               // 8192 positions per CTA iteration
+constexpr int kTile = kScanTile;               // 8192 positions per tile
 constexpr int kCandCap = 512;                  // candidates staged per round (a tile rarely has more)
 static_assert(kTile == kThreads * kPerThread, "tile geometry");
+static_assert(kTile <= (1 << 14) && kTile * PPP_MAX_OVERLAPS <= (1 << 20), "block-scan fields: 20 bits of records, 16 of candidates, 16 of ping-pong records");
 
 __device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
 #pragma unroll
@@ -45,9 +47,46 @@ __device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
     }
     return v;
 }
+__device__ __forceinline__ unsigned long long warp_inclusive64(unsigned long long v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+
+// Decoupled look-back, executed by one whole warp: the packed sum of the aggregates of all tiles before `tile`.  A tile's
+// state is ONE 64-bit word (flag + value), so a plain volatile load sees a consistent pair and no fence is needed.
+// Tiles are claimed in ticket order, hence every earlier tile belongs to a block that is already running.
+__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* __restrict__ state, uint32_t tile, int lane) {
+    unsigned long long sum = 0;
+    int64_t j = (int64_t)tile - 1;  // the nearest tile of the current window
+    while (j >= 0) {
+        const int64_t mine = j - lane;
+        unsigned long long v = kLbPrefix;  // before the first tile: an inclusive prefix of zero
+        if (mine >= 0) {
+            v = ld_state(state + mine);
+            while ((v >> 62) == 0ull) v = ld_state(state + mine);
+        }
+        const unsigned prefixLanes = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+        const int stop = prefixLanes ? __ffs(prefixLanes) - 1 : 32;  // the nearest tile that already knows its inclusive prefix
+        unsigned long long part = lane <= stop ? (v & kLbValueMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        sum += part;
+        if (prefixLanes) break;
+        j -= 32;
+    }
+    return sum;
+}
 
 // a stack taller than the shared-memory bins (rare): out of line, so that it costs the streaming loop no registers
 __device__ __noinline__ void count_tall(uint32_t* freqTail, uint32_t* tallList, unsigned int* tallCount, uint32_t tallCap, uint32_t r) {
+    if (r >= kFreqCapacity) r = kFreqCapacity - 1;  // (+inf of a malformed NH:i:0 record: never index past the table)
     if (tallList) {
         unsigned int i = atomicAdd(tallCount, 1u);
         if (i < tallCap) tallList[i] = r;
@@ -56,28 +95,43 @@ __device__ __noinline__ void count_tall(uint32_t* freqTail, uint32_t* tallList, 
     }
 }
 
+// 4-byte asynchronous copy global -> shared (LDGSTS): the next tile's occupancy words travel without occupying registers
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int REPR>
-__global__ void __launch_bounds__(kThreads, 8) k_scan(ScanParams P) {
-    __shared__ uint32_t sMask[2][kThreads + 2];  // minus-strand occupancy words of the tile + the word after it
+__global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
+    __shared__ uint32_t sMask[2][kThreads + 2];   // minus-strand occupancy words of the tile + the word after it + a zero
+    __shared__ uint32_t sPlus[2][kThreads];       // plus-strand occupancy words of the tile
+    __shared__ uint32_t sOff[2][4];               // compact index of the tile's first / past-the-last plus stack, first / past-the-last minus stack
+    __shared__ uint16_t sPrefM[kThreads + 2];     // minus stacks of the tile before each word of sMask
     __shared__ uint32_t sHist[kScanLowBins];
-    __shared__ uint32_t sWarpTot[kThreads / 32];
-    __shared__ unsigned long long sBase;
+    __shared__ uint32_t sWarpA[kWarps];               // per warp: plus stacks | minus stacks << 16
+    __shared__ unsigned long long sWarpB[kWarps];     // per warp: records | candidates << 20 | ping-pong records << 36
+    __shared__ unsigned long long sBase;              // packed number of records before this tile (kLb* layout)
+    __shared__ unsigned long long sCarry;             // (thread 0) the same for the next tile of the batch
+    __shared__ unsigned long long sFound[2];          // (thread 0) records / ping-pong records this block found
+    __shared__ uint32_t sNextBatch;
     __shared__ uint32_t sCandBits[kCandCap], sCandOff[kCandCap];  // per candidate: present overlaps / first record (tile-relative)
-    __shared__ uint16_t sCandTp[kCandCap];                        // its tile position
+    __shared__ uint16_t sCandTp[kCandCap], sCandRank[kCandCap], sCandPp[kCandCap];  // tile position / rank among the tile's plus stacks / ping-pong record
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < (int)kScanLowBins; k += kThreads) sHist[k] = 0;
     if (tid < 2) sMask[tid][kThreads + 1] = 0;
+    if (tid == 0) {
+        sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
+        sCarry = 0;
+        sFound[0] = sFound[1] = 0;
+    }
     __syncthreads();
 
     const uint32_t ONE = REPR == kReprInt ? 1u : 0x3f800000u;
     const uint32_t wMask = P.W >= 32 ? 0xffffffffu : ((1u << P.W) - 1u);
     const float fW = (float)P.W;
     const uint32_t myPos = (uint32_t)tid * kPerThread;  // this thread owns 32 consecutive positions of the tile
-    const uint32_t* __restrict__ occP = P.occ;
-    const uint32_t* __restrict__ occM = P.occ + P.G / 32;
-    const uint32_t* __restrict__ Hp = P.H;
-    const uint32_t* __restrict__ Hm = P.H + P.G;
     uint32_t ones = 0, localMax = 0, small = 0;  // small: four 8-bit counters for rounded heights 0..3
     auto flush_small = [&]() {
 #pragma unroll
@@ -85,151 +139,208 @@ __global__ void __launch_bounds__(kThreads, 8) k_scan(ScanParams P) {
             if ((small >> (8 * r)) & 0xffu) atomicAdd(&sHist[r], (small >> (8 * r)) & 0xffu);
         small = 0;
     };
-
-    // the occupancy words of the next tile are fetched while the current one is processed
-    uint32_t nextP = 0, nextM = 0, nextHalo = 0;
-    auto fetch = [&](uint32_t t) {
-        const size_t w = (size_t)t * kThreads;
-        nextP = __ldg(occP + w + tid);
-        nextM = __ldg(occM + w + tid);
-        if (tid == 0) nextHalo = __ldg(occM + w + kThreads);
+    auto classify = [&](uint32_t w) {  // K2: freq[(unsigned)(0.5 + reads)] += 1 (:508)
+        if ((w & kValueMask) == ONE) { ++ones; return; }
+        const uint32_t r = word_round_height<REPR>(w);
+        if (r < 4u) { small += 1u << (8 * r); if ((small & 0x80808080u) != 0u) flush_small(); }  // heights 0..3: byte counters in a register
+        else if (r < kScanLowBins) atomicAdd(&sHist[r], 1u);
+        else count_tall(P.freqTail, P.tallList, P.tallCount, P.tallCap, r);
+        localMax = max(localMax, r);
     };
-    if (blockIdx.x < P.nTiles) fetch(blockIdx.x);
-
+    // the occupancy words and compact offsets of a tile, global -> shared, asynchronously
+    auto fetch = [&](uint32_t t, int into) {
+        const size_t w = (size_t)t * kThreads;
+        cp_async4(&sPlus[into][tid], P.occ + w + tid);
+        cp_async4(&sMask[into][tid], P.occ + P.G / 32 + w + tid);
+        if (tid == 0) cp_async4(&sMask[into][kThreads], P.occ + P.G / 32 + w + kThreads);
+        if (tid >= 32 && tid < 36) cp_async4(&sOff[into][tid - 32], ((tid & 2) ? P.tileOffM : P.tileOffP) + t + (tid & 1));
+        cp_async_commit();
+    };
+    uint32_t batch = sNextBatch;
     int buf = 0;
-    for (uint32_t tile = blockIdx.x; tile < P.nTiles; tile += gridDim.x, buf ^= 1) {
-        const uint32_t tileBase = tile * (uint32_t)kTile;
-        const uint32_t nzP = nextP, nzM = nextM;
-        sMask[buf][tid] = nzM;
-        if (tid == 0) sMask[buf][kThreads] = nextHalo;
-        if (tile + gridDim.x < P.nTiles) fetch(tile + gridDim.x);
+    if (batch < P.nTiles) fetch(batch, buf);
 
-        // K2: height histogram over the stacks that exist (set bits), gathered from the dense arrays.
-        {
-            uint32_t mm = nzM;
-            if (tileBase < P.haloHi && tileBase + kTile > P.haloLo) {  // halo copies of a neighbouring shard are not counted
-                uint32_t first = tileBase + myPos;
-                uint32_t lo = P.haloLo > first ? P.haloLo - first : 0u, hi = P.haloHi > first ? P.haloHi - first : 0u;
-                uint32_t below = lo >= 32 ? 0xffffffffu : ((1u << lo) - 1u), upto = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
-                mm &= below | ~upto;
-            }
-            // up to four gathers (two per strand) are in flight per trip before any of them is classified
-            uint32_t nzA = nzP, nzB = mm;
-            while (nzA | nzB) {
-                uint32_t wv[4] = {0u, 0u, 0u, 0u};
-                if (nzA) { wv[0] = __ldg(Hp + tileBase + myPos + (uint32_t)(__ffs(nzA) - 1)); nzA &= nzA - 1; }
-                if (nzB) { wv[1] = __ldg(Hm + tileBase + myPos + (uint32_t)(__ffs(nzB) - 1)); nzB &= nzB - 1; }
-                if (nzA) { wv[2] = __ldg(Hp + tileBase + myPos + (uint32_t)(__ffs(nzA) - 1)); nzA &= nzA - 1; }
-                if (nzB) { wv[3] = __ldg(Hm + tileBase + myPos + (uint32_t)(__ffs(nzB) - 1)); nzB &= nzB - 1; }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (!wv[k]) continue;
-                    if ((wv[k] & kValueMask) == ONE) { ++ones; continue; }
-                    uint32_t r = word_round_height<REPR>(wv[k]);
-                    if (r < 4u) { small += 1u << (8 * r); if ((small & 0x80808080u) != 0u) flush_small(); }  // heights 0..3: byte counters in a register
-                    else if (r < kScanLowBins) atomicAdd(&sHist[r], 1u);
-                    else count_tall(P.freqTail, P.tallList, P.tallCount, P.tallCap, r);
-                    localMax = max(localMax, r);
+    while (batch < P.nTiles) {
+        const uint32_t batchEnd = min(batch + P.batchTiles, P.nTiles);
+        for (uint32_t tile = batch; tile < batchEnd; ++tile, buf ^= 1) {
+            const uint32_t tileBase = tile * (uint32_t)kTile;
+            cp_async_wait();
+            __syncthreads();  // (A) the tile's occupancy words are complete
+            const uint32_t nzP = sPlus[buf][tid], nzM = sMask[buf][tid];
+
+            // K3, bitmaps only: candidates = plus stacks with at least one minus stack at overlaps min..max
+            uint32_t cnt = 0, ncand = 0, npp = 0, cand = 0;
+            {
+                uint32_t nz = nzP;
+                while (nz) {
+                    const int b = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const uint32_t bit = myPos + b + P.minOv;
+                    const uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
+                    if (bits) { cnt += __popc(bits); ++ncand; cand |= 1u << b; npp += (bits >> P.ppIdx) & 1u; }
                 }
             }
-        }
-        __syncthreads();  // (A) the tile's minus occupancy words are complete
-
-        // K3: candidates = plus stacks with at least one minus stack at overlaps min..max (bitmaps only)
-        uint32_t cnt = 0, ncand = 0, cand = 0;
-        {
-            uint32_t nz = nzP;
-            while (nz) {
-                int b = __ffs(nz) - 1;
-                nz &= nz - 1;
-                uint32_t bit = myPos + b + P.minOv;
-                uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
-                if (bits) { cnt += __popc(bits); ++ncand; cand |= 1u << b; }
-            }
-        }
-        // records and candidates are ordered (thread, position[, overlap]) == (position[, overlap]);
-        // one warp scan carries both counters (records in the low 20 bits, candidates above)
-        const uint32_t packed = cnt | (ncand << 20);
-        const uint32_t inc = warp_inclusive(packed, lane);
-        if (lane == 31) sWarpTot[warp] = inc;
-        __syncthreads();  // (B)
-        uint32_t beforeP = 0, totalP = 0;
+            // block scans: stacks per strand (their ranks index the compact arrays), and (records, candidates, ping-pong
+            // records), which are ordered (thread, position[, overlap]) == (position[, overlap])
+            const uint32_t packA = (uint32_t)__popc(nzP) | ((uint32_t)__popc(nzM) << 16);
+            const unsigned long long packB = (unsigned long long)cnt | ((unsigned long long)ncand << 20) | ((unsigned long long)npp << 36);
+            uint32_t exA = warp_inclusive(packA, lane);
+            unsigned long long exB = warp_inclusive64(packB, lane);
+            if (lane == 31) { sWarpA[warp] = exA; sWarpB[warp] = exB; }
+            exA -= packA;
+            exB -= packB;
+            __syncthreads();  // (B)
+            unsigned long long totalB = 0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) {
-            uint32_t t = sWarpTot[w];
-            if (w < warp) beforeP += t;
-            totalP += t;
-        }
-        const uint32_t total = totalP & 0xfffffu, candTotal = totalP >> 20;
-        if (tid == 0) {
-            unsigned long long base = total ? atomicAdd(P.cursor, (unsigned long long)total) : 0ull;
-            sBase = base;
-            P.tileCnt[tile] = total;
-            P.tileBase[tile] = (uint32_t)base;
-        }
-        if (total) {  // block-uniform: the rare path, processed densely (one thread per candidate)
-            const uint32_t mine = beforeP + inc - packed;
-            const uint32_t firstRec = mine & 0xfffffu, firstCand = mine >> 20;  // tile-relative ranks of this thread's first record / candidate
-            for (uint32_t cbase = 0; cbase < candTotal; cbase += kCandCap) {
-                if (cbase) __syncthreads();  // the previous round's list is no longer read
-                uint32_t off = firstRec, rank = firstCand, cm = cand;
-                while (cm) {
-                    int b = __ffs(cm) - 1;
-                    cm &= cm - 1;
-                    uint32_t tp = myPos + b, bit = tp + P.minOv;
-                    uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
-                    uint32_t slot = rank - cbase;  // wraps to a huge value for earlier rounds
-                    if (slot < (uint32_t)kCandCap) { sCandTp[slot] = (uint16_t)tp; sCandBits[slot] = bits; sCandOff[slot] = off; }
-                    off += __popc(bits);
-                    ++rank;
+            for (int w = 0; w < kWarps; ++w) {
+                const unsigned long long b = sWarpB[w];
+                if (w < warp) { exA += sWarpA[w]; exB += b; }
+                totalB += b;
+            }
+            // exA: stacks of the tile before this thread's positions; exB: records / candidates / ping-pong records before them
+            const uint32_t total = (uint32_t)(totalB & 0xfffffu), candTotal = (uint32_t)((totalB >> 20) & 0xffffu);
+            sPrefM[tid] = (uint16_t)(exA >> 16);
+            if (tid == kThreads - 1) sPrefM[kThreads] = (uint16_t)((exA >> 16) + __popc(nzM));
+            const unsigned long long aggregate = (unsigned long long)total | ((totalB >> 36) << kLbRecBits);
+            const bool knowsPrefix = tile == 0 || tile != batch;  // the first tile of all, or a tile whose predecessor this block scanned itself
+            if (tid == 0) {
+                sFound[0] += total;
+                sFound[1] += totalB >> 36;
+                st_state(P.tileState + tile, knowsPrefix ? (kLbPrefix | ((sCarry + aggregate) & kLbValueMask)) : (kLbAggregate | aggregate));
+                if (tile + 1 == batchEnd) sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
+            }
+
+            // K2: height histogram, dense over the tile's compact words (halo copies of a neighbouring shard are not counted)
+            {
+                const uint32_t offP = sOff[buf][0], endP = sOff[buf][1], offM = sOff[buf][2], endM = sOff[buf][3];
+                for (uint32_t i = offP + tid; i < endP; i += kThreads * 2) {
+                    const uint32_t w0 = __ldg(P.cmpP + i);
+                    const uint32_t w1 = i + kThreads < endP ? __ldg(P.cmpP + i + kThreads) : 0u;
+                    classify(w0);
+                    if (w1) classify(w1);
                 }
-                __syncthreads();  // (C)
+                uint32_t skipLo = 0xffffffffu, skipHi = 0xffffffffu;  // ranks (within the tile) of the halo copies
+                if (tileBase < P.haloHi && tileBase + kTile > P.haloLo) {  // block-uniform, at most a few tiles per shard
+                    __syncthreads();  // sPrefM of this tile
+                    auto rankOf = [&](uint32_t q) {  // minus stacks of the tile at tile positions < q
+                        if (q >= (uint32_t)kTile) return (uint32_t)sPrefM[kThreads];
+                        return (uint32_t)sPrefM[q >> 5] + (uint32_t)__popc(sMask[buf][q >> 5] & ((1u << (q & 31)) - 1u));
+                    };
+                    skipLo = rankOf(P.haloLo > tileBase ? P.haloLo - tileBase : 0u);
+                    skipHi = rankOf(P.haloHi - tileBase);
+                }
+                for (uint32_t i = offM + tid; i < endM; i += kThreads * 2) {
+                    const uint32_t r0 = i - offM, r1 = r0 + kThreads;
+                    const uint32_t w0 = (r0 >= skipLo && r0 < skipHi) ? 0u : __ldg(P.cmpM + i);
+                    const uint32_t w1 = (i + kThreads < endM && !(r1 >= skipLo && r1 < skipHi)) ? __ldg(P.cmpM + i + kThreads) : 0u;
+                    if (w0) classify(w0);
+                    if (w1) classify(w1);
+                }
+            }
+
+            // where the tile's records go: look back over the tiles before it (warp 0; the other warps stage meanwhile)
+            if (warp == 0) {
+                unsigned long long before;
+                if (knowsPrefix) {
+                    before = sCarry;
+                } else {
+                    before = lookback_exclusive(P.tileState, tile, lane);
+                    if (lane == 0) st_state(P.tileState + tile, kLbPrefix | ((before + aggregate) & kLbValueMask));
+                }
+                if (lane == 0) { sBase = before; sCarry = before + aggregate; }
+            }
+
+            const uint32_t rounds = total ? (candTotal + kCandCap - 1) / kCandCap : 1u;  // (block-uniform)
+            for (uint32_t round = 0; round < rounds; ++round) {
+                const uint32_t cbase = round * kCandCap;
+                if (round) __syncthreads();  // the previous round's list is no longer read
+                {
+                    uint32_t off = (uint32_t)(exB & 0xfffffu), rank = (uint32_t)((exB >> 20) & 0xffffu), pp = (uint32_t)(exB >> 36), cm = cand;
+                    while (cm) {
+                        const int b = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        const uint32_t tp = myPos + b, bit = tp + P.minOv;
+                        const uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
+                        const uint32_t slot = rank - cbase;  // wraps to a huge value for earlier rounds
+                        if (slot < (uint32_t)kCandCap) {
+                            sCandTp[slot] = (uint16_t)tp;
+                            sCandBits[slot] = bits;
+                            sCandOff[slot] = off;
+                            sCandRank[slot] = (uint16_t)((exA & 0xffffu) + __popc(nzP & ((1u << b) - 1u)));
+                            sCandPp[slot] = (uint16_t)pp;
+                        }
+                        off += __popc(bits);
+                        pp += (bits >> P.ppIdx) & 1u;
+                        ++rank;
+                    }
+                }
+                __syncthreads();  // (C) the list, sBase, sPrefM and sNextBatch are visible
+                if (round == 0) {  // the next tile's occupancy words travel while the records are written
+                    const uint32_t nextTile = tile + 1 < batchEnd ? tile + 1 : sNextBatch;
+                    if (nextTile < P.nTiles) fetch(nextTile, buf ^ 1);
+                }
+                if (!total) break;
+                const unsigned long long recBase = sBase & kLbRecMask, ppBase = sBase >> kLbRecBits;
                 const uint32_t nIn = min((uint32_t)kCandCap, candTotal - cbase);
-                for (uint32_t c = tid; c < nIn; c += kThreads) {
+                for (uint32_t c = tid; c < nIn; c += kThreads) {  // dense: one thread per candidate
                     const uint32_t tp = sCandTp[c];
                     uint32_t bits = sCandBits[c];
-                    const uint32_t wp = __ldg(Hp + tileBase + tp);
-                    const uint32_t* win = Hm + tileBase + tp + P.minOv;  // first window word
+                    const uint32_t wp = __ldg(P.cmpP + sOff[buf][0] + sCandRank[c]);
+                    const uint32_t bit = tp + P.minOv, word = bit >> 5;
+                    // the present stacks of the window are consecutive compact words, starting at the rank of its first position
+                    const uint32_t* win = P.cmpM + sOff[buf][2] + sPrefM[word] + __popc(sMask[buf][word] & ((1u << (bit & 31)) - 1u));
+                    const int n = __popc(bits);
                     // vicinity sum / max over the PRESENT stacks only, in overlap order: an absent stack would add
                     // +0.0f, which is an exact no-op (:564-577)
                     float sum = 0.0f, mx = 0.0f;
-                    for (uint32_t rest = bits; rest; rest &= rest - 1) {
-                        float mq = word_height<REPR>(__ldg(win + (__ffs(rest) - 1)));
+                    for (int k = 0; k < n; ++k) {
+                        const float mq = word_height<REPR>(__ldg(win + k));
                         sum = __fadd_rn(sum, mq);
                         mx = fmaxf(mx, mq);
                     }
                     const float mean = __fdiv_rn(sum, fW);                    // :578
                     const float hp = word_height<REPR>(wp);
-                    unsigned long long idx = sBase + sCandOff[c];
-                    while (bits) {                                            // :584-586
+                    unsigned long long idx = recBase + sCandOff[c];
+                    for (int k = 0; k < n; ++k, ++idx) {                      // :584-586
                         const int o = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        const uint32_t wm = __ldg(win + o);  // second touch: served by L1
+                        const uint32_t wm = __ldg(win + k);  // second touch: served by L1
                         const float mo = word_height<REPR>(wm);
                         const float local = __fdiv_rn(__fsub_rn(mo, __fsub_rn(mean, __fdiv_rn(mo, fW))), mx);  // :597
                         const uint32_t lbin = ((double)local < 0.2) ? 1u : 0u;     // :599
                         const uint32_t bbin = ((wp | wm) & kA10Bit) ? 0u : 1u;     // :602
-                        if (idx < P.capacity) {
-                            PairRec r;
-                            r.lpos = tileBase + tp;
-                            r.rp = hp;
-                            r.rm = mo;
-                            r.misc = (uint32_t)o | (lbin << 5) | (bbin << 6);
-                            *reinterpret_cast<uint4*>(&P.pairsRaw[idx]) = *reinterpret_cast<uint4*>(&r);
+                        const uint32_t misc = (uint32_t)o | (lbin << 5) | (bbin << 6);
+                        if (idx < P.capacity) {                                    // :608
+                            P.recPos[idx] = tileBase + tp;
+                            P.recRp[idx] = hp;
+                            P.recRm[idx] = mo;
+                            P.recMisc[idx] = (uint8_t)misc;
                         }
-                        ++idx;
+                        if (o == P.ppIdx) {
+                            const unsigned long long j = ppBase + sCandPp[c];
+                            if (j < P.ppCapacity) {
+                                PairRec r;
+                                r.lpos = tileBase + tp;
+                                r.rp = hp;
+                                r.rm = mo;
+                                r.misc = misc;
+                                *reinterpret_cast<uint4*>(&P.ppRecs[j]) = *reinterpret_cast<uint4*>(&r);
+                            }
+                        }
                     }
                 }
             }
         }
+        batch = sNextBatch;  // (published by the last tile's barrier C; rewritten only after the next batch's barrier B)
     }
 
-    // flush the privatised histogram
+    // flush the privatised histogram and this block's record counts
     flush_small();
     if (ones) { atomicAdd(&sHist[1], ones); localMax = max(localMax, 1u); }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) localMax = max(localMax, __shfl_xor_sync(0xffffffffu, localMax, d));
     if (lane == 0 && localMax) atomicMax(P.maxHeight, localMax);
+    if (tid == 0 && (sFound[0] | sFound[1])) { atomicAdd(&P.state->totals[0], sFound[0]); atomicAdd(&P.state->totals[1], sFound[1]); }
     __syncthreads();
     for (int k = tid; k < (int)kScanLowBins; k += kThreads) {
         uint32_t c = sHist[k];
@@ -276,31 +387,30 @@ __global__ void __launch_bounds__(256) k_freq_lut(const unsigned long long* __re
     if ((threadIdx.x & 31) == 0 && best) atomicMax(maxCount, best);
 }
 
-// K3 part 2: height-score bin (:589-594) + grouped counter (:605) of every signature, and the copy of the
-// per-tile runs into global (position, overlap) order.  Persistent blocks; each WARP takes whole tiles, so a
-// record's tile (and with it its ordered destination) is known without a search.
+// K3 part 2: height-score bin (:589-594) + grouped counter (:605) of every signature record.
 // The bin of a height-score product is the number of host-built thresholds <= hs (see api.cu).  A device log10
 // approximation proposes the bin, two short loops against the exact thresholds correct it, so the result is the
-// exact step function whatever the approximation error.
-// The grouped counters are concentrated on a few hundred hot cells (singleton x singleton pairs all land in the
-// top bin), so updates are merged per warp (match.any), then per block in a shared-memory hash table that lives
-// for the whole kernel; only the table's entries reach the global (L2) counters.
-constexpr int kBgThreads = 512;
-constexpr int kBgWarps = kBgThreads / 32;
-constexpr int kBgHash = 4096;
-constexpr int kBgPerLane = 2;               // records per lane in flight
-constexpr int kBgItem = 32 * kBgPerLane;    // records per work item
-constexpr uint32_t kBgEmpty = 0xffffffffu;
-__global__ void __launch_bounds__(kBgThreads) k_bin_group(const PairRec* __restrict__ raw, PairRec* __restrict__ ordered, const uint32_t* __restrict__ tileCnt,
-                                                          const uint32_t* __restrict__ tileBase, const uint32_t* __restrict__ tileDst, uint32_t nTiles,
-                                                          const float* __restrict__ lut, const float* __restrict__ thresholds, float binScale, int W,
-                                                          uint32_t* __restrict__ grouped, uint32_t* __restrict__ tileCursor) {
+// exact step function whatever the approximation error.  Pairs of stacks with rounded heights below 4 (the bulk:
+// singletons) take their bin from a 16-entry table evaluated once per block.
+// The grouped counters are concentrated on few cells: those of the (height 1, height 1) bin are counted in per-warp
+// private shared-memory tables (index = the record's 7 misc bits), all others in a direct-mapped shared-memory cache of
+// (cell, count) slots; a record whose slot is taken by another cell goes straight to the global (L2-resident) table.
+constexpr int kBinThreads = 512;
+constexpr int kBinWarps = kBinThreads / 32;
+constexpr int kBinCache = 4096;
+constexpr uint32_t kBinEmpty = 0xffffffffu;
+__global__ void __launch_bounds__(kBinThreads) k_bin(const float* __restrict__ recRp, const float* __restrict__ recRm, const uint8_t* __restrict__ recMisc,
+                                                     uint16_t* __restrict__ recBin, const unsigned long long* __restrict__ totals, uint64_t capacity,
+                                                     const float* __restrict__ lut, const float* __restrict__ thresholds, float binScale, int W,
+                                                     uint32_t* __restrict__ grouped) {
     __shared__ float sThr[kBins];
-    __shared__ uint32_t sKey[kBgHash], sVal[kBgHash];
-    __shared__ uint32_t sFirst, sItemStart[33 + 16], sCnt[32], sSrc[32], sDst[32];
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int k = tid; k < kBins - 1; k += kBgThreads) sThr[k] = thresholds[k];
-    for (int k = tid; k < kBgHash; k += kBgThreads) { sKey[k] = kBgEmpty; sVal[k] = 0; }
+    __shared__ uint32_t sKey[kBinCache], sVal[kBinCache];
+    __shared__ uint32_t sOnes[kBinWarps][128];
+    __shared__ uint16_t sSmallBin[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < kBins - 1; k += kBinThreads) sThr[k] = thresholds[k];
+    for (int k = tid; k < kBinCache; k += kBinThreads) { sKey[k] = kBinEmpty; sVal[k] = 0; }
+    for (int k = tid; k < kBinWarps * 128; k += kBinThreads) (&sOnes[0][0])[k] = 0;
     __syncthreads();
     auto bin_of = [&](float hs) {
         int b = (int)(__log10f(hs) * binScale + 0.5f);             // proposal only
@@ -309,81 +419,57 @@ __global__ void __launch_bounds__(kBgThreads) k_bin_group(const PairRec* __restr
         while (b < kBins - 1 && sThr[b] <= hs) ++b;
         return b;
     };
-    auto count_cell = [&](bool ok, uint32_t cell) {                // :605, one update per distinct cell per warp
-        const unsigned act = __ballot_sync(0xffffffffu, ok);
-        if (!ok) return;
-        const unsigned peers = __match_any_sync(act, cell);
-        if (lane != __ffs(peers) - 1) return;
-        const uint32_t n = (uint32_t)__popc(peers);
-        uint32_t h = (cell * 2654435761u) >> 20;
-        for (int probe = 0; probe < 32; ++probe) {
-            uint32_t old = atomicCAS(&sKey[h], kBgEmpty, cell);
-            if (old == kBgEmpty || old == cell) { atomicAdd(&sVal[h], n); return; }
-            h = (h + 1) & (kBgHash - 1);
-        }
-        atomicAdd(&grouped[cell], n);
-    };
-    // Work is handed out dynamically, 32 tiles per block at a time (one atomic per batch: a single global counter
-    // serialises at ~1 ns per atomic).  Signature-dense tiles hold thousands of records and every 64-record step is
-    // latency bound, so the block's warps share the 64-record items of ALL tiles of the batch instead of owning tiles.
-    const int warp = tid >> 5;
-    for (;;) {
-        if (tid == 0) sFirst = atomicAdd(tileCursor, 32u);
-        __syncthreads();
-        const uint32_t first = sFirst;
-        if (first >= nTiles) break;
-        if (warp == 0) {
-            const uint32_t tile = first + lane;
-            const uint32_t cnt = tile < nTiles ? tileCnt[tile] : 0u;
-            sCnt[lane] = cnt;
-            sSrc[lane] = tile < nTiles ? tileBase[tile] : 0u;
-            sDst[lane] = tile < nTiles ? tileDst[tile] : 0u;
-            const uint32_t items = (cnt + (uint32_t)kBgItem - 1u) / (uint32_t)kBgItem;
-            const uint32_t inc = warp_inclusive(items, lane);
-            sItemStart[lane] = inc - items;
-            if (lane == 31) sItemStart[32] = inc;
-        }
-        __syncthreads();
-        const uint32_t totalItems = sItemStart[32];
-        for (uint32_t item = warp; item < totalItems; item += kBgWarps) {
-            int t = 0;  // tile slot with sItemStart[t] <= item < sItemStart[t + 1] (warp-uniform)
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (sItemStart[t + step] <= item) t += step;
-            const uint32_t cnt = sCnt[t], base = (item - sItemStart[t]) * (uint32_t)kBgItem;
-            const size_t src = sSrc[t], dst = sDst[t];
-            PairRec r[kBgPerLane];
-            bool ok[kBgPerLane];
-            float fp[kBgPerLane], fm[kBgPerLane];
-#pragma unroll
-            for (int u = 0; u < kBgPerLane; ++u) {  // kBgPerLane independent record loads in flight per lane
-                const uint32_t i = base + u * 32 + lane;
-                ok[u] = i < cnt;
-                r[u] = PairRec{0, 1.f, 1.f, 0};
-                if (ok[u]) *reinterpret_cast<uint4*>(&r[u]) = *reinterpret_cast<const uint4*>(&raw[src + i]);
-            }
-#pragma unroll
-            for (int u = 0; u < kBgPerLane; ++u) {  // heightScoreMap[0.5 + reads], :582 / :589
-                fp[u] = lut[round_height(r[u].rp)];
-                fm[u] = lut[round_height(r[u].rm)];
-            }
-#pragma unroll
-            for (int u = 0; u < kBgPerLane; ++u) {
-                uint32_t cell = 0;
-                if (ok[u]) {
-                    int b = bin_of(__fmul_rn(fp[u], fm[u]));
-                    r[u].misc |= (uint32_t)b << 7;
-                    cell = ((((uint32_t)b * (uint32_t)W + (r[u].misc & 31u)) * 2u + ((r[u].misc >> 6) & 1u)) * 2u) + ((r[u].misc >> 5) & 1u);  // bin-major table
-                    *reinterpret_cast<uint4*>(&ordered[dst + base + u * 32 + lane]) = *reinterpret_cast<uint4*>(&r[u]);
-                }
-                count_cell(ok[u], cell);
-            }
-        }
-        __syncthreads();  // the batch descriptors are overwritten next
+    if (tid < 16) sSmallBin[tid] = (uint16_t)bin_of(__fmul_rn(lut[tid >> 2], lut[tid & 3]));  // (a height that never occurs has lut 0: never looked up)
+    __syncthreads();
+    const uint32_t onesBin = sSmallBin[5];  // rounded heights (1, 1)
+    unsigned long long n = totals[0];
+    if (n > capacity) n = capacity;
+    for (size_t i = (size_t)blockIdx.x * kBinThreads + tid; i < n; i += (size_t)gridDim.x * kBinThreads) {
+        const float rp = recRp[i], rm = recRm[i];
+        const uint32_t misc = recMisc[i];
+        const uint32_t hp = round_height(rp), hm = round_height(rm);  // heightScoreMap[0.5 + reads], :582 / :589
+        uint32_t b;
+        if ((hp | hm) < 4u) b = sSmallBin[hp * 4 + hm];
+        else b = (uint32_t)bin_of(__fmul_rn(lut[hp], lut[hm]));
+        recBin[i] = (uint16_t)b;
+        if (b == onesBin) { atomicAdd(&sOnes[warp][misc & 127u], 1u); continue; }
+        const uint32_t cell = (((b * (uint32_t)W + (misc & 31u)) * 2u + ((misc >> 6) & 1u)) * 2u) + ((misc >> 5) & 1u);  // bin-major table, :605
+        const uint32_t h = (cell * 2654435761u) >> 20;
+        uint32_t key = sKey[h];
+        if (key == kBinEmpty) key = atomicCAS(&sKey[h], kBinEmpty, cell);
+        if (key == kBinEmpty || key == cell) atomicAdd(&sVal[h], 1u);
+        else atomicAdd(&grouped[cell], 1u);
     }
     __syncthreads();
-    for (int k = tid; k < kBgHash; k += kBgThreads)
-        if (sKey[k] != kBgEmpty) atomicAdd(&grouped[sKey[k]], sVal[k]);
+    for (int k = tid; k < kBinCache; k += kBinThreads)
+        if (sKey[k] != kBinEmpty && sVal[k]) atomicAdd(&grouped[sKey[k]], sVal[k]);
+    if (tid < 128) {
+        uint32_t c = 0;
+        for (int w = 0; w < kBinWarps; ++w) c += sOnes[w][tid];
+        if (c) {
+            const uint32_t misc = (uint32_t)tid;
+            atomicAdd(&grouped[(((onesBin * (uint32_t)W + (misc & 31u)) * 2u + ((misc >> 6) & 1u)) * 2u) + ((misc >> 5) & 1u)], c);
+        }
+    }
+    (void)lane;
+}
+
+// Test / writer / K5 view of the records: array-of-structures PairRec with the bin in misc bits 7..16 and the FDR of every
+// record (:750-753), materialised on demand (ppp_pairs_download, ppp_transposons) -- never inside a scan + score pass.
+__global__ void __launch_bounds__(256) k_pairs_view(const uint32_t* __restrict__ recPos, const float* __restrict__ recRp, const float* __restrict__ recRm,
+                                                    const uint8_t* __restrict__ recMisc, const uint16_t* __restrict__ recBin, size_t n,
+                                                    const float* __restrict__ fdrTable, const uint16_t* __restrict__ binMap, int W, PairRec* __restrict__ pairs,
+                                                    float* __restrict__ pairFdr) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t misc = recMisc[i], bin = recBin[i];
+    PairRec r;
+    r.lpos = recPos[i];
+    r.rp = recRp[i];
+    r.rm = recRm[i];
+    r.misc = misc | (bin << 7);
+    *reinterpret_cast<uint4*>(&pairs[i]) = *reinterpret_cast<uint4*>(&r);
+    if (fdrTable) pairFdr[i] = fdrTable[((size_t)binMap[bin] * W + (misc & 31u)) * 4 + ((misc >> 6) & 1u) * 2 + ((misc >> 5) & 1u)];  // :682, :753
 }
 
 }  // namespace
@@ -393,16 +479,23 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int perSm = 8;
+    int perSm = 5;
     if (repr == kReprInt) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprInt>, kThreads, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprFloat>, kThreads, 0);
     if (perSm < 1) perSm = 1;
     unsigned grid = (unsigned)sms * (unsigned)perSm;
-    if (grid > p.nTiles) grid = p.nTiles;
+    const unsigned batches = (p.nTiles + p.batchTiles - 1) / p.batchTiles;
+    if (grid > batches) grid = batches;
     if (repr == kReprInt) k_scan<kReprInt><<<grid, kThreads, 0, s>>>(p);
     else k_scan<kReprFloat><<<grid, kThreads, 0, s>>>(p);
     if (launches) *launches += 1;
     return cudaGetLastError();
+}
+
+// tiles claimed per ticket: one atomic on a single address costs ~1 ns, so large genomes take several tiles at a time
+uint32_t scan_batch_tiles(uint32_t nTiles) {
+    uint32_t b = nTiles / (148u * 6u * 8u);
+    return b < 1u ? 1u : (b > 8u ? 8u : b);
 }
 
 cudaError_t launch_tall_apply(const uint32_t* gather, int world, uint32_t cap, unsigned long long* freqLow, uint32_t* freqTail, uint32_t* maxHeight,
@@ -419,18 +512,22 @@ cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* f
     return cudaGetLastError();
 }
 
-cudaError_t launch_bin_group(const PairRec* raw, PairRec* ordered, const uint32_t* tileCnt, const uint32_t* tileBase, const uint32_t* tileDst, uint32_t nTiles,
-                             const float* lut, const float* thresholds, float binScale, int W, uint32_t* grouped, uint32_t* tileCursor, cudaStream_t s,
-                             int* launches) {
-    if (nTiles == 0) return cudaSuccess;
+cudaError_t launch_bin(const float* recRp, const float* recRm, const uint8_t* recMisc, uint16_t* recBin, const unsigned long long* totals, uint64_t capacity,
+                       uint64_t expected, const float* lut, const float* thresholds, float binScale, int W, uint32_t* grouped, cudaStream_t s, int* launches) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    unsigned blocks = (nTiles + kBgWarps - 1) / kBgWarps;
-    if (blocks > (unsigned)sms * 4u) blocks = (unsigned)sms * 4u;  // 4 x 512 threads = full occupancy; the kernel is load-latency bound
-    cudaError_t e = cudaMemsetAsync(tileCursor, 0, sizeof(uint32_t), s);
-    if (e != cudaSuccess) return e;
-    k_bin_group<<<blocks, kBgThreads, 0, s>>>(raw, ordered, tileCnt, tileBase, tileDst, nTiles, lut, thresholds, binScale, W, grouped, tileCursor);
+    uint64_t want = (expected + kBinThreads * 8 - 1) / (kBinThreads * 8);  // >= 8 records per thread: the tables are flushed once per block
+    unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)sms * 4);
+    k_bin<<<blocks, kBinThreads, 0, s>>>(recRp, recRm, recMisc, recBin, totals, capacity, lut, thresholds, binScale, W, grouped);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pairs_view(const uint32_t* recPos, const float* recRp, const float* recRm, const uint8_t* recMisc, const uint16_t* recBin, size_t n,
+                              const float* fdrTable, const uint16_t* binMap, int W, PairRec* pairs, float* pairFdr, cudaStream_t s, int* launches) {
+    if (n == 0) return cudaSuccess;
+    k_pairs_view<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(recPos, recRp, recRm, recMisc, recBin, n, fdrTable, binMap, W, pairs, pairFdr);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

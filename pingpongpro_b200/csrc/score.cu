@@ -11,6 +11,8 @@
 //   k_score_*     per-signature FDR lookup (:750-753) fused with the -s filter (:903) and an
 //                 order-preserving compaction (count -> scan -> write) of the overlap-10 loci.
 // All of it is latency-bound bookkeeping on kilobytes .. a few megabytes.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pppk {
@@ -180,65 +182,122 @@ __global__ void __launch_bounds__(kFdrWarps * 32) k_fdr_table(const float* __res
     }
 }
 
+// K4, per-locus half: the reported loci = the overlap-`pingpong` records (the stream k_scan wrote in position order) that
+// pass the -s filter (:903), each with the FDR of its (collapsed bin, bias, local) cell (:750-753), compacted in order in
+// ONE pass: blocks claim tiles of 1024 records from a ticket counter and find their first output slot by decoupled
+// look-back (see scan.cu).  The height-score bin of a record is re-evaluated here (same thresholds, same step function as
+// k_bin) instead of being fetched from the all-overlap record arrays.
 constexpr int kScoreThreads = 256;
+constexpr int kScoreRounds = 4;
+constexpr int kScoreTile = kScoreThreads * kScoreRounds;
+constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagValue = (1ull << 62) - 1;
 
-__device__ __forceinline__ bool reported(const PairRec& r, int ppIdx, float minHeight) {
-    return (int)(r.misc & 31u) == ppIdx && r.rp >= minHeight && r.rm >= minHeight;  // :903
-}
-
-__global__ void __launch_bounds__(kScoreThreads) k_score_count(const PairRec* __restrict__ pairs, size_t n, int ppIdx, float minHeight, uint32_t* __restrict__ blockCnt) {
-    size_t i = (size_t)blockIdx.x * kScoreThreads + threadIdx.x;
-    bool keep = false;
-    if (i < n) {
-        PairRec r;
-        *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(&pairs[i]);
-        keep = reported(r, ppIdx, minHeight);
-    }
-    int c = __syncthreads_count(keep);
-    if (threadIdx.x == 0) blockCnt[blockIdx.x] = (uint32_t)c;
-}
-
-__global__ void __launch_bounds__(kScoreThreads) k_score_write(const PairRec* __restrict__ pairs, size_t n, const float* __restrict__ fdrTable,
-                                                               const uint16_t* __restrict__ binMap, int W, int ppIdx, float minHeight, const Slot* __restrict__ slots,
-                                                               uint32_t nSlots, const uint32_t* __restrict__ blockOff, uint32_t nBlocks, float* __restrict__ pairFdr,
-                                                               LocusOut* __restrict__ loci, unsigned long long* nLoci) {
-    __shared__ uint32_t sWarp[kScoreThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    size_t i = (size_t)blockIdx.x * kScoreThreads + threadIdx.x;
-    bool keep = false;
-    PairRec r;
-    float fdr = 0.f;
-    if (i < n) {
-        *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(&pairs[i]);
-        uint32_t ov = r.misc & 31u, bin = binMap[(r.misc >> 7) & 1023u];                      // :682
-        fdr = fdrTable[((size_t)bin * W + ov) * 4 + ((r.misc >> 6) & 1u) * 2 + ((r.misc >> 5) & 1u)];  // :753
-        pairFdr[i] = fdr;
-        keep = reported(r, ppIdx, minHeight);
-    }
-    unsigned ballot = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) sWarp[warp] = __popc(ballot);
+__global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restrict__ pp, const unsigned long long* __restrict__ totals, uint64_t ppCapacity,
+                                                         ScoreState* __restrict__ st, unsigned long long* __restrict__ tileState, const float* __restrict__ lut,
+                                                         const float* __restrict__ thresholds, float binScale, const float* __restrict__ fdrTable,
+                                                         const uint16_t* __restrict__ binMap, int W, int ppIdx, float minHeight, const Slot* __restrict__ slots,
+                                                         uint32_t nSlots, LocusOut* __restrict__ loci) {
+    __shared__ float sThr[kBins];
+    __shared__ uint16_t sSmallBin[16];
+    __shared__ uint32_t sCnt[kScoreRounds * (kScoreThreads / 32) + 1];
+    __shared__ uint32_t sTile;
+    __shared__ unsigned long long sBase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < kBins - 1; k += kScoreThreads) sThr[k] = thresholds[k];
     __syncthreads();
-    uint32_t before = 0;
-    for (int w = 0; w < warp; ++w) before += sWarp[w];
-    if (keep) {
-        uint32_t dst = blockOff[blockIdx.x] + before + __popc(ballot & ((1u << lane) - 1u));
-        uint32_t lo = 0, hi = nSlots;  // slot that contains lpos
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (slots[mid].off <= r.lpos) lo = mid; else hi = mid;
+    auto bin_of = [&](float hs) {
+        int b = (int)(__log10f(hs) * binScale + 0.5f);             // proposal only
+        b = min(max(b, 0), kBins - 1);
+        while (b > 0 && sThr[b - 1] > hs) --b;                    // exact: bin = #thresholds <= hs
+        while (b < kBins - 1 && sThr[b] <= hs) ++b;
+        return b;
+    };
+    if (tid < 16) sSmallBin[tid] = (uint16_t)bin_of(__fmul_rn(lut[tid >> 2], lut[tid & 3]));
+    unsigned long long n = totals[1];
+    if (n > ppCapacity) n = ppCapacity;
+    const uint32_t nTiles = (uint32_t)((n + kScoreTile - 1) / kScoreTile);
+    for (;;) {
+        __syncthreads();  // sTile / sCnt / sBase of the previous tile are no longer read; sSmallBin is complete
+        if (tid == 0) sTile = atomicAdd(&st->ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if (tile >= nTiles) break;
+        const size_t first = (size_t)tile * kScoreTile;
+        PairRec r[kScoreRounds];
+        bool keep[kScoreRounds];
+        unsigned ballot[kScoreRounds];
+#pragma unroll
+        for (int k = 0; k < kScoreRounds; ++k) {  // record order inside the tile = (round, thread)
+            const size_t i = first + (size_t)k * kScoreThreads + tid;
+            keep[k] = false;
+            if (i < n) {
+                *reinterpret_cast<uint4*>(&r[k]) = *reinterpret_cast<const uint4*>(&pp[i]);
+                keep[k] = r[k].rp >= minHeight && r[k].rm >= minHeight;  // :903
+            }
+            ballot[k] = __ballot_sync(0xffffffffu, keep[k]);
+            if (lane == 0) sCnt[k * (kScoreThreads / 32) + warp] = __popc(ballot[k]);
         }
-        LocusOut o;
-        o.contig = slots[lo].contig;
-        o.position = r.lpos - slots[lo].off + slots[lo].first;
-        o.fdr = fdr;
-        o.rp = r.rp;
-        o.rm = r.rm;
-        loci[dst] = o;
-    }
-    if (blockIdx.x == nBlocks - 1 && threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < kScoreThreads / 32; ++w) tot += sWarp[w];
-        *nLoci = (unsigned long long)blockOff[blockIdx.x] + tot;
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the 32 (round, warp) counts, then the look-back over the tiles before this one
+            const uint32_t c = sCnt[lane];
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+            sCnt[lane] = inc - c;
+            unsigned long long before = 0;
+            if (tile == 0) {
+                if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(tileState) = kFlagPrefix | total;
+            } else {
+                if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(tileState + tile) = kFlagAggregate | total;
+                int64_t j = (int64_t)tile - 1;
+                while (j >= 0) {
+                    const int64_t mine = j - lane;
+                    unsigned long long v = kFlagPrefix;
+                    if (mine >= 0) {
+                        v = *reinterpret_cast<const volatile unsigned long long*>(tileState + mine);
+                        while ((v >> 62) == 0ull) v = *reinterpret_cast<const volatile unsigned long long*>(tileState + mine);
+                    }
+                    const unsigned prefixLanes = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+                    const int stop = prefixLanes ? __ffs(prefixLanes) - 1 : 32;
+                    unsigned long long part = lane <= stop ? (v & kFlagValue) : 0ull;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                    before += part;
+                    if (prefixLanes) break;
+                    j -= 32;
+                }
+                if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(tileState + tile) = kFlagPrefix | (before + total);
+            }
+            if (lane == 0) {
+                sBase = before;
+                if (tile + 1 == nTiles) st->nLoci = before + total;
+            }
+        }
+        __syncthreads();
+        const unsigned long long base = sBase;
+#pragma unroll
+        for (int k = 0; k < kScoreRounds; ++k) {
+            if (!keep[k]) continue;
+            const uint32_t hp = round_height(r[k].rp), hm = round_height(r[k].rm);  // heightScoreMap[0.5 + reads], :582 / :589
+            const uint32_t bin = (hp | hm) < 4u ? sSmallBin[hp * 4 + hm] : (uint32_t)bin_of(__fmul_rn(lut[hp], lut[hm]));
+            const uint32_t cb = binMap[bin];                                                      // :682
+            LocusOut o;
+            o.fdr = fdrTable[((size_t)cb * W + ppIdx) * 4 + ((r[k].misc >> 6) & 1u) * 2 + ((r[k].misc >> 5) & 1u)];  // :753
+            uint32_t lo = 0, hi = nSlots;  // slot that contains lpos
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (slots[mid].off <= r[k].lpos) lo = mid; else hi = mid;
+            }
+            o.contig = slots[lo].contig;
+            o.position = r[k].lpos - slots[lo].off + slots[lo].first;
+            o.rp = r[k].rp;
+            o.rm = r[k].rm;
+            loci[base + sCnt[k * (kScoreThreads / 32) + warp] + __popc(ballot[k] & ((1u << lane) - 1u))] = o;
+        }
     }
 }
 
@@ -265,25 +324,21 @@ cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, uint32_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_score_count(const PairRec* pairs, size_t nPairs, int ppIdx, uint32_t minHeight, uint32_t* blockCnt, uint32_t* scanScratch,
-                               size_t scanScratchWords, cudaStream_t s, int* launches) {
-    if (nPairs == 0) return cudaSuccess;
-    unsigned blocks = (unsigned)((nPairs + kScoreThreads - 1) / kScoreThreads);
+cudaError_t launch_score(const PairRec* pp, const unsigned long long* totals, uint64_t ppCapacity, uint64_t expected, ScoreState* state,
+                         unsigned long long* tileState, const float* lut,
+                         const float* thresholds, float binScale, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
+                         const Slot* slots, uint32_t nSlots, LocusOut* loci, cudaStream_t s, int* launches) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t tiles = (expected + kScoreTile - 1) / kScoreTile;
+    unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)sms * 6);
     float mh = (float)minHeight;  // `reads >= minStackHeight` compares float with unsigned converted to float (:903)
-    k_score_count<<<blocks, kScoreThreads, 0, s>>>(pairs, nPairs, ppIdx, mh, blockCnt);
-    if (launches) *launches += 1;
-    return exclusive_scan_u32(blockCnt, blockCnt, blocks, scanScratch, scanScratchWords, s, launches);
-}
-
-cudaError_t launch_score_write(const PairRec* pairs, size_t nPairs, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
-                               const Slot* slots, uint32_t nSlots, float* pairFdr, LocusOut* loci, unsigned long long* nLoci, const uint32_t* blockCnt,
-                               cudaStream_t s, int* launches) {
-    if (nPairs == 0) return cudaMemsetAsync(nLoci, 0, sizeof(unsigned long long), s);
-    unsigned blocks = (unsigned)((nPairs + kScoreThreads - 1) / kScoreThreads);
-    float mh = (float)minHeight;
-    k_score_write<<<blocks, kScoreThreads, 0, s>>>(pairs, nPairs, fdrTable, binMap, W, ppIdx, mh, slots, nSlots, blockCnt, blocks, pairFdr, loci, nLoci);
+    k_score<<<blocks, kScoreThreads, 0, s>>>(pp, totals, ppCapacity, state, tileState, lut, thresholds, binScale, fdrTable, binMap, W, ppIdx, mh, slots, nSlots, loci);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
+
+size_t score_tiles(uint64_t records) { return (size_t)((records + kScoreTile - 1) / kScoreTile) + 1; }
 
 }  // namespace pppk

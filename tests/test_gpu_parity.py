@@ -287,7 +287,7 @@ def test_saturation_of_float_counters():
         assert len(s) == 1 and s["reads_plus"][0] == np.float32(1 << 24) and s["overlap"][0] == 10
 
 
-def _sharded(lengths, reads, mode, n_shards, min_stack_height=0, known_rank=False):
+def _sharded(lengths, reads, mode, n_shards, min_stack_height=0, known_rank=False, pair_capacity=None):
     """n_shards contexts on one GPU, one host thread each; the collective hook is a host-side barrier exchange."""
     total = sum(lengths)
     cuts = [total * k // n_shards for k in range(n_shards + 1)]
@@ -299,7 +299,8 @@ def _sharded(lengths, reads, mode, n_shards, min_stack_height=0, known_rank=Fals
 
     def work(rank):
         try:
-            with api.Context(lengths, mode=mode, range_begin=cuts[rank], range_end=cuts[rank + 1]) as ctx:
+            cap = pair_capacity[rank] if pair_capacity else 0
+            with api.Context(lengths, mode=mode, range_begin=cuts[rank], range_end=cuts[rank + 1], pair_capacity=cap) as ctx:
                 def hook(ptr, count, dtype, op, stream):
                     torch.cuda.synchronize()
                     t = dist.device_tensor(ptr, count, dtype)
@@ -354,6 +355,65 @@ def test_range_sharding_equals_single_context(mode, n_shards, exchange, monkeypa
     for p in parts:
         assert p[0].n_bins == single["score"].n_bins
         assert np.array_equal(bits(p[0].fdr_table), bits(single["score"].fdr_table))
+
+
+def test_shard_with_too_small_signature_store_makes_every_rank_rerun():
+    """A rank whose signature store overflows cannot re-run its scan alone (the pass contains collectives): the overflow
+    travels with the all-reduced grouped counts and every rank repeats the pass (api.cu)."""
+    m = host.SynthModel("tiny", n_reads=150_000, seed=12)
+    reads = m.generate(mode="weighted")
+    single = run_gpu(m.lengths, reads, "weighted")
+    assert len(single["signatures"]) > 3000
+    for caps in ([0, 64, 0], [128, 0, 256]):
+        parts = _sharded(m.lengths, reads, "weighted", 3, known_rank=True, pair_capacity=caps)
+        assert np.array_equal(np.concatenate([p[0].loci for p in parts]), single["score"].loci)
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), single["signatures"])
+    # one context: the store grows and the pass is repeated
+    small = run_gpu(m.lengths, reads, "weighted", pair_capacity=100)
+    assert np.array_equal(small["signatures"], single["signatures"]) and np.array_equal(small["score"].loci, single["score"].loci)
+    assert np.array_equal(small["grouped"], single["grouped"])
+
+
+def test_tile_with_a_stack_at_every_position():
+    """More than 4096 candidate plus stacks in one 8192-position tile (the block scan of the candidate counts
+    must not wrap), and more candidates than one staging round holds; every window is full, so every plus stack has
+    a record at each of the 21 overlaps."""
+    L = 3 * 8192 + 100
+    rng = np.random.default_rng(3)
+    pos = np.arange(40, L - 40, dtype=np.uint32)
+    key = np.concatenate([pos, pos, pos[::7], pos[::5]])
+    minus = np.concatenate([np.zeros(len(pos)), np.ones(len(pos)), np.zeros(len(pos[::7])), np.ones(len(pos[::5]))]).astype(np.uint32)
+    a10 = (rng.random(len(key)) < 0.3).astype(np.uint32)
+    nh = rng.choice(np.array([1, 1, 1, 2, 3], dtype=np.uint32), size=len(key))
+    order = rng.permutation(len(key))
+    reads = [host.pack_reads(key[order], minus[order], a10[order], nh[order])]
+    for mode in ("unique", "weighted"):
+        o, sigs = oracle_reference([L], reads, mode)
+        res = run_gpu([L], reads, mode)
+        assert len(sigs) > 21 * 3 * 8000
+        check_against(res, sigs, o.freq(), o.grouped_pre(), o.grouped_post(), 21, 7, 3)
+
+
+def test_counters_beyond_2_pow_24_against_the_oracle():
+    """The reference counts stacks per height (:508), signatures per cell (:605) and collapsed cells (:658) in FLOATS,
+    which stop at 2^24 = 16 777 216; BASELINE.json's human-sized config has ~190 M singleton stacks.  Here: 2 x 17.3 M
+    singleton stacks (height frequency 34.6 M), three overlaps (9..11) with 17.3 M signatures each in ONE cell, and a few
+    taller stacks so that the collapse adds a small odd count to a saturated cell.  Compared with oracle/ppp_oracle.c."""
+    n = (1 << 24) + 500_000
+    L = n + 4096
+    pos = np.arange(0, n, dtype=np.uint32)
+    extra_p = np.repeat(np.arange(n + 100, n + 100 + 41 * 50, 50, dtype=np.uint32), 3)       # 41 plus stacks of height 3 ...
+    extra_m = np.repeat(np.arange(n + 110, n + 110 + 41 * 50, 50, dtype=np.uint32), 2)       # ... each 10 nt from a minus stack of height 2
+    key = np.concatenate([pos, pos + 9, extra_p, extra_m])
+    minus = np.concatenate([np.zeros(n), np.ones(n), np.zeros(len(extra_p)), np.ones(len(extra_m))]).astype(np.uint32)
+    reads = [host.pack_reads(key, minus, np.zeros(len(key), np.uint32), np.ones(len(key), np.uint32))]
+    o, sigs = oracle_reference([L], reads, "unique", 9, 11, 10)
+    res = run_gpu([L], reads, "unique", 9, 11, 10)
+    # the saturation must actually have fired, in all three places
+    assert res["freq"][1] > (1 << 24) and o.freq()[1] == np.float32(1 << 24)
+    assert res["grouped"].max() > (1 << 24) and o.grouped_pre().max() == np.float32(1 << 24)
+    assert res["score"].cells.max() > np.float32(1 << 24)  # collapse: 41 (an odd count: a rounding tie) + 2^24 in single precision (:658)
+    check_against(res, sigs, o.freq(), o.grouped_pre(), o.grouped_post(), 3, 1, 9)
 
 
 def test_builtin_nccl_collective_single_rank():
