@@ -37,6 +37,8 @@ constexpr int kPerThread = 32;                 // consecutive positions owned by
 constexpr int kTile = kScanTile;               // 8192 positions per tile
 constexpr int kCandCap = 512;                  // candidates staged per round (a tile rarely has more)
 static_assert(kTile == kThreads * kPerThread, "tile geometry");
+constexpr int kBatch = 4;  // tiles claimed per ticket (one atomic on a single address costs ~1 ns: a human-sized genome has 378 k tiles)
+static_assert((kBatch & (kBatch - 1)) == 0 && kBatch <= 32, "the batch aggregate is a butterfly sum over kBatch lanes");
 static_assert(kTile <= (1 << 14) && kTile * PPP_MAX_OVERLAPS <= (1 << 20), "block-scan fields: 20 bits of records, 16 of candidates, 16 of ping-pong records");
 
 __device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
@@ -59,27 +61,38 @@ __device__ __forceinline__ unsigned long long warp_inclusive64(unsigned long lon
 __device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
 __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
 
-// Decoupled look-back, executed by one whole warp: the packed sum of the aggregates of all tiles before `tile`.  A tile's
-// state is ONE 64-bit word (flag + value), so a plain volatile load sees a consistent pair and no fence is needed.
-// Tiles are claimed in ticket order, hence every earlier tile belongs to a block that is already running.
-__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* __restrict__ state, uint32_t tile, int lane) {
+// Decoupled look-back, executed by one whole warp: the packed sum of the aggregates of all batches before `batch`.  A
+// batch's state is ONE 64-bit word (flag + value), so a plain volatile load sees a consistent pair and no fence is
+// needed.  Batches are claimed in ticket order, hence every earlier batch belongs to a block that is already running.
+// The resident blocks tend to run in step (they all publish, then all look back), so a batch may have to walk over every
+// batch of its wave before it meets a finished prefix: a step covers 128 batches (four independent loads per lane).
+__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* __restrict__ state, uint32_t batch, int lane) {
     unsigned long long sum = 0;
-    int64_t j = (int64_t)tile - 1;  // the nearest tile of the current window
+    int64_t j = (int64_t)batch - 1;  // the nearest batch of the current window
     while (j >= 0) {
-        const int64_t mine = j - lane;
-        unsigned long long v = kLbPrefix;  // before the first tile: an inclusive prefix of zero
-        if (mine >= 0) {
-            v = ld_state(state + mine);
-            while ((v >> 62) == 0ull) v = ld_state(state + mine);
+        unsigned long long v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t mine = j - 4 * lane - k;
+            v[k] = mine >= 0 ? ld_state(state + mine) : kLbPrefix;  // before the first batch: an inclusive prefix of zero
         }
-        const unsigned prefixLanes = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-        const int stop = prefixLanes ? __ffs(prefixLanes) - 1 : 32;  // the nearest tile that already knows its inclusive prefix
-        unsigned long long part = lane <= stop ? (v & kLbValueMask) : 0ull;
+        unsigned long long part = 0;
+        bool closed = false;  // this lane met a batch that knows its inclusive prefix
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t mine = j - 4 * lane - k;
+            while ((v[k] >> 62) == 0ull) v[k] = ld_state(state + mine);
+            if (!closed) part += v[k] & kLbValueMask;
+            closed = closed || (v[k] >> 62) == 2ull;
+        }
+        const unsigned closedLanes = __ballot_sync(0xffffffffu, closed);
+        const int stop = closedLanes ? __ffs(closedLanes) - 1 : 32;
+        if (lane > stop) part = 0;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
         sum += part;
-        if (prefixLanes) break;
-        j -= 32;
+        if (closedLanes) break;
+        j -= 128;
     }
     return sum;
 }
@@ -104,35 +117,36 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int REPR>
 __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
-    __shared__ uint32_t sMask[2][kThreads + 2];   // minus-strand occupancy words of the tile + the word after it + a zero
-    __shared__ uint32_t sPlus[2][kThreads];       // plus-strand occupancy words of the tile
-    __shared__ uint32_t sOff[2][4];               // compact index of the tile's first / past-the-last plus stack, first / past-the-last minus stack
-    __shared__ uint16_t sPrefM[kThreads + 2];     // minus stacks of the tile before each word of sMask
+    // occupancy words of the batch's tiles (double buffered: the next batch's words travel while this one is processed)
+    __shared__ uint32_t sMask[2][kBatch][kThreads + 2];  // minus strand + the word after the tile + a zero
+    __shared__ uint32_t sPlus[2][kBatch][kThreads];      // plus strand
+    __shared__ uint32_t sOff[2][kBatch][4];              // compact index of the tile's first / past-the-last plus stack, first / past-the-last minus stack
+    // per thread and tile, between the counting phase and the record phase
+    __shared__ uint32_t sCand[kBatch][kThreads];         // which of the thread's plus stacks are candidates
+    __shared__ uint32_t sExA[kBatch][kThreads];          // within the warp: plus stacks | minus stacks << 16 before the thread's positions
+    __shared__ uint32_t sExB[kBatch][kThreads];          // within the warp: records | candidates << 18 before them
+    __shared__ uint16_t sExPp[kBatch][kThreads];         // within the warp: ping-pong records before them
+    __shared__ uint16_t sPrefM[kBatch][kThreads + 2];    // minus stacks of the tile before each word of sMask
+    __shared__ uint32_t sWarpA[kBatch][kWarps];              // per warp: plus stacks | minus stacks << 16
+    __shared__ unsigned long long sWarpB[kBatch][kWarps];    // per warp: records | candidates << 20 | ping-pong records << 36
+    __shared__ unsigned long long sAgg[kBatch + 1], sBase[kBatch];  // packed (kLb* layout) records of the tile (last: of the batch) / before the tile
     __shared__ uint32_t sHist[kScanLowBins];
-    __shared__ uint32_t sWarpA[kWarps];               // per warp: plus stacks | minus stacks << 16
-    __shared__ unsigned long long sWarpB[kWarps];     // per warp: records | candidates << 20 | ping-pong records << 36
-    __shared__ unsigned long long sBase;              // packed number of records before this tile (kLb* layout)
-    __shared__ unsigned long long sCarry;             // (thread 0) the same for the next tile of the batch
-    __shared__ unsigned long long sFound[2];          // (thread 0) records / ping-pong records this block found
     __shared__ uint32_t sNextBatch;
     __shared__ uint32_t sCandBits[kCandCap], sCandOff[kCandCap];  // per candidate: present overlaps / first record (tile-relative)
     __shared__ uint16_t sCandTp[kCandCap], sCandRank[kCandCap], sCandPp[kCandCap];  // tile position / rank among the tile's plus stacks / ping-pong record
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < (int)kScanLowBins; k += kThreads) sHist[k] = 0;
-    if (tid < 2) sMask[tid][kThreads + 1] = 0;
-    if (tid == 0) {
-        sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
-        sCarry = 0;
-        sFound[0] = sFound[1] = 0;
-    }
+    if (tid < 2 * kBatch) sMask[tid / kBatch][tid % kBatch][kThreads + 1] = 0;
+    if (tid == 0) sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
     __syncthreads();
 
     const uint32_t ONE = REPR == kReprInt ? 1u : 0x3f800000u;
     const uint32_t wMask = P.W >= 32 ? 0xffffffffu : ((1u << P.W) - 1u);
     const float fW = (float)P.W;
-    const uint32_t myPos = (uint32_t)tid * kPerThread;  // this thread owns 32 consecutive positions of the tile
+    const uint32_t myPos = (uint32_t)tid * kPerThread;  // this thread owns 32 consecutive positions of a tile
     uint32_t ones = 0, localMax = 0, small = 0;  // small: four 8-bit counters for rounded heights 0..3
+    unsigned long long found = 0;                // (thread 0) packed records this block found
     auto flush_small = [&]() {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -147,126 +161,161 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
         else count_tall(P.freqTail, P.tallList, P.tallCount, P.tallCap, r);
         localMax = max(localMax, r);
     };
-    // the occupancy words and compact offsets of a tile, global -> shared, asynchronously
-    auto fetch = [&](uint32_t t, int into) {
-        const size_t w = (size_t)t * kThreads;
-        cp_async4(&sPlus[into][tid], P.occ + w + tid);
-        cp_async4(&sMask[into][tid], P.occ + P.G / 32 + w + tid);
-        if (tid == 0) cp_async4(&sMask[into][kThreads], P.occ + P.G / 32 + w + kThreads);
-        if (tid >= 32 && tid < 36) cp_async4(&sOff[into][tid - 32], ((tid & 2) ? P.tileOffM : P.tileOffP) + t + (tid & 1));
+    // the occupancy words and compact offsets of a batch of tiles, global -> shared, asynchronously
+    auto fetch = [&](uint32_t first, int into) {
+        const uint32_t n = min(P.batchTiles, P.nTiles - first);
+        for (uint32_t s = 0; s < n; ++s) {
+            const size_t w = (size_t)(first + s) * kThreads;
+            cp_async4(&sPlus[into][s][tid], P.occ + w + tid);
+            cp_async4(&sMask[into][s][tid], P.occ + P.G / 32 + w + tid);
+            if (tid == 0) cp_async4(&sMask[into][s][kThreads], P.occ + P.G / 32 + w + kThreads);
+            if (tid >= 32 && tid < 36) cp_async4(&sOff[into][s][tid - 32], ((tid & 2) ? P.tileOffM : P.tileOffP) + first + s + (tid & 1));
+        }
         cp_async_commit();
     };
     uint32_t batch = sNextBatch;
     int buf = 0;
     if (batch < P.nTiles) fetch(batch, buf);
 
-    while (batch < P.nTiles) {
-        const uint32_t batchEnd = min(batch + P.batchTiles, P.nTiles);
-        for (uint32_t tile = batch; tile < batchEnd; ++tile, buf ^= 1) {
-            const uint32_t tileBase = tile * (uint32_t)kTile;
-            cp_async_wait();
-            __syncthreads();  // (A) the tile's occupancy words are complete
-            const uint32_t nzP = sPlus[buf][tid], nzM = sMask[buf][tid];
+    for (; batch < P.nTiles; buf ^= 1) {
+        const uint32_t nb = min(P.batchTiles, P.nTiles - batch);
+        cp_async_wait();
+        __syncthreads();  // (A) the batch's occupancy words are complete
 
-            // K3, bitmaps only: candidates = plus stacks with at least one minus stack at overlaps min..max
+        // ---- counting phase (bitmaps only): how many records every tile of the batch holds, published at once, so that
+        // the blocks holding later tiles never wait for this block's record phase
+        for (uint32_t s = 0; s < nb; ++s) {
+            const uint32_t nzP = sPlus[buf][s][tid], nzM = sMask[buf][s][tid];
             uint32_t cnt = 0, ncand = 0, npp = 0, cand = 0;
-            {
-                uint32_t nz = nzP;
-                while (nz) {
-                    const int b = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    const uint32_t bit = myPos + b + P.minOv;
-                    const uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
-                    if (bits) { cnt += __popc(bits); ++ncand; cand |= 1u << b; npp += (bits >> P.ppIdx) & 1u; }
-                }
+            uint32_t nz = nzP;
+            while (nz) {  // candidates = plus stacks with at least one minus stack at overlaps min..max
+                const int b = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const uint32_t bit = myPos + b + P.minOv;
+                const uint32_t bits = __funnelshift_r(sMask[buf][s][bit >> 5], sMask[buf][s][(bit >> 5) + 1], bit & 31) & wMask;
+                if (bits) { cnt += __popc(bits); ++ncand; cand |= 1u << b; npp += (bits >> P.ppIdx) & 1u; }
             }
-            // block scans: stacks per strand (their ranks index the compact arrays), and (records, candidates, ping-pong
-            // records), which are ordered (thread, position[, overlap]) == (position[, overlap])
+            // scans over the warp: stacks per strand (their ranks index the compact arrays), and (records, candidates,
+            // ping-pong records), which are ordered (thread, position[, overlap]) == (position[, overlap])
             const uint32_t packA = (uint32_t)__popc(nzP) | ((uint32_t)__popc(nzM) << 16);
             const unsigned long long packB = (unsigned long long)cnt | ((unsigned long long)ncand << 20) | ((unsigned long long)npp << 36);
-            uint32_t exA = warp_inclusive(packA, lane);
-            unsigned long long exB = warp_inclusive64(packB, lane);
-            if (lane == 31) { sWarpA[warp] = exA; sWarpB[warp] = exB; }
-            exA -= packA;
-            exB -= packB;
-            __syncthreads();  // (B)
-            unsigned long long totalB = 0;
+            const uint32_t incA = warp_inclusive(packA, lane);
+            const unsigned long long incB = warp_inclusive64(packB, lane);
+            if (lane == 31) { sWarpA[s][warp] = incA; sWarpB[s][warp] = incB; }
+            const unsigned long long exB = incB - packB;
+            sCand[s][tid] = cand;
+            sExA[s][tid] = incA - packA;
+            sExB[s][tid] = (uint32_t)(exB & 0xfffffu) | ((uint32_t)((exB >> 20) & 0xffffu) << 18);  // (within a warp: records < 2^15, candidates < 2^10)
+            sExPp[s][tid] = (uint16_t)(exB >> 36);
+        }
+        __syncthreads();  // (B)
+        const uint32_t bi = batch / P.batchTiles;  // (tickets are multiples of batchTiles)
+        if (tid < 32) {  // the batch's aggregate, published before any of its records is written
+            unsigned long long agg = 0;
+            if (tid < (int)nb) {
+                unsigned long long t = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) t += sWarpB[tid][w];
+                agg = (t & 0xfffffull) | ((t >> 36) << kLbRecBits);
+                sAgg[tid] = agg;
+            }
+#pragma unroll
+            for (int d = 1; d < kBatch; d <<= 1) agg += __shfl_xor_sync(0xffffffffu, agg, d);
+            if (tid == 0) { sAgg[kBatch] = agg; st_state(P.tileState + bi, kLbAggregate | agg); }
+        }
+        if (tid == 32) sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
+        // complete the ranks of the minus strand (window starts, halo exclusion)
+        for (uint32_t s = 0; s < nb; ++s) {
+            uint32_t before = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w)
+                if (w < warp) before += sWarpA[s][w];
+            const uint32_t exM = (before + sExA[s][tid]) >> 16;
+            sPrefM[s][tid] = (uint16_t)exM;
+            if (tid == kThreads - 1) sPrefM[s][kThreads] = (uint16_t)(exM + __popc(sMask[buf][s][tid]));
+        }
+        __syncthreads();  // (C) aggregates, sPrefM and the next ticket are visible
+        {
+            const uint32_t nextBatch = sNextBatch;
+            if (nextBatch < P.nTiles) fetch(nextBatch, buf ^ 1);
+        }
+
+        // where the batch's records go: look back over the tiles before it (warp 0; the other warps start on K2)
+        if (warp == 0) {
+            unsigned long long before = lookback_exclusive(P.tileState, bi, lane);
+            if (lane == 0) {
+                st_state(P.tileState + bi, kLbPrefix | ((before + sAgg[kBatch]) & kLbValueMask));
+                found += sAgg[kBatch];
+                for (uint32_t s = 0; s < nb; ++s) {
+                    sBase[s] = before;
+                    before += sAgg[s];
+                }
+            }
+        }
+
+        // ---- K2: height histogram, dense over the tiles' compact words (halo copies of a neighbouring shard are not counted)
+        for (uint32_t s = 0; s < nb; ++s) {
+            const uint32_t tileBase = (batch + s) * (uint32_t)kTile;
+            const uint32_t offP = sOff[buf][s][0], endP = sOff[buf][s][1], offM = sOff[buf][s][2], endM = sOff[buf][s][3];
+            for (uint32_t i = offP + tid; i < endP; i += kThreads * 2) {
+                const uint32_t w0 = __ldg(P.cmpP + i);
+                const uint32_t w1 = i + kThreads < endP ? __ldg(P.cmpP + i + kThreads) : 0u;
+                classify(w0);
+                if (w1) classify(w1);
+            }
+            uint32_t skipLo = 0xffffffffu, skipHi = 0xffffffffu;  // ranks (within the tile) of the halo copies
+            if (tileBase < P.haloHi && tileBase + kTile > P.haloLo) {
+                auto rankOf = [&](uint32_t q) {  // minus stacks of the tile at tile positions < q
+                    if (q >= (uint32_t)kTile) return (uint32_t)sPrefM[s][kThreads];
+                    return (uint32_t)sPrefM[s][q >> 5] + (uint32_t)__popc(sMask[buf][s][q >> 5] & ((1u << (q & 31)) - 1u));
+                };
+                skipLo = rankOf(P.haloLo > tileBase ? P.haloLo - tileBase : 0u);
+                skipHi = rankOf(P.haloHi - tileBase);
+            }
+            for (uint32_t i = offM + tid; i < endM; i += kThreads * 2) {
+                const uint32_t r0 = i - offM, r1 = r0 + kThreads;
+                const uint32_t w0 = (r0 >= skipLo && r0 < skipHi) ? 0u : __ldg(P.cmpM + i);
+                const uint32_t w1 = (i + kThreads < endM && !(r1 >= skipLo && r1 < skipHi)) ? __ldg(P.cmpM + i + kThreads) : 0u;
+                if (w0) classify(w0);
+                if (w1) classify(w1);
+            }
+        }
+
+        // ---- record phase, tile by tile
+        for (uint32_t s = 0; s < nb; ++s) {
+            unsigned long long totalB = 0, exB = 0;
+            uint32_t beforeA = 0;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) {
-                const unsigned long long b = sWarpB[w];
-                if (w < warp) { exA += sWarpA[w]; exB += b; }
+                const unsigned long long b = sWarpB[s][w];
+                if (w < warp) { exB += b; beforeA += sWarpA[s][w]; }
                 totalB += b;
             }
-            // exA: stacks of the tile before this thread's positions; exB: records / candidates / ping-pong records before them
             const uint32_t total = (uint32_t)(totalB & 0xfffffu), candTotal = (uint32_t)((totalB >> 20) & 0xffffu);
-            sPrefM[tid] = (uint16_t)(exA >> 16);
-            if (tid == kThreads - 1) sPrefM[kThreads] = (uint16_t)((exA >> 16) + __popc(nzM));
-            const unsigned long long aggregate = (unsigned long long)total | ((totalB >> 36) << kLbRecBits);
-            const bool knowsPrefix = tile == 0 || tile != batch;  // the first tile of all, or a tile whose predecessor this block scanned itself
-            if (tid == 0) {
-                sFound[0] += total;
-                sFound[1] += totalB >> 36;
-                st_state(P.tileState + tile, knowsPrefix ? (kLbPrefix | ((sCarry + aggregate) & kLbValueMask)) : (kLbAggregate | aggregate));
-                if (tile + 1 == batchEnd) sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
-            }
-
-            // K2: height histogram, dense over the tile's compact words (halo copies of a neighbouring shard are not counted)
-            {
-                const uint32_t offP = sOff[buf][0], endP = sOff[buf][1], offM = sOff[buf][2], endM = sOff[buf][3];
-                for (uint32_t i = offP + tid; i < endP; i += kThreads * 2) {
-                    const uint32_t w0 = __ldg(P.cmpP + i);
-                    const uint32_t w1 = i + kThreads < endP ? __ldg(P.cmpP + i + kThreads) : 0u;
-                    classify(w0);
-                    if (w1) classify(w1);
-                }
-                uint32_t skipLo = 0xffffffffu, skipHi = 0xffffffffu;  // ranks (within the tile) of the halo copies
-                if (tileBase < P.haloHi && tileBase + kTile > P.haloLo) {  // block-uniform, at most a few tiles per shard
-                    __syncthreads();  // sPrefM of this tile
-                    auto rankOf = [&](uint32_t q) {  // minus stacks of the tile at tile positions < q
-                        if (q >= (uint32_t)kTile) return (uint32_t)sPrefM[kThreads];
-                        return (uint32_t)sPrefM[q >> 5] + (uint32_t)__popc(sMask[buf][q >> 5] & ((1u << (q & 31)) - 1u));
-                    };
-                    skipLo = rankOf(P.haloLo > tileBase ? P.haloLo - tileBase : 0u);
-                    skipHi = rankOf(P.haloHi - tileBase);
-                }
-                for (uint32_t i = offM + tid; i < endM; i += kThreads * 2) {
-                    const uint32_t r0 = i - offM, r1 = r0 + kThreads;
-                    const uint32_t w0 = (r0 >= skipLo && r0 < skipHi) ? 0u : __ldg(P.cmpM + i);
-                    const uint32_t w1 = (i + kThreads < endM && !(r1 >= skipLo && r1 < skipHi)) ? __ldg(P.cmpM + i + kThreads) : 0u;
-                    if (w0) classify(w0);
-                    if (w1) classify(w1);
-                }
-            }
-
-            // where the tile's records go: look back over the tiles before it (warp 0; the other warps stage meanwhile)
-            if (warp == 0) {
-                unsigned long long before;
-                if (knowsPrefix) {
-                    before = sCarry;
-                } else {
-                    before = lookback_exclusive(P.tileState, tile, lane);
-                    if (lane == 0) st_state(P.tileState + tile, kLbPrefix | ((before + aggregate) & kLbValueMask));
-                }
-                if (lane == 0) { sBase = before; sCarry = before + aggregate; }
-            }
-
-            const uint32_t rounds = total ? (candTotal + kCandCap - 1) / kCandCap : 1u;  // (block-uniform)
+            if (!total) continue;  // (block-uniform)
+            const uint32_t tileBase = (batch + s) * (uint32_t)kTile;
+            const uint32_t nzP = sPlus[buf][s][tid], cand = sCand[s][tid];
+            const uint32_t rankP = ((beforeA + sExA[s][tid]) & 0xffffu);  // plus stacks of the tile before this thread's positions
+            const uint32_t firstRec = (uint32_t)(exB & 0xfffffu) + (sExB[s][tid] & 0x3ffffu);
+            const uint32_t firstCand = (uint32_t)((exB >> 20) & 0xffffu) + (sExB[s][tid] >> 18);
+            const uint32_t firstPp = (uint32_t)(exB >> 36) + sExPp[s][tid];
+            const uint32_t rounds = (candTotal + kCandCap - 1) / kCandCap;
             for (uint32_t round = 0; round < rounds; ++round) {
                 const uint32_t cbase = round * kCandCap;
-                if (round) __syncthreads();  // the previous round's list is no longer read
+                __syncthreads();  // the previous list is no longer read (first round: sBase of this batch is visible, too)
                 {
-                    uint32_t off = (uint32_t)(exB & 0xfffffu), rank = (uint32_t)((exB >> 20) & 0xffffu), pp = (uint32_t)(exB >> 36), cm = cand;
+                    uint32_t off = firstRec, rank = firstCand, pp = firstPp, cm = cand;
                     while (cm) {
                         const int b = __ffs(cm) - 1;
                         cm &= cm - 1;
                         const uint32_t tp = myPos + b, bit = tp + P.minOv;
-                        const uint32_t bits = __funnelshift_r(sMask[buf][bit >> 5], sMask[buf][(bit >> 5) + 1], bit & 31) & wMask;
+                        const uint32_t bits = __funnelshift_r(sMask[buf][s][bit >> 5], sMask[buf][s][(bit >> 5) + 1], bit & 31) & wMask;
                         const uint32_t slot = rank - cbase;  // wraps to a huge value for earlier rounds
                         if (slot < (uint32_t)kCandCap) {
                             sCandTp[slot] = (uint16_t)tp;
                             sCandBits[slot] = bits;
                             sCandOff[slot] = off;
-                            sCandRank[slot] = (uint16_t)((exA & 0xffffu) + __popc(nzP & ((1u << b) - 1u)));
+                            sCandRank[slot] = (uint16_t)(rankP + __popc(nzP & ((1u << b) - 1u)));
                             sCandPp[slot] = (uint16_t)pp;
                         }
                         off += __popc(bits);
@@ -274,21 +323,16 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                         ++rank;
                     }
                 }
-                __syncthreads();  // (C) the list, sBase, sPrefM and sNextBatch are visible
-                if (round == 0) {  // the next tile's occupancy words travel while the records are written
-                    const uint32_t nextTile = tile + 1 < batchEnd ? tile + 1 : sNextBatch;
-                    if (nextTile < P.nTiles) fetch(nextTile, buf ^ 1);
-                }
-                if (!total) break;
-                const unsigned long long recBase = sBase & kLbRecMask, ppBase = sBase >> kLbRecBits;
+                __syncthreads();  // the list is complete
+                const unsigned long long recBase = sBase[s] & kLbRecMask, ppBase = sBase[s] >> kLbRecBits;
                 const uint32_t nIn = min((uint32_t)kCandCap, candTotal - cbase);
                 for (uint32_t c = tid; c < nIn; c += kThreads) {  // dense: one thread per candidate
                     const uint32_t tp = sCandTp[c];
                     uint32_t bits = sCandBits[c];
-                    const uint32_t wp = __ldg(P.cmpP + sOff[buf][0] + sCandRank[c]);
+                    const uint32_t wp = __ldg(P.cmpP + sOff[buf][s][0] + sCandRank[c]);
                     const uint32_t bit = tp + P.minOv, word = bit >> 5;
                     // the present stacks of the window are consecutive compact words, starting at the rank of its first position
-                    const uint32_t* win = P.cmpM + sOff[buf][2] + sPrefM[word] + __popc(sMask[buf][word] & ((1u << (bit & 31)) - 1u));
+                    const uint32_t* win = P.cmpM + sOff[buf][s][2] + sPrefM[s][word] + __popc(sMask[buf][s][word] & ((1u << (bit & 31)) - 1u));
                     const int n = __popc(bits);
                     // vicinity sum / max over the PRESENT stacks only, in overlap order: an absent stack would add
                     // +0.0f, which is an exact no-op (:564-577)
@@ -331,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                 }
             }
         }
-        batch = sNextBatch;  // (published by the last tile's barrier C; rewritten only after the next batch's barrier B)
+        batch = sNextBatch;  // (written before barrier C of this batch; rewritten after barrier B of the next one)
     }
 
     // flush the privatised histogram and this block's record counts
@@ -340,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) localMax = max(localMax, __shfl_xor_sync(0xffffffffu, localMax, d));
     if (lane == 0 && localMax) atomicMax(P.maxHeight, localMax);
-    if (tid == 0 && (sFound[0] | sFound[1])) { atomicAdd(&P.state->totals[0], sFound[0]); atomicAdd(&P.state->totals[1], sFound[1]); }
+    if (tid == 0 && found) { atomicAdd(&P.state->totals[0], found & kLbRecMask); atomicAdd(&P.state->totals[1], found >> kLbRecBits); }
     __syncthreads();
     for (int k = tid; k < (int)kScanLowBins; k += kThreads) {
         uint32_t c = sHist[k];
@@ -492,10 +536,10 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
     return cudaGetLastError();
 }
 
-// tiles claimed per ticket: one atomic on a single address costs ~1 ns, so large genomes take several tiles at a time
+// tiles claimed per ticket: as many as keep every block busy for a few tickets, at most kBatch
 uint32_t scan_batch_tiles(uint32_t nTiles) {
-    uint32_t b = nTiles / (148u * 6u * 8u);
-    return b < 1u ? 1u : (b > 8u ? 8u : b);
+    uint32_t b = nTiles / (148u * 5u * 4u);
+    return b < 1u ? 1u : (b > (uint32_t)kBatch ? (uint32_t)kBatch : b);
 }
 
 cudaError_t launch_tall_apply(const uint32_t* gather, int world, uint32_t cap, unsigned long long* freqLow, uint32_t* freqTail, uint32_t* maxHeight,
