@@ -258,8 +258,10 @@ def main():
     max_height = [0]
 
     def scan_and_score(loci_to_host):
-        max_height[0] = ctx.map_heights_to_scores(want_table=False)[1]
-        ctx.count_stacks_by_group(want_table=False)
+        # the three seams of the reference's main(), asking for nothing before the last one: one stream of kernels, one
+        # host synchronisation (ppp_height_hist)
+        ctx.map_heights_to_scores(want_table=False, want_max_height=False)
+        ctx.count_stacks_by_group(want_table=False, want_count=False)
         # loci_to_host: the compacted loci are also copied into the library's pinned host buffer (20 B per locus)
         return ctx.calculate_fdrs(args.min_stack_height, want_tables=False, want_loci=loci_to_host, copy_loci=False)
 
@@ -281,7 +283,9 @@ def main():
     dt = max_over_ranks(time.perf_counter() - t0)
     tm = ctx.timings()  # device time of the LAST step's kernels (CUDA events on the context's stream)
     launches_per_step = tm["launches"] / args.steps
-    n_pairs, n_loci = ctx.n_pairs, res.n_loci
+    info = ctx.pass_info()
+    max_height[0] = info["max_height"]
+    n_pairs, n_loci = info["n_pairs"], res.n_loci
     value = work_positions / (dt / args.steps)
 
     # ---- e2e: host buffers -> H2D -> stack build -> scan + score -> loci on the host

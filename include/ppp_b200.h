@@ -178,7 +178,9 @@ PPP_API int ppp_stacks_download(ppp_ctx* ctx, int32_t contig, int32_t strand, ui
  * strands.  Runs the fused streaming pass over the stack arrays (which also collects the overlap
  * candidates for ppp_scan).  *freq (optional) receives a library-owned host array of max_height + 1
  * exact counts; the reference's float counter is min(count, 2^24) (:116, :508).  All-reduced when a
- * collective hook is set. */
+ * collective hook is set.  With both outputs NULL the call only enqueues its kernels (so do ppp_scan without
+ * outputs): ppp_height_hist(NULL, NULL), ppp_scan(NULL, NULL), ppp_score(...) run as one stream of kernels with a
+ * single host synchronisation at the end. */
 PPP_API int ppp_height_hist(ppp_ctx* ctx, const uint64_t** freq, uint32_t* max_height);
 
 /* Replaces countStacksByGroup, pingpongpro.cpp:523-624: height-score bin, local-height bin and base-bias
@@ -220,6 +222,16 @@ PPP_API int ppp_transposons_sharded(ppp_ctx* const* ctxs, int n_ctx, const ppp_i
  * with the host libm; +inf when max_freq^2 does not reach bin b.  max_freq must be > 1.  Returns PPP_ERR_STATE when
  * the host's log10f is not monotone around a threshold (the device-side bin = number of thresholds <= hs needs that). */
 PPP_API int ppp_host_bin_thresholds(float max_freq, float* thresholds /* 999 */);
+
+/* Test hooks, host only: the same table from the restatement of glibc's log10f that the DEVICE evaluates
+ * (csrc/log10f_emul.h; the device's table is compared with ppp_host_bin_thresholds' on every pass), and that log10f itself
+ * for n floats >= 1. */
+PPP_API int ppp_emul_bin_thresholds(float max_freq, float* thresholds /* 999 */);
+PPP_API int ppp_emul_log10f(const float* x, size_t n, float* out);
+
+/* What the last pass found, once it is known to the host (waits for the pass): the tallest stack (rounded height), the
+ * signatures and overlap-`pingpong` signatures of this context, the stacks in its compact store.  Each optional. */
+PPP_API int ppp_pass_info(ppp_ctx* ctx, uint32_t* max_height, uint64_t* n_pairs, uint64_t* n_pingpong, uint64_t* n_stacks);
 
 PPP_API int ppp_timings_get(ppp_ctx* ctx, ppp_timings* out);
 PPP_API int ppp_timings_reset(ppp_ctx* ctx);

@@ -103,9 +103,13 @@ def lib() -> C.CDLL:
     L.ppp_timings_reset.argtypes = [vp]
     L.ppp_layout.argtypes = [vp, u64p, u64p]
     L.ppp_host_bin_thresholds.argtypes = [C.c_float, vp]
+    L.ppp_emul_bin_thresholds.argtypes = [C.c_float, vp]
+    L.ppp_emul_log10f.argtypes = [vp, C.c_size_t, vp]
+    L.ppp_pass_info.argtypes = [vp, C.POINTER(C.c_uint32), u64p, u64p, u64p]
     for name in ("ppp_device_count", "ppp_warmup", "ppp_init", "ppp_reset", "ppp_set_allreduce", "ppp_set_rank", "ppp_nccl_unique_id", "ppp_nccl_attach", "ppp_pinned_alloc", "ppp_pinned_free", "ppp_reads_submit",
                  "ppp_reads_submit_device", "ppp_stacks_finish", "ppp_reads_foreign", "ppp_stacks_download", "ppp_height_hist", "ppp_scan", "ppp_score",
-                 "ppp_pairs_download", "ppp_transposons", "ppp_timings_get", "ppp_timings_reset", "ppp_layout", "ppp_host_bin_thresholds"):
+                 "ppp_pairs_download", "ppp_transposons", "ppp_timings_get", "ppp_timings_reset", "ppp_layout", "ppp_host_bin_thresholds", "ppp_emul_bin_thresholds",
+                 "ppp_emul_log10f", "ppp_pass_info"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -120,6 +124,20 @@ def bin_thresholds(max_freq: float) -> np.ndarray:
     """The 999 height-score bin thresholds for a maximum frequency (host only; pingpongpro.cpp:551, :591-594)."""
     out = np.empty(999, dtype=np.float32)
     _check(lib().ppp_host_bin_thresholds(C.c_float(max_freq), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def emulated_bin_thresholds(max_freq: float) -> np.ndarray:
+    """The same table from the restatement of glibc's log10f that the device evaluates (csrc/log10f_emul.h), run on the host."""
+    out = np.empty(999, dtype=np.float32)
+    _check(lib().ppp_emul_bin_thresholds(C.c_float(max_freq), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def emulated_log10f(x) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    _check(lib().ppp_emul_log10f(x.ctypes.data_as(C.c_void_p), len(x), out.ctypes.data_as(C.c_void_p)))
     return out
 
 
@@ -228,19 +246,28 @@ class Context:
         return reads, a10
 
     # -- scan / score --------------------------------------------------------------------------------
-    def map_heights_to_scores(self, want_table=True):
+    def map_heights_to_scores(self, want_table=True, want_max_height=True):
+        """want_table=False, want_max_height=False only enqueues the kernels (no host synchronisation): see ppp_height_hist."""
         fp = C.POINTER(C.c_uint64)()
         mh = C.c_uint32(0)
-        _check(lib().ppp_height_hist(self._h, C.byref(fp) if want_table else None, C.byref(mh)))
+        _check(lib().ppp_height_hist(self._h, C.byref(fp) if want_table else None, C.byref(mh) if (want_table or want_max_height) else None))
         freq = np.ctypeslib.as_array(fp, shape=(mh.value + 1,)).copy() if want_table else None
         return freq, mh.value
 
-    def count_stacks_by_group(self, want_table=True):
+    def count_stacks_by_group(self, want_table=True, want_count=True):
         g = np.empty((self.W, BINS, 2, 2), np.uint64) if want_table else None
         n = C.c_uint64(0)
-        _check(lib().ppp_scan(self._h, g.ctypes.data if want_table else None, C.byref(n)))
-        self.n_pairs = n.value
+        _check(lib().ppp_scan(self._h, g.ctypes.data if want_table else None, C.byref(n) if (want_table or want_count) else None))
+        if want_table or want_count:
+            self.n_pairs = n.value
         return g
+
+    def pass_info(self) -> dict:
+        """Tallest stack, signatures, overlap-10 signatures and stacks of the last pass (waits for it)."""
+        mh, a, b, s = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().ppp_pass_info(self._h, C.byref(mh), C.byref(a), C.byref(b), C.byref(s)))
+        self.n_pairs = a.value
+        return dict(max_height=mh.value, n_pairs=a.value, n_pingpong=b.value, n_stacks=s.value)
 
     def calculate_fdrs(self, min_stack_height=0, want_tables=True, want_loci=True, copy_loci=True) -> ScoreResult:
         """copy_loci=False returns a view of the library's pinned result buffer (valid until the next call)."""

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "host_tables.h"
 #include "local_group.h"
+#include "log10f_emul.h"
 #include "nccl_loader.h"
 #include "ppp_b200.h"
 #include "transposons.cuh"
@@ -156,6 +157,15 @@ struct ppp_ctx {
     float binScale = 0.f;  // 999 / maxHeightScore: only seeds the device's bin proposal
     bool finished = false, haveHist = false, haveScan = false, haveScore = false;
     bool localOverflow = false;  // this context's signature store was too small in the last scan pass
+    // pass bookkeeping (see "the scan + score pass" below)
+    bool stageScan = false, stageBin = false, stageScore = false, settled = true;
+    uint32_t scoreMinHeight = 0;
+    cudaEvent_t evLut = nullptr;           // the pass scalars (counts, maximum frequency) are in host memory
+    bool deviceThresholds = true;          // bin thresholds from log10f_emul.h on the device, verified against the host libm
+    float* hDevThresholds = nullptr;       // (pinned) the device's table, for that verification
+    float hostTableFreq = -1.0f;           // maximum frequency hThresholds was computed for in this pass
+    BinParams* dBinParams = nullptr;
+    BinParams* hBinParams = nullptr;       // (pinned)
 
     ppp_allreduce_fn allreduce = nullptr;
     void* allreduceUser = nullptr;
@@ -388,7 +398,11 @@ struct Trace {
     }
 };
 
-void invalidateResults(ppp_ctx* c) { c->haveHist = c->haveScan = c->haveScore = c->viewValid = false; }
+void invalidateResults(ppp_ctx* c) {
+    c->haveHist = c->haveScan = c->haveScore = c->viewValid = false;
+    c->stageScan = c->stageBin = c->stageScore = false;
+    c->settled = true;
+}
 
 // ---- built-in collective: NCCL, bound at run time (nccl_loader.cpp) --------------------------------
 int ncclFail(const char* what, int rc) { return fail(PPP_ERR_CUDA, "%s: %s", what, nccl().getErrorString(rc)); }
@@ -535,6 +549,12 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     CKI(cudaMalloc(&c->dThresholds, kBins * sizeof(float)));
     initMark("device tables allocated");
     CKI(cudaMallocHost(&c->hThresholds, kBins * sizeof(float)));
+    CKI(cudaMallocHost(&c->hDevThresholds, kBins * sizeof(float)));
+    CKI(cudaMallocHost(&c->hBinParams, sizeof(BinParams)));
+    CKI(cudaMalloc(&c->dBinParams, sizeof(BinParams)));
+    CKI(cudaMemsetAsync(c->dBinParams, 0, sizeof(BinParams), c->stream));
+    CKI(cudaEventCreateWithFlags(&c->evLut, cudaEventDisableTiming));
+    if (getenv("PPP_HOST_THRESHOLDS")) c->deviceThresholds = false;  // test knob: the fall-back of a host whose libm differs
     CKI(cudaMallocHost(&c->hs, sizeof(PinnedScalars)));
     memset(c->hs, 0, sizeof(PinnedScalars));
     std::vector<double> xs, ws;
@@ -566,7 +586,7 @@ void ppp_destroy(ppp_ctx* c) {
     if (c->dGather) cudaFree(c->dGather);
     void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dCmp, c->dTileCntP, c->dTileCntM, c->dTileOffP, c->dTileOffM, c->dState, c->dFreqTail, c->dLut,
                    c->dRecPos, c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dPP, c->dLoci, c->dScoreState, c->dPairs, c->dPairFdr, c->dScanScratch,
-                   c->dGrouped, c->dThresholds, c->dCells, c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums};
+                   c->dGrouped, c->dThresholds, c->dCells, c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dBinParams};
     for (void* p : dev)
         if (p) cudaFree(p);
     for (int k = 0; k < kStages; ++k) {
@@ -574,7 +594,7 @@ void ppp_destroy(ppp_ctx* c) {
         for (void* p : stage)
             if (p) cudaFree(p);
     }
-    void* pinned[] = {c->hStage[0], c->hStage[1], c->hThresholds, c->hs, c->hLoci};
+    void* pinned[] = {c->hStage[0], c->hStage[1], c->hThresholds, c->hDevThresholds, c->hBinParams, c->hs, c->hLoci};
     for (void* p : pinned)
         if (p) cudaFreeHost(p);
     for (int k = 0; k < kStages; ++k) {
@@ -590,6 +610,7 @@ void ppp_destroy(ppp_ctx* c) {
     if (c->sortStream) cudaStreamDestroy(c->sortStream);
     for (int k = 0; k < kFoldStreams; ++k)
         if (c->foldStream[k]) cudaStreamDestroy(c->foldStream[k]);
+    if (c->evLut) cudaEventDestroy(c->evLut);
     if (c->evReset) cudaEventDestroy(c->evReset);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
@@ -801,10 +822,19 @@ int ppp_stacks_download(ppp_ctx* c, int32_t contig, int32_t strand, uint64_t beg
 
 namespace {
 
-// One scan pass: state reset, k_scan, exchange of the height histogram, frequency LUT; leaves the pass scalars on their way
-// to the host (no synchronisation).
-int enqueueScanPass(ppp_ctx* c, Trace& tr) {
+// ---- the scan + score pass ---------------------------------------------------------------------------------------
+// A pass has three stages -- scan (k_scan, histogram exchange, frequency LUT, bin thresholds), bin (k_bin, exchange of the
+// grouped counts) and score (collapse, FDR table, k_score) -- which ppp_height_hist / ppp_scan / ppp_score ENQUEUE.  The host
+// looks at the pass (`settle`) only when a call has to return something: a caller that asks for nothing before ppp_score
+// gets the whole pass as one stream of kernels with a single synchronisation at its end.  What the host has to decide --
+// did the signature store overflow (on any rank), did the tall-stack lists overflow, does the device's threshold table
+// equal the one the host libm gives -- is decided then, and when the answer is "no good" the cause is removed and every
+// stage that had been enqueued is enqueued again.  All of these decisions are functions of all-reduced data (or of this
+// host's libm), so the ranks of a sharded run take them together.
+
+int enqueueScanStage(ppp_ctx* c) {
     int rc;
+    Trace tr("scan stage");
     CK(cudaMemsetAsync(c->dState, 0, sizeof(PassState) + (size_t)c->nTiles * sizeof(unsigned long long), c->stream));
     if (c->prevMaxHeight >= kScanLowBins)
         CK(cudaMemsetAsync(c->dFreqTail + kScanLowBins, 0, ((size_t)c->prevMaxHeight - kScanLowBins + 1) * sizeof(uint32_t), c->stream));
@@ -865,67 +895,131 @@ int enqueueScanPass(ppp_ctx* c, Trace& tr) {
         tr.mark("scan + max-height reduce");
         if ((rc = hookReduce(c, c->dState->freqLow, kScanLowBins, 1, 0))) return rc;
         if (c->hs->maxHeight >= kScanLowBins && (rc = hookReduce(c, c->dFreqTail + kScanLowBins, (size_t)c->hs->maxHeight - kScanLowBins + 1, 0, 0))) return rc;
-        if (tr.on) { CK(cudaStreamSynchronize(c->stream)); tr.mark("histogram reduce"); }
     }
     if ((rc = timerStart(c, c->tLut))) return rc;
     CK(launch_freq_lut(c->dState->freqLow, c->dFreqTail, &c->dState->maxHeight, c->dLut, &c->dState->maxCount, c->stream, &c->launches));
     if ((rc = timerStop(c, c->tLut))) return rc;
     CK(cudaMemcpyAsync(c->hs->totals, c->dState->totals, 40, cudaMemcpyDeviceToHost, c->stream));  // totals[2], maxCount, maxHeight, ticket, overflow, pad
+    CK(cudaEventRecord(c->evLut, c->stream));
+    if (c->deviceThresholds) {
+        CK(launch_bin_thresholds(&c->dState->maxCount, c->dThresholds, c->dBinParams, c->stream, &c->launches));
+        CK(cudaMemcpyAsync(c->hDevThresholds, c->dThresholds, kBins * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    c->hostTableFreq = -1.0f;
+    c->stageScan = true;
+    c->stageBin = c->stageScore = false;
+    c->settled = false;
+    tr.mark("enqueued");
     return PPP_OK;
 }
 
-// Scan pass + what the host must know before the binning kernel: counts, overflow flags, the bin thresholds.
-int scanPass(ppp_ctx* c) {
-    Trace tr("height_hist");
+// The threshold table of the host libm for the pass's maximum frequency (needs the scalars of the scan stage: waits for them).
+int hostThresholds(ppp_ctx* c) {
+    CK(cudaEventSynchronize(c->evLut));
+    const float maxFreq = (float)(c->hs->maxCount < kSaturate ? (uint32_t)c->hs->maxCount : kSaturate);  // :547-550
+    if (c->hostTableFreq == maxFreq) return PPP_OK;
+    for (int b = 0; b < kBins; ++b) c->hThresholds[b] = std::numeric_limits<float>::infinity();
+    if (maxFreq > 1.0f) {
+        computeThresholds(maxFreq, c->hThresholds);
+        if (!validateThresholds(maxFreq, c->hThresholds)) return fail(PPP_ERR_STATE, "host log10f is not monotone around a bin threshold");
+    }
+    c->hostTableFreq = maxFreq;
+    return PPP_OK;
+}
+
+int enqueueBinStage(ppp_ctx* c) {
+    int rc;
+    const size_t tableWords = (size_t)c->W * kBins * 4;
+    if (!c->deviceThresholds) {  // this host's libm is not the one log10f_emul.h restates: the table comes from the host, in mid-pass
+        if ((rc = hostThresholds(c))) return rc;
+        const float maxFreq = c->hostTableFreq;
+        c->hBinParams->maxFreq = maxFreq;
+        c->hBinParams->binScale = maxFreq > 1.0f ? 999.0f / log10f(maxFreq * maxFreq) : 0.0f;
+        CK(cudaMemcpyAsync(c->dThresholds, c->hThresholds, kBins * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->dBinParams, c->hBinParams, sizeof(BinParams), cudaMemcpyHostToDevice, c->stream));
+    }
+    if ((rc = timerStart(c, c->tBin))) return rc;
+    CK(cudaMemsetAsync(c->dGrouped, 0, (tableWords + 1) * 4, c->stream));
+    // (the record count is on the device; the grid is sized for a full store, surplus blocks leave at once)
+    CK(launch_bin(c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dState->totals, c->pairCapacity, c->pairCapacity, c->dLut, c->dThresholds, c->dBinParams, c->W,
+                  c->dGrouped, c->stream, &c->launches));
+    if (c->allreduce) {
+        // a shard whose signature store overflowed cannot re-run alone (the pass contains collectives): the number of
+        // such ranks travels with the grouped counts, and when it is not zero EVERY rank repeats the pass (settle)
+        CK(launch_overflow_flag(c->dState->totals, c->pairCapacity, c->ppCapacity, c->dGrouped + tableWords, c->stream, &c->launches));
+    }
+    if ((rc = timerStop(c, c->tBin))) return rc;
+    if ((rc = hookReduce(c, c->dGrouped, tableWords + 1, 0, 0))) return rc;
+    if (c->allreduce) CK(cudaMemcpyAsync(&c->hs->rerun, c->dGrouped + tableWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->stageBin = true;
+    c->stageScore = false;
+    c->settled = false;
+    return PPP_OK;
+}
+
+int enqueueScoreStage(ppp_ctx* c, uint32_t minStackHeight) {
+    int rc;
+    const int ppIdx = c->ppOv - c->minOv;
+    if ((rc = timerStart(c, c->tScore))) return rc;
+    CK(cudaMemsetAsync(c->dScoreState, 0, sizeof(ScoreState) + c->scoreTileWords * sizeof(unsigned long long), c->stream));
+    CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dCellSums, c->stream, &c->launches));
+    CK(launch_fdr_table(c->dCells, c->dNBins, kBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
+    CK(launch_score(c->dPP, c->dState->totals, c->ppCapacity, c->ppCapacity, c->dScoreState, c->dScoreTiles, c->dLut, c->dThresholds, c->dBinParams, c->dFdr,
+                    c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dLoci, c->stream, &c->launches));
+    if ((rc = timerStop(c, c->tScore))) return rc;
+    CK(cudaMemcpyAsync(&c->hs->nLoci, c->dScoreState, sizeof(ScoreState), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->hs->nBins, c->dNBins, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->scoreMinHeight = minStackHeight;
+    c->stageScore = true;
+    c->settled = false;
+    return PPP_OK;
+}
+
+// Waits for everything enqueued so far, validates it and repairs + repeats the pass when it has to (see above).
+int settle(ppp_ctx* c) {
+    if (c->settled || !c->stageScan) return PPP_OK;
+    Trace tr("settle");
     int rc;
     for (int attempt = 0;; ++attempt) {
-        if ((rc = enqueueScanPass(c, tr))) return rc;
+        if ((rc = hostThresholds(c))) return rc;  // with the host libm, while the device works on the later stages
+        tr.mark("host thresholds");
         CK(cudaStreamSynchronize(c->stream));
-        tr.mark("scan + histogram + table");
+        tr.mark("stream");
         c->prevMaxHeight = std::max(c->prevMaxHeight, c->hs->maxHeight);
-        if (c->hs->tallOverflow) {  // (the same on every rank: it is read from the reduced buffer) -> dense tables, once and for all
+        bool again = false;
+        if (c->hs->tallOverflow) {  // (the same on every rank: read from the reduced buffer) -> dense height tables, once and for all
             c->denseTail = true;
-            continue;
+            again = true;
         }
         c->localOverflow = c->hs->totals[0] > c->pairCapacity || c->hs->totals[1] > c->ppCapacity;
-        if (!c->localOverflow) break;
-        if (c->allreduce) break;  // shards decide together, after the grouped counts were exchanged (ppp_scan)
-        if (attempt >= 2) return fail(PPP_ERR_NOMEM, "signature store overflow");
-        if ((rc = ensurePairCapacity(c, c->hs->totals[0] + c->hs->totals[0] / 8 + 1024))) return rc;  // rerun with room for every record
+        if (c->allreduce) {
+            if (c->stageBin && c->hs->rerun) again = true;  // some rank overflowed: every rank repeats, the overflowed ones with a larger store
+        } else if (c->localOverflow) {
+            again = true;
+        }
+        if (c->deviceThresholds && memcmp(c->hDevThresholds, c->hThresholds, (kBins - 1) * sizeof(float)) != 0) {
+            c->deviceThresholds = false;  // another libm than the one restated in log10f_emul.h: host tables from now on
+            again = true;
+        }
+        if (!again) break;
+        if (attempt >= 3) return fail(PPP_ERR_NOMEM, "signature store overflow");
+        if (c->localOverflow) {
+            const uint64_t want = std::max<uint64_t>(c->hs->totals[0], c->hs->totals[1]);
+            if ((rc = ensurePairCapacity(c, want + want / 8 + 1024))) return rc;
+        }
+        const bool bin = c->stageBin, score = c->stageScore;
+        if ((rc = enqueueScanStage(c))) return rc;
+        if (bin && (rc = enqueueBinStage(c))) return rc;
+        if (score && (rc = enqueueScoreStage(c, c->scoreMinHeight))) return rc;
     }
     c->maxHeight = c->hs->maxHeight;
     c->nPairs = std::min<uint64_t>(c->hs->totals[0], c->pairCapacity);
     c->nPP = std::min<uint64_t>(c->hs->totals[1], c->ppCapacity);
-
-    // bin thresholds from the (global) maximum frequency, with the host libm
-    float maxFreq = (float)(c->hs->maxCount < kSaturate ? (uint32_t)c->hs->maxCount : kSaturate);  // :547-550
-    for (int b = 0; b < kBins; ++b) c->hThresholds[b] = std::numeric_limits<float>::infinity();
-    c->binScale = maxFreq > 1.0f ? 999.0f / log10f(maxFreq * maxFreq) : 0.0f;
-    c->thresholdFreq = maxFreq > 1.0f ? maxFreq : 0.0f;
-    if (maxFreq > 1.0f) {
-        computeThresholds(maxFreq, c->hThresholds);
-    } else if (c->nPairs > 0 && !c->allreduce) {
+    c->thresholdFreq = c->hostTableFreq > 1.0f ? c->hostTableFreq : 0.0f;
+    c->settled = !c->localOverflow;  // (a shard that overflowed before its bin stage is settled by ppp_scan)
+    if (!(c->hostTableFreq > 1.0f) && c->nPairs > 0 && !c->allreduce)
         return fail(PPP_ERR_DEGENERATE, "every rounded stack height occurs once: the reference's height score is 0/0 (pingpongpro.cpp:551/:593)");
-    }
-    CK(cudaMemcpyAsync(c->dThresholds, c->hThresholds, kBins * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    tr.mark("bin thresholds (host)");
     return PPP_OK;
-}
-
-// Height-score bins + grouped counts of the records of the last scan pass, and their exchange.
-int binPass(ppp_ctx* c) {
-    int rc;
-    const size_t tableWords = (size_t)c->W * kBins * 4;
-    if ((rc = timerStart(c, c->tBin))) return rc;
-    CK(cudaMemsetAsync(c->dGrouped, 0, (tableWords + 1) * 4, c->stream));
-    if (c->localOverflow) CK(cudaMemsetAsync(c->dGrouped + tableWords, 1, 1, c->stream));  // little endian: the word becomes 1
-    if (c->nPairs) CK(launch_bin(c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dState->totals, c->pairCapacity, c->nPairs, c->dLut, c->dThresholds, c->binScale, c->W,
-                                 c->dGrouped, c->stream, &c->launches));
-    if ((rc = timerStop(c, c->tBin))) return rc;
-    // while the binning kernel runs: the monotonicity assumption behind the threshold table is checked on the host
-    if (c->thresholdFreq > 1.0f && !validateThresholds(c->thresholdFreq, c->hThresholds))
-        return fail(PPP_ERR_STATE, "host log10f is not monotone around a bin threshold");
-    return hookReduce(c, c->dGrouped, tableWords + 1, 0, 0);
 }
 
 }  // namespace
@@ -937,14 +1031,16 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
     if (!c->finished) return fail(PPP_ERR_STATE, "call ppp_stacks_finish before ppp_height_hist");
     CK(cudaSetDevice(c->device));
     invalidateResults(c);
-    // signatures are ~0.1-0.3 per read on real densities; a scan that overflows the store reports the exact count and is re-run
-    // (a shard sizes the store for one signature per read; when that is still too small every rank re-runs, see ppp_scan)
+    // signatures are ~0.1-0.3 per read on real densities; a scan that overflows the store reports the exact count and the
+    // pass is repeated with a larger one (a shard sizes the store for one signature per read)
     uint64_t want = c->cfgPairCapacity ? c->cfgPairCapacity : std::max<uint64_t>((uint64_t)1 << 20, c->allreduce ? c->readsSubmitted : c->readsSubmitted / 3);
     if (want < c->pairCapacity) want = c->pairCapacity;
     int rc = ensurePairCapacity(c, want);
     if (rc) return rc;
-    if ((rc = scanPass(c))) return rc;
-
+    if ((rc = enqueueScanStage(c))) return rc;
+    c->haveHist = true;
+    if (!freq && !maxHeight) return PPP_OK;  // nothing to return: the host looks at the pass later
+    if ((rc = settle(c))) { c->haveHist = false; return rc; }
     if (freq) {
         uint32_t mh = c->maxHeight;
         c->hFreq.assign((size_t)mh + 1, 0);
@@ -960,7 +1056,6 @@ int ppp_height_hist(ppp_ctx* c, const uint64_t** freq, uint32_t* maxHeight) {
         *freq = c->hFreq.data();
     }
     if (maxHeight) *maxHeight = c->maxHeight;
-    c->haveHist = true;
     return PPP_OK;
 }
 
@@ -970,21 +1065,11 @@ int ppp_scan(ppp_ctx* c, uint64_t* grouped, uint64_t* nPairs) {
     CK(cudaSetDevice(c->device));
     int rc;
     const size_t tableWords = (size_t)c->W * kBins * 4;
-    if ((rc = binPass(c))) return rc;
-    if (c->allreduce) {
-        // A shard whose signature store overflowed cannot re-run alone (the pass contains collectives): the number of such
-        // ranks travels with the grouped counts, and when it is not zero EVERY rank repeats the pass, the overflowed ones
-        // with a larger store.
-        for (int attempt = 0;; ++attempt) {
-            CK(cudaMemcpyAsync(&c->hs->rerun, c->dGrouped + tableWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            if (!c->hs->rerun) break;
-            if (attempt >= 2) return fail(PPP_ERR_NOMEM, "signature store overflow");
-            if (c->localOverflow && (rc = ensurePairCapacity(c, c->hs->totals[0] + c->hs->totals[0] / 8 + 1024))) return rc;
-            if ((rc = scanPass(c))) return rc;
-            if ((rc = binPass(c))) return rc;
-        }
-    }
+    if ((rc = enqueueBinStage(c))) return rc;
+    c->haveScan = true;
+    c->viewValid = false;
+    if (!grouped && !nPairs) return PPP_OK;
+    if ((rc = settle(c))) { c->haveScan = false; return rc; }
     if (grouped) {
         std::vector<uint32_t> g(tableWords);
         CK(cudaMemcpyAsync(g.data(), c->dGrouped, tableWords * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -994,8 +1079,6 @@ int ppp_scan(ppp_ctx* c, uint64_t* grouped, uint64_t* nPairs) {
                 for (int k = 0; k < 4; ++k) grouped[((size_t)o * kBins + b) * 4 + k] = g[((size_t)b * c->W + o) * 4 + k];
     }
     if (nPairs) *nPairs = c->nPairs;
-    c->haveScan = true;
-    c->viewValid = false;
     return PPP_OK;
 }
 
@@ -1004,19 +1087,10 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     if (!c->haveScan) return fail(PPP_ERR_STATE, "call ppp_scan before ppp_score");
     CK(cudaSetDevice(c->device));
     int rc;
-    const int ppIdx = c->ppOv - c->minOv;
     Trace tr("score");
-    if ((rc = timerStart(c, c->tScore))) return rc;
-    CK(cudaMemsetAsync(c->dScoreState, 0, sizeof(ScoreState) + score_tiles(c->nPP) * sizeof(unsigned long long), c->stream));
-    CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dCellSums, c->stream, &c->launches));
-    CK(launch_fdr_table(c->dCells, c->dNBins, kBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
-    if (c->nPP) CK(launch_score(c->dPP, c->dState->totals, c->ppCapacity, c->nPP, c->dScoreState, c->dScoreTiles, c->dLut, c->dThresholds, c->binScale, c->dFdr,
-                                c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dLoci, c->stream, &c->launches));
-    if ((rc = timerStop(c, c->tScore))) return rc;
-    CK(cudaMemcpyAsync(&c->hs->nLoci, c->dScoreState, sizeof(ScoreState), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&c->hs->nBins, c->dNBins, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    tr.mark("binning + reduce + scoring");
+    if ((rc = enqueueScoreStage(c, minStackHeight))) return rc;
+    if ((rc = settle(c))) return rc;
+    tr.mark("pass settled");
     size_t n = (size_t)c->hs->nLoci;
     uint32_t C = c->hs->nBins;
     if (loci) {
@@ -1051,10 +1125,24 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     return PPP_OK;
 }
 
+int ppp_pass_info(ppp_ctx* c, uint32_t* maxHeight, uint64_t* nPairs, uint64_t* nLoci, uint64_t* nStacks) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (!c->haveHist) return fail(PPP_ERR_STATE, "call ppp_height_hist before ppp_pass_info");
+    CK(cudaSetDevice(c->device));
+    int rc = settle(c);
+    if (rc) return rc;
+    if (maxHeight) *maxHeight = c->maxHeight;
+    if (nPairs) *nPairs = c->nPairs;
+    if (nLoci) *nLoci = c->nPP;
+    if (nStacks) *nStacks = c->nStacksP + c->nStacksM;
+    return PPP_OK;
+}
+
 int ppp_pairs_download(ppp_ctx* c, ppp_pair* out, size_t capacity, size_t* n) {
     if (!c) return fail(PPP_ERR_ARG, "null context");
     if (!c->haveScan) return fail(PPP_ERR_STATE, "call ppp_scan before ppp_pairs_download");
     CK(cudaSetDevice(c->device));
+    { int rcSettle = settle(c); if (rcSettle) return rcSettle; }
     if (n) *n = (size_t)c->nPairs;
     if (!out) return PPP_OK;
     if (capacity < c->nPairs) return fail(PPP_ERR_ARG, "capacity %zu < %llu signatures", capacity, (unsigned long long)c->nPairs);
@@ -1155,6 +1243,18 @@ int ppp_transposons_sharded(ppp_ctx* const* ctxs, int n_ctx, const ppp_interval*
                                : run_transposons_sharded(jobs.data(), devices.data(), n_ctx, intervals, n, results, order, err);
     if (e != cudaSuccess) return fail(PPP_ERR_CUDA, "transposons: %s %s", cudaGetErrorString(e), err.c_str());
     if (!err.empty()) return fail(PPP_ERR_ARG, "%s", err.c_str());
+    return PPP_OK;
+}
+
+int ppp_emul_bin_thresholds(float max_freq, float* thresholds) {
+    if (!thresholds || !(max_freq > 1.0f)) return fail(PPP_ERR_ARG, "ppp_emul_bin_thresholds: max_freq must be > 1");
+    for (int b = 1; b < kBins; ++b) thresholds[b - 1] = emul_bin_threshold(b, max_freq);
+    return PPP_OK;
+}
+
+int ppp_emul_log10f(const float* x, size_t n, float* out) {
+    if (n && (!x || !out)) return fail(PPP_ERR_ARG, "null argument");
+    for (size_t i = 0; i < n; ++i) out[i] = emul_log10f(x[i]);
     return PPP_OK;
 }
 

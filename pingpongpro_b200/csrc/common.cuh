@@ -59,6 +59,11 @@ struct PassState {
     uint32_t overflow;                         // multi-GPU: some rank listed more tall stacks than fit
     uint32_t pad;
 };
+// What the binning kernels need besides the threshold table (written by k_bin_thresholds, or by the host)
+struct BinParams {
+    float binScale;  // 999 / maxHeightScore: only seeds the device's bin proposal
+    float maxFreq;   // the maximum frequency the thresholds were built for
+};
 // State of one k_score launch (zeroed together with the look-back states that follow it).
 struct ScoreState {
     unsigned long long nLoci;                  // reported loci
@@ -164,8 +169,10 @@ cudaError_t launch_tall_apply(const uint32_t* gather, int world, uint32_t cap, u
 cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* freqTail, const uint32_t* maxHeight, float* lut,
                             unsigned long long* maxCount, cudaStream_t s, int* launches);
 // `expected`: the host's idea of the number of records (sizes the grid; the kernel reads the exact count from `totals`)
+cudaError_t launch_bin_thresholds(const unsigned long long* maxCount, float* thresholds, BinParams* params, cudaStream_t s, int* launches);
 cudaError_t launch_bin(const float* recRp, const float* recRm, const uint8_t* recMisc, uint16_t* recBin, const unsigned long long* totals, uint64_t capacity,
-                       uint64_t expected, const float* lut, const float* thresholds, float binScale, int W, uint32_t* grouped, cudaStream_t s, int* launches);
+                       uint64_t expected, const float* lut, const float* thresholds, const BinParams* params, int W, uint32_t* grouped, cudaStream_t s, int* launches);
+cudaError_t launch_overflow_flag(const unsigned long long* totals, uint64_t capacity, uint64_t ppCapacity, uint32_t* flag, cudaStream_t s, int* launches);
 cudaError_t launch_pairs_view(const uint32_t* recPos, const float* recRp, const float* recRm, const uint8_t* recMisc, const uint16_t* recBin, size_t n,
                               const float* fdrTable, const uint16_t* binMap, int W, PairRec* pairs, float* pairFdr, cudaStream_t s, int* launches);
 cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, uint16_t* groupStart, unsigned long long* sums,
@@ -179,7 +186,7 @@ struct LocusOut {
 // K4, per-locus half (single pass, ordered): see score.cu.  `tileState` holds score_tiles(ppCapacity) words and is zeroed,
 // together with `state`, before every launch.
 cudaError_t launch_score(const PairRec* pp, const unsigned long long* totals, uint64_t ppCapacity, uint64_t expected, ScoreState* state,
-                         unsigned long long* tileState, const float* lut, const float* thresholds, float binScale, const float* fdrTable,
+                         unsigned long long* tileState, const float* lut, const float* thresholds, const BinParams* params, const float* fdrTable,
                          const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight, const Slot* slots, uint32_t nSlots, LocusOut* loci, cudaStream_t s,
                          int* launches);
 size_t score_tiles(uint64_t records);

@@ -26,6 +26,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "log10f_emul.h"
 
 namespace pppk {
 
@@ -117,10 +118,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int REPR>
 __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
-    // occupancy words of the batch's tiles (double buffered: the next batch's words travel while this one is processed)
-    __shared__ uint32_t sMask[2][kBatch][kThreads + 2];  // minus strand + the word after the tile + a zero
-    __shared__ uint32_t sPlus[2][kBatch][kThreads];      // plus strand
-    __shared__ uint32_t sOff[2][kBatch][4];              // compact index of the tile's first / past-the-last plus stack, first / past-the-last minus stack
+    // occupancy words of the batch's tiles
+    __shared__ uint32_t sMask[kBatch][kThreads + 2];  // minus strand + the word after the tile + a zero
+    __shared__ uint32_t sPlus[kBatch][kThreads];      // plus strand
+    __shared__ uint32_t sOff[kBatch][4];              // compact index of the tile's first / past-the-last plus stack, first / past-the-last minus stack
     // per thread and tile, between the counting phase and the record phase
     __shared__ uint32_t sCand[kBatch][kThreads];         // which of the thread's plus stacks are candidates
     __shared__ uint32_t sExA[kBatch][kThreads];          // within the warp: plus stacks | minus stacks << 16 before the thread's positions
@@ -137,9 +138,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < (int)kScanLowBins; k += kThreads) sHist[k] = 0;
-    if (tid < 2 * kBatch) sMask[tid / kBatch][tid % kBatch][kThreads + 1] = 0;
-    if (tid == 0) sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
-    __syncthreads();
+    if (tid < kBatch) sMask[tid][kThreads + 1] = 0;
 
     const uint32_t ONE = REPR == kReprInt ? 1u : 0x3f800000u;
     const uint32_t wMask = P.W >= 32 ? 0xffffffffu : ((1u << P.W) - 1u);
@@ -162,37 +161,43 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
         localMax = max(localMax, r);
     };
     // the occupancy words and compact offsets of a batch of tiles, global -> shared, asynchronously
-    auto fetch = [&](uint32_t first, int into) {
+    auto fetch = [&](uint32_t first) {
         const uint32_t n = min(P.batchTiles, P.nTiles - first);
         for (uint32_t s = 0; s < n; ++s) {
             const size_t w = (size_t)(first + s) * kThreads;
-            cp_async4(&sPlus[into][s][tid], P.occ + w + tid);
-            cp_async4(&sMask[into][s][tid], P.occ + P.G / 32 + w + tid);
-            if (tid == 0) cp_async4(&sMask[into][s][kThreads], P.occ + P.G / 32 + w + kThreads);
-            if (tid >= 32 && tid < 36) cp_async4(&sOff[into][s][tid - 32], ((tid & 2) ? P.tileOffM : P.tileOffP) + first + s + (tid & 1));
+            cp_async4(&sPlus[s][tid], P.occ + w + tid);
+            cp_async4(&sMask[s][tid], P.occ + P.G / 32 + w + tid);
+            if (tid == 0) cp_async4(&sMask[s][kThreads], P.occ + P.G / 32 + w + kThreads);
+            if (tid >= 32 && tid < 36) cp_async4(&sOff[s][tid - 32], ((tid & 2) ? P.tileOffM : P.tileOffP) + first + s + (tid & 1));
         }
         cp_async_commit();
     };
-    uint32_t batch = sNextBatch;
-    int buf = 0;
-    if (batch < P.nTiles) fetch(batch, buf);
 
-    for (; batch < P.nTiles; buf ^= 1) {
+    // A batch is claimed only when the block is ready to count and publish it at once: whoever holds an earlier ticket
+    // publishes its record counts within microseconds, whatever its record phase takes afterwards.  (Claiming ahead, to
+    // prefetch the occupancy words, made every block wait for the slowest record phase of the previous round.)
+    for (;;) {
+        __syncthreads();  // the previous batch's shared state is no longer read
+        if (tid == 0) sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
+        __syncthreads();
+        const uint32_t batch = sNextBatch;
+        if (batch >= P.nTiles) break;
         const uint32_t nb = min(P.batchTiles, P.nTiles - batch);
+        fetch(batch);
         cp_async_wait();
         __syncthreads();  // (A) the batch's occupancy words are complete
 
         // ---- counting phase (bitmaps only): how many records every tile of the batch holds, published at once, so that
         // the blocks holding later tiles never wait for this block's record phase
         for (uint32_t s = 0; s < nb; ++s) {
-            const uint32_t nzP = sPlus[buf][s][tid], nzM = sMask[buf][s][tid];
+            const uint32_t nzP = sPlus[s][tid], nzM = sMask[s][tid];
             uint32_t cnt = 0, ncand = 0, npp = 0, cand = 0;
             uint32_t nz = nzP;
             while (nz) {  // candidates = plus stacks with at least one minus stack at overlaps min..max
                 const int b = __ffs(nz) - 1;
                 nz &= nz - 1;
                 const uint32_t bit = myPos + b + P.minOv;
-                const uint32_t bits = __funnelshift_r(sMask[buf][s][bit >> 5], sMask[buf][s][(bit >> 5) + 1], bit & 31) & wMask;
+                const uint32_t bits = __funnelshift_r(sMask[s][bit >> 5], sMask[s][(bit >> 5) + 1], bit & 31) & wMask;
                 if (bits) { cnt += __popc(bits); ++ncand; cand |= 1u << b; npp += (bits >> P.ppIdx) & 1u; }
             }
             // scans over the warp: stacks per strand (their ranks index the compact arrays), and (records, candidates,
@@ -223,7 +228,6 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
             for (int d = 1; d < kBatch; d <<= 1) agg += __shfl_xor_sync(0xffffffffu, agg, d);
             if (tid == 0) { sAgg[kBatch] = agg; st_state(P.tileState + bi, kLbAggregate | agg); }
         }
-        if (tid == 32) sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
         // complete the ranks of the minus strand (window starts, halo exclusion)
         for (uint32_t s = 0; s < nb; ++s) {
             uint32_t before = 0;
@@ -232,31 +236,14 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                 if (w < warp) before += sWarpA[s][w];
             const uint32_t exM = (before + sExA[s][tid]) >> 16;
             sPrefM[s][tid] = (uint16_t)exM;
-            if (tid == kThreads - 1) sPrefM[s][kThreads] = (uint16_t)(exM + __popc(sMask[buf][s][tid]));
+            if (tid == kThreads - 1) sPrefM[s][kThreads] = (uint16_t)(exM + __popc(sMask[s][tid]));
         }
-        __syncthreads();  // (C) aggregates, sPrefM and the next ticket are visible
-        {
-            const uint32_t nextBatch = sNextBatch;
-            if (nextBatch < P.nTiles) fetch(nextBatch, buf ^ 1);
-        }
-
-        // where the batch's records go: look back over the tiles before it (warp 0; the other warps start on K2)
-        if (warp == 0) {
-            unsigned long long before = lookback_exclusive(P.tileState, bi, lane);
-            if (lane == 0) {
-                st_state(P.tileState + bi, kLbPrefix | ((before + sAgg[kBatch]) & kLbValueMask));
-                found += sAgg[kBatch];
-                for (uint32_t s = 0; s < nb; ++s) {
-                    sBase[s] = before;
-                    before += sAgg[s];
-                }
-            }
-        }
+        __syncthreads();  // (C) aggregates and sPrefM are visible
 
         // ---- K2: height histogram, dense over the tiles' compact words (halo copies of a neighbouring shard are not counted)
         for (uint32_t s = 0; s < nb; ++s) {
             const uint32_t tileBase = (batch + s) * (uint32_t)kTile;
-            const uint32_t offP = sOff[buf][s][0], endP = sOff[buf][s][1], offM = sOff[buf][s][2], endM = sOff[buf][s][3];
+            const uint32_t offP = sOff[s][0], endP = sOff[s][1], offM = sOff[s][2], endM = sOff[s][3];
             for (uint32_t i = offP + tid; i < endP; i += kThreads * 2) {
                 const uint32_t w0 = __ldg(P.cmpP + i);
                 const uint32_t w1 = i + kThreads < endP ? __ldg(P.cmpP + i + kThreads) : 0u;
@@ -267,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
             if (tileBase < P.haloHi && tileBase + kTile > P.haloLo) {
                 auto rankOf = [&](uint32_t q) {  // minus stacks of the tile at tile positions < q
                     if (q >= (uint32_t)kTile) return (uint32_t)sPrefM[s][kThreads];
-                    return (uint32_t)sPrefM[s][q >> 5] + (uint32_t)__popc(sMask[buf][s][q >> 5] & ((1u << (q & 31)) - 1u));
+                    return (uint32_t)sPrefM[s][q >> 5] + (uint32_t)__popc(sMask[s][q >> 5] & ((1u << (q & 31)) - 1u));
                 };
                 skipLo = rankOf(P.haloLo > tileBase ? P.haloLo - tileBase : 0u);
                 skipHi = rankOf(P.haloHi - tileBase);
@@ -278,6 +265,19 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                 const uint32_t w1 = (i + kThreads < endM && !(r1 >= skipLo && r1 < skipHi)) ? __ldg(P.cmpM + i + kThreads) : 0u;
                 if (w0) classify(w0);
                 if (w1) classify(w1);
+            }
+        }
+
+        // where the batch's records go: look back over the batches before it (by now they have published)
+        if (warp == 0) {
+            unsigned long long before = lookback_exclusive(P.tileState, bi, lane);
+            if (lane == 0) {
+                st_state(P.tileState + bi, kLbPrefix | ((before + sAgg[kBatch]) & kLbValueMask));
+                found += sAgg[kBatch];
+                for (uint32_t s = 0; s < nb; ++s) {
+                    sBase[s] = before;
+                    before += sAgg[s];
+                }
             }
         }
 
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
             const uint32_t total = (uint32_t)(totalB & 0xfffffu), candTotal = (uint32_t)((totalB >> 20) & 0xffffu);
             if (!total) continue;  // (block-uniform)
             const uint32_t tileBase = (batch + s) * (uint32_t)kTile;
-            const uint32_t nzP = sPlus[buf][s][tid], cand = sCand[s][tid];
+            const uint32_t nzP = sPlus[s][tid], cand = sCand[s][tid];
             const uint32_t rankP = ((beforeA + sExA[s][tid]) & 0xffffu);  // plus stacks of the tile before this thread's positions
             const uint32_t firstRec = (uint32_t)(exB & 0xfffffu) + (sExB[s][tid] & 0x3ffffu);
             const uint32_t firstCand = (uint32_t)((exB >> 20) & 0xffffu) + (sExB[s][tid] >> 18);
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                         const int b = __ffs(cm) - 1;
                         cm &= cm - 1;
                         const uint32_t tp = myPos + b, bit = tp + P.minOv;
-                        const uint32_t bits = __funnelshift_r(sMask[buf][s][bit >> 5], sMask[buf][s][(bit >> 5) + 1], bit & 31) & wMask;
+                        const uint32_t bits = __funnelshift_r(sMask[s][bit >> 5], sMask[s][(bit >> 5) + 1], bit & 31) & wMask;
                         const uint32_t slot = rank - cbase;  // wraps to a huge value for earlier rounds
                         if (slot < (uint32_t)kCandCap) {
                             sCandTp[slot] = (uint16_t)tp;
@@ -329,10 +329,10 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                 for (uint32_t c = tid; c < nIn; c += kThreads) {  // dense: one thread per candidate
                     const uint32_t tp = sCandTp[c];
                     uint32_t bits = sCandBits[c];
-                    const uint32_t wp = __ldg(P.cmpP + sOff[buf][s][0] + sCandRank[c]);
+                    const uint32_t wp = __ldg(P.cmpP + sOff[s][0] + sCandRank[c]);
                     const uint32_t bit = tp + P.minOv, word = bit >> 5;
                     // the present stacks of the window are consecutive compact words, starting at the rank of its first position
-                    const uint32_t* win = P.cmpM + sOff[buf][s][2] + sPrefM[s][word] + __popc(sMask[buf][s][word] & ((1u << (bit & 31)) - 1u));
+                    const uint32_t* win = P.cmpM + sOff[s][2] + sPrefM[s][word] + __popc(sMask[s][word] & ((1u << (bit & 31)) - 1u));
                     const int n = __popc(bits);
                     // vicinity sum / max over the PRESENT stacks only, in overlap order: an absent stack would add
                     // +0.0f, which is an exact no-op (:564-577)
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                         const uint32_t wm = __ldg(win + k);  // second touch: served by L1
                         const float mo = word_height<REPR>(wm);
                         const float local = __fdiv_rn(__fsub_rn(mo, __fsub_rn(mean, __fdiv_rn(mo, fW))), mx);  // :597
-                        const uint32_t lbin = ((double)local < 0.2) ? 1u : 0u;     // :599
+                        const uint32_t lbin = local < 0.2f ? 1u : 0u;               // :599 ((double)local < 0.2: no float lies in [0.2, 0.2f))
                         const uint32_t bbin = ((wp | wm) & kA10Bit) ? 0u : 1u;     // :602
                         const uint32_t misc = (uint32_t)o | (lbin << 5) | (bbin << 6);
                         if (idx < P.capacity) {                                    // :608
@@ -375,7 +375,6 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                 }
             }
         }
-        batch = sNextBatch;  // (written before barrier C of this batch; rewritten after barrier B of the next one)
     }
 
     // flush the privatised histogram and this block's record counts
@@ -431,6 +430,21 @@ __global__ void __launch_bounds__(256) k_freq_lut(const unsigned long long* __re
     if ((threadIdx.x & 31) == 0 && best) atomicMax(maxCount, best);
 }
 
+// The bin thresholds of k_bin / k_score from the (global) maximum height frequency, on the device (log10f_emul.h): one
+// thread per threshold.  The host recomputes the table with its libm while the device works on, and compares (api.cu).
+__global__ void __launch_bounds__(32) k_bin_thresholds(const unsigned long long* __restrict__ maxCount, float* __restrict__ thresholds, BinParams* __restrict__ params) {
+    const unsigned long long c = *maxCount;
+    const float maxFreq = (float)(c < kSaturate ? (uint32_t)c : kSaturate);  // the float counter of :508, :547-550
+    const int b = blockIdx.x * 32 + threadIdx.x;  // threshold of bin b (1..999) lives at [b - 1]; one warp per SM: the search is a dependent chain
+    if (b == 0) {
+        params->maxFreq = maxFreq;
+        params->binScale = maxFreq > 1.0f ? __fdiv_rn(999.0f, emul_log10f(__fmul_rn(maxFreq, maxFreq))) : 0.0f;
+        thresholds[kBins - 1] = __uint_as_float(0x7f800000u);
+    } else if (b < kBins) {
+        thresholds[b - 1] = maxFreq > 1.0f ? emul_bin_threshold(b, maxFreq) : __uint_as_float(0x7f800000u);
+    }
+}
+
 // K3 part 2: height-score bin (:589-594) + grouped counter (:605) of every signature record.
 // The bin of a height-score product is the number of host-built thresholds <= hs (see api.cu).  A device log10
 // approximation proposes the bin, two short loops against the exact thresholds correct it, so the result is the
@@ -445,7 +459,7 @@ constexpr int kBinCache = 4096;
 constexpr uint32_t kBinEmpty = 0xffffffffu;
 __global__ void __launch_bounds__(kBinThreads) k_bin(const float* __restrict__ recRp, const float* __restrict__ recRm, const uint8_t* __restrict__ recMisc,
                                                      uint16_t* __restrict__ recBin, const unsigned long long* __restrict__ totals, uint64_t capacity,
-                                                     const float* __restrict__ lut, const float* __restrict__ thresholds, float binScale, int W,
+                                                     const float* __restrict__ lut, const float* __restrict__ thresholds, const BinParams* __restrict__ params, int W,
                                                      uint32_t* __restrict__ grouped) {
     __shared__ float sThr[kBins];
     __shared__ uint32_t sKey[kBinCache], sVal[kBinCache];
@@ -455,6 +469,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const float* __restrict__ r
     for (int k = tid; k < kBins - 1; k += kBinThreads) sThr[k] = thresholds[k];
     for (int k = tid; k < kBinCache; k += kBinThreads) { sKey[k] = kBinEmpty; sVal[k] = 0; }
     for (int k = tid; k < kBinWarps * 128; k += kBinThreads) (&sOnes[0][0])[k] = 0;
+    const float binScale = params->binScale;
     __syncthreads();
     auto bin_of = [&](float hs) {
         int b = (int)(__log10f(hs) * binScale + 0.5f);             // proposal only
@@ -496,6 +511,11 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const float* __restrict__ r
         }
     }
     (void)lane;
+}
+
+// Multi-GPU: this rank's "my signature store was too small" as a 0/1 word behind the grouped counts (summed by their all-reduce)
+__global__ void k_overflow_flag(const unsigned long long* __restrict__ totals, uint64_t capacity, uint64_t ppCapacity, uint32_t* __restrict__ flag) {
+    *flag = (totals[0] > capacity || totals[1] > ppCapacity) ? 1u : 0u;
 }
 
 // Test / writer / K5 view of the records: array-of-structures PairRec with the bin in misc bits 7..16 and the FDR of every
@@ -556,14 +576,26 @@ cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* f
     return cudaGetLastError();
 }
 
+cudaError_t launch_bin_thresholds(const unsigned long long* maxCount, float* thresholds, BinParams* params, cudaStream_t s, int* launches) {
+    k_bin_thresholds<<<(kBins + 31) / 32, 32, 0, s>>>(maxCount, thresholds, params);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_bin(const float* recRp, const float* recRm, const uint8_t* recMisc, uint16_t* recBin, const unsigned long long* totals, uint64_t capacity,
-                       uint64_t expected, const float* lut, const float* thresholds, float binScale, int W, uint32_t* grouped, cudaStream_t s, int* launches) {
+                       uint64_t expected, const float* lut, const float* thresholds, const BinParams* params, int W, uint32_t* grouped, cudaStream_t s, int* launches) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     uint64_t want = (expected + kBinThreads * 8 - 1) / (kBinThreads * 8);  // >= 8 records per thread: the tables are flushed once per block
     unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)sms * 4);
-    k_bin<<<blocks, kBinThreads, 0, s>>>(recRp, recRm, recMisc, recBin, totals, capacity, lut, thresholds, binScale, W, grouped);
+    k_bin<<<blocks, kBinThreads, 0, s>>>(recRp, recRm, recMisc, recBin, totals, capacity, lut, thresholds, params, W, grouped);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_overflow_flag(const unsigned long long* totals, uint64_t capacity, uint64_t ppCapacity, uint32_t* flag, cudaStream_t s, int* launches) {
+    k_overflow_flag<<<1, 1, 0, s>>>(totals, capacity, ppCapacity, flag);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -194,7 +194,7 @@ constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 
 
 __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restrict__ pp, const unsigned long long* __restrict__ totals, uint64_t ppCapacity,
                                                          ScoreState* __restrict__ st, unsigned long long* __restrict__ tileState, const float* __restrict__ lut,
-                                                         const float* __restrict__ thresholds, float binScale, const float* __restrict__ fdrTable,
+                                                         const float* __restrict__ thresholds, const BinParams* __restrict__ params, const float* __restrict__ fdrTable,
                                                          const uint16_t* __restrict__ binMap, int W, int ppIdx, float minHeight, const Slot* __restrict__ slots,
                                                          uint32_t nSlots, LocusOut* __restrict__ loci) {
     __shared__ float sThr[kBins];
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restri
     __shared__ unsigned long long sBase;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < kBins - 1; k += kScoreThreads) sThr[k] = thresholds[k];
+    const float binScale = params->binScale;
     __syncthreads();
     auto bin_of = [&](float hs) {
         int b = (int)(__log10f(hs) * binScale + 0.5f);             // proposal only
@@ -326,7 +327,7 @@ cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, uint32_t
 
 cudaError_t launch_score(const PairRec* pp, const unsigned long long* totals, uint64_t ppCapacity, uint64_t expected, ScoreState* state,
                          unsigned long long* tileState, const float* lut,
-                         const float* thresholds, float binScale, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
+                         const float* thresholds, const BinParams* params, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
                          const Slot* slots, uint32_t nSlots, LocusOut* loci, cudaStream_t s, int* launches) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -334,7 +335,7 @@ cudaError_t launch_score(const PairRec* pp, const unsigned long long* totals, ui
     uint64_t tiles = (expected + kScoreTile - 1) / kScoreTile;
     unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)sms * 6);
     float mh = (float)minHeight;  // `reads >= minStackHeight` compares float with unsigned converted to float (:903)
-    k_score<<<blocks, kScoreThreads, 0, s>>>(pp, totals, ppCapacity, state, tileState, lut, thresholds, binScale, fdrTable, binMap, W, ppIdx, mh, slots, nSlots, loci);
+    k_score<<<blocks, kScoreThreads, 0, s>>>(pp, totals, ppCapacity, state, tileState, lut, thresholds, params, fdrTable, binMap, W, ppIdx, mh, slots, nSlots, loci);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
