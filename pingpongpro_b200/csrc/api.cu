@@ -846,7 +846,6 @@ int enqueueScanStage(ppp_ctx* c) {
     p.tileOffM = c->dTileOffM;
     p.G = c->G;
     p.nTiles = c->nTiles;
-    p.batchTiles = scan_batch_tiles(c->nTiles);
     p.minOv = c->minOv;
     p.W = c->W;
     p.ppIdx = c->ppOv - c->minOv;

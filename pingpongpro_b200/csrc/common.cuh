@@ -23,7 +23,7 @@ constexpr uint32_t kValueMask = 0x7fffffffu;
 constexpr uint32_t kSaturate = 1u << 24;        // float counters stop at 2^24
 constexpr int kBins = 1000;                     // HEIGHT_SCORE_BINS, pingpongpro.cpp:164
 constexpr uint32_t kScanLowBins = 512;          // smem-privatised part of the height histogram
-constexpr int kScanTile = 8192;                 // positions per CTA iteration of the fused scan (G is a multiple)
+constexpr int kScanTile = 32768;                // positions per tile of the scan (G is a multiple): 256 threads x 4 occupancy words
 constexpr uint32_t kFreqCapacity = kSaturate + 1;  // rounded heights never exceed 2^24
 constexpr uint32_t kInvalidPos = 0xffffffffu;
 
@@ -87,7 +87,7 @@ struct ScanParams {
     const uint32_t* tileOffP;  // [nTiles + 1] index in cmpP of the first stack of every tile
     const uint32_t* tileOffM;
     uint64_t G;             // words per strand
-    uint32_t nTiles, batchTiles;
+    uint32_t nTiles;
     int minOv, W, ppIdx;
     uint32_t haloLo, haloHi;  // minus-strand words in [haloLo, haloHi) are halo copies (not counted)
     PassState* state;
@@ -156,7 +156,6 @@ cudaError_t launch_compact_write(const uint32_t* H, const uint32_t* occ, uint64_
                                  uint32_t* cmpP, uint32_t* cmpM, cudaStream_t s, int* launches);
 
 cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* launches);
-uint32_t scan_batch_tiles(uint32_t nTiles);
 // Multi-GPU exchange of the height histogram in ONE collective.  `gather` holds one slot of kTallHeader + cap words
 // per rank: [count of tall stacks, local maximum height, the rank's low bins (kScanLowBins x u64), tall heights...];
 // every rank fills its own slot of a zeroed buffer and a sum all-reduce turns that into an all-gather.  The kernel

@@ -7,7 +7,7 @@
 // file writes them down as such -- per strand the non-empty words in position order, next to the occupancy bitmap the
 // builder maintained -- so that every later pass streams 4 bytes per stack instead of gathering one 32-byte sector per
 // stack from arrays that are ~96 % zeros:
-//   k_tile_popc      stacks per tile of 8192 positions and strand (reads the bitmaps: G/4 bytes)
+//   k_tile_popc      stacks per tile of 32768 positions and strand (reads the bitmaps: G/4 bytes)
 //   exclusive scan   -> index of every tile's first stack (tileOff, nTiles + 1 entries per strand)
 //   k_compact_write  rank of every stack inside its tile (block scan of popcounts), gather of the words, dense write
 // Bound: the sector gathers of k_compact_write (32 B per occupied sector), once per input instead of once per scan.
@@ -19,7 +19,9 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kTile = kScanTile;
-static_assert(kTile == kThreads * 32, "one occupancy word per thread and strand");
+constexpr int kTileWords = kTile / 32;             // occupancy words per tile and strand
+constexpr int kWords = kTileWords / kThreads;      // consecutive words owned by one thread of k_compact_write
+static_assert(kTile == kThreads * kWords * 32 && kTileWords % 32 == 0, "tile geometry");
 
 __global__ void __launch_bounds__(kThreads) k_tile_popc(const uint32_t* __restrict__ occ, uint64_t G, uint32_t nTiles, uint32_t* __restrict__ cntP,
                                                         uint32_t* __restrict__ cntM) {
@@ -27,10 +29,10 @@ __global__ void __launch_bounds__(kThreads) k_tile_popc(const uint32_t* __restri
     const uint32_t warpsPerGrid = gridDim.x * (kThreads / 32);
     const uint32_t* __restrict__ occM = occ + G / 32;
     for (uint32_t tile = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); tile < nTiles; tile += warpsPerGrid) {
-        const size_t w = (size_t)tile * kThreads;
+        const size_t w = (size_t)tile * kTileWords;
         uint32_t p = 0, m = 0;
-#pragma unroll
-        for (int k = 0; k < kThreads / 32; ++k) {
+#pragma unroll 8
+        for (int k = 0; k < kTileWords / 32; ++k) {
             p += __popc(__ldg(occ + w + k * 32 + lane));
             m += __popc(__ldg(occM + w + k * 32 + lane));
         }
@@ -50,9 +52,14 @@ __global__ void __launch_bounds__(kThreads) k_compact_write(const uint32_t* __re
     const uint32_t* __restrict__ Hp = H;
     const uint32_t* __restrict__ Hm = H + G;
     for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-        const size_t w = (size_t)tile * kThreads + tid;
-        const uint32_t nzP = __ldg(occ + w), nzM = __ldg(occM + w);
-        const uint32_t pack = (uint32_t)__popc(nzP) | ((uint32_t)__popc(nzM) << 16);
+        const size_t w = (size_t)tile * kTileWords + (size_t)tid * kWords;  // this thread's kWords consecutive words
+        uint32_t nzP[kWords], nzM[kWords], pack = 0;
+#pragma unroll
+        for (int k = 0; k < kWords; ++k) {
+            nzP[k] = __ldg(occ + w + k);
+            nzM[k] = __ldg(occM + w + k);
+            pack += (uint32_t)__popc(nzP[k]) | ((uint32_t)__popc(nzM[k]) << 16);
+        }
         uint32_t inc = pack;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -65,22 +72,25 @@ __global__ void __launch_bounds__(kThreads) k_compact_write(const uint32_t* __re
 #pragma unroll
         for (int k = 0; k < kThreads / 32; ++k)
             if (k < warp) before += sWarp[k];
-        const uint32_t ex = before + inc - pack;
-        const uint32_t base = tile * (uint32_t)kTile + (uint32_t)tid * 32u;
+        const uint32_t ex = before + inc - pack;  // plus stacks | minus stacks << 16 of the tile before this thread's words (a tile holds at most 2^15 of each)
         uint32_t* __restrict__ dp = cmpP + offP[tile] + (ex & 0xffffu);
         uint32_t* __restrict__ dm = cmpM + offM[tile] + (ex >> 16);
-        // up to four gathers (two per strand) in flight per trip
-        uint32_t a = nzP, b = nzM;
-        while (a | b) {
-            uint32_t v[4] = {0u, 0u, 0u, 0u};
-            if (a) { v[0] = __ldg(Hp + base + (uint32_t)(__ffs(a) - 1)); a &= a - 1; }
-            if (b) { v[1] = __ldg(Hm + base + (uint32_t)(__ffs(b) - 1)); b &= b - 1; }
-            if (a) { v[2] = __ldg(Hp + base + (uint32_t)(__ffs(a) - 1)); a &= a - 1; }
-            if (b) { v[3] = __ldg(Hm + base + (uint32_t)(__ffs(b) - 1)); b &= b - 1; }
-            if (v[0]) *dp++ = v[0];
-            if (v[2]) *dp++ = v[2];
-            if (v[1]) *dm++ = v[1];
-            if (v[3]) *dm++ = v[3];
+#pragma unroll
+        for (int k = 0; k < kWords; ++k) {
+            const uint32_t base = tile * (uint32_t)kTile + ((uint32_t)tid * kWords + k) * 32u;
+            // up to four gathers (two per strand) in flight per trip
+            uint32_t a = nzP[k], b = nzM[k];
+            while (a | b) {
+                uint32_t v[4] = {0u, 0u, 0u, 0u};
+                if (a) { v[0] = __ldg(Hp + base + (uint32_t)(__ffs(a) - 1)); a &= a - 1; }
+                if (b) { v[1] = __ldg(Hm + base + (uint32_t)(__ffs(b) - 1)); b &= b - 1; }
+                if (a) { v[2] = __ldg(Hp + base + (uint32_t)(__ffs(a) - 1)); a &= a - 1; }
+                if (b) { v[3] = __ldg(Hm + base + (uint32_t)(__ffs(b) - 1)); b &= b - 1; }
+                if (v[0]) *dp++ = v[0];
+                if (v[2]) *dp++ = v[2];
+                if (v[1]) *dm++ = v[1];
+                if (v[3]) *dm++ = v[3];
+            }
         }
         __syncthreads();  // sWarp is rewritten by the next tile
     }

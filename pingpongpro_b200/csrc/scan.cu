@@ -34,22 +34,12 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kPerThread = 32;                 // consecutive positions owned by one thread = one occupancy word per strand
-constexpr int kTile = kScanTile;               // 8192 positions per tile
-constexpr int kCandCap = 512;                  // candidates staged per round (a tile rarely has more)
-static_assert(kTile == kThreads * kPerThread, "tile geometry");
-constexpr int kBatch = 4;  // tiles claimed per ticket (one atomic on a single address costs ~1 ns: a human-sized genome has 378 k tiles)
-static_assert((kBatch & (kBatch - 1)) == 0 && kBatch <= 32, "the batch aggregate is a butterfly sum over kBatch lanes");
-static_assert(kTile <= (1 << 14) && kTile * PPP_MAX_OVERLAPS <= (1 << 20), "block-scan fields: 20 bits of records, 16 of candidates, 16 of ping-pong records");
+constexpr int kWords = 4;                      // consecutive 32-position occupancy words owned by one thread, per strand
+constexpr int kTile = kScanTile;               // positions per tile
+constexpr int kTileWords = kTile / 32;         // occupancy words per tile and strand
+static_assert(kTile == kThreads * kWords * 32, "tile geometry");
+static_assert(kTile <= (1 << 15) && PPP_MAX_OVERLAPS <= 32, "prefix arrays are 16 bit; a window fits the 64 positions after a word's first");
 
-__device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
 __device__ __forceinline__ unsigned long long warp_inclusive64(unsigned long long v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -62,23 +52,23 @@ __device__ __forceinline__ unsigned long long warp_inclusive64(unsigned long lon
 __device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
 __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
 
-// Decoupled look-back, executed by one whole warp: the packed sum of the aggregates of all batches before `batch`.  A
-// batch's state is ONE 64-bit word (flag + value), so a plain volatile load sees a consistent pair and no fence is
-// needed.  Batches are claimed in ticket order, hence every earlier batch belongs to a block that is already running.
-// The resident blocks tend to run in step (they all publish, then all look back), so a batch may have to walk over every
-// batch of its wave before it meets a finished prefix: a step covers 128 batches (four independent loads per lane).
-__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* __restrict__ state, uint32_t batch, int lane) {
+// Decoupled look-back, executed by one whole warp: the packed sum of the aggregates of all tiles before `tile`.  A
+// tile's state is ONE 64-bit word (flag + value), so a plain volatile load sees a consistent pair and no fence is
+// needed.  Tiles are claimed in ticket order, hence every earlier tile belongs to a block that is already running --
+// and a block publishes a tile's aggregate within microseconds of claiming it.  A step covers 128 tiles (four
+// independent loads per lane): the resident blocks tend to run in step, so a tile may have to walk over a whole wave.
+__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* __restrict__ state, uint32_t tile, int lane) {
     unsigned long long sum = 0;
-    int64_t j = (int64_t)batch - 1;  // the nearest batch of the current window
+    int64_t j = (int64_t)tile - 1;  // the nearest tile of the current window
     while (j >= 0) {
         unsigned long long v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int64_t mine = j - 4 * lane - k;
-            v[k] = mine >= 0 ? ld_state(state + mine) : kLbPrefix;  // before the first batch: an inclusive prefix of zero
+            v[k] = mine >= 0 ? ld_state(state + mine) : kLbPrefix;  // before the first tile: an inclusive prefix of zero
         }
         unsigned long long part = 0;
-        bool closed = false;  // this lane met a batch that knows its inclusive prefix
+        bool closed = false;  // this lane met a tile that knows its inclusive prefix
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int64_t mine = j - 4 * lane - k;
@@ -109,41 +99,49 @@ __device__ __noinline__ void count_tall(uint32_t* freqTail, uint32_t* tallList, 
     }
 }
 
-// 4-byte asynchronous copy global -> shared (LDGSTS): the next tile's occupancy words travel without occupying registers
+// 4-byte asynchronous copy global -> shared (LDGSTS): the tile's occupancy words travel without occupying registers
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// per-thread counts of a tile in one 64-bit word, so that ONE warp scan carries all four:
+//   bits 0..17 records, 18..30 ping-pong records, 31..43 plus stacks, 44..56 minus stacks  (warp totals: <= 2^17, 2^12, 2^12, 2^12)
+constexpr int kPkPp = 18, kPkPlus = 31, kPkMinus = 44;
+__device__ __forceinline__ uint32_t pk_rec(unsigned long long v) { return (uint32_t)v & 0x3ffffu; }
+__device__ __forceinline__ uint32_t pk_pp(unsigned long long v) { return (uint32_t)(v >> kPkPp) & 0x1fffu; }
+__device__ __forceinline__ uint32_t pk_plus(unsigned long long v) { return (uint32_t)(v >> kPkPlus) & 0x1fffu; }
+__device__ __forceinline__ uint32_t pk_minus(unsigned long long v) { return (uint32_t)(v >> kPkMinus) & 0x1fffu; }
+
+// the minus-strand occupancy bits at distance sh.. of a position whose word and the following one are (w0, w1), sh < 64
+__device__ __forceinline__ uint32_t window_bits(uint32_t w0, uint32_t w1, uint32_t sh, uint32_t wMask) {
+    return (sh < 32u ? __funnelshift_r(w0, w1, sh) : (w1 >> (sh - 32u))) & wMask;
+}
+
 template <int REPR>
-__global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
-    // occupancy words of the batch's tiles
-    __shared__ uint32_t sMask[kBatch][kThreads + 2];  // minus strand + the word after the tile + a zero
-    __shared__ uint32_t sPlus[kBatch][kThreads];      // plus strand
-    __shared__ uint32_t sOff[kBatch][4];              // compact index of the tile's first / past-the-last plus stack, first / past-the-last minus stack
-    // per thread and tile, between the counting phase and the record phase
-    __shared__ uint32_t sCand[kBatch][kThreads];         // which of the thread's plus stacks are candidates
-    __shared__ uint32_t sExA[kBatch][kThreads];          // within the warp: plus stacks | minus stacks << 16 before the thread's positions
-    __shared__ uint32_t sExB[kBatch][kThreads];          // within the warp: records | candidates << 18 before them
-    __shared__ uint16_t sExPp[kBatch][kThreads];         // within the warp: ping-pong records before them
-    __shared__ uint16_t sPrefM[kBatch][kThreads + 2];    // minus stacks of the tile before each word of sMask
-    __shared__ uint32_t sWarpA[kBatch][kWarps];              // per warp: plus stacks | minus stacks << 16
-    __shared__ unsigned long long sWarpB[kBatch][kWarps];    // per warp: records | candidates << 20 | ping-pong records << 36
-    __shared__ unsigned long long sAgg[kBatch + 1], sBase[kBatch];  // packed (kLb* layout) records of the tile (last: of the batch) / before the tile
+__global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
+    __shared__ uint32_t sMask[kTileWords + 2];     // minus-strand occupancy words of the tile + the word after the tile + a zero
+    __shared__ uint32_t sPlus[kTileWords];         // plus strand
+    __shared__ uint32_t sOff[4];                   // compact index of the tile's first / past-the-last plus stack, first / past-the-last minus stack
+    // per occupancy word, what the tile holds BEFORE the word's positions:
+    __shared__ uint32_t sRecOff[kTileWords + 1];   // records (last entry: of the whole tile)
+    __shared__ uint16_t sPpOff[kTileWords];        // ping-pong records
+    __shared__ uint16_t sPrefP[kTileWords];        // plus stacks
+    __shared__ uint16_t sPrefM[kTileWords + 2];    // minus stacks (entry kTileWords: the tile's total = rank of the halo word)
+    __shared__ unsigned long long sWarp[kWarps];   // per warp: packed totals
+    __shared__ unsigned long long sAgg, sBase;     // packed (kLb* layout) records of the tile / before the tile
     __shared__ uint32_t sHist[kScanLowBins];
-    __shared__ uint32_t sNextBatch;
-    __shared__ uint32_t sCandBits[kCandCap], sCandOff[kCandCap];  // per candidate: present overlaps / first record (tile-relative)
-    __shared__ uint16_t sCandTp[kCandCap], sCandRank[kCandCap], sCandPp[kCandCap];  // tile position / rank among the tile's plus stacks / ping-pong record
+    __shared__ uint32_t sTile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < (int)kScanLowBins; k += kThreads) sHist[k] = 0;
-    if (tid < kBatch) sMask[tid][kThreads + 1] = 0;
+    if (tid == 0) sMask[kTileWords + 1] = 0;
 
     const uint32_t ONE = REPR == kReprInt ? 1u : 0x3f800000u;
     const uint32_t wMask = P.W >= 32 ? 0xffffffffu : ((1u << P.W) - 1u);
     const float fW = (float)P.W;
-    const uint32_t myPos = (uint32_t)tid * kPerThread;  // this thread owns 32 consecutive positions of a tile
+    const uint32_t myWord = (uint32_t)tid * kWords;  // this thread owns kWords consecutive occupancy words of a tile
     uint32_t ones = 0, localMax = 0, small = 0;  // small: four 8-bit counters for rounded heights 0..3
     unsigned long long found = 0;                // (thread 0) packed records this block found
     auto flush_small = [&]() {
@@ -160,90 +158,99 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
         else count_tall(P.freqTail, P.tallList, P.tallCount, P.tallCap, r);
         localMax = max(localMax, r);
     };
-    // the occupancy words and compact offsets of a batch of tiles, global -> shared, asynchronously
-    auto fetch = [&](uint32_t first) {
-        const uint32_t n = min(P.batchTiles, P.nTiles - first);
-        for (uint32_t s = 0; s < n; ++s) {
-            const size_t w = (size_t)(first + s) * kThreads;
-            cp_async4(&sPlus[s][tid], P.occ + w + tid);
-            cp_async4(&sMask[s][tid], P.occ + P.G / 32 + w + tid);
-            if (tid == 0) cp_async4(&sMask[s][kThreads], P.occ + P.G / 32 + w + kThreads);
-            if (tid >= 32 && tid < 36) cp_async4(&sOff[s][tid - 32], ((tid & 2) ? P.tileOffM : P.tileOffP) + first + s + (tid & 1));
-        }
-        cp_async_commit();
-    };
 
-    // A batch is claimed only when the block is ready to count and publish it at once: whoever holds an earlier ticket
+    // A tile is claimed only when the block is ready to count and publish it at once: whoever holds an earlier ticket
     // publishes its record counts within microseconds, whatever its record phase takes afterwards.  (Claiming ahead, to
     // prefetch the occupancy words, made every block wait for the slowest record phase of the previous round.)
     for (;;) {
-        __syncthreads();  // the previous batch's shared state is no longer read
-        if (tid == 0) sNextBatch = atomicAdd(&P.state->ticket, P.batchTiles);
+        __syncthreads();  // the previous tile's shared state is no longer read
+        if (tid == 0) sTile = atomicAdd(&P.state->ticket, 1u);
         __syncthreads();
-        const uint32_t batch = sNextBatch;
-        if (batch >= P.nTiles) break;
-        const uint32_t nb = min(P.batchTiles, P.nTiles - batch);
-        fetch(batch);
-        cp_async_wait();
-        __syncthreads();  // (A) the batch's occupancy words are complete
-
-        // ---- counting phase (bitmaps only): how many records every tile of the batch holds, published at once, so that
-        // the blocks holding later tiles never wait for this block's record phase
-        for (uint32_t s = 0; s < nb; ++s) {
-            const uint32_t nzP = sPlus[s][tid], nzM = sMask[s][tid];
-            uint32_t cnt = 0, ncand = 0, npp = 0, cand = 0;
-            uint32_t nz = nzP;
-            while (nz) {  // candidates = plus stacks with at least one minus stack at overlaps min..max
-                const int b = __ffs(nz) - 1;
-                nz &= nz - 1;
-                const uint32_t bit = myPos + b + P.minOv;
-                const uint32_t bits = __funnelshift_r(sMask[s][bit >> 5], sMask[s][(bit >> 5) + 1], bit & 31) & wMask;
-                if (bits) { cnt += __popc(bits); ++ncand; cand |= 1u << b; npp += (bits >> P.ppIdx) & 1u; }
+        const uint32_t tile = sTile;
+        if (tile >= P.nTiles) break;
+        const uint32_t tileBase = tile * (uint32_t)kTile;
+        {   // the tile's occupancy words and compact offsets, global -> shared, asynchronously
+            const size_t w = (size_t)tile * kTileWords;
+#pragma unroll
+            for (int k = 0; k < kWords; ++k) {
+                cp_async4(&sPlus[k * kThreads + tid], P.occ + w + k * kThreads + tid);
+                cp_async4(&sMask[k * kThreads + tid], P.occ + P.G / 32 + w + k * kThreads + tid);
             }
-            // scans over the warp: stacks per strand (their ranks index the compact arrays), and (records, candidates,
-            // ping-pong records), which are ordered (thread, position[, overlap]) == (position[, overlap])
-            const uint32_t packA = (uint32_t)__popc(nzP) | ((uint32_t)__popc(nzM) << 16);
-            const unsigned long long packB = (unsigned long long)cnt | ((unsigned long long)ncand << 20) | ((unsigned long long)npp << 36);
-            const uint32_t incA = warp_inclusive(packA, lane);
-            const unsigned long long incB = warp_inclusive64(packB, lane);
-            if (lane == 31) { sWarpA[s][warp] = incA; sWarpB[s][warp] = incB; }
-            const unsigned long long exB = incB - packB;
-            sCand[s][tid] = cand;
-            sExA[s][tid] = incA - packA;
-            sExB[s][tid] = (uint32_t)(exB & 0xfffffu) | ((uint32_t)((exB >> 20) & 0xffffu) << 18);  // (within a warp: records < 2^15, candidates < 2^10)
-            sExPp[s][tid] = (uint16_t)(exB >> 36);
+            if (tid == 0) cp_async4(&sMask[kTileWords], P.occ + P.G / 32 + w + kTileWords);
+            if (tid >= 32 && tid < 36) cp_async4(&sOff[tid - 32], ((tid & 2) ? P.tileOffM : P.tileOffP) + tile + (tid & 1));
+            cp_async_commit();
+            cp_async_wait();
+        }
+        __syncthreads();  // (A) the tile's occupancy words are complete
+
+        // ---- counting phase (bitmaps only): how many records the tile holds, published at once, so that the blocks
+        // holding later tiles never wait for this block's record phase
+        uint32_t cntW[kWords], ppW[kWords], popP[kWords], popM[kWords];
+        {
+            uint32_t mw = sMask[myWord];
+#pragma unroll
+            for (int k = 0; k < kWords; ++k) {
+                const uint32_t pw = sPlus[myWord + k], w0 = mw, w1 = sMask[myWord + k + 1];
+                mw = w1;
+                uint32_t cnt = 0, npp = 0;
+                for (uint32_t nz = pw; nz; nz &= nz - 1) {  // a plus stack has one record per minus stack at overlaps min..max (:559-577)
+                    const uint32_t bits = window_bits(w0, w1, (uint32_t)(__ffs(nz) - 1) + (uint32_t)P.minOv, wMask);
+                    cnt += __popc(bits);
+                    npp += (bits >> P.ppIdx) & 1u;
+                }
+                cntW[k] = cnt;
+                ppW[k] = npp;
+                popP[k] = (uint32_t)__popc(pw);
+                popM[k] = (uint32_t)__popc(w0);
+            }
+        }
+        // one scan over the warp for all four counts; records are ordered (word, position, overlap) == (position, overlap)
+        unsigned long long ex;
+        {
+            uint32_t a = 0, b = 0, c = 0, d = 0;
+#pragma unroll
+            for (int k = 0; k < kWords; ++k) { a += cntW[k]; b += ppW[k]; c += popP[k]; d += popM[k]; }
+            const unsigned long long pack = (unsigned long long)a | ((unsigned long long)b << kPkPp) | ((unsigned long long)c << kPkPlus) | ((unsigned long long)d << kPkMinus);
+            const unsigned long long inc = warp_inclusive64(pack, lane);
+            if (lane == 31) sWarp[warp] = inc;
+            ex = inc - pack;
         }
         __syncthreads();  // (B)
-        const uint32_t bi = batch / P.batchTiles;  // (tickets are multiples of batchTiles)
-        if (tid < 32) {  // the batch's aggregate, published before any of its records is written
-            unsigned long long agg = 0;
-            if (tid < (int)nb) {
-                unsigned long long t = 0;
+        {   // complete the counts before this thread's words over the tile, word by word
+            uint32_t rec = pk_rec(ex), pp = pk_pp(ex), plus = pk_plus(ex), minus = pk_minus(ex), totRec = 0, totPp = 0, totMinus = 0;
 #pragma unroll
-                for (int w = 0; w < kWarps; ++w) t += sWarpB[tid][w];
-                agg = (t & 0xfffffull) | ((t >> 36) << kLbRecBits);
-                sAgg[tid] = agg;
+            for (int w = 0; w < kWarps; ++w) {
+                const unsigned long long t = sWarp[w];
+                if (w < warp) { rec += pk_rec(t); pp += pk_pp(t); plus += pk_plus(t); minus += pk_minus(t); }
+                totRec += pk_rec(t);
+                totPp += pk_pp(t);
+                totMinus += pk_minus(t);
             }
 #pragma unroll
-            for (int d = 1; d < kBatch; d <<= 1) agg += __shfl_xor_sync(0xffffffffu, agg, d);
-            if (tid == 0) { sAgg[kBatch] = agg; st_state(P.tileState + bi, kLbAggregate | agg); }
+            for (int k = 0; k < kWords; ++k) {
+                sRecOff[myWord + k] = rec;
+                sPpOff[myWord + k] = (uint16_t)pp;
+                sPrefP[myWord + k] = (uint16_t)plus;
+                sPrefM[myWord + k] = (uint16_t)minus;
+                rec += cntW[k];
+                pp += ppW[k];
+                plus += popP[k];
+                minus += popM[k];
+            }
+            if (tid == 0) {  // the tile's aggregate, published before any of its records is written
+                const unsigned long long agg = (unsigned long long)totRec | ((unsigned long long)totPp << kLbRecBits);
+                sAgg = agg;
+                sRecOff[kTileWords] = totRec;
+                sPrefM[kTileWords] = (uint16_t)totMinus;
+                sPrefM[kTileWords + 1] = (uint16_t)totMinus;
+                st_state(P.tileState + tile, kLbAggregate | agg);
+            }
         }
-        // complete the ranks of the minus strand (window starts, halo exclusion)
-        for (uint32_t s = 0; s < nb; ++s) {
-            uint32_t before = 0;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w)
-                if (w < warp) before += sWarpA[s][w];
-            const uint32_t exM = (before + sExA[s][tid]) >> 16;
-            sPrefM[s][tid] = (uint16_t)exM;
-            if (tid == kThreads - 1) sPrefM[s][kThreads] = (uint16_t)(exM + __popc(sMask[s][tid]));
-        }
-        __syncthreads();  // (C) aggregates and sPrefM are visible
+        __syncthreads();  // (C) the aggregate and the per-word counts are visible
 
-        // ---- K2: height histogram, dense over the tiles' compact words (halo copies of a neighbouring shard are not counted)
-        for (uint32_t s = 0; s < nb; ++s) {
-            const uint32_t tileBase = (batch + s) * (uint32_t)kTile;
-            const uint32_t offP = sOff[s][0], endP = sOff[s][1], offM = sOff[s][2], endM = sOff[s][3];
+        // ---- K2: height histogram, dense over the tile's compact words (halo copies of a neighbouring shard are not counted)
+        {
+            const uint32_t offP = sOff[0], endP = sOff[1], offM = sOff[2], endM = sOff[3];
             for (uint32_t i = offP + tid; i < endP; i += kThreads * 2) {
                 const uint32_t w0 = __ldg(P.cmpP + i);
                 const uint32_t w1 = i + kThreads < endP ? __ldg(P.cmpP + i + kThreads) : 0u;
@@ -253,8 +260,8 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
             uint32_t skipLo = 0xffffffffu, skipHi = 0xffffffffu;  // ranks (within the tile) of the halo copies
             if (tileBase < P.haloHi && tileBase + kTile > P.haloLo) {
                 auto rankOf = [&](uint32_t q) {  // minus stacks of the tile at tile positions < q
-                    if (q >= (uint32_t)kTile) return (uint32_t)sPrefM[s][kThreads];
-                    return (uint32_t)sPrefM[s][q >> 5] + (uint32_t)__popc(sMask[s][q >> 5] & ((1u << (q & 31)) - 1u));
+                    if (q >= (uint32_t)kTile) return (uint32_t)sPrefM[kTileWords];
+                    return (uint32_t)sPrefM[q >> 5] + (uint32_t)__popc(sMask[q >> 5] & ((1u << (q & 31)) - 1u));
                 };
                 skipLo = rankOf(P.haloLo > tileBase ? P.haloLo - tileBase : 0u);
                 skipHi = rankOf(P.haloHi - tileBase);
@@ -268,110 +275,80 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
             }
         }
 
-        // where the batch's records go: look back over the batches before it (by now they have published)
+        // where the tile's records go: look back over the tiles before it (by now they have published)
         if (warp == 0) {
-            unsigned long long before = lookback_exclusive(P.tileState, bi, lane);
+            const unsigned long long before = lookback_exclusive(P.tileState, tile, lane);
             if (lane == 0) {
-                st_state(P.tileState + bi, kLbPrefix | ((before + sAgg[kBatch]) & kLbValueMask));
-                found += sAgg[kBatch];
-                for (uint32_t s = 0; s < nb; ++s) {
-                    sBase[s] = before;
-                    before += sAgg[s];
-                }
+                st_state(P.tileState + tile, kLbPrefix | ((before + sAgg) & kLbValueMask));
+                found += sAgg;
+                sBase = before;
             }
         }
+        const uint32_t total = sRecOff[kTileWords];
+        if (!total) continue;  // (block-uniform)
+        __syncthreads();  // sBase is visible
 
-        // ---- record phase, tile by tile
-        for (uint32_t s = 0; s < nb; ++s) {
-            unsigned long long totalB = 0, exB = 0;
-            uint32_t beforeA = 0;
+        // ---- record phase: ONE THREAD PER RECORD (dense, whatever the stacks' window sizes).  Record r of the tile belongs
+        // to the last occupancy word whose record offset is <= r (binary search over the per-word offsets), inside the word
+        // to the plus stack whose windows cover it, and to the k-th present minus stack of that window.
+        const unsigned long long recBase = sBase & kLbRecMask, ppBase = sBase >> kLbRecBits;
+        const uint32_t offP = sOff[0], offM = sOff[2];
+        for (uint32_t r = tid; r < total; r += kThreads) {
+            uint32_t word = 0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const unsigned long long b = sWarpB[s][w];
-                if (w < warp) { exB += b; beforeA += sWarpA[s][w]; }
-                totalB += b;
+            for (int step = kTileWords / 2; step > 0; step >>= 1)
+                if (sRecOff[word + step] <= r) word += step;
+            const uint32_t pw = sPlus[word], w0 = sMask[word], w1 = sMask[word + 1];
+            uint32_t left = r - sRecOff[word], b = 0, bits = 0;
+            for (uint32_t nz = pw; nz; nz &= nz - 1) {  // (a word with records has a plus stack that covers `left`)
+                b = (uint32_t)(__ffs(nz) - 1);
+                bits = window_bits(w0, w1, b + (uint32_t)P.minOv, wMask);
+                const uint32_t n = (uint32_t)__popc(bits);
+                if (left < n) break;
+                left -= n;
             }
-            const uint32_t total = (uint32_t)(totalB & 0xfffffu), candTotal = (uint32_t)((totalB >> 20) & 0xffffu);
-            if (!total) continue;  // (block-uniform)
-            const uint32_t tileBase = (batch + s) * (uint32_t)kTile;
-            const uint32_t nzP = sPlus[s][tid], cand = sCand[s][tid];
-            const uint32_t rankP = ((beforeA + sExA[s][tid]) & 0xffffu);  // plus stacks of the tile before this thread's positions
-            const uint32_t firstRec = (uint32_t)(exB & 0xfffffu) + (sExB[s][tid] & 0x3ffffu);
-            const uint32_t firstCand = (uint32_t)((exB >> 20) & 0xffffu) + (sExB[s][tid] >> 18);
-            const uint32_t firstPp = (uint32_t)(exB >> 36) + sExPp[s][tid];
-            const uint32_t rounds = (candTotal + kCandCap - 1) / kCandCap;
-            for (uint32_t round = 0; round < rounds; ++round) {
-                const uint32_t cbase = round * kCandCap;
-                __syncthreads();  // the previous list is no longer read (first round: sBase of this batch is visible, too)
-                {
-                    uint32_t off = firstRec, rank = firstCand, pp = firstPp, cm = cand;
-                    while (cm) {
-                        const int b = __ffs(cm) - 1;
-                        cm &= cm - 1;
-                        const uint32_t tp = myPos + b, bit = tp + P.minOv;
-                        const uint32_t bits = __funnelshift_r(sMask[s][bit >> 5], sMask[s][(bit >> 5) + 1], bit & 31) & wMask;
-                        const uint32_t slot = rank - cbase;  // wraps to a huge value for earlier rounds
-                        if (slot < (uint32_t)kCandCap) {
-                            sCandTp[slot] = (uint16_t)tp;
-                            sCandBits[slot] = bits;
-                            sCandOff[slot] = off;
-                            sCandRank[slot] = (uint16_t)(rankP + __popc(nzP & ((1u << b) - 1u)));
-                            sCandPp[slot] = (uint16_t)pp;
-                        }
-                        off += __popc(bits);
-                        pp += (bits >> P.ppIdx) & 1u;
-                        ++rank;
-                    }
-                }
-                __syncthreads();  // the list is complete
-                const unsigned long long recBase = sBase[s] & kLbRecMask, ppBase = sBase[s] >> kLbRecBits;
-                const uint32_t nIn = min((uint32_t)kCandCap, candTotal - cbase);
-                for (uint32_t c = tid; c < nIn; c += kThreads) {  // dense: one thread per candidate
-                    const uint32_t tp = sCandTp[c];
-                    uint32_t bits = sCandBits[c];
-                    const uint32_t wp = __ldg(P.cmpP + sOff[s][0] + sCandRank[c]);
-                    const uint32_t bit = tp + P.minOv, word = bit >> 5;
-                    // the present stacks of the window are consecutive compact words, starting at the rank of its first position
-                    const uint32_t* win = P.cmpM + sOff[s][2] + sPrefM[s][word] + __popc(sMask[s][word] & ((1u << (bit & 31)) - 1u));
-                    const int n = __popc(bits);
-                    // vicinity sum / max over the PRESENT stacks only, in overlap order: an absent stack would add
-                    // +0.0f, which is an exact no-op (:564-577)
-                    float sum = 0.0f, mx = 0.0f;
-                    for (int k = 0; k < n; ++k) {
-                        const float mq = word_height<REPR>(__ldg(win + k));
-                        sum = __fadd_rn(sum, mq);
-                        mx = fmaxf(mx, mq);
-                    }
-                    const float mean = __fdiv_rn(sum, fW);                    // :578
-                    const float hp = word_height<REPR>(wp);
-                    unsigned long long idx = recBase + sCandOff[c];
-                    for (int k = 0; k < n; ++k, ++idx) {                      // :584-586
-                        const int o = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        const uint32_t wm = __ldg(win + k);  // second touch: served by L1
-                        const float mo = word_height<REPR>(wm);
-                        const float local = __fdiv_rn(__fsub_rn(mo, __fsub_rn(mean, __fdiv_rn(mo, fW))), mx);  // :597
-                        const uint32_t lbin = local < 0.2f ? 1u : 0u;               // :599 ((double)local < 0.2: no float lies in [0.2, 0.2f))
-                        const uint32_t bbin = ((wp | wm) & kA10Bit) ? 0u : 1u;     // :602
-                        const uint32_t misc = (uint32_t)o | (lbin << 5) | (bbin << 6);
-                        if (idx < P.capacity) {                                    // :608
-                            P.recPos[idx] = tileBase + tp;
-                            P.recRp[idx] = hp;
-                            P.recRm[idx] = mo;
-                            P.recMisc[idx] = (uint8_t)misc;
-                        }
-                        if (o == P.ppIdx) {
-                            const unsigned long long j = ppBase + sCandPp[c];
-                            if (j < P.ppCapacity) {
-                                PairRec r;
-                                r.lpos = tileBase + tp;
-                                r.rp = hp;
-                                r.rm = mo;
-                                r.misc = misc;
-                                *reinterpret_cast<uint4*>(&P.ppRecs[j]) = *reinterpret_cast<uint4*>(&r);
-                            }
-                        }
-                    }
+            const int k = (int)left;                              // the record is the k-th present stack of the window
+            const uint32_t tp = word * 32u + b;
+            const uint32_t wp = __ldg(P.cmpP + offP + sPrefP[word] + __popc(pw & ((1u << b) - 1u)));
+            // the present stacks of the window are consecutive compact words, starting at the rank of its first position
+            const uint32_t q = tp + (uint32_t)P.minOv, qw = q >> 5;
+            const uint32_t* win = P.cmpM + offM + sPrefM[qw] + __popc(sMask[qw] & ((1u << (q & 31u)) - 1u));
+            const int n = __popc(bits);
+            // vicinity sum / max over the PRESENT stacks only, in overlap order: an absent stack would add
+            // +0.0f, which is an exact no-op (:564-577)
+            float sum = 0.0f, mx = 0.0f;
+            uint32_t wm = 0, o = 0, rest = bits;
+            for (int j = 0; j < n; ++j, rest &= rest - 1) {
+                const uint32_t w = __ldg(win + j);
+                const float mq = word_height<REPR>(w);
+                sum = __fadd_rn(sum, mq);
+                mx = fmaxf(mx, mq);
+                if (j == k) { wm = w; o = (uint32_t)(__ffs(rest) - 1); }  // ... at overlap index o
+            }
+            const float mean = __fdiv_rn(sum, fW);                    // :578
+            const float hp = word_height<REPR>(wp), mo = word_height<REPR>(wm);
+            const float local = __fdiv_rn(__fsub_rn(mo, __fsub_rn(mean, __fdiv_rn(mo, fW))), mx);  // :597
+            const uint32_t lbin = local < 0.2f ? 1u : 0u;               // :599 ((double)local < 0.2: no float lies in [0.2, 0.2f))
+            const uint32_t bbin = ((wp | wm) & kA10Bit) ? 0u : 1u;     // :602
+            const uint32_t misc = o | (lbin << 5) | (bbin << 6);
+            const unsigned long long idx = recBase + r;
+            if (idx < P.capacity) {                                    // :608
+                P.recPos[idx] = tileBase + tp;
+                P.recRp[idx] = hp;
+                P.recRm[idx] = mo;
+                P.recMisc[idx] = (uint8_t)misc;
+            }
+            if ((int)o == P.ppIdx) {
+                // its index in the ping-pong stream: ping-pong records before the word + those of the word's earlier positions
+                const uint32_t ppMask = pw & window_bits(w0, w1, (uint32_t)(P.minOv + P.ppIdx), 0xffffffffu);
+                const unsigned long long j = ppBase + sPpOff[word] + __popc(ppMask & ((1u << b) - 1u));
+                if (j < P.ppCapacity) {
+                    PairRec rr;
+                    rr.lpos = tileBase + tp;
+                    rr.rp = hp;
+                    rr.rm = mo;
+                    rr.misc = misc;
+                    *reinterpret_cast<uint4*>(&P.ppRecs[j]) = *reinterpret_cast<uint4*>(&rr);
                 }
             }
         }
@@ -543,23 +520,16 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int perSm = 5;
+    int perSm = 4;
     if (repr == kReprInt) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprInt>, kThreads, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprFloat>, kThreads, 0);
     if (perSm < 1) perSm = 1;
     unsigned grid = (unsigned)sms * (unsigned)perSm;
-    const unsigned batches = (p.nTiles + p.batchTiles - 1) / p.batchTiles;
-    if (grid > batches) grid = batches;
+    if (grid > p.nTiles) grid = p.nTiles;
     if (repr == kReprInt) k_scan<kReprInt><<<grid, kThreads, 0, s>>>(p);
     else k_scan<kReprFloat><<<grid, kThreads, 0, s>>>(p);
     if (launches) *launches += 1;
     return cudaGetLastError();
-}
-
-// tiles claimed per ticket: as many as keep every block busy for a few tickets, at most kBatch
-uint32_t scan_batch_tiles(uint32_t nTiles) {
-    uint32_t b = nTiles / (148u * 5u * 4u);
-    return b < 1u ? 1u : (b > (uint32_t)kBatch ? (uint32_t)kBatch : b);
 }
 
 cudaError_t launch_tall_apply(const uint32_t* gather, int world, uint32_t cap, unsigned long long* freqLow, uint32_t* freqTail, uint32_t* maxHeight,
