@@ -1,26 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- the reference's headline metric on BASELINE.json's configuration.
+"""bench.py -- the reference's headline metric on BASELINE.json's configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R] [--genome G]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--genome G --reads R] [--scaling strong|weak]
 
-Metric: overlap-scan genome positions / second (BASELINE.json `metric`):
-  value  G / (one pass of mapHeightsToScores + countStacksByGroup + collapseBins + calculateFDRs through the
-         C ABI), stacks resident in HBM when the timed region starts, the scored loci resident in HBM (and
-         their count on the host) when it ends;
-  e2e    the same metric through the C ABI from HOST buffers: packed reads in pinned memory -> H2D ->
-         stack build -> the pass above -> loci in host memory (reads/s of the same region reported beside it).
-A step is one pass over the whole synthetic data set.  N=1 workload: BASELINE.json configs[1] (50 M reads,
-dm6-sized genome, default parameters).  N>1: weak scaling -- every rank holds one dm6-sized position range of
-an N-times larger genome (range sharding of SURVEY §8(e)); the data path has no collective, the histogram
-tables are all-reduced over NCCL.  --scaling strong cuts ONE genome into N position ranges instead (the
-human-sized configs[3] study: --genome human --reads 500000000).
+Metric: overlap-scan genome positions / second (BASELINE.json `metric`).
+  value  G / (one pass of mapHeightsToScores + countStacksByGroup + collapseBins + calculateFDRs through the C ABI:
+         ppp_height_hist, ppp_scan, ppp_score), the stack store resident in HBM when the timed region starts, the scored
+         loci resident in HBM (and their count on the host) when it ends;
+  e2e    the same metric through the C ABI from HOST buffers: packed reads in pinned memory -> H2D -> stack build ->
+         the pass above -> loci in host memory (reads/s of the same region reported beside it).
+A step is one pass over the whole synthetic data set.
 
---impl reference times the UNMODIFIED reference (oracle/_ref/ppp_harness, its own functions on decoded records
-held in memory) on one host core, on a bounded genome-range sample of the same workload.
+Workload (every N): BASELINE.json configs[3] -- 500 M synthetic reads on the human-sized genome (3.1 G positions, seed 4,
+-m weighted), the configuration the north star's scaling target is set on and the largest that fits one GPU.  N > 1 is
+STRONG scaling: the one genome is cut into N position ranges of equal estimated cost (range sharding of SURVEY §8(e), a halo
+of max_overlap minus-strand keys per cut); the data path has no collective, the height histogram and the grouped counts
+are all-reduced over NCCL.  After the timed regions the loci of all ranks are gathered and their SHA-256 is compared with
+the digest the UNMODIFIED reference produced for this data set on the CPU container (tests/golden/fullsize/): a run whose
+results differ exits non-zero.  `secondary` carries configs[1] (50 M reads, dm6-sized genome) measured the same way at N = 1.
+--genome / --reads / --scaling weak select other workloads (weak: one dm6-sized genome per rank).
+
+--impl reference times the UNMODIFIED reference (oracle/_ref/ppp_harness: its own functions on decoded records held in
+memory) on one host core -- it has no threads -- on a bounded genome-range sample of the same workload.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -34,7 +40,12 @@ sys.path.insert(0, ROOT)
 
 METRIC = "overlap-scan genome positions/sec"
 UNIT = "positions/s"
-SEED = 2  # seed = config number
+# seed = config number
+WORKLOADS = {("dm6", 50_000_000): ("configs[1]", 2, "config2"), ("mouse", 200_000_000): ("configs[2]", 3, "config3"), ("human", 500_000_000): ("configs[3]", 4, "config4")}
+
+
+def workload_id(genome, reads):
+    return WORKLOADS.get((genome, reads), ("(custom size)", 2, None))
 
 
 def measured_peak_hbm():
@@ -46,16 +57,28 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def profiled_traffic(args):
+def profiled_traffic(genome, reads, mode):
     """DRAM bytes per k_scan launch from the committed ncu --set full capture of this workload (profiles/), else None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_k_scan_traffic.json")) as f:
-            t = json.load(f)
-        if (t["genome"], t["reads"], t["mode"]) == (args.genome, args.reads, args.mode):
-            return t["traffic_bytes_per_launch"]
+        with open(os.path.join(ROOT, "profiles", "r2_k_scan_traffic.json")) as f:
+            for t in json.load(f)["captures"]:
+                if (t["genome"], t["reads"], t["mode"]) == (genome, reads, mode):
+                    return t["traffic_bytes_per_launch"]
     except Exception:
         pass
     return None
+
+
+def reference_digest(genome, reads, mode):
+    """What the unmodified reference found on this data set (tests/golden/fullsize/, made on the CPU container), or None."""
+    case = workload_id(genome, reads)[2]
+    if case is None:
+        return None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "fullsize", f"{case}_{mode}.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -77,12 +100,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self, windows):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        rows = [r for t, r in self.rows if any(a <= t <= b for a, b in windows)] or [r for _, r in self.rows]
         sm, mx, reasons = [], [], set()
         for r in rows:
             f = [x.strip() for x in r.split(",")]
@@ -97,131 +120,154 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---- the reference on the host cores ----------------------------------------------------------------------------------
 def reference_sample(genome_size, n_reads):
     """Bounded sample for the CPU arms: a genome range that holds about 2 M reads of the workload."""
     frac = min(1.0, 2.0e6 / max(1, n_reads))
     return 0, max(1, int(genome_size * frac))
 
 
-def run_harness(args, steps, warmup, genome_size):
+def run_harness(genome, reads, seed, mode, steps, warmup, genome_size, whole=False):
     harness = os.path.join(ROOT, "oracle", "_ref", "ppp_harness")
     if not os.path.exists(harness):
         return None
-    lo, hi = reference_sample(genome_size, args.reads)
-    cmd = [harness, "time", "--genome", args.genome, "--reads", str(args.reads), "--seed", str(SEED), "--gpos", f"{lo}:{hi}", "-m", args.mode,
-           "--steps", str(steps), "--warmup", str(warmup)]
+    lo, hi = (0, genome_size) if whole else reference_sample(genome_size, reads)
+    cmd = [harness, "time", "--genome", genome, "--reads", str(reads), "--seed", str(seed), "--gpos", f"{lo}:{hi}", "-m", mode, "--steps", str(steps),
+           "--warmup", str(warmup)]
     out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
     rows = [json.loads(line) for line in out.splitlines() if line.startswith("{")]
     timed = [r for r in rows if r["timed"]]
-    return dict(rows=timed, positions=hi - lo, sample=f"genome range [{lo},{hi}) of the {args.reads}-read {args.genome} workload: "
+    return dict(rows=timed, positions=hi - lo, sample=f"genome range [{lo},{hi}) of the {reads}-read {genome} workload: "
                 f"{timed[0]['records']} decoded records held in memory, {timed[0]['pairs']} signatures")
+
+
+SCAN_STAGES = ("t_heights", "t_group", "t_collapse", "t_fdr")  # mapHeightsToScores, countStacksByGroup, collapseBins, calculateFDRs
+ALL_STAGES = ("t_count",) + SCAN_STAGES                         # + countReadsInBamFile (the stack build)
+
+
+def cpu_baseline_block(h, full_size=None):
+    rows = h["rows"]
+    mean = {k: sum(r[k] for r in rows) / len(rows) for k in ALL_STAGES}
+    t_scan = sum(mean[k] for k in SCAN_STAGES)
+    t_all = t_scan + mean["t_count"]
+    d = {"value": h["positions"] / t_scan, "unit": UNIT, "cores": 1, "kind": "reference", "sample": h["sample"],
+         "scope": "value: mapHeightsToScores + countStacksByGroup + collapseBins + calculateFDRs (what the GPU arm's `value` times); "
+                  "e2e_value adds countReadsInBamFile on decoded records (what the GPU arm's `e2e` times)",
+         "e2e_value": h["positions"] / t_all, "reads_per_s": rows[0]["records"] / t_all, "stage_seconds": mean}
+    if full_size:
+        d["full_size_reference"] = full_size
+    return d
+
+
+def full_size_reference_note(genome, reads, mode, genome_size):
+    """Stage times of the reference on the WHOLE data set, measured on the CPU container when the digests were made."""
+    ref = reference_digest(genome, reads, mode)
+    if not ref:
+        return None
+    s = ref["seconds"]
+    t_scan = s["heights"] + s["group"] + s["collapse_fdr"]
+    return {"where": "CPU container, one core, tests/golden/make_fullsize_digests.py (record generation included in count)", "seconds": s,
+            "value": genome_size / t_scan, "e2e_value": genome_size / (t_scan + s["count"])}
 
 
 def reference_arm(args, rank, world, json_out):
     if rank != 0:
         return
     from pingpongpro_b200 import host
-    m = host.SynthModel(args.genome, n_reads=args.reads, seed=SEED)
-    h = run_harness(args, args.steps, args.warmup, m.genome_size)
+    which, seed, _ = workload_id(args.genome, args.reads)
+    m = host.SynthModel(args.genome, n_reads=args.reads, seed=seed)
+    h = run_harness(args.genome, args.reads, seed, args.mode, args.steps, args.warmup, m.genome_size)
     if h is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ppp_harness was not built (needs /root/reference at build time)"}), file=json_out, flush=True)
         return
-    full = [r["t_count"] + r["t_heights"] + r["t_group"] + r["t_collapse"] + r["t_fdr"] for r in h["rows"]]
-    scan = [r["t_heights"] + r["t_group"] + r["t_collapse"] + r["t_fdr"] for r in h["rows"]]
-    t = sum(full) / len(full)
-    v = h["positions"] / t
+    cb = cpu_baseline_block(h, full_size_reference_note(args.genome, args.reads, args.mode, m.genome_size))
+    if (args.genome, args.reads) == ("dm6", 50_000_000):  # small enough for one whole-data-set step beside the sample (~100 s)
+        try:
+            w = run_harness(args.genome, args.reads, seed, args.mode, 1, 0, m.genome_size, whole=True)
+            cb["whole_data_set_step"] = {k: cpu_baseline_block(w)[k] for k in ("value", "e2e_value", "stage_seconds")}
+        except Exception as e:
+            cb["whole_data_set_step"] = f"failed: {e}"
+    t_scan = sum(cb["stage_seconds"][k] for k in SCAN_STAGES)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE.json configs[1]: {args.reads} synthetic reads on the {args.genome}-sized genome, -m {args.mode}, default parameters; "
-                               "reference timed on a bounded genome-range sample", "sample": h["sample"]},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "sample": h["sample"],
-                         "scan_and_scoring_only": h["positions"] / (sum(scan) / len(scan)),
-                         "stage_seconds": {k: sum(r[k] for r in h["rows"]) / len(h["rows"]) for k in ("t_count", "t_heights", "t_group", "t_collapse", "t_fdr")},
-                         "reads_per_s": h["rows"][0]["records"] / t},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_scan, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE.json {which}: {args.reads} synthetic reads on the {args.genome}-sized genome, -m {args.mode}, default parameters; "
+                               "the reference's own functions, timed on a bounded genome-range sample and scaled by positions", "sample": h["sample"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=json_out, flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU-sized genome (configs[1]: 50 M)")
-    ap.add_argument("--genome", default="dm6")
-    ap.add_argument("--mode", default="weighted")
-    ap.add_argument("--min-stack-height", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N>1: weak = one genome + read set per GPU (default); strong = one genome cut into N position ranges")
-    ap.add_argument("--collective", default="nccl", choices=["nccl", "torch"], help="N>1: the library's NCCL binding, or the torch.distributed hook")
-    args = ap.parse_args()
-    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr
-    sys.stdout.flush()
-    json_out = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        reference_arm(args, rank, world, json_out)
-        return
+# ---- the GPU arm ----------------------------------------------------------------------------------------------------
+def balanced_cuts(model, world, mode):
+    """Position ranges of equal estimated scan cost: the pass streams 1 bit per strand and position plus a few bytes per
+    stack and record, so cost = positions / 24 + reads, estimated from a 1/64 sample of the read set (1 Mb bins)."""
+    import numpy as np
+    G = model.genome_size
+    if world == 1:
+        return [0, G]
+    bin_size = 1 << 20
+    nb = (G + bin_size - 1) // bin_size
+    sample = model.generate(i0=0, i1=max(1, model.n_reads // 64), mode=mode)
+    hist = np.zeros(nb, np.float64)
+    start = 0
+    for c, r in enumerate(sample):
+        if len(r):
+            hist += np.bincount((start + r["key"].astype(np.int64)) // bin_size, minlength=nb)[:nb]
+        start += model.lengths[c]
+    cost = hist * 64.0 + bin_size / 24.0
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for k in range(1, world):
+        target = cum[-1] * k / world
+        b = int(np.searchsorted(cum, target, "right")) - 1
+        frac = (target - cum[b]) / max(cost[b], 1e-9)
+        cuts.append(min(G, int((b + frac) * bin_size)))
+    cuts.append(G)
+    return cuts
 
+
+def measure(args, genome, reads_n, seed, rank, world, local_rank, tdist, strong, check=True):
     import numpy as np
     import torch
 
     from pingpongpro_b200 import api, dist as pdist, host
-
-    if not torch.cuda.is_available() or api.device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    tdist = None
-    if world > 1:
-        import torch.distributed as tdist
-        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
         torch.cuda.synchronize()
         if tdist is not None:
             tdist.barrier()
 
-    def max_over_ranks(x):
+    def reduce(x, op):
         if tdist is None:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        tdist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if tdist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
-        return float(t.item())
+    MAX = tdist.ReduceOp.MAX if tdist is not None else None
+    SUM = tdist.ReduceOp.SUM if tdist is not None else None
 
-    # ---- workload.  weak (default): rank r owns copy r of the genome (contigs [r*nc, (r+1)*nc)) with its own seeded
-    # read set.  strong: ONE genome and read set, cut into `world` equal position ranges (SURVEY 8(e)); every rank
-    # generates the reads of its range plus the minus-strand halo.
-    strong = args.scaling == "strong" and world > 1
-    model = host.SynthModel(args.genome, n_reads=args.reads, seed=SEED + (0 if strong else rank))
+    # ---- workload.  strong: ONE genome and read set, cut into `world` ranges; every rank generates the reads of its range
+    # plus the minus-strand halo.  weak: rank r owns copy r of the genome with its own seeded read set.
+    model = host.SynthModel(genome, n_reads=reads_n, seed=seed + (0 if strong else rank))
     nc = len(model.lengths)
     G = model.genome_size
+    t_gen = time.perf_counter()
     if strong:
         lengths = list(model.lengths)
-        cuts = pdist.shard_ranges(G, world)
+        cuts = balanced_cuts(model, world, args.mode)
         r_lo, r_hi = cuts[rank], cuts[rank + 1]
         contig0 = 0
-        work_positions = G           # whole-job positions per step
+        work_positions = G
     else:
         lengths = model.lengths * world
+        cuts = [k * G for k in range(world + 1)]
         r_lo, r_hi = rank * G, (rank + 1) * G
         contig0 = rank * nc
         work_positions = world * G
-    t_gen = time.perf_counter()
     pinned = []
 
     def alloc(k):
@@ -229,7 +275,7 @@ def main():
         pinned.append(b)
         return b.array
 
-    if strong:  # (+64: keys at or just past a contig's end belong to the shard holding its last base)
+    if strong and world > 1:  # (+64: keys at or just past a contig's end belong to the shard holding its last base)
         reads = model.generate(mode=args.mode, alloc=alloc, g_lo=r_lo, g_hi=r_hi, halo=23 + 64)
     else:
         reads = model.generate(mode=args.mode, alloc=alloc)
@@ -255,8 +301,6 @@ def main():
                 ctx.count_reads(contig0 + c, pinned[c])
         ctx.finish()
 
-    max_height = [0]
-
     def scan_and_score(loci_to_host):
         # the three seams of the reference's main(), asking for nothing before the last one: one stream of kernels, one
         # host synchronisation (ppp_height_hist)
@@ -265,12 +309,9 @@ def main():
         # loci_to_host: the compacted loci are also copied into the library's pinned host buffer (20 B per locus)
         return ctx.calculate_fdrs(args.min_stack_height, want_tables=False, want_loci=loci_to_host, copy_loci=False)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    t_clock0 = time.perf_counter()
-
-    # ---- value: stacks resident in HBM (1.1 GB per strand pair >> 126 MB L2: no L2 flush needed); the step ends
-    # with the compacted, scored loci resident in HBM and their count on the host (the device->host copy of the
-    # loci themselves belongs to the end-to-end figure below)
+    windows = []
+    # ---- value: the stack store resident in HBM; the step ends with the compacted, scored loci resident in HBM and their
+    # count on the host (the device->host copy of the loci themselves belongs to the end-to-end figure below)
     upload()
     for _ in range(args.warmup):
         res = scan_and_score(False)
@@ -280,13 +321,12 @@ def main():
     for _ in range(args.steps):
         res = scan_and_score(False)
     barrier()
-    dt = max_over_ranks(time.perf_counter() - t0)
+    t1 = time.perf_counter()
+    windows.append((t0, t1))
+    dt = reduce(t1 - t0, MAX)
     tm = ctx.timings()  # device time of the LAST step's kernels (CUDA events on the context's stream)
-    launches_per_step = tm["launches"] / args.steps
+    launches = tm["launches"]
     info = ctx.pass_info()
-    max_height[0] = info["max_height"]
-    n_pairs, n_loci = info["n_pairs"], res.n_loci
-    value = work_positions / (dt / args.steps)
 
     # ---- e2e: host buffers -> H2D -> stack build -> scan + score -> loci on the host
     for _ in range(args.warmup):
@@ -299,62 +339,160 @@ def main():
         upload()
         res = scan_and_score(True)
     barrier()
-    dt_e2e = max_over_ranks(time.perf_counter() - t0)
+    t1 = time.perf_counter()
+    windows.append((t0, t1))
+    dt_e2e = reduce(t1 - t0, MAX)
     tm_e2e = ctx.timings()
-    t_clock1 = time.perf_counter()
-    e2e_value = work_positions / (dt_e2e / args.steps)
-    total_reads = sum_over_ranks(float(n_reads))
-    total_pairs = sum_over_ranks(float(n_pairs))
-    total_loci = sum_over_ranks(float(n_loci))
+    launches += tm_e2e["launches"]
+
+    out = dict(G=G, work_positions=work_positions, words=words, owned=owned, n_reads=n_reads, t_gen=t_gen, dt=dt, dt_e2e=dt_e2e, tm=tm, tm_e2e=tm_e2e,
+               launches=launches, info=info, n_loci=res.n_loci, windows=windows, cuts=cuts, strong=strong)
+    out["total_reads"] = reduce(float(n_reads), SUM)
+    out["total_pairs"] = reduce(float(info["n_pairs"]), SUM)
+    out["total_loci"] = reduce(float(res.n_loci), SUM)
+    out["total_stacks"] = reduce(float(info["n_stacks"]), SUM)
+    out["max_reads_per_rank"] = reduce(float(n_reads), MAX)
+    out["scan_ms_max"] = reduce(float(tm["scan_ms"]), MAX)
+
+    # ---- verification (outside the timed regions): the loci of all ranks, in rank order, against the reference's digest
+    out["verified"] = None
+    want = reference_digest(genome, reads_n, args.mode) if (check and strong and args.min_stack_height == 0) else None
+    if want is not None:
+        loci = np.ascontiguousarray(res.loci) if res.loci is not None else np.empty(0, api.LOCUS_DTYPE)
+        if tdist is not None:
+            gathered = [None] * world
+            tdist.all_gather_object(gathered, loci.tobytes())
+        else:
+            gathered = [loci.tobytes()]
+        if rank == 0:
+            h = hashlib.sha256()
+            for part in gathered:
+                h.update(part)
+            n = sum(len(p) for p in gathered) // api.LOCUS_DTYPE.itemsize
+            ok = (n, h.hexdigest()) == (want["loci"]["0"]["n"], want["loci"]["0"]["sha256"]) and int(out["total_pairs"]) == want["n_signatures"]
+            out["verified"] = {"against": f"tests/golden/fullsize/{workload_id(genome, reads_n)[2]}_{args.mode}.json (unmodified reference, CPU container)",
+                               "loci": n, "loci_sha256": h.hexdigest(), "signatures": int(out["total_pairs"]), "identical": bool(ok)}
+    ctx.close()
+    for b in pinned:
+        b.free()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--reads", type=int, default=500_000_000, help="reads of the data set (configs[3]: 500 M)")
+    ap.add_argument("--genome", default="human")
+    ap.add_argument("--mode", default="weighted")
+    ap.add_argument("--min-stack-height", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[1] measurement at N = 1")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N>1: strong = one genome cut into N position ranges (default); weak = one genome + read set per GPU")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "torch"], help="N>1: the library's NCCL binding, or the torch.distributed hook")
+    args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world, json_out)
+        return
+
+    import torch
+
+    from pingpongpro_b200 import api
+
+    if not torch.cuda.is_available() or api.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    tdist = None
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    which, seed, _ = workload_id(args.genome, args.reads)
+    strong = args.scaling == "strong"
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    m = measure(args, args.genome, args.reads, seed, rank, world, local_rank, tdist, strong)
+    secondary = None
+    if world == 1 and not args.no_secondary and (args.genome, args.reads) != ("dm6", 50_000_000):
+        secondary = measure(args, "dm6", 50_000_000, 2, rank, world, local_rank, tdist, True)
 
     if rank != 0:
         if tdist is not None:
             tdist.destroy_process_group()
         return
 
-    clocks = sampler.stop(t_clock0, t_clock1)
+    clocks = sampler.stop(m["windows"])
     peak, peak_src = measured_peak_hbm()
-    # dominant kernel: the fused streaming pass k_scan.  Algorithmic bytes per launch: every word of
-    # both strand arrays once (8 B per padded position) + 16 B per signature record written.
-    scan_bytes = 8.0 * words + 16.0 * n_pairs
-    achieved = scan_bytes / (tm["scan_ms"] * 1e-3) / 1e9
-    survey_bytes = 16.0 * words + 16.0 * n_pairs  # SURVEY §8(d) counts K2 and K3 as two passes of 8 B/position
-    which = {("dm6", 50_000_000): "configs[1]", ("mouse", 200_000_000): "configs[2]", ("human", 500_000_000): "configs[3]"}.get((args.genome, args.reads), "(custom size)")
-    per = "in total" if strong else "per GPU"
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE.json {which}: {args.reads} synthetic piRNA-seq reads {per} on a {args.genome}-sized genome ({G} positions {per}), "
-                               f"-m {args.mode}, overlaps 3..23, default parameters", "positions_per_gpu": owned, "reads_per_gpu_after_filters": n_reads,
-                   "signatures": total_pairs, "loci": total_loci, "max_stack_height": max_height[0],
-                   "sharding": ("one genome cut into equal position ranges, one per rank" if strong else "one genome per rank (a position range of the concatenation)") if world > 1 else "none",
-                   "l2": "inputs (8 B x positions = %.2f GB) are far larger than the 126 MB L2; no flush between steps" % (8e-9 * words),
-                   "synthetic_generation_s": t_gen},
-        "roofline": {"bound": "hbm", "kernel": "k_scan (fused height histogram + overlap scan)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": profiled_traffic(args), "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes,
-                     "kernel_ms": tm["scan_ms"], "achieved_two_pass_accounting_gbs": survey_bytes / (tm["scan_ms"] * 1e-3) / 1e9,
-                     "device_ms_per_step": {k: tm[k] for k in ("scan_ms", "lut_ms", "bin_ms", "score_ms")}},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * total_reads), "d2h_bytes_per_step": int(20 * total_loci + 64 * world),
-                "ms_per_step": 1e3 * dt_e2e / args.steps, "reads_per_s": total_reads / (dt_e2e / args.steps),
-                "stack_build_device_ms_per_step": tm_e2e["stack_build_ms"] / args.steps},
-        "gpu_launches": int(round(launches_per_step * args.steps)),
-    }
+
+    def roofline(r, genome, reads_n):
+        # dominant kernel: the fused pass k_scan.  Algorithmic bytes per launch -- what the compact stack store
+        # makes the kernel stream: 1 bit per strand and position, 4 B per stack, 13 B per signature record, 16 B per
+        # overlap-10 record, 8 B of compact offsets per tile.
+        per_rank = 1.0 / world
+        scan_bytes = (r["words"] / 4.0 + (4.0 * r["total_stacks"] + 13.0 * r["total_pairs"] + 16.0 * r["total_loci"]) * per_rank + 8.0 * r["words"] / 32768)
+        ms = r["scan_ms_max"]
+        achieved = scan_bytes / (ms * 1e-3) / 1e9
+        dense = (8.0 * r["words"] + 16.0 * r["total_pairs"] * per_rank) / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "k_scan (fused height histogram + overlap scan)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": profiled_traffic(genome, reads_n, args.mode) if world == 1 else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": scan_bytes,
+                "algorithmic_bytes": "per rank: G/4 (occupancy bitmaps) + 4 S (compact stack words) + 13 P (signature records) + 16 P10 (overlap-10 stream) + 8 per tile",
+                "kernel_ms": ms, "survey_dense_accounting_gbs": dense,
+                "survey_dense_accounting": "SURVEY §8(d) counts 8 B per position + 16 B per record for this work; the kernel streams a compact store instead, "
+                                           "so that figure exceeds the HBM peak on sparse genomes and is NOT a fraction of anything",
+                "device_ms_per_step": {k: r["tm"][k] for k in ("scan_ms", "lut_ms", "bin_ms", "score_ms")}}
+
+    def block(r, genome, reads_n, label):
+        per = "in total" if r["strong"] else "per GPU"
+        value = r["work_positions"] / (r["dt"] / args.steps)
+        return {
+            "value": value, "ms_per_step": 1e3 * r["dt"] / args.steps,
+            "config": {"workload": f"BASELINE.json {label}: {reads_n} synthetic piRNA-seq reads {per} on a {genome}-sized genome ({r['G']} positions {per}), "
+                                   f"-m {args.mode}, overlaps 3..23, default parameters", "positions_per_gpu": r["owned"], "reads_after_filters": r["total_reads"],
+                       "reads_on_heaviest_rank": r["max_reads_per_rank"], "stacks": r["total_stacks"], "signatures": r["total_pairs"], "loci": r["total_loci"],
+                       "max_stack_height": r["info"]["max_height"],
+                       "sharding": (f"one genome cut into {world} position ranges of equal estimated cost (positions / 24 + reads), cuts {r['cuts']}" if r["strong"]
+                                    else "one genome per rank (a position range of the concatenation)") if world > 1 else "none",
+                       "l2": "stack store (bitmaps %.2f GB + compact words %.2f GB per rank) larger than the 126 MB L2; no flush between steps"
+                             % (r["words"] / 4e9, 4e-9 * r["total_stacks"] / world),
+                       "synthetic_generation_s": r["t_gen"], "verified": r["verified"]},
+            "roofline": roofline(r, genome, reads_n),
+            "e2e": {"value": r["work_positions"] / (r["dt_e2e"] / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(8 * r["total_reads"]),
+                    "d2h_bytes_per_step": int(20 * r["total_loci"] + 64 * world), "ms_per_step": 1e3 * r["dt_e2e"] / args.steps,
+                    "reads_per_s": r["total_reads"] / (r["dt_e2e"] / args.steps), "stack_build_device_ms_per_step": r["tm_e2e"]["stack_build_ms"] / args.steps},
+        }
+
+    main_block = block(m, args.genome, args.reads, which)
+    line = {"metric": METRIC, "value": main_block["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main_block["ms_per_step"], "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": main_block["config"], "roofline": main_block["roofline"], "clocks": clocks,
+            "e2e": main_block["e2e"], "gpu_launches": int(m["launches"])}
+    if secondary is not None:
+        sb = block(secondary, "dm6", 50_000_000, "configs[1]")
+        line["secondary"] = {"metric": METRIC, "unit": UNIT, **sb}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            h = run_harness(args, 1, 0, G)
+            h = run_harness(args.genome, args.reads, seed, args.mode, 1, 0, m["G"])
             if h:
-                r = h["rows"][0]
-                t_scan = r["t_heights"] + r["t_group"] + r["t_collapse"] + r["t_fdr"]
-                line["cpu_baseline"] = {"value": h["positions"] / t_scan, "unit": UNIT, "cores": 1, "kind": "reference", "sample": h["sample"],
-                                        "e2e_value": h["positions"] / (t_scan + r["t_count"]), "reads_per_s": r["records"] / (t_scan + r["t_count"]),
-                                        "stage_seconds": {k: r[k] for k in ("t_count", "t_heights", "t_group", "t_collapse", "t_fdr")}}
+                line["cpu_baseline"] = cpu_baseline_block(h, full_size_reference_note(args.genome, args.reads, args.mode, m["G"]))
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
     print(json.dumps(line), file=json_out, flush=True)
     if tdist is not None:
         tdist.destroy_process_group()
+    bad = [b for b in (m, secondary) if b is not None and b["verified"] is not None and not b["verified"]["identical"]]
+    if bad:
+        print("bench.py: results differ from the reference's digest", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

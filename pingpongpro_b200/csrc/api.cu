@@ -146,6 +146,7 @@ struct ppp_ctx {
     uint16_t* dGroupStart = nullptr;
     unsigned long long* dCellSums = nullptr;
     uint32_t* dNBins = nullptr;
+    uint32_t* dBinOcc = nullptr;
     double *dXs = nullptr, *dWs = nullptr;
     int nSteps = 0;
     PinnedScalars* hs = nullptr;
@@ -546,6 +547,7 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     CKI(cudaMalloc(&c->dGroupStart, (kBins + 1) * sizeof(uint16_t)));
     CKI(cudaMalloc(&c->dCellSums, tableWords * sizeof(unsigned long long)));
     CKI(cudaMalloc(&c->dNBins, sizeof(uint32_t)));
+    CKI(cudaMalloc(&c->dBinOcc, collapse_occ_words() * sizeof(uint32_t)));
     CKI(cudaMalloc(&c->dThresholds, kBins * sizeof(float)));
     initMark("device tables allocated");
     CKI(cudaMallocHost(&c->hThresholds, kBins * sizeof(float)));
@@ -586,7 +588,7 @@ void ppp_destroy(ppp_ctx* c) {
     if (c->dGather) cudaFree(c->dGather);
     void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dCmp, c->dTileCntP, c->dTileCntM, c->dTileOffP, c->dTileOffM, c->dState, c->dFreqTail, c->dLut,
                    c->dRecPos, c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dPP, c->dLoci, c->dScoreState, c->dPairs, c->dPairFdr, c->dScanScratch,
-                   c->dGrouped, c->dThresholds, c->dCells, c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dBinParams};
+                   c->dGrouped, c->dThresholds, c->dCells, c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dBinParams, c->dBinOcc};
     for (void* p : dev)
         if (p) cudaFree(p);
     for (int k = 0; k < kStages; ++k) {
@@ -961,7 +963,7 @@ int enqueueScoreStage(ppp_ctx* c, uint32_t minStackHeight) {
     const int ppIdx = c->ppOv - c->minOv;
     if ((rc = timerStart(c, c->tScore))) return rc;
     CK(cudaMemsetAsync(c->dScoreState, 0, sizeof(ScoreState) + c->scoreTileWords * sizeof(unsigned long long), c->stream));
-    CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dCellSums, c->stream, &c->launches));
+    CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dCellSums, c->dBinOcc, c->stream, &c->launches));
     CK(launch_fdr_table(c->dCells, c->dNBins, kBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
     CK(launch_score(c->dPP, c->dState->totals, c->ppCapacity, c->ppCapacity, c->dScoreState, c->dScoreTiles, c->dLut, c->dThresholds, c->dBinParams, c->dFdr,
                     c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dLoci, c->stream, &c->launches));

@@ -21,38 +21,37 @@ namespace {
 
 // Device tables are BIN-MAJOR: cell(bin, overlap, bias, local) = ((bin * W + overlap) * 2 + bias) * 2 + local, so
 // that the W*4 cells of one height-score bin are contiguous (the ABI transposes to [overlap][bin][bias][local]).
-constexpr int kCollapseThreads = 1024;
 constexpr int kMaxCellWords = (PPP_MAX_OVERLAPS * 4 + 31) / 32;  // occupancy bits of one bin's cells
 
 // collapseBins, pingpongpro.cpp:631-686.  A merged bin is closed at the first source bin after which none of its
 // W*4 cells is <= 0 (:661, :670).  Counts are >= 0 and float additions of non-negative numbers never return to 0,
 // so that decision depends only on WHICH cells of each source bin are non-zero:
-//   k_collapse_map   (one CTA) one occupancy bit per (bin, cell); then warp 0 replays the serial walk of :641-673
-//                    32 bins at a time with a prefix-OR over the lanes -> oldBinCollapsedBinMap, group starts, C;
+//   k_collapse_occ   one occupancy bit per (bin, cell);
+//   k_collapse_map   one warp replays the serial walk of :641-673 on those bits, 32 bins at a time with a prefix-OR
+//                    over the lanes -> oldBinCollapsedBinMap, group starts, C;
 //   k_collapse_sum   every non-zero cell adds min(count, 2^24) (the reference's float counter) to an exact 64-bit
 //                    sum of its merged bin;
 //   k_collapse_final a sum below 2^24 equals the float additions of :658 exactly (no rounding can have happened);
 //                    a larger one is recomputed with the literal in-order float additions.
-__global__ void __launch_bounds__(kCollapseThreads) k_collapse_map(const uint32_t* __restrict__ grouped, int W, uint16_t* __restrict__ binMap,
-                                                                    uint16_t* __restrict__ groupStart, uint32_t* __restrict__ nBins) {
-    __shared__ uint32_t sOcc[kBins][kMaxCellWords];
-    const int cellsPerBin = W * 4, tid = threadIdx.x;
-    for (int k = tid; k < kBins * kMaxCellWords; k += kCollapseThreads) (&sOcc[0][0])[k] = 0;
-    __syncthreads();
-    const int total = kBins * cellsPerBin;
-    for (int k0 = tid; k0 < total; k0 += kCollapseThreads * 4) {  // 4 independent loads in flight per thread
-        uint32_t v[4];
+// one occupancy bit per (bin, cell): one WARP per bin (many blocks: the table is 336 KB of L2-resident counters, and one
+// block reading all of it was 30 us of load latency)
+__global__ void __launch_bounds__(256) k_collapse_occ(const uint32_t* __restrict__ grouped, int W, uint32_t* __restrict__ binOcc /*[kBins][kMaxCellWords]*/) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= kBins) return;
+    const int cellsPerBin = W * 4;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { int k = k0 + u * kCollapseThreads; v[u] = k < total ? grouped[k] : 0u; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (v[u]) {
-                int k = k0 + u * kCollapseThreads, b = k / cellsPerBin, c = k - b * cellsPerBin;
-                atomicOr(&sOcc[b][c >> 5], 1u << (c & 31));
-            }
+    for (int w = 0; w < kMaxCellWords; ++w) {
+        const int c = w * 32 + lane;
+        const uint32_t v = c < cellsPerBin ? grouped[(size_t)b * cellsPerBin + c] : 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, v != 0u);
+        if (lane == 0) binOcc[b * kMaxCellWords + w] = m;
     }
-    __syncthreads();
-    if (tid >= 32) return;
+}
+
+__global__ void __launch_bounds__(32) k_collapse_map(const uint32_t* __restrict__ binOcc, int W, uint16_t* __restrict__ binMap,
+                                                     uint16_t* __restrict__ groupStart, uint32_t* __restrict__ nBins) {
+    const int cellsPerBin = W * 4, tid = threadIdx.x;
     const int lane = tid;
     uint32_t full[kMaxCellWords], carry[kMaxCellWords];
 #pragma unroll
@@ -69,7 +68,7 @@ __global__ void __launch_bounds__(kCollapseThreads) k_collapse_map(const uint32_
         const bool valid = b < kBins;
         uint32_t m[kMaxCellWords];
 #pragma unroll
-        for (int w = 0; w < kMaxCellWords; ++w) m[w] = valid ? sOcc[b][w] : 0u;
+        for (int w = 0; w < kMaxCellWords; ++w) m[w] = valid ? binOcc[b * kMaxCellWords + w] : 0u;
         int start = 0;
         while (start < 32) {
             uint32_t pre[kMaxCellWords];
@@ -148,8 +147,7 @@ __global__ void __launch_bounds__(kFdrWarps * 32) k_fdr_table(const float* __res
     __shared__ double sTerm[kFdrWarps][kFdrMaxSteps];
     const uint32_t C = *nBins;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t item = blockIdx.x * kFdrWarps + warp;
-    if (item >= C * 4u * (uint32_t)W) return;
+    for (uint32_t item = blockIdx.x * kFdrWarps + warp; item < C * 4u * (uint32_t)W; item += gridDim.x * kFdrWarps) {
     const uint32_t ov = item % (uint32_t)W, cell = item / (uint32_t)W;  // cell = bin * 4 + bias * 2 + local
     const uint32_t bin = cell >> 2, k = cell & 3u;
     auto at = [&](int o) { return cells[((size_t)bin * W + o) * 4 + k]; };
@@ -179,6 +177,8 @@ __global__ void __launch_bounds__(kFdrWarps * 32) k_fdr_table(const float* __res
         for (int i = 0; i < nSteps; ++i) acc = __dadd_rn(acc, sTerm[warp][i]);
         if (acc < 0.0) acc = 0.0; else if (acc > 1.0) acc = 1.0;             // :736-743 (NaN stays NaN)
         fdr[((size_t)bin * W + ov) * 4 + k] = __double2float_rn(acc);        // :745
+    }
+    __syncwarp();  // the terms are rewritten by the warp's next item
     }
 }
 
@@ -305,22 +305,25 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restri
 }  // namespace
 
 cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, uint16_t* groupStart, unsigned long long* sums,
-                            cudaStream_t s, int* launches) {
+                            uint32_t* binOcc, cudaStream_t s, int* launches) {
     const int entries = kBins * W * 4;
     cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)entries * sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    k_collapse_map<<<1, kCollapseThreads, 0, s>>>(grouped, W, binMap, groupStart, nBins);
+    k_collapse_occ<<<(kBins + 7) / 8, 256, 0, s>>>(grouped, W, binOcc);
+    k_collapse_map<<<1, 32, 0, s>>>(binOcc, W, binMap, groupStart, nBins);
     k_collapse_sum<<<(entries + 255) / 256, 256, 0, s>>>(grouped, W, binMap, sums);
     k_collapse_final<<<(entries + 255) / 256, 256, 0, s>>>(grouped, W, groupStart, nBins, sums, cells);
-    if (launches) *launches += 3;
+    if (launches) *launches += 4;
     return cudaGetLastError();
 }
+
+size_t collapse_occ_words() { return (size_t)kBins * kMaxCellWords; }
 
 cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, uint32_t maxBins, int W, int ppIdx, const double* xs, const double* ws, int nSteps,
                              float* fdr, cudaStream_t s, int* launches) {
     if (nSteps > kFdrMaxSteps) return cudaErrorInvalidValue;
-    unsigned items = (unsigned)maxBins * 4u * (unsigned)W;  // upper bound on the bin count; the kernel reads the real one
-    k_fdr_table<<<(items + kFdrWarps - 1) / kFdrWarps, kFdrWarps * 32, 0, s>>>(cells, nBins, W, ppIdx, xs, ws, nSteps, fdr);
+    (void)maxBins;  // the kernel reads the real bin count; one warp per cell, the warps of 4 blocks per SM share the cells
+    k_fdr_table<<<148 * 4, kFdrWarps * 32, 0, s>>>(cells, nBins, W, ppIdx, xs, ws, nSteps, fdr);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

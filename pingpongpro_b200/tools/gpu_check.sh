@@ -12,14 +12,16 @@ if [ "$mode" = quick ]; then
 else
   timeout 2400 python -m pytest tests -m gpu -x -q --durations=15 > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/pytest_gpu.log
 fi
-timeout 600 python bench.py --steps 20 --warmup 5 --genome dm6 --reads 50000000 --no-cpu-baseline > $out/bench_dm6.json 2> $out/bench_dm6.err; echo "bench dm6 rc=$?"
-timeout 900 python bench.py --steps 10 --warmup 3 --genome human --reads 500000000 --no-cpu-baseline > $out/bench_human.json 2> $out/bench_human.err; echo "bench human rc=$?"
+timeout 900 python bench.py > $out/bench.json 2> $out/bench.err; echo "bench rc=$?"
 tail -3 $out/smoke.log; tail -5 $out/pytest_*.log; python - <<'PY'
 import json
-for f in ("bench_dm6", "bench_human"):
-    try:
-        d = json.load(open("gpurun_out/%s.json" % f))
-        print(f, "ms/step", round(d["ms_per_step"], 4), "e2e ms", round(d["e2e"]["ms_per_step"], 3), d["roofline"]["device_ms_per_step"], "build ms", round(d["e2e"]["stack_build_device_ms_per_step"], 3))
-    except Exception as e:
-        print(f, "failed", e)
+try:
+    d = json.load(open("gpurun_out/bench.json"))
+    for name, b in (("human", d), ("dm6", d.get("secondary"))):
+        if not b: continue
+        print(name, "ms/step", round(b["ms_per_step"], 4), "value %.3g" % b["value"], "e2e ms", round(b["e2e"]["ms_per_step"], 3), b["roofline"]["device_ms_per_step"],
+              "frac", round(b["roofline"]["frac"], 3), "build ms", round(b["e2e"]["stack_build_device_ms_per_step"], 3), "verified", (b["config"]["verified"] or {}).get("identical"))
+    print("cpu_baseline", {k: d.get("cpu_baseline", {}).get(k) for k in ("value", "e2e_value")}, "launches", d["gpu_launches"])
+except Exception as e:
+    print("bench failed", e); print(open("gpurun_out/bench.err").read()[-2000:])
 PY
