@@ -29,6 +29,7 @@ typedef struct {
     uint32_t contig, strand, start, end;
     float p, q, reads_plus, reads_minus;
     float hist[64];
+    double z64, p64; /* zValue (:1266) and pValue (:1267-1269) BEFORE the narrowing store of :1271 (NaN / 1 on the shortcut of :1250) */
 } ppo_tp;
 
 typedef struct { uint32_t strand, contig, key; float reads; uint32_t a10; } stack_t;
@@ -318,6 +319,7 @@ int ppo_transposons(ppo* o, const ppo_interval* iv, size_t n, ppo_tp* out) {
     for (size_t i = 0; i < n; ++i) {
         t[i].t.contig = iv[i].contig; t[i].t.strand = iv[i].strand; t[i].t.start = iv[i].start; t[i].t.end = iv[i].end;
         t[i].t.p = 1; t[i].t.q = 1; t[i].order = i;                           /* :187 */
+        t[i].t.z64 = NAN; t[i].t.p64 = 1.0;
     }
     qsort(t, n, sizeof(tp_sort_t), cmp_tp_pos);                               /* :1174 + map order */
     for (size_t i = 0; i < n; ++i) t[i].order = i;
@@ -372,6 +374,7 @@ int ppo_transposons(ppo* o, const ppo_interval* iv, size_t n, ppo_tp* out) {
             for (double x = z; x <= z + 5.0; x += 0.01)                        /* :1268 */
                 p += 0.01 * 1 / sqrt(2 * pi) * exp(-0.5 * x * x);              /* :1269 */
         }
+        tp->z64 = z; tp->p64 = p;
         tp->p = p;                                                             /* :1271 */
     }
     /* q-values, :1276-1312 */

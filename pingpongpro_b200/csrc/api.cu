@@ -116,7 +116,8 @@ struct ppp_ctx {
     uint64_t nStacksP = 0, nStacksM = 0;
 
     // scan state
-    PassState* dState = nullptr;             // + the look-back states of the tiles (one allocation, one memset per pass)
+    PassState* dState = nullptr;             // + the look-back states of the tiles + the grouped counts (one allocation, one memset per pass)
+    size_t passZeroBytes = 0;
     unsigned long long* dTileState = nullptr;
     uint32_t* dFreqTail = nullptr;
     float* dLut = nullptr;
@@ -144,7 +145,6 @@ struct ppp_ctx {
     float *dCells = nullptr, *dFdr = nullptr;
     uint16_t* dBinMap = nullptr;
     uint16_t* dGroupStart = nullptr;
-    unsigned long long* dCellSums = nullptr;
     uint32_t* dNBins = nullptr;
     uint32_t* dBinOcc = nullptr;
     double *dXs = nullptr, *dWs = nullptr;
@@ -527,8 +527,13 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
         CKI(cudaEventCreateWithFlags(&c->evCopied[k], cudaEventDisableTiming));
         CKI(cudaEventCreateWithFlags(&c->evConsumed[k], cudaEventDisableTiming));
     }
-    CKI(cudaMalloc(&c->dState, sizeof(PassState) + (size_t)c->nTiles * sizeof(unsigned long long)));
-    c->dTileState = reinterpret_cast<unsigned long long*>(c->dState + 1);
+    {   // everything a pass zeroes at its start, in one allocation: pass scalars, look-back states, grouped counts (+ rerun word)
+        const size_t groupedBytes = (((size_t)c->W * kBins * 4 + 1) * sizeof(uint32_t) + 15) & ~(size_t)15;
+        c->passZeroBytes = sizeof(PassState) + (size_t)c->nTiles * sizeof(unsigned long long) + groupedBytes;
+        CKI(cudaMalloc(&c->dState, c->passZeroBytes));
+        c->dTileState = reinterpret_cast<unsigned long long*>(c->dState + 1);
+        c->dGrouped = reinterpret_cast<uint32_t*>(c->dTileState + c->nTiles);
+    }
     CKI(cudaMalloc(&c->dFreqTail, (size_t)kFreqCapacity * sizeof(uint32_t)));
     CKI(cudaMemsetAsync(c->dFreqTail, 0, (size_t)kFreqCapacity * sizeof(uint32_t), c->stream));
     CKI(cudaMalloc(&c->dLut, (size_t)kFreqCapacity * sizeof(float)));
@@ -540,12 +545,10 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     c->scanScratchWords = exclusive_scan_scratch_words((size_t)c->nTiles + 1);
     CKI(cudaMalloc(&c->dScanScratch, c->scanScratchWords * 4));
     size_t tableWords = (size_t)c->W * kBins * 4;
-    CKI(cudaMalloc(&c->dGrouped, (tableWords + 1) * 4));
     CKI(cudaMalloc(&c->dCells, tableWords * 4));
     CKI(cudaMalloc(&c->dFdr, tableWords * 4));
     CKI(cudaMalloc(&c->dBinMap, kBins * sizeof(uint16_t)));
     CKI(cudaMalloc(&c->dGroupStart, (kBins + 1) * sizeof(uint16_t)));
-    CKI(cudaMalloc(&c->dCellSums, tableWords * sizeof(unsigned long long)));
     CKI(cudaMalloc(&c->dNBins, sizeof(uint32_t)));
     CKI(cudaMalloc(&c->dBinOcc, collapse_occ_words() * sizeof(uint32_t)));
     CKI(cudaMalloc(&c->dThresholds, kBins * sizeof(float)));
@@ -588,7 +591,7 @@ void ppp_destroy(ppp_ctx* c) {
     if (c->dGather) cudaFree(c->dGather);
     void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dCmp, c->dTileCntP, c->dTileCntM, c->dTileOffP, c->dTileOffM, c->dState, c->dFreqTail, c->dLut,
                    c->dRecPos, c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dPP, c->dLoci, c->dScoreState, c->dPairs, c->dPairFdr, c->dScanScratch,
-                   c->dGrouped, c->dThresholds, c->dCells, c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dCellSums, c->dBinParams, c->dBinOcc};
+                   c->dThresholds, c->dCells, c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dBinParams, c->dBinOcc};
     for (void* p : dev)
         if (p) cudaFree(p);
     for (int k = 0; k < kStages; ++k) {
@@ -837,7 +840,7 @@ namespace {
 int enqueueScanStage(ppp_ctx* c) {
     int rc;
     Trace tr("scan stage");
-    CK(cudaMemsetAsync(c->dState, 0, sizeof(PassState) + (size_t)c->nTiles * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->dState, 0, c->passZeroBytes, c->stream));  // pass scalars, look-back states, grouped counts
     if (c->prevMaxHeight >= kScanLowBins)
         CK(cudaMemsetAsync(c->dFreqTail + kScanLowBins, 0, ((size_t)c->prevMaxHeight - kScanLowBins + 1) * sizeof(uint32_t), c->stream));
     ScanParams p;
@@ -940,7 +943,7 @@ int enqueueBinStage(ppp_ctx* c) {
         CK(cudaMemcpyAsync(c->dBinParams, c->hBinParams, sizeof(BinParams), cudaMemcpyHostToDevice, c->stream));
     }
     if ((rc = timerStart(c, c->tBin))) return rc;
-    CK(cudaMemsetAsync(c->dGrouped, 0, (tableWords + 1) * 4, c->stream));
+    if (c->stageBin) CK(cudaMemsetAsync(c->dGrouped, 0, (tableWords + 1) * 4, c->stream));  // (a second ppp_scan on one scan pass: the scan stage zeroed them for the first)
     // (the record count is on the device; the grid is sized for a full store, surplus blocks leave at once)
     CK(launch_bin(c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dState->totals, c->pairCapacity, c->pairCapacity, c->dLut, c->dThresholds, c->dBinParams, c->W,
                   c->dGrouped, c->stream, &c->launches));
@@ -962,13 +965,13 @@ int enqueueScoreStage(ppp_ctx* c, uint32_t minStackHeight) {
     int rc;
     const int ppIdx = c->ppOv - c->minOv;
     if ((rc = timerStart(c, c->tScore))) return rc;
-    CK(cudaMemsetAsync(c->dScoreState, 0, sizeof(ScoreState) + c->scoreTileWords * sizeof(unsigned long long), c->stream));
-    CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dCellSums, c->dBinOcc, c->stream, &c->launches));
+    if (minStackHeight > 0) CK(cudaMemsetAsync(c->dScoreState, 0, sizeof(ScoreState) + c->scoreTileWords * sizeof(unsigned long long), c->stream));
+    CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dBinOcc, c->stream, &c->launches));
     CK(launch_fdr_table(c->dCells, c->dNBins, kBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
     CK(launch_score(c->dPP, c->dState->totals, c->ppCapacity, c->ppCapacity, c->dScoreState, c->dScoreTiles, c->dLut, c->dThresholds, c->dBinParams, c->dFdr,
                     c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dLoci, c->stream, &c->launches));
     if ((rc = timerStop(c, c->tScore))) return rc;
-    CK(cudaMemcpyAsync(&c->hs->nLoci, c->dScoreState, sizeof(ScoreState), cudaMemcpyDeviceToHost, c->stream));
+    if (minStackHeight > 0) CK(cudaMemcpyAsync(&c->hs->nLoci, c->dScoreState, sizeof(ScoreState), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&c->hs->nBins, c->dNBins, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     c->scoreMinHeight = minStackHeight;
     c->stageScore = true;
@@ -1092,7 +1095,7 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     if ((rc = enqueueScoreStage(c, minStackHeight))) return rc;
     if ((rc = settle(c))) return rc;
     tr.mark("pass settled");
-    size_t n = (size_t)c->hs->nLoci;
+    size_t n = minStackHeight > 0 ? (size_t)c->hs->nLoci : (size_t)c->nPP;  // -s 0: every overlap-`pingpong` record is a locus
     uint32_t C = c->hs->nBins;
     if (loci) {
         if (n > c->hLociCap) {
@@ -1196,7 +1199,11 @@ int ppp_transposons(ppp_ctx* c, const ppp_interval* intervals, size_t n, ppp_tp_
     job.stream = c->stream;
     job.launches = &c->launches;
     std::string err;
-    cudaError_t e = run_transposons(job, intervals, n, results, order, err);
+    // one process per GPU: the shards score the transposons together (those that straddle a range boundary included)
+    const bool collective = c->allreduce && c->world > 1;
+    cudaError_t e = collective ? run_transposons_collective(job, c->rank, c->world, [c](void* buf, size_t words) { return hookReduce(c, buf, words, 0, 0); },
+                                                            intervals, n, results, order, err)
+                               : run_transposons(job, intervals, n, results, order, err);
     if (e != cudaSuccess) return fail(PPP_ERR_CUDA, "transposons: %s %s", cudaGetErrorString(e), err.c_str());
     if (!err.empty()) return fail(PPP_ERR_ARG, "%s", err.c_str());
     if ((rc = timerStop(c, c->tTransposon))) return rc;

@@ -174,8 +174,8 @@ cudaError_t launch_bin(const float* recRp, const float* recRm, const uint8_t* re
 cudaError_t launch_overflow_flag(const unsigned long long* totals, uint64_t capacity, uint64_t ppCapacity, uint32_t* flag, cudaStream_t s, int* launches);
 cudaError_t launch_pairs_view(const uint32_t* recPos, const float* recRp, const float* recRm, const uint8_t* recMisc, const uint16_t* recBin, size_t n,
                               const float* fdrTable, const uint16_t* binMap, int W, PairRec* pairs, float* pairFdr, cudaStream_t s, int* launches);
-cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, uint16_t* groupStart, unsigned long long* sums,
-                            uint32_t* binOcc, cudaStream_t s, int* launches);
+cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, uint16_t* groupStart, uint32_t* binOcc,
+                            cudaStream_t s, int* launches);
 size_t collapse_occ_words();
 cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, uint32_t maxBins, int W, int ppIdx, const double* xs, const double* ws, int nSteps,
                              float* fdr, cudaStream_t s, int* launches);

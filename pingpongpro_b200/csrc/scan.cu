@@ -460,21 +460,35 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const float* __restrict__ r
     const uint32_t onesBin = sSmallBin[5];  // rounded heights (1, 1)
     unsigned long long n = totals[0];
     if (n > capacity) n = capacity;
-    for (size_t i = (size_t)blockIdx.x * kBinThreads + tid; i < n; i += (size_t)gridDim.x * kBinThreads) {
-        const float rp = recRp[i], rm = recRm[i];
-        const uint32_t misc = recMisc[i];
-        const uint32_t hp = round_height(rp), hm = round_height(rm);  // heightScoreMap[0.5 + reads], :582 / :589
-        uint32_t b;
-        if ((hp | hm) < 4u) b = sSmallBin[hp * 4 + hm];
-        else b = (uint32_t)bin_of(__fmul_rn(lut[hp], lut[hm]));
-        recBin[i] = (uint16_t)b;
-        if (b == onesBin) { atomicAdd(&sOnes[warp][misc & 127u], 1u); continue; }
-        const uint32_t cell = (((b * (uint32_t)W + (misc & 31u)) * 2u + ((misc >> 6) & 1u)) * 2u) + ((misc >> 5) & 1u);  // bin-major table, :605
-        const uint32_t h = (cell * 2654435761u) >> 20;
-        uint32_t key = sKey[h];
-        if (key == kBinEmpty) key = atomicCAS(&sKey[h], kBinEmpty, cell);
-        if (key == kBinEmpty || key == cell) atomicAdd(&sVal[h], 1u);
-        else atomicAdd(&grouped[cell], 1u);
+    constexpr int kUnroll = 4;  // records in flight per thread: the loop is bound by the latency of its three loads
+    for (size_t i0 = (size_t)blockIdx.x * kBinThreads * kUnroll + tid; i0 < n; i0 += (size_t)gridDim.x * kBinThreads * kUnroll) {
+        float rp[kUnroll], rm[kUnroll];
+        uint32_t mi[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const size_t i = i0 + (size_t)u * kBinThreads;
+            const bool in = i < n;
+            rp[u] = in ? recRp[i] : 0.0f;
+            rm[u] = in ? recRm[i] : 0.0f;
+            mi[u] = in ? (uint32_t)recMisc[i] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (mi[u] == 0xffffffffu) continue;
+            const uint32_t misc = mi[u];
+            const uint32_t hp = round_height(rp[u]), hm = round_height(rm[u]);  // heightScoreMap[0.5 + reads], :582 / :589
+            uint32_t b;
+            if ((hp | hm) < 4u) b = sSmallBin[hp * 4 + hm];
+            else b = (uint32_t)bin_of(__fmul_rn(lut[hp], lut[hm]));
+            recBin[i0 + (size_t)u * kBinThreads] = (uint16_t)b;
+            if (b == onesBin) { atomicAdd(&sOnes[warp][misc & 127u], 1u); continue; }
+            const uint32_t cell = (((b * (uint32_t)W + (misc & 31u)) * 2u + ((misc >> 6) & 1u)) * 2u) + ((misc >> 5) & 1u);  // bin-major table, :605
+            const uint32_t h = (cell * 2654435761u) >> 20;
+            uint32_t key = sKey[h];
+            if (key == kBinEmpty) key = atomicCAS(&sKey[h], kBinEmpty, cell);
+            if (key == kBinEmpty || key == cell) atomicAdd(&sVal[h], 1u);
+            else atomicAdd(&grouped[cell], 1u);
+        }
     }
     __syncthreads();
     for (int k = tid; k < kBinCache; k += kBinThreads)
@@ -557,7 +571,7 @@ cudaError_t launch_bin(const float* recRp, const float* recRm, const uint8_t* re
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    uint64_t want = (expected + kBinThreads * 8 - 1) / (kBinThreads * 8);  // >= 8 records per thread: the tables are flushed once per block
+    uint64_t want = (expected + kBinThreads * 16 - 1) / (kBinThreads * 16);  // >= 16 records per thread: the tables are flushed once per block
     unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)sms * 4);
     k_bin<<<blocks, kBinThreads, 0, s>>>(recRp, recRm, recMisc, recBin, totals, capacity, lut, thresholds, params, W, grouped);
     if (launches) *launches += 1;

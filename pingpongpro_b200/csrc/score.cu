@@ -29,10 +29,8 @@ constexpr int kMaxCellWords = (PPP_MAX_OVERLAPS * 4 + 31) / 32;  // occupancy bi
 //   k_collapse_occ   one occupancy bit per (bin, cell);
 //   k_collapse_map   one warp replays the serial walk of :641-673 on those bits, 32 bins at a time with a prefix-OR
 //                    over the lanes -> oldBinCollapsedBinMap, group starts, C;
-//   k_collapse_sum   every non-zero cell adds min(count, 2^24) (the reference's float counter) to an exact 64-bit
-//                    sum of its merged bin;
-//   k_collapse_final a sum below 2^24 equals the float additions of :658 exactly (no rounding can have happened);
-//                    a larger one is recomputed with the literal in-order float additions.
+//   k_collapse_cells one warp per cell of a merged bin adds min(count, 2^24) (the reference's float counter) of its source
+//                    bins: exactly when the sum stays below 2^24, else with the literal in-order float additions of :658.
 // one occupancy bit per (bin, cell): one WARP per bin (many blocks: the table is 336 KB of L2-resident counters, and one
 // block reading all of it was 30 us of load latency)
 __global__ void __launch_bounds__(256) k_collapse_occ(const uint32_t* __restrict__ grouped, int W, uint32_t* __restrict__ binOcc /*[kBins][kMaxCellWords]*/) {
@@ -49,9 +47,13 @@ __global__ void __launch_bounds__(256) k_collapse_occ(const uint32_t* __restrict
     }
 }
 
-__global__ void __launch_bounds__(32) k_collapse_map(const uint32_t* __restrict__ binOcc, int W, uint16_t* __restrict__ binMap,
-                                                     uint16_t* __restrict__ groupStart, uint32_t* __restrict__ nBins) {
+__global__ void __launch_bounds__(256) k_collapse_map(const uint32_t* __restrict__ binOcc, int W, uint16_t* __restrict__ binMap,
+                                                      uint16_t* __restrict__ groupStart, uint32_t* __restrict__ nBins) {
+    __shared__ uint32_t sOcc[kBins * kMaxCellWords];  // (one round of parallel loads instead of one L2 latency per 32 bins)
     const int cellsPerBin = W * 4, tid = threadIdx.x;
+    for (int k = tid; k < kBins * kMaxCellWords; k += 256) sOcc[k] = binOcc[k];
+    __syncthreads();
+    if (tid >= 32) return;
     const int lane = tid;
     uint32_t full[kMaxCellWords], carry[kMaxCellWords];
 #pragma unroll
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(32) k_collapse_map(const uint32_t* __restrict_
         const bool valid = b < kBins;
         uint32_t m[kMaxCellWords];
 #pragma unroll
-        for (int w = 0; w < kMaxCellWords; ++w) m[w] = valid ? binOcc[b * kMaxCellWords + w] : 0u;
+        for (int w = 0; w < kMaxCellWords; ++w) m[w] = valid ? sOcc[b * kMaxCellWords + w] : 0u;
         int start = 0;
         while (start < 32) {
             uint32_t pre[kMaxCellWords];
@@ -105,32 +107,32 @@ __global__ void __launch_bounds__(32) k_collapse_map(const uint32_t* __restrict_
     if (lane == 0) { groupStart[collapsed] = (uint16_t)kBins; *nBins = collapsed; }
 }
 
-__global__ void __launch_bounds__(256) k_collapse_sum(const uint32_t* __restrict__ grouped, int W, const uint16_t* __restrict__ binMap,
-                                                      unsigned long long* __restrict__ sums) {
-    const int cellsPerBin = W * 4;
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= kBins * cellsPerBin) return;
-    uint32_t v = grouped[k];
-    if (!v) return;
-    int b = k / cellsPerBin, c = k - b * cellsPerBin;
-    atomicAdd(&sums[(size_t)binMap[b] * cellsPerBin + c], (unsigned long long)(v < kSaturate ? v : kSaturate));
-}
-
-__global__ void __launch_bounds__(256) k_collapse_final(const uint32_t* __restrict__ grouped, int W, const uint16_t* __restrict__ groupStart,
-                                                        const uint32_t* __restrict__ nBins, const unsigned long long* __restrict__ sums,
-                                                        float* __restrict__ cells) {
-    const int cellsPerBin = W * 4;
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+// The cells of the merged bins (:658: float additions of the source bins' counters, clipped at 2^24 like the reference's
+// float counters, in bin order): one WARP per (merged bin, cell).  The lanes add the source bins exactly in 64-bit
+// integers; a sum below 2^24 IS the result of the in-order float additions (no rounding can have happened), a larger one
+// is recomputed by one lane with the literal sequence of float additions.
+__global__ void __launch_bounds__(256) k_collapse_cells(const uint32_t* __restrict__ grouped, int W, const uint16_t* __restrict__ groupStart,
+                                                        const uint32_t* __restrict__ nBins, float* __restrict__ cells) {
+    const int cellsPerBin = W * 4, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (k >= (int)*nBins * cellsPerBin) return;
-    unsigned long long total = sums[k];
+    const int g = k / cellsPerBin, c = k - g * cellsPerBin;
+    const int first = groupStart[g], last = groupStart[g + 1];
+    unsigned long long total = 0;
+    for (int b = first + lane; b < last; b += 32) {
+        const uint32_t v = grouped[(size_t)b * cellsPerBin + c];
+        total += v < kSaturate ? v : kSaturate;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+    if (lane) return;
     float a;
     if (total < kSaturate) {
         a = (float)(uint32_t)total;
-    } else {  // partial sums may have rounded: literal in-order float additions of :658
-        int g = k / cellsPerBin, c = k - g * cellsPerBin;
+    } else {
         a = 0.f;
-        for (int b = groupStart[g]; b < (int)groupStart[g + 1]; ++b) {
-            uint32_t v = grouped[(size_t)b * cellsPerBin + c];
+        for (int b = first; b < last; ++b) {
+            const uint32_t v = grouped[(size_t)b * cellsPerBin + c];
             a = __fadd_rn(a, (float)(v < kSaturate ? v : kSaturate));
         }
     }
@@ -150,7 +152,8 @@ __global__ void __launch_bounds__(kFdrWarps * 32) k_fdr_table(const float* __res
     for (uint32_t item = blockIdx.x * kFdrWarps + warp; item < C * 4u * (uint32_t)W; item += gridDim.x * kFdrWarps) {
     const uint32_t ov = item % (uint32_t)W, cell = item / (uint32_t)W;  // cell = bin * 4 + bias * 2 + local
     const uint32_t bin = cell >> 2, k = cell & 3u;
-    auto at = [&](int o) { return cells[((size_t)bin * W + o) * 4 + k]; };
+    const float mine = lane < W ? cells[((size_t)bin * W + lane) * 4 + k] : 0.f;  // lane o holds c_o: one round of loads
+    auto at = [&](int o) { return __shfl_sync(0xffffffffu, mine, o); };
     float mean = 0.f;
     for (int o = 0; o < W; ++o)
         if (o != ppIdx) mean = __fadd_rn(mean, at(o));                       // :705-708
@@ -174,7 +177,15 @@ __global__ void __launch_bounds__(kFdrWarps * 32) k_fdr_table(const float* __res
     __syncwarp();
     if (lane == 0) {
         double acc = 0.0;
-        for (int i = 0; i < nSteps; ++i) acc = __dadd_rn(acc, sTerm[warp][i]);
+        int i = 0;
+        for (; i + 8 <= nSteps; i += 8) {  // eight loads in flight, the additions in the reference's order
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = sTerm[warp][i + u];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, t[u]);
+        }
+        for (; i < nSteps; ++i) acc = __dadd_rn(acc, sTerm[warp][i]);
         if (acc < 0.0) acc = 0.0; else if (acc > 1.0) acc = 1.0;             // :736-743 (NaN stays NaN)
         fdr[((size_t)bin * W + ov) * 4 + k] = __double2float_rn(acc);        // :745
     }
@@ -217,11 +228,14 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restri
     unsigned long long n = totals[1];
     if (n > ppCapacity) n = ppCapacity;
     const uint32_t nTiles = (uint32_t)((n + kScoreTile - 1) / kScoreTile);
-    for (;;) {
+    const bool keepAll = !(minHeight > 0.0f);  // -s 0 (the default): every record is reported (heights are > 0), record i is locus i
+    for (uint32_t staticTile = blockIdx.x;; staticTile += gridDim.x) {
         __syncthreads();  // sTile / sCnt / sBase of the previous tile are no longer read; sSmallBin is complete
-        if (tid == 0) sTile = atomicAdd(&st->ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = sTile;
+        if (!keepAll) {
+            if (tid == 0) sTile = atomicAdd(&st->ticket, 1u);
+            __syncthreads();
+        }
+        const uint32_t tile = keepAll ? staticTile : sTile;
         if (tile >= nTiles) break;
         const size_t first = (size_t)tile * kScoreTile;
         PairRec r[kScoreRounds];
@@ -236,8 +250,12 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restri
                 keep[k] = r[k].rp >= minHeight && r[k].rm >= minHeight;  // :903
             }
             ballot[k] = __ballot_sync(0xffffffffu, keep[k]);
-            if (lane == 0) sCnt[k * (kScoreThreads / 32) + warp] = __popc(ballot[k]);
+            if (lane == 0) sCnt[k * (kScoreThreads / 32) + warp] = keepAll ? (uint32_t)(k * kScoreThreads + warp * 32) : (uint32_t)__popc(ballot[k]);
         }
+        if (keepAll) {
+            if (tid == 0) sBase = first;
+            __syncthreads();
+        } else {
         __syncthreads();
         if (warp == 0) {  // exclusive scan of the 32 (round, warp) counts, then the look-back over the tiles before this one
             const uint32_t c = sCnt[lane];
@@ -279,6 +297,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restri
             }
         }
         __syncthreads();
+        }
         const unsigned long long base = sBase;
 #pragma unroll
         for (int k = 0; k < kScoreRounds; ++k) {
@@ -297,23 +316,20 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restri
             o.position = r[k].lpos - slots[lo].off + slots[lo].first;
             o.rp = r[k].rp;
             o.rm = r[k].rm;
-            loci[base + sCnt[k * (kScoreThreads / 32) + warp] + __popc(ballot[k] & ((1u << lane) - 1u))] = o;
+            loci[base + sCnt[k * (kScoreThreads / 32) + warp] + (keepAll ? (uint32_t)lane : (uint32_t)__popc(ballot[k] & ((1u << lane) - 1u)))] = o;
         }
     }
 }
 
 }  // namespace
 
-cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, uint16_t* groupStart, unsigned long long* sums,
-                            uint32_t* binOcc, cudaStream_t s, int* launches) {
+cudaError_t launch_collapse(const uint32_t* grouped, int W, float* cells, uint16_t* binMap, uint32_t* nBins, uint16_t* groupStart, uint32_t* binOcc,
+                            cudaStream_t s, int* launches) {
     const int entries = kBins * W * 4;
-    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)entries * sizeof(unsigned long long), s);
-    if (e != cudaSuccess) return e;
     k_collapse_occ<<<(kBins + 7) / 8, 256, 0, s>>>(grouped, W, binOcc);
-    k_collapse_map<<<1, 32, 0, s>>>(binOcc, W, binMap, groupStart, nBins);
-    k_collapse_sum<<<(entries + 255) / 256, 256, 0, s>>>(grouped, W, binMap, sums);
-    k_collapse_final<<<(entries + 255) / 256, 256, 0, s>>>(grouped, W, groupStart, nBins, sums, cells);
-    if (launches) *launches += 4;
+    k_collapse_map<<<1, 256, 0, s>>>(binOcc, W, binMap, groupStart, nBins);
+    k_collapse_cells<<<(entries + 7) / 8, 256, 0, s>>>(grouped, W, groupStart, nBins, cells);
+    if (launches) *launches += 3;
     return cudaGetLastError();
 }
 

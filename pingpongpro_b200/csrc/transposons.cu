@@ -513,4 +513,122 @@ cudaError_t run_transposons_sharded(const TransposonJob* jobs, const int* device
     return cudaSuccess;
 }
 
+namespace {
+
+__global__ void k_tp_list_facts(uint32_t nCells, const uint32_t* __restrict__ bounds, uint32_t* __restrict__ facts) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nCells) return;
+    const uint32_t* b = bounds + (size_t)g * 4;
+    facts[2 * g] = b[1] - b[0];                 // signatures of this (transposon, overlap)'s list held here
+    facts[2 * g + 1] = b[3] == b[1] ? 1u : 0u;  // the transposon's range reaches the end of the local list
+}
+
+// bounds of the WHOLE list for k_tp_skip: [0, total length, 0, consumed on every rank ? length : none]
+__global__ void k_tp_whole_bounds(uint32_t nCells, const uint32_t* __restrict__ facts, uint32_t world, uint32_t* __restrict__ whole) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nCells) return;
+    uint32_t* w = whole + (size_t)g * 4;
+    w[0] = 0;
+    w[1] = facts[2 * g];
+    w[2] = 0;
+    w[3] = facts[2 * g + 1] == world ? facts[2 * g] : 0xffffffffu;  // k_tp_skip only asks whether [3] == [1]
+}
+
+}  // namespace
+
+cudaError_t run_transposons_collective(const TransposonJob& job, int rank, int world, const std::function<int(void*, size_t)>& reduce, const ppp_interval* intervals,
+                                       size_t n, ppp_tp_result* results, uint32_t* order, std::string& err) {
+    if (n == 0) return cudaSuccess;
+    if (n >= 0x7fffffffull / 64) { err = "too many intervals"; return cudaSuccess; }
+    const int W = job.W;
+    std::vector<uint32_t> perm, groupStart;
+    sortIntervals(intervals, n, perm, groupStart);
+    std::vector<TpDev> tp;
+    localIntervals(*job.slots, intervals, perm, tp);
+    const uint32_t nGroups = (uint32_t)groupStart.size() - 1;
+    const uint32_t nTp = (uint32_t)n;
+    const uint32_t nCells = nTp * (uint32_t)W;
+    const uint32_t nPairs = (uint32_t)job.nPairs;
+    const uint32_t nBlocks = std::max<uint32_t>(1, (nPairs + kPartThreads - 1) / kPartThreads);
+    const size_t histWords = (size_t)32 * nBlocks;
+    const size_t scratchWords = exclusive_scan_scratch_words(histWords);
+    const unsigned th = 128;
+    cudaStream_t s = job.stream;
+
+    DevBuf bHist, bScratch, bPos, bScore, bRp, bRm, bTp, bGroups, bBounds, bWhole, bFacts, bSkip, bRun, bZ, bP;
+    TCK(bHist.alloc(histWords * 4));
+    TCK(bScratch.alloc(scratchWords * 4));
+    TCK(bPos.alloc((size_t)nPairs * 4));
+    TCK(bScore.alloc((size_t)nPairs * 4));
+    TCK(bRp.alloc((size_t)nPairs * 4));
+    TCK(bRm.alloc((size_t)nPairs * 4));
+    TCK(bTp.alloc(n * sizeof(TpDev)));
+    TCK(bGroups.alloc(groupStart.size() * 4));
+    TCK(bBounds.alloc((size_t)nCells * 4 * sizeof(uint32_t)));
+    TCK(bWhole.alloc((size_t)nCells * 4 * sizeof(uint32_t)));
+    TCK(bFacts.alloc((size_t)nCells * 2 * sizeof(uint32_t)));
+    TCK(bSkip.alloc(nCells));
+    const size_t runWords = n * 34;  // running sums: hist[n][32], R+[n], R-[n] (floats, exchanged as 32-bit patterns)
+    TCK(bRun.alloc(runWords * sizeof(float)));
+    TCK(bZ.alloc(n * sizeof(double)));
+    TCK(bP.alloc(n * sizeof(double)));
+    float* runHist = bRun.as<float>();
+    float* runRp = runHist + n * 32;
+    float* runRm = runRp + n;
+
+    // 1. this rank's partition by overlap and its local bounds per (transposon, overlap)
+    TCK(cudaMemcpyAsync(bTp.p, tp.data(), n * sizeof(TpDev), cudaMemcpyHostToDevice, s));
+    TCK(cudaMemcpyAsync(bGroups.p, groupStart.data(), groupStart.size() * 4, cudaMemcpyHostToDevice, s));
+    TCK(cudaMemsetAsync(bHist.p, 0, histWords * 4, s));
+    if (nPairs) {
+        k_ov_count<<<nBlocks, kPartThreads, 0, s>>>(job.pairs, nPairs, bHist.as<uint32_t>(), nBlocks);
+        *job.launches += 1;
+    }
+    TCK(exclusive_scan_u32(bHist.as<uint32_t>(), bHist.as<uint32_t>(), histWords, bScratch.as<uint32_t>(), scratchWords, s, job.launches));
+    if (nPairs) {
+        k_ov_scatter<<<nBlocks, kPartThreads, 0, s>>>(job.pairs, job.pairFdr, nPairs, bHist.as<uint32_t>(), nBlocks, bPos.as<uint32_t>(), bScore.as<float>(),
+                                                      bRp.as<float>(), bRm.as<float>());
+        *job.launches += 1;
+    }
+    k_tp_bounds<<<(nCells + th - 1) / th, th, 0, s>>>(bTp.as<TpDev>(), nTp, W, bHist.as<uint32_t>(), nBlocks, nPairs, bPos.as<uint32_t>(), bBounds.as<uint32_t>());
+    // 2. whole-list facts (summed over the ranks) -> the iterator history, replayed identically on every rank
+    k_tp_list_facts<<<(nCells + th - 1) / th, th, 0, s>>>(nCells, bBounds.as<uint32_t>(), bFacts.as<uint32_t>());
+    *job.launches += 2;
+    TCK(cudaGetLastError());
+    if (reduce(bFacts.p, (size_t)nCells * 2) != 0) { err = "all-reduce failed"; return cudaSuccess; }
+    k_tp_whole_bounds<<<(nCells + th - 1) / th, th, 0, s>>>(nCells, bFacts.as<uint32_t>(), (uint32_t)world, bWhole.as<uint32_t>());
+    k_tp_skip<<<(nGroups * W + th - 1) / th, th, 0, s>>>(bTp.as<TpDev>(), bGroups.as<uint32_t>(), nGroups, W, bWhole.as<uint32_t>(), bSkip.as<uint8_t>());
+    *job.launches += 2;
+    TCK(cudaGetLastError());
+    // 3. the sums, rank after rank in position order
+    TCK(cudaMemsetAsync(bRun.p, 0, runWords * sizeof(float), s));
+    for (int k = 0; k < world; ++k) {
+        if (k == rank) {
+            k_tp_sums_chain<<<(nCells + th - 1) / th, th, 0, s>>>(nTp, W, job.ppIdx, bBounds.as<uint32_t>(), bSkip.as<uint8_t>(), bScore.as<float>(), bRp.as<float>(),
+                                                                  bRm.as<float>(), runHist, runRp, runRm);
+            *job.launches += 1;
+            TCK(cudaGetLastError());
+        } else {
+            TCK(cudaMemsetAsync(bRun.p, 0, runWords * sizeof(float), s));  // (+0.0f is the all-zero pattern)
+        }
+        if (reduce(bRun.p, runWords) != 0) { err = "all-reduce failed"; return cudaSuccess; }
+    }
+    // 4. statistics, replicated
+    const double pi = 3.14159265358979323846;  // :50
+    const double coeff = 0.01 * 1 / sqrt(2 * pi);
+    k_tp_stats<<<(nTp + th - 1) / th, th, 0, s>>>(nTp, W, job.ppIdx, coeff, runHist, bZ.as<double>(), bP.as<double>());
+    *job.launches += 1;
+    TCK(cudaGetLastError());
+    std::vector<float> hist(n * 32), rp(n), rm(n);
+    std::vector<double> z(n), p(n);
+    TCK(cudaMemcpyAsync(hist.data(), runHist, n * 32 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    TCK(cudaMemcpyAsync(rp.data(), runRp, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    TCK(cudaMemcpyAsync(rm.data(), runRm, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    TCK(cudaMemcpyAsync(z.data(), bZ.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    TCK(cudaMemcpyAsync(p.data(), bP.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    TCK(cudaStreamSynchronize(s));
+    finishResults(n, job.ppIdx, hist, rp, rm, z, p, perm, results, order);
+    return cudaSuccess;
+}
+
 }  // namespace pppk

@@ -1,5 +1,6 @@
 // transposons.cuh -- K5 interface (transposons.cu).
 #pragma once
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -26,5 +27,13 @@ cudaError_t run_transposons(const TransposonJob& job, const ppp_interval* interv
 // straddle a range boundary get the sums (and the iterator history) of the unsharded run.
 cudaError_t run_transposons_sharded(const TransposonJob* jobs, const int* devices, int nShards, const ppp_interval* intervals, size_t n, ppp_tp_result* results,
                                     uint32_t* order, std::string& err);
+
+// The same when every shard lives in its OWN process (one process per GPU): called collectively by all ranks with the same
+// intervals; `reduce(buffer, words)` sums a device buffer of 32-bit words over the ranks in place (the context's all-reduce
+// hook).  The whole-list facts behind the iterator history are summed over the ranks; the sequential single-precision sums
+// travel rank by rank in position order (round k: rank k continues the running sums and shares them -- the others
+// contribute zeros to the sum).  Every rank ends up with the complete results.
+cudaError_t run_transposons_collective(const TransposonJob& job, int rank, int world, const std::function<int(void*, size_t)>& reduce, const ppp_interval* intervals,
+                                       size_t n, ppp_tp_result* results, uint32_t* order, std::string& err);
 
 }  // namespace pppk

@@ -67,7 +67,7 @@ def _lib() -> C.CDLL:
 _L = None
 
 TP_DTYPE = np.dtype([("contig", "<u4"), ("strand", "<u4"), ("start", "<u4"), ("end", "<u4"), ("p", "<f4"), ("q", "<f4"),
-                     ("reads_plus", "<f4"), ("reads_minus", "<f4"), ("hist", "<f4", (64,))])
+                     ("reads_plus", "<f4"), ("reads_minus", "<f4"), ("hist", "<f4", (64,)), ("z64", "<f8"), ("p64", "<f8")])
 IV_DTYPE = np.dtype([("contig", "<u4"), ("strand", "<u4"), ("start", "<u4"), ("end", "<u4")])
 
 
