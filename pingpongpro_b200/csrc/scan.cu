@@ -120,7 +120,7 @@ __device__ __forceinline__ uint32_t window_bits(uint32_t w0, uint32_t w1, uint32
 }
 
 template <int REPR>
-__global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
+__global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
     __shared__ uint32_t sMask[kTileWords + 2];     // minus-strand occupancy words of the tile + the word after the tile + a zero
     __shared__ uint32_t sPlus[kTileWords];         // plus strand
     __shared__ uint32_t sOff[4];                   // compact index of the tile's first / past-the-last plus stack, first / past-the-last minus stack
@@ -182,6 +182,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_scan(ScanParams P) {
             cp_async_wait();
         }
         __syncthreads();  // (A) the tile's occupancy words are complete
+        {   // whoever claims the tile one grid ahead finds its occupancy words in L2 (one 128-byte line per thread)
+            const uint32_t ahead = tile + gridDim.x;
+            if (ahead < P.nTiles && tid < 2 * (kTileWords / 32)) {
+                const uint32_t* line = P.occ + (tid < kTileWords / 32 ? 0 : P.G / 32) + (size_t)ahead * kTileWords + (size_t)(tid % (kTileWords / 32)) * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+            }
+        }
 
         // ---- counting phase (bitmaps only): how many records the tile holds, published at once, so that the blocks
         // holding later tiles never wait for this block's record phase
@@ -534,7 +541,7 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int perSm = 4;
+    int perSm = 5;
     if (repr == kReprInt) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprInt>, kThreads, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprFloat>, kThreads, 0);
     if (perSm < 1) perSm = 1;

@@ -71,6 +71,20 @@ __global__ void __launch_bounds__(256) k_collapse_map(const uint32_t* __restrict
         uint32_t m[kMaxCellWords];
 #pragma unroll
         for (int w = 0; w < kMaxCellWords; ++w) m[w] = valid ? sOcc[b * kMaxCellWords + w] : 0u;
+        {   // most chunks cannot close a merged bin (all 32 bins together still leave a cell empty): no prefix scan for those
+            bool canClose = true;
+#pragma unroll
+            for (int w = 0; w < kMaxCellWords; ++w) {
+                const uint32_t all = __reduce_or_sync(0xffffffffu, m[w]) | carry[w];
+                canClose = canClose && all == full[w];
+            }
+            if (!canClose) {
+                if (valid) binMap[b] = (uint16_t)collapsed;  // :666
+#pragma unroll
+                for (int w = 0; w < kMaxCellWords; ++w) carry[w] |= __reduce_or_sync(0xffffffffu, m[w]);
+                continue;
+            }
+        }
         int start = 0;
         while (start < 32) {
             uint32_t pre[kMaxCellWords];
@@ -147,6 +161,9 @@ constexpr int kFdrMaxSteps = 1008;
 __global__ void __launch_bounds__(kFdrWarps * 32) k_fdr_table(const float* __restrict__ cells, const uint32_t* __restrict__ nBins, int W, int ppIdx,
                                                                const double* __restrict__ xs, const double* __restrict__ ws, int nSteps, float* __restrict__ fdr) {
     __shared__ double sTerm[kFdrWarps][kFdrMaxSteps];
+    __shared__ double sX[kFdrMaxSteps], sWt[kFdrMaxSteps];  // the integration grid and its Gaussian weights (host libm), once per block
+    for (int i = threadIdx.x; i < nSteps; i += kFdrWarps * 32) { sX[i] = xs[i]; sWt[i] = ws[i]; }
+    __syncthreads();
     const uint32_t C = *nBins;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t item = blockIdx.x * kFdrWarps + warp; item < C * 4u * (uint32_t)W; item += gridDim.x * kFdrWarps) {
@@ -170,7 +187,7 @@ __global__ void __launch_bounds__(kFdrWarps * 32) k_fdr_table(const float* __res
     const double thr = (double)__fdiv_rn(__fsub_rn(c, mean), sd);            // :726
     const double dsd = (double)sd, dmean = (double)mean, dc = (double)c;
     for (int i = lane; i < nSteps; i += 32) {                                // :724
-        double x = xs[i], w = ws[i];
+        const double x = sX[i], w = sWt[i];
         sTerm[warp][i] = (x >= thr) ? w                                                           // :728
                                     : __ddiv_rn(__dmul_rn(w, __dadd_rn(__dmul_rn(x, dsd), dmean)), dc);  // :732
     }
