@@ -120,7 +120,6 @@ struct ppp_ctx {
     size_t passZeroBytes = 0;
     unsigned long long* dTileState = nullptr;
     uint32_t* dFreqTail = nullptr;
-    float* dLut = nullptr;
     uint32_t prevMaxHeight = 0;
     // signature records (structure of arrays, (position, overlap) order) and the overlap-`pingpong` stream
     uint32_t* dRecPos = nullptr;
@@ -536,8 +535,6 @@ int ppp_init(const ppp_config* cfg, ppp_ctx** out) {
     }
     CKI(cudaMalloc(&c->dFreqTail, (size_t)kFreqCapacity * sizeof(uint32_t)));
     CKI(cudaMemsetAsync(c->dFreqTail, 0, (size_t)kFreqCapacity * sizeof(uint32_t), c->stream));
-    CKI(cudaMalloc(&c->dLut, (size_t)kFreqCapacity * sizeof(float)));
-    CKI(cudaMemsetAsync(c->dLut, 0, 4 * sizeof(float), c->stream));  // heights 0..3 are looked up even when they never occur
     CKI(cudaMalloc(&c->dTileCntP, ((size_t)c->nTiles + 1) * 4));
     CKI(cudaMalloc(&c->dTileCntM, ((size_t)c->nTiles + 1) * 4));
     CKI(cudaMalloc(&c->dTileOffP, ((size_t)c->nTiles + 1) * 4));
@@ -589,7 +586,7 @@ void ppp_destroy(ppp_ctx* c) {
     if (c->ncclComm) nccl().commDestroy(c->ncclComm);
     delete c->groupMember;
     if (c->dGather) cudaFree(c->dGather);
-    void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dCmp, c->dTileCntP, c->dTileCntM, c->dTileOffP, c->dTileOffM, c->dState, c->dFreqTail, c->dLut,
+    void* dev[] = {c->H, c->occ, c->dSlots, c->dCounters, c->dCmp, c->dTileCntP, c->dTileCntM, c->dTileOffP, c->dTileOffM, c->dState, c->dFreqTail,
                    c->dRecPos, c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dPP, c->dLoci, c->dScoreState, c->dPairs, c->dPairFdr, c->dScanScratch,
                    c->dThresholds, c->dCells, c->dFdr, c->dBinMap, c->dNBins, c->dXs, c->dWs, c->dGroupStart, c->dBinParams, c->dBinOcc};
     for (void* p : dev)
@@ -874,6 +871,7 @@ int enqueueScanStage(ppp_ctx* c) {
     p.tallList = nullptr;
     p.tallCount = nullptr;
     p.tallCap = 0;
+    p.maxTail = &c->dState->maxTail;
     if (gatherTall) {
         if (!c->dGather) CK(cudaMalloc(&c->dGather, (size_t)c->world * slotWords * sizeof(uint32_t)));
         CK(cudaMemsetAsync(c->dGather, 0, (size_t)c->world * slotWords * sizeof(uint32_t), c->stream));
@@ -890,7 +888,8 @@ int enqueueScanStage(ppp_ctx* c) {
     if (gatherTall) {
         // one all-reduce carries every rank's low bins, tall stacks and maximum height; no host round trip in between
         if ((rc = hookReduce(c, c->dGather, (size_t)c->world * slotWords, 0, 0))) return rc;
-        CK(launch_tall_apply(c->dGather, c->world, c->tallCap, c->dState->freqLow, c->dFreqTail, &c->dState->maxHeight, &c->dState->overflow, c->stream, &c->launches));
+        CK(launch_tall_apply(c->dGather, c->world, c->tallCap, c->dState->freqLow, c->dFreqTail, &c->dState->maxHeight, &c->dState->overflow, &c->dState->maxTail,
+                             c->stream, &c->launches));
     } else if (c->allreduce) {
         // sizes of the table reductions depend on the global maximum height: one extra round trip
         if ((rc = hookReduce(c, &c->dState->maxHeight, 1, 0, 1))) return rc;
@@ -898,17 +897,19 @@ int enqueueScanStage(ppp_ctx* c) {
         CK(cudaStreamSynchronize(c->stream));
         tr.mark("scan + max-height reduce");
         if ((rc = hookReduce(c, c->dState->freqLow, kScanLowBins, 1, 0))) return rc;
-        if (c->hs->maxHeight >= kScanLowBins && (rc = hookReduce(c, c->dFreqTail + kScanLowBins, (size_t)c->hs->maxHeight - kScanLowBins + 1, 0, 0))) return rc;
+        if (c->hs->maxHeight >= kScanLowBins) {
+            if ((rc = hookReduce(c, c->dFreqTail + kScanLowBins, (size_t)c->hs->maxHeight - kScanLowBins + 1, 0, 0))) return rc;
+            CK(launch_tail_max(c->dFreqTail, &c->dState->maxHeight, &c->dState->maxTail, c->stream, &c->launches));
+        }
     }
+    // the largest height frequency and, from it, the bin thresholds (one small kernel; no frequency table is materialised:
+    // the binning kernels read the counts themselves)
     if ((rc = timerStart(c, c->tLut))) return rc;
-    CK(launch_freq_lut(c->dState->freqLow, c->dFreqTail, &c->dState->maxHeight, c->dLut, &c->dState->maxCount, c->stream, &c->launches));
+    CK(launch_bin_thresholds(c->dState, c->dThresholds, c->dBinParams, c->stream, &c->launches));
     if ((rc = timerStop(c, c->tLut))) return rc;
-    CK(cudaMemcpyAsync(c->hs->totals, c->dState->totals, 40, cudaMemcpyDeviceToHost, c->stream));  // totals[2], maxCount, maxHeight, ticket, overflow, pad
+    CK(cudaMemcpyAsync(c->hs->totals, c->dState->totals, 40, cudaMemcpyDeviceToHost, c->stream));  // totals[2], maxCount, maxHeight, ticket, overflow, maxTail
     CK(cudaEventRecord(c->evLut, c->stream));
-    if (c->deviceThresholds) {
-        CK(launch_bin_thresholds(&c->dState->maxCount, c->dThresholds, c->dBinParams, c->stream, &c->launches));
-        CK(cudaMemcpyAsync(c->hDevThresholds, c->dThresholds, kBins * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    }
+    if (c->deviceThresholds) CK(cudaMemcpyAsync(c->hDevThresholds, c->dThresholds, kBins * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     c->hostTableFreq = -1.0f;
     c->stageScan = true;
     c->stageBin = c->stageScore = false;
@@ -945,7 +946,7 @@ int enqueueBinStage(ppp_ctx* c) {
     if ((rc = timerStart(c, c->tBin))) return rc;
     if (c->stageBin) CK(cudaMemsetAsync(c->dGrouped, 0, (tableWords + 1) * 4, c->stream));  // (a second ppp_scan on one scan pass: the scan stage zeroed them for the first)
     // (the record count is on the device; the grid is sized for a full store, surplus blocks leave at once)
-    CK(launch_bin(c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dState->totals, c->pairCapacity, c->pairCapacity, c->dLut, c->dThresholds, c->dBinParams, c->W,
+    CK(launch_bin(c->dRecRp, c->dRecRm, c->dRecMisc, c->dRecBin, c->dState->totals, c->pairCapacity, c->pairCapacity, FreqTables{c->dState->freqLow, c->dFreqTail}, c->dThresholds, c->dBinParams, c->W,
                   c->dGrouped, c->stream, &c->launches));
     if (c->allreduce) {
         // a shard whose signature store overflowed cannot re-run alone (the pass contains collectives): the number of
@@ -968,7 +969,7 @@ int enqueueScoreStage(ppp_ctx* c, uint32_t minStackHeight) {
     if (minStackHeight > 0) CK(cudaMemsetAsync(c->dScoreState, 0, sizeof(ScoreState) + c->scoreTileWords * sizeof(unsigned long long), c->stream));
     CK(launch_collapse(c->dGrouped, c->W, c->dCells, c->dBinMap, c->dNBins, c->dGroupStart, c->dBinOcc, c->stream, &c->launches));
     CK(launch_fdr_table(c->dCells, c->dNBins, kBins, c->W, ppIdx, c->dXs, c->dWs, c->nSteps, c->dFdr, c->stream, &c->launches));
-    CK(launch_score(c->dPP, c->dState->totals, c->ppCapacity, c->ppCapacity, c->dScoreState, c->dScoreTiles, c->dLut, c->dThresholds, c->dBinParams, c->dFdr,
+    CK(launch_score(c->dPP, c->dState->totals, c->ppCapacity, c->ppCapacity, c->dScoreState, c->dScoreTiles, FreqTables{c->dState->freqLow, c->dFreqTail}, c->dThresholds, c->dBinParams, c->dFdr,
                     c->dBinMap, c->W, ppIdx, minStackHeight, c->dSlots, (uint32_t)c->ownedSlots.size(), c->dLoci, c->stream, &c->launches));
     if ((rc = timerStop(c, c->tScore))) return rc;
     if (minStackHeight > 0) CK(cudaMemcpyAsync(&c->hs->nLoci, c->dScoreState, sizeof(ScoreState), cudaMemcpyDeviceToHost, c->stream));

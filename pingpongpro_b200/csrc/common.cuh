@@ -53,11 +53,11 @@ struct __align__(16) PairRec {
 struct PassState {
     unsigned long long freqLow[kScanLowBins];  // height histogram, rounded heights < kScanLowBins
     unsigned long long totals[2];              // signature records / overlap-`pingpong` records found (may exceed the capacities)
-    unsigned long long maxCount;               // largest height frequency (k_freq_lut)
+    unsigned long long maxCount;               // largest height frequency (k_bin_thresholds)
     uint32_t maxHeight;
     uint32_t ticket;                           // next unclaimed tile of k_scan
     uint32_t overflow;                         // multi-GPU: some rank listed more tall stacks than fit
-    uint32_t pad;
+    uint32_t maxTail;                          // largest frequency among the heights >= kScanLowBins
 };
 // What the binning kernels need besides the threshold table (written by k_bin_thresholds, or by the host)
 struct BinParams {
@@ -99,6 +99,7 @@ struct ScanParams {
     uint32_t* tallList;           // null: count in freqTail
     unsigned int* tallCount;
     uint32_t tallCap;
+    uint32_t* maxTail;            // largest count reached in freqTail
     // signature records in (position, overlap) order, structure of arrays
     uint32_t* recPos;             // padded position of the plus stack
     float* recRp;
@@ -109,7 +110,18 @@ struct ScanParams {
     uint64_t ppCapacity;
 };
 
+// The height -> frequency histogram as the kernels read it: exact counts, 64-bit for rounded heights < kScanLowBins,
+// 32-bit beyond; the reference's float counter (:508) holds min(count, 2^24).
+struct FreqTables {
+    const unsigned long long* low;
+    const uint32_t* tail;
+};
+
 // ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float freq_of(const FreqTables& f, uint32_t h) {  // heightScoreMap[h], :582 / :589
+    const unsigned long long c = h < kScanLowBins ? f.low[h] : (unsigned long long)f.tail[h];
+    return (float)(c < kSaturate ? (uint32_t)c : kSaturate);
+}
 template <int REPR>
 __device__ __forceinline__ float word_height(uint32_t w) {
     uint32_t v = w & kValueMask;
@@ -164,13 +176,14 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
 constexpr uint32_t kTallLow = 2;                            // word offset of the low bins inside a slot
 constexpr uint32_t kTallHeader = kTallLow + 2 * kScanLowBins;
 cudaError_t launch_tall_apply(const uint32_t* gather, int world, uint32_t cap, unsigned long long* freqLow, uint32_t* freqTail, uint32_t* maxHeight,
-                              uint32_t* overflow, cudaStream_t s, int* launches);
-cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* freqTail, const uint32_t* maxHeight, float* lut,
-                            unsigned long long* maxCount, cudaStream_t s, int* launches);
+                              uint32_t* overflow, uint32_t* maxTail, cudaStream_t s, int* launches);
+// (only where the tail counts were all-reduced as dense tables) the largest of freqTail[kScanLowBins .. maxHeight]
+cudaError_t launch_tail_max(const uint32_t* freqTail, const uint32_t* maxHeight, uint32_t* maxTail, cudaStream_t s, int* launches);
 // `expected`: the host's idea of the number of records (sizes the grid; the kernel reads the exact count from `totals`)
-cudaError_t launch_bin_thresholds(const unsigned long long* maxCount, float* thresholds, BinParams* params, cudaStream_t s, int* launches);
+// the largest height frequency (-> state->maxCount) and the bin thresholds / parameters for it
+cudaError_t launch_bin_thresholds(PassState* state, float* thresholds, BinParams* params, cudaStream_t s, int* launches);
 cudaError_t launch_bin(const float* recRp, const float* recRm, const uint8_t* recMisc, uint16_t* recBin, const unsigned long long* totals, uint64_t capacity,
-                       uint64_t expected, const float* lut, const float* thresholds, const BinParams* params, int W, uint32_t* grouped, cudaStream_t s, int* launches);
+                       uint64_t expected, FreqTables freq, const float* thresholds, const BinParams* params, int W, uint32_t* grouped, cudaStream_t s, int* launches);
 cudaError_t launch_overflow_flag(const unsigned long long* totals, uint64_t capacity, uint64_t ppCapacity, uint32_t* flag, cudaStream_t s, int* launches);
 cudaError_t launch_pairs_view(const uint32_t* recPos, const float* recRp, const float* recRm, const uint8_t* recMisc, const uint16_t* recBin, size_t n,
                               const float* fdrTable, const uint16_t* binMap, int W, PairRec* pairs, float* pairFdr, cudaStream_t s, int* launches);
@@ -186,7 +199,7 @@ struct LocusOut {
 // K4, per-locus half (single pass, ordered): see score.cu.  `tileState` holds score_tiles(ppCapacity) words and is zeroed,
 // together with `state`, before every launch.
 cudaError_t launch_score(const PairRec* pp, const unsigned long long* totals, uint64_t ppCapacity, uint64_t expected, ScoreState* state,
-                         unsigned long long* tileState, const float* lut, const float* thresholds, const BinParams* params, const float* fdrTable,
+                         unsigned long long* tileState, FreqTables freq, const float* thresholds, const BinParams* params, const float* fdrTable,
                          const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight, const Slot* slots, uint32_t nSlots, LocusOut* loci, cudaStream_t s,
                          int* launches);
 size_t score_tiles(uint64_t records);

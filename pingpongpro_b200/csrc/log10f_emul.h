@@ -141,6 +141,14 @@ PPP_HD float emul_bin_threshold(int b, float maxFreq) {
     const float maxHs = emul_log10f(top);  // :551
     if (emul_height_score_bin(top, maxHs) < b) return emul_float(0x7f800000u);
     uint32_t lo = 0x3f800000u, hi = emul_bits(top);  // invariant: bin(hi) >= b
+    {   // a narrow bracket around 10^(maxHs * (b - 0.5) / 999), kept only if it really brackets the step (it only saves probes)
+        const double est = pow(10.0, (double)maxHs * ((double)b - 0.5) / 999.0);
+        const float fl = (float)(est * (1.0 - 3e-5)), fh = (float)(est * (1.0 + 3e-5));
+        if (fl > 1.0f && fh < top) {
+            const uint32_t bl = emul_bits(fl), bh = emul_bits(fh);
+            if (emul_height_score_bin(fl, maxHs) < b && emul_height_score_bin(fh, maxHs) >= b) { lo = bl + 1u; hi = bh; }
+        }
+    }
     while (lo < hi) {
         const uint32_t mid = lo + (hi - lo) / 2u;
         if (emul_height_score_bin(emul_float(mid), maxHs) >= b) hi = mid; else lo = mid + 1u;

@@ -89,13 +89,13 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
 }
 
 // a stack taller than the shared-memory bins (rare): out of line, so that it costs the streaming loop no registers
-__device__ __noinline__ void count_tall(uint32_t* freqTail, uint32_t* tallList, unsigned int* tallCount, uint32_t tallCap, uint32_t r) {
+__device__ __noinline__ void count_tall(uint32_t* freqTail, uint32_t* tallList, unsigned int* tallCount, uint32_t tallCap, uint32_t* maxTail, uint32_t r) {
     if (r >= kFreqCapacity) r = kFreqCapacity - 1;  // (+inf of a malformed NH:i:0 record: never index past the table)
     if (tallList) {
         unsigned int i = atomicAdd(tallCount, 1u);
         if (i < tallCap) tallList[i] = r;
     } else {
-        atomicAdd(&freqTail[r], 1u);
+        atomicMax(maxTail, atomicAdd(&freqTail[r], 1u) + 1u);
     }
 }
 
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
         const uint32_t r = word_round_height<REPR>(w);
         if (r < 4u) { small += 1u << (8 * r); if ((small & 0x80808080u) != 0u) flush_small(); }  // heights 0..3: byte counters in a register
         else if (r < kScanLowBins) atomicAdd(&sHist[r], 1u);
-        else count_tall(P.freqTail, P.tallList, P.tallCount, P.tallCap, r);
+        else count_tall(P.freqTail, P.tallList, P.tallCount, P.tallCap, P.maxTail, r);
         localMax = max(localMax, r);
     };
 
@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
 
 // see launch_tall_apply in common.cuh
 __global__ void __launch_bounds__(256) k_tall_apply(const uint32_t* __restrict__ gather, int world, uint32_t cap, unsigned long long* __restrict__ freqLow,
-                                                    uint32_t* __restrict__ freqTail, uint32_t* __restrict__ maxHeight, uint32_t* __restrict__ overflow) {
+                                                    uint32_t* __restrict__ freqTail, uint32_t* __restrict__ maxHeight, uint32_t* __restrict__ overflow,
+                                                    uint32_t* __restrict__ maxTail) {
     const size_t slotWords = (size_t)kTallHeader + cap;
     uint32_t best = 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < kScanLowBins; k += gridDim.x * blockDim.x) {
@@ -390,34 +391,38 @@ __global__ void __launch_bounds__(256) k_tall_apply(const uint32_t* __restrict__
         uint32_t n = slot[0];
         best = max(best, slot[1]);
         if (n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1u; n = cap; }
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&freqTail[slot[kTallHeader + i]], 1u);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            atomicMax(maxTail, atomicAdd(&freqTail[slot[kTallHeader + i]], 1u) + 1u);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *maxHeight = best;
 }
 
-// freq LUT: lut[h] = float(min(count[h], 2^24)) -- the value the reference's float counter holds (:508) --
-// and the largest count (for maxHeightScore, :547-551).  Grid-stride up to the device-resident max height.
-__global__ void __launch_bounds__(256) k_freq_lut(const unsigned long long* __restrict__ freqLow, const uint32_t* __restrict__ freqTail,
-                                                  const uint32_t* __restrict__ maxHeight, float* __restrict__ lut, unsigned long long* maxCount) {
+// The largest count of freqTail[kScanLowBins .. maxHeight] -- only where the tail counts were all-reduced as dense tables
+// (the counting kernels track it themselves otherwise).
+__global__ void __launch_bounds__(256) k_tail_max(const uint32_t* __restrict__ freqTail, const uint32_t* __restrict__ maxHeight, uint32_t* __restrict__ maxTail) {
     const uint32_t maxH = *maxHeight;
-    unsigned long long best = 0;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= maxH; h += (uint64_t)gridDim.x * blockDim.x) {
-        unsigned long long c = h < kScanLowBins ? freqLow[h] : (unsigned long long)freqTail[h];
-        lut[h] = (float)(c < kSaturate ? (uint32_t)c : kSaturate);
-        best = c > best ? c : best;
-    }
+    uint32_t best = 0;
+    for (uint64_t h = (uint64_t)kScanLowBins + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= maxH; h += (uint64_t)gridDim.x * blockDim.x) best = max(best, freqTail[h]);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
-        best = o > best ? o : best;
-    }
-    if ((threadIdx.x & 31) == 0 && best) atomicMax(maxCount, best);
+    for (int d = 16; d > 0; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(maxTail, best);
 }
 
 // The bin thresholds of k_bin / k_score from the (global) maximum height frequency, on the device (log10f_emul.h): one
 // thread per threshold.  The host recomputes the table with its libm while the device works on, and compares (api.cu).
-__global__ void __launch_bounds__(32) k_bin_thresholds(const unsigned long long* __restrict__ maxCount, float* __restrict__ thresholds, BinParams* __restrict__ params) {
-    const unsigned long long c = *maxCount;
+__global__ void __launch_bounds__(32) k_bin_thresholds(PassState* __restrict__ state, float* __restrict__ thresholds, BinParams* __restrict__ params) {
+    // the largest height frequency (:547-550): every block finds it for itself (512 low bins + the tracked maximum of the tail)
+    unsigned long long c = state->maxTail;
+    {
+        unsigned long long v[kScanLowBins / 32];
+#pragma unroll
+        for (int k = 0; k < (int)kScanLowBins / 32; ++k) v[k] = state->freqLow[k * 32 + threadIdx.x];  // (all loads in flight together)
+#pragma unroll
+        for (int k = 0; k < (int)kScanLowBins / 32; ++k) c = v[k] > c ? v[k] : c;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, c, d); c = o > c ? o : c; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) state->maxCount = c;
     const float maxFreq = (float)(c < kSaturate ? (uint32_t)c : kSaturate);  // the float counter of :508, :547-550
     const int b = blockIdx.x * 32 + threadIdx.x;  // threshold of bin b (1..999) lives at [b - 1]; one warp per SM: the search is a dependent chain
     if (b == 0) {
@@ -443,7 +448,7 @@ constexpr int kBinCache = 4096;
 constexpr uint32_t kBinEmpty = 0xffffffffu;
 __global__ void __launch_bounds__(kBinThreads) k_bin(const float* __restrict__ recRp, const float* __restrict__ recRm, const uint8_t* __restrict__ recMisc,
                                                      uint16_t* __restrict__ recBin, const unsigned long long* __restrict__ totals, uint64_t capacity,
-                                                     const float* __restrict__ lut, const float* __restrict__ thresholds, const BinParams* __restrict__ params, int W,
+                                                     FreqTables freq, const float* __restrict__ thresholds, const BinParams* __restrict__ params, int W,
                                                      uint32_t* __restrict__ grouped) {
     __shared__ float sThr[kBins];
     __shared__ uint32_t sKey[kBinCache], sVal[kBinCache];
@@ -462,7 +467,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const float* __restrict__ r
         while (b < kBins - 1 && sThr[b] <= hs) ++b;
         return b;
     };
-    if (tid < 16) sSmallBin[tid] = (uint16_t)bin_of(__fmul_rn(lut[tid >> 2], lut[tid & 3]));  // (a height that never occurs has lut 0: never looked up)
+    if (tid < 16) sSmallBin[tid] = (uint16_t)bin_of(__fmul_rn(freq_of(freq, tid >> 2), freq_of(freq, tid & 3)));  // (a height that never occurs has frequency 0: never looked up)
     __syncthreads();
     const uint32_t onesBin = sSmallBin[5];  // rounded heights (1, 1)
     unsigned long long n = totals[0];
@@ -486,7 +491,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const float* __restrict__ r
             const uint32_t hp = round_height(rp[u]), hm = round_height(rm[u]);  // heightScoreMap[0.5 + reads], :582 / :589
             uint32_t b;
             if ((hp | hm) < 4u) b = sSmallBin[hp * 4 + hm];
-            else b = (uint32_t)bin_of(__fmul_rn(lut[hp], lut[hm]));
+            else b = (uint32_t)bin_of(__fmul_rn(freq_of(freq, hp), freq_of(freq, hm)));
             recBin[i0 + (size_t)u * kBinThreads] = (uint16_t)b;
             if (b == onesBin) { atomicAdd(&sOnes[warp][misc & 127u], 1u); continue; }
             const uint32_t cell = (((b * (uint32_t)W + (misc & 31u)) * 2u + ((misc >> 6) & 1u)) * 2u) + ((misc >> 5) & 1u);  // bin-major table, :605
@@ -554,33 +559,32 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
 }
 
 cudaError_t launch_tall_apply(const uint32_t* gather, int world, uint32_t cap, unsigned long long* freqLow, uint32_t* freqTail, uint32_t* maxHeight,
-                              uint32_t* overflow, cudaStream_t s, int* launches) {
-    k_tall_apply<<<148, 256, 0, s>>>(gather, world, cap, freqLow, freqTail, maxHeight, overflow);
+                              uint32_t* overflow, uint32_t* maxTail, cudaStream_t s, int* launches) {
+    k_tall_apply<<<148, 256, 0, s>>>(gather, world, cap, freqLow, freqTail, maxHeight, overflow, maxTail);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
-cudaError_t launch_freq_lut(const unsigned long long* freqLow, const uint32_t* freqTail, const uint32_t* maxHeight, float* lut,
-                            unsigned long long* maxCount, cudaStream_t s, int* launches) {
-    k_freq_lut<<<148 * 4, 256, 0, s>>>(freqLow, freqTail, maxHeight, lut, maxCount);
+cudaError_t launch_tail_max(const uint32_t* freqTail, const uint32_t* maxHeight, uint32_t* maxTail, cudaStream_t s, int* launches) {
+    k_tail_max<<<148 * 4, 256, 0, s>>>(freqTail, maxHeight, maxTail);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
-cudaError_t launch_bin_thresholds(const unsigned long long* maxCount, float* thresholds, BinParams* params, cudaStream_t s, int* launches) {
-    k_bin_thresholds<<<(kBins + 31) / 32, 32, 0, s>>>(maxCount, thresholds, params);
+cudaError_t launch_bin_thresholds(PassState* state, float* thresholds, BinParams* params, cudaStream_t s, int* launches) {
+    k_bin_thresholds<<<(kBins + 31) / 32, 32, 0, s>>>(state, thresholds, params);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t launch_bin(const float* recRp, const float* recRm, const uint8_t* recMisc, uint16_t* recBin, const unsigned long long* totals, uint64_t capacity,
-                       uint64_t expected, const float* lut, const float* thresholds, const BinParams* params, int W, uint32_t* grouped, cudaStream_t s, int* launches) {
+                       uint64_t expected, FreqTables freq, const float* thresholds, const BinParams* params, int W, uint32_t* grouped, cudaStream_t s, int* launches) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     uint64_t want = (expected + kBinThreads * 16 - 1) / (kBinThreads * 16);  // >= 16 records per thread: the tables are flushed once per block
     unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)sms * 4);
-    k_bin<<<blocks, kBinThreads, 0, s>>>(recRp, recRm, recMisc, recBin, totals, capacity, lut, thresholds, params, W, grouped);
+    k_bin<<<blocks, kBinThreads, 0, s>>>(recRp, recRm, recMisc, recBin, totals, capacity, freq, thresholds, params, W, grouped);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

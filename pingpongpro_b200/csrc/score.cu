@@ -221,7 +221,7 @@ constexpr int kScoreTile = kScoreThreads * kScoreRounds;
 constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagValue = (1ull << 62) - 1;
 
 __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restrict__ pp, const unsigned long long* __restrict__ totals, uint64_t ppCapacity,
-                                                         ScoreState* __restrict__ st, unsigned long long* __restrict__ tileState, const float* __restrict__ lut,
+                                                         ScoreState* __restrict__ st, unsigned long long* __restrict__ tileState, FreqTables freq,
                                                          const float* __restrict__ thresholds, const BinParams* __restrict__ params, const float* __restrict__ fdrTable,
                                                          const uint16_t* __restrict__ binMap, int W, int ppIdx, float minHeight, const Slot* __restrict__ slots,
                                                          uint32_t nSlots, LocusOut* __restrict__ loci) {
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restri
         while (b < kBins - 1 && sThr[b] <= hs) ++b;
         return b;
     };
-    if (tid < 16) sSmallBin[tid] = (uint16_t)bin_of(__fmul_rn(lut[tid >> 2], lut[tid & 3]));
+    if (tid < 16) sSmallBin[tid] = (uint16_t)bin_of(__fmul_rn(freq_of(freq, tid >> 2), freq_of(freq, tid & 3)));
     unsigned long long n = totals[1];
     if (n > ppCapacity) n = ppCapacity;
     const uint32_t nTiles = (uint32_t)((n + kScoreTile - 1) / kScoreTile);
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restri
         for (int k = 0; k < kScoreRounds; ++k) {
             if (!keep[k]) continue;
             const uint32_t hp = round_height(r[k].rp), hm = round_height(r[k].rm);  // heightScoreMap[0.5 + reads], :582 / :589
-            const uint32_t bin = (hp | hm) < 4u ? sSmallBin[hp * 4 + hm] : (uint32_t)bin_of(__fmul_rn(lut[hp], lut[hm]));
+            const uint32_t bin = (hp | hm) < 4u ? sSmallBin[hp * 4 + hm] : (uint32_t)bin_of(__fmul_rn(freq_of(freq, hp), freq_of(freq, hm)));
             const uint32_t cb = binMap[bin];                                                      // :682
             LocusOut o;
             o.fdr = fdrTable[((size_t)cb * W + ppIdx) * 4 + ((r[k].misc >> 6) & 1u) * 2 + ((r[k].misc >> 5) & 1u)];  // :753
@@ -362,7 +362,7 @@ cudaError_t launch_fdr_table(const float* cells, const uint32_t* nBins, uint32_t
 }
 
 cudaError_t launch_score(const PairRec* pp, const unsigned long long* totals, uint64_t ppCapacity, uint64_t expected, ScoreState* state,
-                         unsigned long long* tileState, const float* lut,
+                         unsigned long long* tileState, FreqTables freq,
                          const float* thresholds, const BinParams* params, const float* fdrTable, const uint16_t* binMap, int W, int ppIdx, uint32_t minHeight,
                          const Slot* slots, uint32_t nSlots, LocusOut* loci, cudaStream_t s, int* launches) {
     int dev = 0, sms = 148;
@@ -371,7 +371,7 @@ cudaError_t launch_score(const PairRec* pp, const unsigned long long* totals, ui
     uint64_t tiles = (expected + kScoreTile - 1) / kScoreTile;
     unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)sms * 6);
     float mh = (float)minHeight;  // `reads >= minStackHeight` compares float with unsigned converted to float (:903)
-    k_score<<<blocks, kScoreThreads, 0, s>>>(pp, totals, ppCapacity, state, tileState, lut, thresholds, params, fdrTable, binMap, W, ppIdx, mh, slots, nSlots, loci);
+    k_score<<<blocks, kScoreThreads, 0, s>>>(pp, totals, ppCapacity, state, tileState, freq, thresholds, params, fdrTable, binMap, W, ppIdx, mh, slots, nSlots, loci);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

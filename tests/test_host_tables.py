@@ -79,3 +79,28 @@ def test_rejects_degenerate_maximum():
     for bad in (1.0, 0.0, -3.0, float("nan")):
         with pytest.raises(api.PppError):
             api.bin_thresholds(bad)
+
+
+def test_device_restatement_of_log10f_equals_the_host_libm():
+    """csrc/log10f_emul.h (evaluated here on the host; the device runs the same IEEE operations) against this host's
+    log10f: every 97th float of [1, 2^48) plus whole binades.  The device's threshold tables are built on it and are
+    compared with the host's table on every pass (api.cu: settle); this test is why that comparison never fails here."""
+    import ctypes
+
+    libm = ctypes.CDLL("libm.so.6")
+    libm.log10f.restype = ctypes.c_float
+    libm.log10f.argtypes = [ctypes.c_float]
+    bits = np.concatenate([np.arange(0x3f800000, 0x3f800000 + (48 << 23), 9973, dtype=np.uint64),
+                           np.arange(0x3f800000, 0x3f800000 + (1 << 16), dtype=np.uint64), np.arange(0x4b000000, 0x4b000000 + (1 << 16), dtype=np.uint64)]).astype(np.uint32)
+    x = bits.view(np.float32)
+    got = api.emulated_log10f(x)
+    want = np.array([libm.log10f(float(v)) for v in x], dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_device_threshold_tables_equal_the_host_tables():
+    rng = np.random.default_rng(11)
+    freqs = [2.0, 3.0, 7.0, 1000.0, 12327.0, 10716714.0, 12540968.0, float(1 << 24)] + [float(v) for v in rng.integers(2, 1 << 24, size=400)]
+    for mf in freqs:
+        a, b = api.bin_thresholds(mf), api.emulated_bin_thresholds(mf)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), mf
