@@ -89,8 +89,29 @@ ParseResult parseCommandLine(AppOptions& o, int argc, char const** argv) {
     };
     bool predictSet = false;
     std::string multiHits = "weighted";
+    // combined short flags (-bv, -bs 2): expanded into single ones; only the last of a group may take a value
+    std::vector<std::string> args;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
+        bool expanded = false;
+        if (a.size() > 2 && a[0] == '-' && a[1] != '-') {
+            bool ok = true;
+            for (size_t k = 1; k < a.size() && ok; ++k) {
+                const Spec* sp = nullptr;
+                for (const Spec& s : specs)
+                    if (s.shortName[0] && s.shortName[0] == a[k] && !s.shortName[1]) sp = &s;
+                ok = sp && (!sp->takesValue || k + 1 == a.size());
+            }
+            if (ok) {
+                for (size_t k = 1; k < a.size(); ++k) args.push_back(std::string("-") + a[k]);
+                expanded = true;
+            }
+        }
+        if (!expanded) args.push_back(a);
+    }
+    const int nArgs = (int)args.size();
+    for (int i = 0; i < nArgs; ++i) {
+        std::string a = args[i];
         if (a == "-h" || a == "--help") { printHelp(std::cout); return PARSE_HELP; }
         if (a == "--version") { std::cout << kApp << " version: 1.0 (B200)\nLast update Apr 2014" << std::endl; return PARSE_VERSION; }
         std::string name, value;
@@ -111,8 +132,8 @@ ParseResult parseCommandLine(AppOptions& o, int argc, char const** argv) {
         if (!spec) { std::cerr << kApp << ": Unknown option: " << a << std::endl; return PARSE_ERROR; }
         std::string ln = spec->longName;
         if (spec->takesValue && !inlineValue) {
-            if (i + 1 >= argc) { std::cerr << kApp << ": option requires an argument -- " << name << std::endl; return PARSE_ERROR; }
-            value = argv[++i];
+            if (i + 1 >= nArgs) { std::cerr << kApp << ": option requires an argument -- " << name << std::endl; return PARSE_ERROR; }
+            value = args[++i];
         }
         unsigned u = 0;
         if (ln == "browserTracks") o.browserTracks = true;

@@ -4,6 +4,8 @@
 // are computed by the CUDA layer through the C ABI of ppp_b200.h.  There is no CPU fallback.
 #include <sys/stat.h>
 #include <sys/wait.h>
+#include <fcntl.h>
+#include <signal.h>
 #include <unistd.h>
 
 #include <cerrno>
@@ -334,8 +336,14 @@ static int run(int argc, char const** argv) {
             std::cerr << "Failed to read record" << std::endl;
             return 1;
         }
+        // A contig that has no @SQ line: the reference (SeqAn) appends such names while reading and works without lengths;
+        // the dense stack arrays need every length before the first record (documented divergence).
+        if (foreignContig) {
+            std::cerr << "'" << path << "': a record names a contig that has no @SQ header line (contig lengths must be known before the first record)" << std::endl;
+            return 1;
+        }
         // @SQ lines of all inputs must be identical (:1494-1517)
-        if (foreignContig || reader.names() != names) {
+        if (reader.names() != names) {
             std::cerr << "@SQ header lines of '" << path << "' differ from those of previous input files" << std::endl;  // :1514
             return 1;
         }
@@ -461,10 +469,17 @@ static int run(int argc, char const** argv) {
 // process exits -- after every output byte is on disk.  The work therefore runs in a child process, which hands its
 // exit status to this tiny parent the moment it is done; the parent returns to the caller at once and the driver's
 // teardown of the child proceeds in the background.  (The fork happens before anything touches CUDA.)
-// PPP_NO_FORK=1 runs everything in one process.
+// That is OPT-IN (PPP_DETACH_TEARDOWN=1): the child still holds its device memory for a moment after the caller was told
+// the run has finished, and a signal aimed at the parent does not reach it (signals are forwarded below, the race with
+// a GPU job started right afterwards remains).  By default everything runs in one process.
+static volatile pid_t g_child = 0;
+static void forwardSignal(int sig) {
+    if (g_child > 0) kill(g_child, sig);
+}
+
 int main(int argc, char const** argv) {
     int fds[2];
-    if (getenv("PPP_NO_FORK") || pipe(fds) != 0) {
+    if (!getenv("PPP_DETACH_TEARDOWN") || getenv("PPP_NO_FORK") || pipe2(fds, O_CLOEXEC) != 0) {
         int rc = run(argc, argv);
         fflush(nullptr);
         _exit(rc);  // every output stream has been closed; skip the CUDA runtime's atexit teardown
@@ -493,6 +508,9 @@ int main(int argc, char const** argv) {
         _exit(rc);
     }
     close(fds[1]);
+    g_child = pid;
+    signal(SIGTERM, forwardSignal);
+    signal(SIGINT, forwardSignal);
     unsigned char status = 1;
     ssize_t n;
     do n = read(fds[0], &status, 1); while (n < 0 && errno == EINTR);

@@ -35,10 +35,15 @@ static inline bool extract_read(const AlnView& v, const ExtractOptions& o, ppp_r
     if (alnLen < o.minLen || alnLen > o.maxLen) return false;        // :426
     uint32_t nh = 1;                                                 // :442-444 (tags are not read in unique mode, :432)
     if (o.mode != PPP_MULTIHITS_UNIQUE && v.hasNH) nh = v.nh;
+    // NH:i:0 would weigh +inf in -m weighted (:449; the reference then converts inf to unsigned at :508, undefined behaviour):
+    // such a record is malformed and is skipped.  NH beyond 2^30 - 1 does not fit the packed record: host and device use the
+    // same clamped value (a weight below 1e-9 either way).  Both are documented divergences.
+    if (o.mode == PPP_MULTIHITS_WEIGHTED && nh == 0) return false;
+    if (nh > PPP_READ_NH_MAX) nh = PPP_READ_NH_MAX;
     weight = read_weight(o.mode, nh);
     if (weight <= 0) return false;                                   // :458
     if (v.rID < 0) return false;  // no contig: the reference would index its name store out of bounds (documented divergence)
-    uint32_t meta = (nh > PPP_READ_NH_MAX ? PPP_READ_NH_MAX : nh) << PPP_READ_NH_SHIFT;
+    uint32_t meta = nh << PPP_READ_NH_SHIFT;
     if (v.flag & 0x10u) {                                            // :461
         out.key = (uint32_t)((uint64_t)(uint32_t)v.beginPos + alnLen);  // :464
         uint64_t clip = 0;                                           // :467-469

@@ -151,6 +151,20 @@ def test_error_paths_and_exit_codes(cli, tmp_path):
     assert r.returncode == 1 and r.stderr.startswith("Failed to open output directory: ")
 
 
+def test_combined_short_flags(cli, tmp_path):
+    """-bv is -b -v (SeqAn's ArgumentParser accepts grouped flags); the last flag of a group may take a value."""
+    src = os.path.join(GOLDEN, "files", "files_tiny_weighted", "input.sam")
+    a, b, c = tmp_path / "a", tmp_path / "b", tmp_path / "c"
+    assert run(cli, ["-b", "-v", "-s", "2", "-i", src, "-o", str(a)]).returncode == 0
+    assert run(cli, ["-bv", "-s", "2", "-i", src, "-o", str(b)]).returncode == 0
+    assert run(cli, ["-vbs", "2", "-i", src, "-o", str(c)]).returncode == 0
+    names = sorted(os.listdir(a))
+    assert len(names) == 4 and names == sorted(os.listdir(b)) == sorted(os.listdir(c))
+    for n in names:
+        assert (a / n).read_bytes() == (b / n).read_bytes() == (c / n).read_bytes()
+    assert run(cli, ["-sb", "2", "-i", src, "-o", str(tmp_path / "d")]).returncode == 1  # a value flag inside a group
+
+
 def test_output_goes_to_cwd_by_default(cli, tmp_path):
     r = run(cli, ["-i", os.path.join(FILES, "input.bam")], cwd=str(tmp_path))
     assert r.returncode == 0 and os.path.exists(tmp_path / "ping-pong_signatures.tsv")

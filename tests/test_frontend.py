@@ -85,6 +85,19 @@ def test_handwritten_records(tmp_path):
     assert dec.total_weight == pytest.approx(1 + np.float32(1 / 3) + 1 + 1 + 1 + 0.5 + 1, abs=0)
 
 
+def test_nh_zero_is_skipped_in_weighted_mode(tmp_path):
+    """NH:i:0 weighs +inf in -m weighted (:449) and the reference then converts inf to unsigned (:508, undefined
+    behaviour): the record is skipped (documented divergence).  The other modes never divide by NH."""
+    seq = "ACGTACGTAAGTACGTACGTACGTACGTAC"
+    lines = ["@SQ\tSN:c\tLN:100000", f"a\t0\tc\t101\t255\t30M\t*\t0\t0\t{seq}\t*\tNH:i:0", f"b\t0\tc\t101\t255\t30M\t*\t0\t0\t{seq}\t*\tNH:i:2"]
+    p = tmp_path / "nh0.sam"
+    p.write_text("\n".join(lines) + "\n")
+    w = host.decode_file(str(p), mode="weighted")
+    assert w.n_kept == 1 and w.total_weight == 0.5 and int(w.reads[0]["meta"][0] >> 2) == 2
+    assert host.decode_file(str(p), mode="unique").n_kept == 2
+    assert host.decode_file(str(p), mode="discard").n_kept == 0
+
+
 def test_synth_lib_equals_file_route(tmp_path):
     """The packed records libppp_synth generates directly equal what the front end extracts from the
     SAM/BAM that ppp_synth writes for the same model."""
