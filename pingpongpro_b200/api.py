@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
     L.ppp_pinned_free.argtypes = [vp]
     L.ppp_reads_submit.argtypes = [vp, C.c_int32, vp, C.c_size_t, C.c_uint64]
     L.ppp_reads_submit_device.argtypes = [vp, C.c_int32, vp, C.c_size_t]
+    L.ppp_reads_submit_packed.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_size_t]
     L.ppp_stacks_finish.argtypes = [vp]
     L.ppp_reads_foreign.argtypes = [vp, u64p]
     L.ppp_stacks_download.argtypes = [vp, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, vp, vp]
@@ -107,7 +108,7 @@ def lib() -> C.CDLL:
     L.ppp_emul_log10f.argtypes = [vp, C.c_size_t, vp]
     L.ppp_pass_info.argtypes = [vp, C.POINTER(C.c_uint32), u64p, u64p, u64p]
     for name in ("ppp_device_count", "ppp_warmup", "ppp_init", "ppp_reset", "ppp_set_allreduce", "ppp_set_rank", "ppp_nccl_unique_id", "ppp_nccl_attach", "ppp_pinned_alloc", "ppp_pinned_free", "ppp_reads_submit",
-                 "ppp_reads_submit_device", "ppp_stacks_finish", "ppp_reads_foreign", "ppp_stacks_download", "ppp_height_hist", "ppp_scan", "ppp_score",
+                 "ppp_reads_submit_device", "ppp_reads_submit_packed", "ppp_stacks_finish", "ppp_reads_foreign", "ppp_stacks_download", "ppp_height_hist", "ppp_scan", "ppp_score",
                  "ppp_pairs_download", "ppp_transposons", "ppp_timings_get", "ppp_timings_reset", "ppp_layout", "ppp_host_bin_thresholds", "ppp_emul_bin_thresholds",
                  "ppp_emul_log10f", "ppp_pass_info"):
         getattr(L, name).restype = C.c_int
@@ -170,6 +171,55 @@ class PinnedBuffer:
             pass
 
 
+class PackedReads:
+    """The reads of one contig in the 5-byte upload form of ppp_reads_submit_packed, in page-locked host memory: u32 keys,
+    u8 meta (strand, A10, 6-bit index into the NH table of the piece) -- cut into pieces of at most 64 distinct NH values."""
+
+    def __init__(self, reads: np.ndarray):
+        self.n = len(reads)
+        self._keys = self._meta = None
+        self.pieces = []  # (first, count, nh_table[64])
+        if not self.n:
+            return
+        self._keys = _pinned(4 * self.n)
+        self._meta = _pinned(self.n)
+        keys = np.frombuffer((C.c_char * (4 * self.n)).from_address(self._keys.value), dtype=np.uint32)
+        meta = np.frombuffer((C.c_char * self.n).from_address(self._meta.value), dtype=np.uint8)
+        keys[:] = reads["key"]
+        nh = reads["meta"] >> np.uint32(2)
+        first = 0
+        while first < self.n:  # pieces of at most 64 distinct NH values (nearly always one piece)
+            last = self.n
+            table = np.unique(nh[first:last])
+            while len(table) > 64:
+                last = first + max(1, (last - first) // 2)
+                table = np.unique(nh[first:last])
+            code = np.searchsorted(table, nh[first:last]).astype(np.uint8)
+            meta[first:last] = (reads["meta"][first:last] & np.uint32(3)).astype(np.uint8) | (code << np.uint8(2))
+            t = np.ones(64, np.uint32)
+            t[: len(table)] = table
+            self.pieces.append((first, last - first, t))
+            first = last
+
+    def free(self):
+        for p in (self._keys, self._meta):
+            if p:
+                lib().ppp_pinned_free(p)
+        self._keys = self._meta = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _pinned(nbytes: int) -> C.c_void_p:
+    p = C.c_void_p()
+    _check(lib().ppp_pinned_alloc(max(8, nbytes), C.byref(p)))
+    return p
+
+
 class ScoreResult:
     def __init__(self, n_bins, bin_map, cells, fdr_table, loci):
         self.n_bins = n_bins
@@ -224,6 +274,12 @@ class Context:
             reads = np.ascontiguousarray(reads, dtype=READ_DTYPE)
             ptr, n = C.c_void_p(reads.ctypes.data), len(reads)
         _check(lib().ppp_reads_submit(self._h, contig, ptr, n, first_record_index))
+
+    def count_reads_packed(self, contig: int, packed: "PackedReads"):
+        """The same from the 5-byte upload form (ppp_reads_submit_packed)."""
+        for first, count, table in packed.pieces:
+            _check(lib().ppp_reads_submit_packed(self._h, contig, C.c_void_p(packed._keys.value + 4 * first), C.c_void_p(packed._meta.value + first),
+                                                 table.ctypes.data_as(C.c_void_p), count))
 
     def count_reads_raw(self, contig: int, host_ptr: int, n: int):
         _check(lib().ppp_reads_submit(self._h, contig, C.c_void_p(host_ptr), n, 0))

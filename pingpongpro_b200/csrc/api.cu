@@ -96,6 +96,8 @@ struct ppp_ctx {
     // upload ring: kStages device buffers (a long fold must not hold up the copies and sorts behind it), two pinned
     // bounce buffers for callers whose memory is pageable
     ppp_read* dStage[kStages] = {};
+    uint8_t* dPacked[kStages] = {};          // ppp_reads_submit_packed: keys (4 B x kChunk), meta (1 B x kChunk), NH table
+    uint32_t* hNhTable = nullptr;            // (pinned) one NH table per stage
     ppp_read* hStage[2] = {nullptr, nullptr};
     cudaEvent_t evCopied[kStages] = {}, evConsumed[kStages] = {};
     bool slotUsed[kStages] = {};
@@ -592,11 +594,11 @@ void ppp_destroy(ppp_ctx* c) {
     for (void* p : dev)
         if (p) cudaFree(p);
     for (int k = 0; k < kStages; ++k) {
-        void* stage[] = {c->dStage[k], c->sort[k].keysA, c->sort[k].keysB, c->sort[k].valsA, c->sort[k].valsB, c->sort[k].blockHist, c->sort[k].scanScratch};
+        void* stage[] = {c->dStage[k], c->dPacked[k], c->sort[k].keysA, c->sort[k].keysB, c->sort[k].valsA, c->sort[k].valsB, c->sort[k].blockHist, c->sort[k].scanScratch};
         for (void* p : stage)
             if (p) cudaFree(p);
     }
-    void* pinned[] = {c->hStage[0], c->hStage[1], c->hThresholds, c->hDevThresholds, c->hBinParams, c->hs, c->hLoci};
+    void* pinned[] = {c->hStage[0], c->hStage[1], c->hNhTable, c->hThresholds, c->hDevThresholds, c->hBinParams, c->hs, c->hLoci};
     for (void* p : pinned)
         if (p) cudaFreeHost(p);
     for (int k = 0; k < kStages; ++k) {
@@ -743,6 +745,42 @@ int ppp_reads_submit(ppp_ctx* c, int32_t contig, const ppp_read* reads, size_t n
         }
         if (c->slotUsed[s]) CK(cudaStreamWaitEvent(c->copyStream, c->evConsumed[s], 0));  // kernels done with dStage[s]
         CK(cudaMemcpyAsync(c->dStage[s], src, k * sizeof(ppp_read), cudaMemcpyHostToDevice, c->copyStream));
+        CK(cudaEventRecord(c->evCopied[s], c->copyStream));
+        int rc = buildChunk(c, slot, c->dStage[s], k, c->evCopied[s], c->evConsumed[s]);
+        if (rc) return rc;
+        c->slotUsed[s] = true;
+        c->submitCount++;
+    }
+    c->readsSubmitted += n;
+    return PPP_OK;
+}
+
+int ppp_reads_submit_packed(ppp_ctx* c, int32_t contig, const uint32_t* keys, const uint8_t* meta, const uint32_t* nhTable, size_t n) {
+    if (!c) return fail(PPP_ERR_ARG, "null context");
+    if (contig < 0 || (size_t)contig >= c->slotOfContig.size()) return fail(PPP_ERR_ARG, "contig %d out of range", contig);
+    if (n && (!keys || !meta || !nhTable)) return fail(PPP_ERR_ARG, "null reads");
+    CK(cudaSetDevice(c->device));
+    invalidateResults(c);
+    c->finished = false;
+    const Slot& slot = c->slotOfContig[contig];
+    if (!c->hNhTable) CK(cudaMallocHost(&c->hNhTable, (size_t)kStages * PPP_PACKED_NH_CODES * sizeof(uint32_t)));
+    for (size_t o = 0; o < n; o += kChunk) {
+        size_t k = std::min(kChunk, n - o);
+        const int s = (int)(c->submitCount % kStages), prev = (int)((c->submitCount + kStages - 1) % kStages);
+        if (c->slotUsed[prev]) CK(cudaEventSynchronize(c->evCopied[prev]));  // the double-buffer contract of ppp_reads_submit
+        if (c->slotUsed[s]) CK(cudaEventSynchronize(c->evCopied[s]));        // this stage's NH table slot is free again
+        if (!c->dStage[s]) CK(cudaMalloc(&c->dStage[s], kChunk * sizeof(ppp_read)));
+        if (!c->dPacked[s]) CK(cudaMalloc(&c->dPacked[s], kChunk * 5 + PPP_PACKED_NH_CODES * sizeof(uint32_t)));
+        uint32_t* dKeys = reinterpret_cast<uint32_t*>(c->dPacked[s]);
+        uint32_t* dTable = reinterpret_cast<uint32_t*>(c->dPacked[s] + kChunk * 4);
+        uint8_t* dMeta = c->dPacked[s] + kChunk * 4 + PPP_PACKED_NH_CODES * sizeof(uint32_t);
+        uint32_t* hTable = c->hNhTable + (size_t)s * PPP_PACKED_NH_CODES;
+        memcpy(hTable, nhTable, PPP_PACKED_NH_CODES * sizeof(uint32_t));
+        if (c->slotUsed[s]) CK(cudaStreamWaitEvent(c->copyStream, c->evConsumed[s], 0));  // kernels done with dStage[s]
+        CK(cudaMemcpyAsync(dKeys, keys + o, k * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copyStream));
+        CK(cudaMemcpyAsync(dMeta, meta + o, k, cudaMemcpyHostToDevice, c->copyStream));
+        CK(cudaMemcpyAsync(dTable, hTable, PPP_PACKED_NH_CODES * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copyStream));
+        CK(launch_unpack_reads(dKeys, dMeta, dTable, k, c->dStage[s], c->copyStream, &c->launches));
         CK(cudaEventRecord(c->evCopied[s], c->copyStream));
         int rc = buildChunk(c, slot, c->dStage[s], k, c->evCopied[s], c->evConsumed[s]);
         if (rc) return rc;

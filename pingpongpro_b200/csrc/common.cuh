@@ -143,6 +143,7 @@ size_t exclusive_scan_scratch_words(size_t n);
 
 cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H, uint64_t G, uint32_t* occ, Slot slot, int mode,
                                    unsigned long long* counters, cudaStream_t s, int* launches);
+cudaError_t launch_unpack_reads(const uint32_t* keys, const uint8_t* meta, const uint32_t* nhTable, size_t n, ppp_read* out, cudaStream_t s, int* launches);
 struct SortScratch {
     uint32_t *keysA, *keysB, *valsA, *valsB, *blockHist, *scanScratch;
     size_t capacity, blockHistWords, scanScratchWords;

@@ -442,6 +442,21 @@ __global__ void __launch_bounds__(kBuildThreads) k_small_batch(const ppp_read* _
     }
 }
 
+// 5-byte upload form -> ppp_read records (ppp_reads_submit_packed): meta bits 2..7 index the call's NH table
+__global__ void __launch_bounds__(kBuildThreads) k_unpack_reads(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ meta, const uint32_t* __restrict__ nhTable,
+                                                                 size_t n, ppp_read* __restrict__ out) {
+    __shared__ uint32_t sNh[PPP_PACKED_NH_CODES];
+    if (threadIdx.x < PPP_PACKED_NH_CODES) sNh[threadIdx.x] = nhTable[threadIdx.x];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t m = meta[i];
+        uint2 r;
+        r.x = keys[i];
+        r.y = (sNh[m >> 2] << PPP_READ_NH_SHIFT) | (m & 3u);
+        reinterpret_cast<uint2*>(out)[i] = r;
+    }
+}
+
 inline unsigned grid_for(size_t n, int threads, unsigned cap) {
     size_t b = (n + threads - 1) / threads;
     if (b < 1) b = 1;
@@ -454,6 +469,13 @@ cudaError_t launch_stack_build_int(const ppp_read* reads, size_t n, uint32_t* H,
                                    unsigned long long* counters, cudaStream_t s, int* launches) {
     if (n == 0) return cudaSuccess;
     k_stack_build_int<<<grid_for(n, kBuildThreads, 148 * 16), kBuildThreads, 0, s>>>(reads, n, H, G, occ, slot, mode, counters);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_reads(const uint32_t* keys, const uint8_t* meta, const uint32_t* nhTable, size_t n, ppp_read* out, cudaStream_t s, int* launches) {
+    if (n == 0) return cudaSuccess;
+    k_unpack_reads<<<grid_for(n, kBuildThreads * 4, 148 * 8), kBuildThreads, 0, s>>>(keys, meta, nhTable, n, out);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

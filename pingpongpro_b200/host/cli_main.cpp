@@ -65,7 +65,9 @@ int gpuError(const char* what) {
 struct Uploader {
     static const size_t kBatch = (size_t)1 << 20;
     ppp_ctx* ctx = nullptr;
-    ppp_read* pinned[2] = {nullptr, nullptr};
+    // two pinned buffers in the 5-byte upload form of ppp_reads_submit_packed: u32 keys + u8 meta (strand, A10, NH code)
+    uint32_t* pinnedKeys[2] = {nullptr, nullptr};
+    uint8_t* pinnedMeta[2] = {nullptr, nullptr};
     int which = 0;
     std::vector<std::vector<ppp_read> > pending;  // per contig
     uint64_t submitted = 0;
@@ -74,18 +76,46 @@ struct Uploader {
     // Called once the context exists (it is created on a helper thread while decoding has already started).
     bool attach(ppp_ctx* c) {
         ctx = c;
-        for (int k = 0; k < 2; ++k)
-            if (ppp_pinned_alloc(kBatch * sizeof(ppp_read), (void**)&pinned[k]) != PPP_OK) return false;
+        for (int k = 0; k < 2; ++k) {
+            if (ppp_pinned_alloc(kBatch * sizeof(uint32_t), (void**)&pinnedKeys[k]) != PPP_OK) return false;
+            if (ppp_pinned_alloc(kBatch, (void**)&pinnedMeta[k]) != PPP_OK) return false;
+        }
         return true;
     }
     bool flush(size_t contig) {
         std::vector<ppp_read>& v = pending[contig];
-        for (size_t o = 0; o < v.size(); o += kBatch) {
-            size_t k = std::min(kBatch, v.size() - o);
-            memcpy(pinned[which], v.data() + o, k * sizeof(ppp_read));
-            if (ppp_reads_submit(ctx, (int32_t)contig, pinned[which], k, submitted) != PPP_OK) return false;
-            submitted += k;
+        for (size_t o = 0; o < v.size();) {
+            // pack up to kBatch reads; the multi-hit counts travel as 6-bit codes into a table of the (at most 64) distinct
+            // values of the piece -- a 65th value closes the piece early
+            uint32_t table[PPP_PACKED_NH_CODES];
+            int nCodes = 0;
+            int8_t codeOfSmall[256];
+            memset(codeOfSmall, -1, sizeof codeOfSmall);
+            uint32_t* keys = pinnedKeys[which];
+            uint8_t* meta = pinnedMeta[which];
+            const size_t end = std::min(v.size(), o + kBatch);
+            size_t j = o;
+            for (; j < end; ++j) {
+                const uint32_t nh = v[j].meta >> PPP_READ_NH_SHIFT;
+                int code = nh < 256 ? codeOfSmall[nh] : -1;
+                if (code < 0) {
+                    for (int t = 0; t < nCodes && code < 0; ++t)
+                        if (table[t] == nh) code = t;
+                    if (code < 0) {
+                        if (nCodes == PPP_PACKED_NH_CODES) break;
+                        code = nCodes;
+                        table[nCodes++] = nh;
+                    }
+                    if (nh < 256) codeOfSmall[nh] = (int8_t)code;
+                }
+                keys[j - o] = v[j].key;
+                meta[j - o] = (uint8_t)((v[j].meta & 3u) | ((uint32_t)code << 2));
+            }
+            for (int t = nCodes; t < PPP_PACKED_NH_CODES; ++t) table[t] = 1;
+            if (ppp_reads_submit_packed(ctx, (int32_t)contig, keys, meta, table, j - o) != PPP_OK) return false;
+            submitted += j - o;
             which ^= 1;  // the other buffer may be refilled as soon as this submit has returned
+            o = j;
         }
         v.clear();
         return true;
@@ -112,8 +142,10 @@ struct Uploader {
         return true;
     }
     ~Uploader() {
-        for (int k = 0; k < 2; ++k)
-            if (pinned[k]) ppp_pinned_free(pinned[k]);
+        for (int k = 0; k < 2; ++k) {
+            if (pinnedKeys[k]) ppp_pinned_free(pinnedKeys[k]);
+            if (pinnedMeta[k]) ppp_pinned_free(pinnedMeta[k]);
+        }
     }
 };
 

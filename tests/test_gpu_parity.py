@@ -218,6 +218,37 @@ def test_pinned_double_buffer_and_batching_equal_single_submit():
     assert np.array_equal(bits(got), bits(ref[3]))
 
 
+def test_packed_five_byte_upload_equals_eight_byte_records():
+    """ppp_reads_submit_packed (u32 key + u8 meta with a 6-bit code into the call's NH table) builds the same stacks as
+    ppp_reads_submit, also when a contig has more than 64 distinct NH values and is sent in several pieces."""
+    m = host.SynthModel("tiny", n_reads=200_000, seed=10)
+    reads = m.generate(mode="weighted")
+    rng = np.random.default_rng(2)
+    r0 = reads[0].copy()
+    nh = rng.integers(1, 300, size=len(r0)).astype(np.uint32)            # ~300 distinct multiplicities in one contig
+    r0["meta"] = (r0["meta"] & np.uint32(3)) | (nh << np.uint32(2))
+    reads[0] = r0
+    for mode in ("weighted", "unique", "discard"):
+        ref = gpu_stacks(m.lengths, reads, mode)
+        rows = []
+        with api.Context(m.lengths, mode=mode) as ctx:
+            for c, r in enumerate(reads):
+                p = api.PackedReads(r)
+                assert (len(p.pieces) > 1) == (c == 0)
+                ctx.count_reads_packed(c, p)
+                p_keep = p  # (pinned memory stays alive until finish)
+                rows.append(p_keep)
+            ctx.finish()
+            got = []
+            for strand in (0, 1):
+                for c, L in enumerate(m.lengths):
+                    h, a = ctx.stacks(c, strand, 0, L + 64)
+                    nz = np.flatnonzero(h)
+                    got.append((h[nz], a[nz]))
+        assert np.array_equal(bits(np.concatenate([g[0] for g in got])), bits(ref[3]))
+        assert np.array_equal(np.concatenate([g[1] for g in got]).astype(np.uint32), ref[4])
+
+
 def test_weighted_depends_on_order_unique_does_not():
     m = host.SynthModel("tiny", n_reads=100_000, seed=11)
     reads = m.generate(mode="weighted")
