@@ -49,7 +49,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr uint32_t kKeySlack = 64;          // keys up to contig length + 63 are accepted (a - key may equal the length, :464)
 constexpr size_t kChunk = (size_t)1 << 23;  // records per upload / sort chunk (64 MB)
 constexpr int kFoldStreams = 4;
-constexpr uint32_t kTallCap = 1u << 14;      // tall stacks (rounded height >= kScanLowBins) per rank in the compact exchange
+constexpr uint32_t kTallCap = 1u << 12;      // tall stacks (rounded height >= kScanLowBins) per rank in the compact exchange
 constexpr int kStages = 4;                  // depth of the upload -> sort -> fold pipeline (buffers are allocated on first use)
 constexpr int kTile = kScanTile;
 

@@ -32,9 +32,9 @@ namespace pppk {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;                  // small blocks, many per SM: a tile is a chain of latencies (ticket, bitmap load, look-back), hidden by other tiles
 constexpr int kWarps = kThreads / 32;
-constexpr int kWords = 4;                      // consecutive 32-position occupancy words owned by one thread, per strand
+constexpr int kWords = 8;                      // consecutive 32-position occupancy words owned by one thread, per strand
 constexpr int kTile = kScanTile;               // positions per tile
 constexpr int kTileWords = kTile / 32;         // occupancy words per tile and strand
 static_assert(kTile == kThreads * kWords * 32, "tile geometry");
@@ -107,12 +107,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // per-thread counts of a tile in one 64-bit word, so that ONE warp scan carries all four:
-//   bits 0..17 records, 18..30 ping-pong records, 31..43 plus stacks, 44..56 minus stacks  (warp totals: <= 2^17, 2^12, 2^12, 2^12)
-constexpr int kPkPp = 18, kPkPlus = 31, kPkMinus = 44;
-__device__ __forceinline__ uint32_t pk_rec(unsigned long long v) { return (uint32_t)v & 0x3ffffu; }
-__device__ __forceinline__ uint32_t pk_pp(unsigned long long v) { return (uint32_t)(v >> kPkPp) & 0x1fffu; }
-__device__ __forceinline__ uint32_t pk_plus(unsigned long long v) { return (uint32_t)(v >> kPkPlus) & 0x1fffu; }
-__device__ __forceinline__ uint32_t pk_minus(unsigned long long v) { return (uint32_t)(v >> kPkMinus) & 0x1fffu; }
+//   bits 0..18 records, 19..32 ping-pong records, 33..46 plus stacks, 47..60 minus stacks
+// (a warp owns 32 * kWords * 32 positions: totals <= 2^18 records, 2^13 of the others)
+constexpr int kPkPp = 19, kPkPlus = 33, kPkMinus = 47;
+static_assert(32 * kWords * 32 * PPP_MAX_OVERLAPS < (1 << kPkPp) && 32 * kWords * 32 < (1 << (kPkPlus - kPkPp)), "packed warp-scan fields");
+__device__ __forceinline__ uint32_t pk_rec(unsigned long long v) { return (uint32_t)v & 0x7ffffu; }
+__device__ __forceinline__ uint32_t pk_pp(unsigned long long v) { return (uint32_t)(v >> kPkPp) & 0x3fffu; }
+__device__ __forceinline__ uint32_t pk_plus(unsigned long long v) { return (uint32_t)(v >> kPkPlus) & 0x3fffu; }
+__device__ __forceinline__ uint32_t pk_minus(unsigned long long v) { return (uint32_t)(v >> kPkMinus) & 0x3fffu; }
 
 // the minus-strand occupancy bits at distance sh.. of a position whose word and the following one are (w0, w1), sh < 64
 __device__ __forceinline__ uint32_t window_bits(uint32_t w0, uint32_t w1, uint32_t sh, uint32_t wMask) {
@@ -120,7 +122,7 @@ __device__ __forceinline__ uint32_t window_bits(uint32_t w0, uint32_t w1, uint32
 }
 
 template <int REPR>
-__global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
+__global__ void __launch_bounds__(kThreads, 10) k_scan(ScanParams P) {
     __shared__ uint32_t sMask[kTileWords + 2];     // minus-strand occupancy words of the tile + the word after the tile + a zero
     __shared__ uint32_t sPlus[kTileWords];         // plus strand
     __shared__ uint32_t sOff[4];                   // compact index of the tile's first / past-the-last plus stack, first / past-the-last minus stack
@@ -192,10 +194,11 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
 
         // ---- counting phase (bitmaps only): how many records the tile holds, published at once, so that the blocks
         // holding later tiles never wait for this block's record phase
-        uint32_t cntW[kWords], ppW[kWords], popP[kWords], popM[kWords];
+        // (per-word counts wait in the shared-memory arrays that will hold their prefixes: no register arrays)
+        uint32_t sumRec = 0, sumPp = 0, sumPlus = 0, sumMinus = 0;
         {
             uint32_t mw = sMask[myWord];
-#pragma unroll
+#pragma unroll 2
             for (int k = 0; k < kWords; ++k) {
                 const uint32_t pw = sPlus[myWord + k], w0 = mw, w1 = sMask[myWord + k + 1];
                 mw = w1;
@@ -205,19 +208,19 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                     cnt += __popc(bits);
                     npp += (bits >> P.ppIdx) & 1u;
                 }
-                cntW[k] = cnt;
-                ppW[k] = npp;
-                popP[k] = (uint32_t)__popc(pw);
-                popM[k] = (uint32_t)__popc(w0);
+                sRecOff[myWord + k] = cnt;
+                sPpOff[myWord + k] = (uint16_t)npp;
+                sumRec += cnt;
+                sumPp += npp;
+                sumPlus += (uint32_t)__popc(pw);
+                sumMinus += (uint32_t)__popc(w0);
             }
         }
         // one scan over the warp for all four counts; records are ordered (word, position, overlap) == (position, overlap)
         unsigned long long ex;
         {
-            uint32_t a = 0, b = 0, c = 0, d = 0;
-#pragma unroll
-            for (int k = 0; k < kWords; ++k) { a += cntW[k]; b += ppW[k]; c += popP[k]; d += popM[k]; }
-            const unsigned long long pack = (unsigned long long)a | ((unsigned long long)b << kPkPp) | ((unsigned long long)c << kPkPlus) | ((unsigned long long)d << kPkMinus);
+            const unsigned long long pack = (unsigned long long)sumRec | ((unsigned long long)sumPp << kPkPp) | ((unsigned long long)sumPlus << kPkPlus) |
+                                            ((unsigned long long)sumMinus << kPkMinus);
             const unsigned long long inc = warp_inclusive64(pack, lane);
             if (lane == 31) sWarp[warp] = inc;
             ex = inc - pack;
@@ -233,16 +236,17 @@ __global__ void __launch_bounds__(kThreads, 5) k_scan(ScanParams P) {
                 totPp += pk_pp(t);
                 totMinus += pk_minus(t);
             }
-#pragma unroll
+#pragma unroll 2
             for (int k = 0; k < kWords; ++k) {
+                const uint32_t cnt = sRecOff[myWord + k], npp = sPpOff[myWord + k];
                 sRecOff[myWord + k] = rec;
                 sPpOff[myWord + k] = (uint16_t)pp;
                 sPrefP[myWord + k] = (uint16_t)plus;
                 sPrefM[myWord + k] = (uint16_t)minus;
-                rec += cntW[k];
-                pp += ppW[k];
-                plus += popP[k];
-                minus += popM[k];
+                rec += cnt;
+                pp += npp;
+                plus += (uint32_t)__popc(sPlus[myWord + k]);
+                minus += (uint32_t)__popc(sMask[myWord + k]);
             }
             if (tid == 0) {  // the tile's aggregate, published before any of its records is written
                 const unsigned long long agg = (unsigned long long)totRec | ((unsigned long long)totPp << kLbRecBits);
@@ -546,7 +550,7 @@ cudaError_t launch_scan(const ScanParams& p, int repr, cudaStream_t s, int* laun
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int perSm = 5;
+    int perSm = 10;
     if (repr == kReprInt) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprInt>, kThreads, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_scan<kReprFloat>, kThreads, 0);
     if (perSm < 1) perSm = 1;
