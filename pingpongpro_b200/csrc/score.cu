@@ -51,7 +51,14 @@ __global__ void __launch_bounds__(256) k_collapse_map(const uint32_t* __restrict
                                                       uint16_t* __restrict__ groupStart, uint32_t* __restrict__ nBins) {
     __shared__ uint32_t sOcc[kBins * kMaxCellWords];  // (one round of parallel loads instead of one L2 latency per 32 bins)
     const int cellsPerBin = W * 4, tid = threadIdx.x;
-    for (int k = tid; k < kBins * kMaxCellWords; k += 256) sOcc[k] = binOcc[k];
+    {
+        constexpr int kRounds = (kBins * kMaxCellWords + 255) / 256;
+        uint32_t v[kRounds];
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) { const int k = r * 256 + tid; v[r] = k < kBins * kMaxCellWords ? binOcc[k] : 0u; }  // all loads in flight together
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) { const int k = r * 256 + tid; if (k < kBins * kMaxCellWords) sOcc[k] = v[r]; }
+    }
     __syncthreads();
     if (tid >= 32) return;
     const int lane = tid;
@@ -133,9 +140,12 @@ __global__ void __launch_bounds__(256) k_collapse_cells(const uint32_t* __restri
     const int g = k / cellsPerBin, c = k - g * cellsPerBin;
     const int first = groupStart[g], last = groupStart[g + 1];
     unsigned long long total = 0;
-    for (int b = first + lane; b < last; b += 32) {
-        const uint32_t v = grouped[(size_t)b * cellsPerBin + c];
-        total += v < kSaturate ? v : kSaturate;
+    for (int b0 = first + lane; b0 < last; b0 += 32 * 8) {  // eight loads in flight per lane
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int b = b0 + 32 * u; v[u] = b < last ? grouped[(size_t)b * cellsPerBin + c] : 0u; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) total += v[u] < kSaturate ? v[u] : kSaturate;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
@@ -162,7 +172,21 @@ __global__ void __launch_bounds__(kFdrWarps * 32) k_fdr_table(const float* __res
                                                                const double* __restrict__ xs, const double* __restrict__ ws, int nSteps, float* __restrict__ fdr) {
     __shared__ double sTerm[kFdrWarps][kFdrMaxSteps];
     __shared__ double sX[kFdrMaxSteps], sWt[kFdrMaxSteps];  // the integration grid and its Gaussian weights (host libm), once per block
-    for (int i = threadIdx.x; i < nSteps; i += kFdrWarps * 32) { sX[i] = xs[i]; sWt[i] = ws[i]; }
+    {
+        constexpr int kRounds = (kFdrMaxSteps + kFdrWarps * 32 - 1) / (kFdrWarps * 32);
+        double vx[kRounds], vw[kRounds];
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {  // all loads in flight together
+            const int i = r * kFdrWarps * 32 + threadIdx.x;
+            vx[r] = i < nSteps ? xs[i] : 0.0;
+            vw[r] = i < nSteps ? ws[i] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int i = r * kFdrWarps * 32 + threadIdx.x;
+            if (i < nSteps) { sX[i] = vx[r]; sWt[i] = vw[r]; }
+        }
+    }
     __syncthreads();
     const uint32_t C = *nBins;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -231,7 +255,13 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const PairRec* __restri
     __shared__ uint32_t sTile;
     __shared__ unsigned long long sBase;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < kBins - 1; k += kScoreThreads) sThr[k] = thresholds[k];
+    {
+        float v[(kBins + kScoreThreads - 1) / kScoreThreads];
+#pragma unroll
+        for (int r = 0; r < (kBins + kScoreThreads - 1) / kScoreThreads; ++r) { const int k = r * kScoreThreads + tid; v[r] = k < kBins - 1 ? thresholds[k] : 0.0f; }
+#pragma unroll
+        for (int r = 0; r < (kBins + kScoreThreads - 1) / kScoreThreads; ++r) { const int k = r * kScoreThreads + tid; if (k < kBins - 1) sThr[k] = v[r]; }
+    }
     const float binScale = params->binScale;
     __syncthreads();
     auto bin_of = [&](float hs) {
