@@ -6,7 +6,7 @@ out=gpurun_out
 mkdir -p $out
 nvidia-smi --query-gpu=index,name --format=csv,noheader > $out/gpus_n$n.txt
 timeout 900 python -m pytest tests/test_zz_nccl_ranks.py -m gpu -x -q -s > $out/nccl_ranks_n$n.log 2>&1; echo "nccl test rc=$?"; grep -E "identical|passed|failed|skipped" $out/nccl_ranks_n$n.log | tail -8
-PPP_TRACE=1 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus $n "$@" > $out/bench_n$n.json 2> $out/bench_n$n.err; echo "bench rc=$?"
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus $n "$@" > $out/bench_n$n.json 2> $out/bench_n$n.err; echo "bench rc=$?"
 python - <<PY
 import json
 d = json.load(open("$out/bench_n$n.json"))
