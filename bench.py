@@ -454,7 +454,7 @@ def main():
                 "kernel_ms": ms, "kernel_ms_mean_over_ranks": r["scan_ms_mean"], "survey_dense_accounting_gbs": dense,
                 "survey_dense_accounting": "SURVEY §8(d) counts 8 B per position + 16 B per record for this work; the kernel streams a compact store instead, "
                                            "so that figure exceeds the HBM peak on sparse genomes and is NOT a fraction of anything",
-                "device_ms_per_step": {k: r["tm"][k] for k in ("scan_ms", "lut_ms", "bin_ms", "score_ms")}}
+                "device_ms_per_step": {k: r["tm"][k] for k in ("scan_ms", "lut_ms", "bin_ms", "score_ms", "exchange_ms", "pass_ms")}}
 
     def block(r, genome, reads_n, label):
         per = "in total" if r["strong"] else "per GPU"

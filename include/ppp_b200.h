@@ -104,6 +104,8 @@ typedef struct ppp_timings {
     float score_ms;         /* collapse + FDR table + per-locus FDR + compaction (ppp_score) */
     float transposon_ms;    /* ppp_transposons */
     uint32_t launches;      /* kernels launched by the library since the last ppp_timings_reset */
+    float exchange_ms;      /* sharded runs: the two table exchanges of the last pass, waiting for the slowest rank included */
+    float pass_ms;          /* first to last device operation of the last pass (ppp_height_hist .. ppp_score) */
     uint32_t reserved;
 } ppp_timings;
 

@@ -43,7 +43,7 @@ class Config(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("stack_build_ms", C.c_float), ("scan_ms", C.c_float), ("lut_ms", C.c_float), ("bin_ms", C.c_float), ("score_ms", C.c_float),
-                ("transposon_ms", C.c_float), ("launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("transposon_ms", C.c_float), ("launches", C.c_uint32), ("exchange_ms", C.c_float), ("pass_ms", C.c_float), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -49,7 +49,8 @@ int fail(int code, const char* fmt, ...) {
 constexpr uint32_t kKeySlack = 64;          // keys up to contig length + 63 are accepted (a - key may equal the length, :464)
 constexpr size_t kChunk = (size_t)1 << 23;  // records per upload / sort chunk (64 MB)
 constexpr int kFoldStreams = 4;
-constexpr uint32_t kTallCap = 1u << 12;      // tall stacks (rounded height >= kScanLowBins) per rank in the compact exchange
+constexpr uint32_t kTallCap = 1u << 12;      // tall stacks (rounded height >= kScanLowBins) per rank in the compact exchange: first size ...
+constexpr uint32_t kTallCapMax = 1u << 20;   // ... and the largest it grows to when a pass finds more
 constexpr int kStages = 4;                  // depth of the upload -> sort -> fold pipeline (buffers are allocated on first use)
 constexpr int kTile = kScanTile;
 
@@ -176,10 +177,11 @@ struct ppp_ctx {
     int rank = 0, world = 0;   // known (ppp_set_rank / ppp_nccl_attach): tall stacks are exchanged as compact lists
     uint32_t* dGather = nullptr;  // [world][kTallHeader + tallCap], see launch_tall_apply
     uint32_t tallCap = 0;
+    bool tallCapFixed = false;  // PPP_TALL_CAP: the list does not grow, an overflow goes to the dense tables
     float thresholdFreq = 0.f;  // the maximum frequency hThresholds was built for (0: none)
     bool denseTail = false;    // a list overflowed once: this context reduces the dense tables from then on
 
-    Timer tScan, tLut, tBin, tScore, tTransposon;
+    Timer tScan, tLut, tBin, tScore, tTransposon, tEx1, tEx2, tPass;
     int launches = 0;
 };
 
@@ -652,7 +654,8 @@ int ppp_set_rank(ppp_ctx* c, int rank, int world) {
     c->rank = rank;
     c->world = world;
     c->tallCap = kTallCap;
-    if (const char* e = getenv("PPP_TALL_CAP")) c->tallCap = (uint32_t)std::max(1L, atol(e));  // test knob: forces the dense fall-back
+    if (const char* e = getenv("PPP_TALL_CAP")) { c->tallCap = (uint32_t)std::max(1L, atol(e)); c->tallCapFixed = true; }  // test knob: forces the dense fall-back
+    if (const char* e = getenv("PPP_TALL_CAP_START")) c->tallCap = (uint32_t)std::max(1L, atol(e));  // test knob: a list that has to grow
     c->tallCap = (c->tallCap + 1u) & ~1u;  // slots stay 8-byte aligned (64-bit low bins inside)
     return PPP_OK;
 }
@@ -875,6 +878,8 @@ namespace {
 int enqueueScanStage(ppp_ctx* c) {
     int rc;
     Trace tr("scan stage");
+    if ((rc = timerStart(c, c->tPass))) return rc;
+    c->tPass.used = false;
     CK(cudaMemsetAsync(c->dState, 0, c->passZeroBytes, c->stream));  // pass scalars, look-back states, grouped counts
     if (c->prevMaxHeight >= kScanLowBins)
         CK(cudaMemsetAsync(c->dFreqTail + kScanLowBins, 0, ((size_t)c->prevMaxHeight - kScanLowBins + 1) * sizeof(uint32_t), c->stream));
@@ -923,6 +928,7 @@ int enqueueScanStage(ppp_ctx* c) {
     if ((rc = timerStart(c, c->tScan))) return rc;
     CK(launch_scan(p, c->repr, c->stream, &c->launches));
     if ((rc = timerStop(c, c->tScan))) return rc;
+    if (c->allreduce && (rc = timerStart(c, c->tEx1))) return rc;
     if (gatherTall) {
         // one all-reduce carries every rank's low bins, tall stacks and maximum height; no host round trip in between
         if ((rc = hookReduce(c, c->dGather, (size_t)c->world * slotWords, 0, 0))) return rc;
@@ -940,6 +946,7 @@ int enqueueScanStage(ppp_ctx* c) {
             CK(launch_tail_max(c->dFreqTail, &c->dState->maxHeight, &c->dState->maxTail, c->stream, &c->launches));
         }
     }
+    if (c->allreduce && (rc = timerStop(c, c->tEx1))) return rc;
     // the largest height frequency and, from it, the bin thresholds (one small kernel; no frequency table is materialised:
     // the binning kernels read the counts themselves)
     if ((rc = timerStart(c, c->tLut))) return rc;
@@ -992,7 +999,9 @@ int enqueueBinStage(ppp_ctx* c) {
         CK(launch_overflow_flag(c->dState->totals, c->pairCapacity, c->ppCapacity, c->dGrouped + tableWords, c->stream, &c->launches));
     }
     if ((rc = timerStop(c, c->tBin))) return rc;
+    if (c->allreduce && (rc = timerStart(c, c->tEx2))) return rc;
     if ((rc = hookReduce(c, c->dGrouped, tableWords + 1, 0, 0))) return rc;
+    if (c->allreduce && (rc = timerStop(c, c->tEx2))) return rc;
     if (c->allreduce) CK(cudaMemcpyAsync(&c->hs->rerun, c->dGrouped + tableWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     c->stageBin = true;
     c->stageScore = false;
@@ -1012,6 +1021,7 @@ int enqueueScoreStage(ppp_ctx* c, uint32_t minStackHeight) {
     if ((rc = timerStop(c, c->tScore))) return rc;
     if (minStackHeight > 0) CK(cudaMemcpyAsync(&c->hs->nLoci, c->dScoreState, sizeof(ScoreState), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&c->hs->nBins, c->dNBins, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (c->tPass.a && (rc = timerStop(c, c->tPass))) return rc;
     c->scoreMinHeight = minStackHeight;
     c->stageScore = true;
     c->settled = false;
@@ -1030,8 +1040,19 @@ int settle(ppp_ctx* c) {
         tr.mark("stream");
         c->prevMaxHeight = std::max(c->prevMaxHeight, c->hs->maxHeight);
         bool again = false;
-        if (c->hs->tallOverflow) {  // (the same on every rank: read from the reduced buffer) -> dense height tables, once and for all
-            c->denseTail = true;
+        if (c->hs->tallOverflow) {
+            // some rank's list of tall stacks did not fit (hs->tallOverflow = the longest list; the same on every rank: read from
+            // the reduced buffer): longer lists, unless dense height tables up to the tallest stack are the smaller exchange
+            const uint64_t need = (uint64_t)c->hs->tallOverflow + c->hs->tallOverflow / 4 + 64;
+            const uint64_t dense = (uint64_t)c->hs->maxHeight + 1;
+            if (c->tallCapFixed || need > kTallCapMax || need * (uint64_t)c->world > dense) {
+                c->denseTail = true;
+            } else {
+                c->tallCap = (uint32_t)((need + 63) & ~(uint64_t)63);
+                if (getenv("PPP_TRACE")) fprintf(stderr, "[ppp_trace settle] tall-stack lists grow to %u entries per rank\n", c->tallCap);
+                if (c->dGather) cudaFree(c->dGather);
+                c->dGather = nullptr;
+            }
             again = true;
         }
         c->localOverflow = c->hs->totals[0] > c->pairCapacity || c->hs->totals[1] > c->ppCapacity;
@@ -1325,6 +1346,8 @@ int ppp_timings_get(ppp_ctx* c, ppp_timings* out) {
     out->score_ms = timerMs(c->tScore);
     out->transposon_ms = timerMs(c->tTransposon);
     out->launches = (uint32_t)c->launches;
+    out->exchange_ms = timerMs(c->tEx1) + timerMs(c->tEx2);
+    out->pass_ms = timerMs(c->tPass);
     return PPP_OK;
 }
 
@@ -1335,7 +1358,7 @@ int ppp_timings_reset(ppp_ctx* c) {
     foldBuildTimers(c);
     c->buildMs = 0.f;
     c->launches = 0;
-    for (Timer* t : {&c->tScan, &c->tLut, &c->tBin, &c->tScore, &c->tTransposon}) t->used = false;
+    for (Timer* t : {&c->tScan, &c->tLut, &c->tBin, &c->tScore, &c->tTransposon, &c->tEx1, &c->tEx2, &c->tPass}) t->used = false;
     return PPP_OK;
 }
 

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) k_tall_apply(const uint32_t* __restrict__
         const uint32_t* slot = gather + (size_t)r * slotWords;
         uint32_t n = slot[0];
         best = max(best, slot[1]);
-        if (n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1u; n = cap; }
+        if (n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(overflow, n); n = cap; }  // (the longest list: the host sizes the next attempt from it)
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
             atomicMax(maxTail, atomicAdd(&freqTail[slot[kTallHeader + i]], 1u) + 1u);
     }

@@ -34,7 +34,7 @@ def test_host_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header_sizes():
     assert api.LOCUS_DTYPE.itemsize == 20 and api.PAIR_DTYPE.itemsize == 40 and api.INTERVAL_DTYPE.itemsize == 16
-    assert api.TP_RESULT_DTYPE.itemsize == 160 and ctypes.sizeof(api.Timings) == 32 and ctypes.sizeof(api.Config) == 56
+    assert api.TP_RESULT_DTYPE.itemsize == 160 and ctypes.sizeof(api.Timings) == 40 and ctypes.sizeof(api.Config) == 56
 
 
 def test_no_cpu_fallback_without_device():

@@ -373,18 +373,21 @@ def _sharded(lengths, reads, mode, n_shards, min_stack_height=0, known_rank=Fals
     return out
 
 
-@pytest.mark.parametrize("mode,n_shards,exchange", [("weighted", 2, "tables"), ("unique", 3, "lists"), ("weighted", 8, "lists"), ("weighted", 4, "overflow")])
+@pytest.mark.parametrize("mode,n_shards,exchange", [("weighted", 2, "tables"), ("unique", 3, "lists"), ("weighted", 8, "lists"), ("weighted", 4, "overflow"),
+                                                    ("weighted", 3, "grow")])
 def test_range_sharding_equals_single_context(mode, n_shards, exchange, monkeypatch):
     """SURVEY §8(e): shards with a max-overlap halo + all-reduced histograms reproduce the single-GPU result;
     loci concatenated in rank order are globally sorted.  `exchange`: how the tall stacks' heights travel -- reduced
     height tables (rank unknown to the context), one compact list per rank (ppp_set_rank), or lists that overflow
-    and fall back to the tables."""
+    and fall back to the tables, or lists that overflow and are made longer (the pass repeats on every rank)."""
     m = host.SynthModel("tiny", n_reads=150_000, seed=12)
     reads = m.generate(mode=mode)
     single = run_gpu(m.lengths, reads, mode)
     assert single["max_height"] >= 512  # the exchange under test is that of the heights beyond the shared-memory bins
     if exchange == "overflow":
         monkeypatch.setenv("PPP_TALL_CAP", "3")
+    if exchange == "grow":
+        monkeypatch.setenv("PPP_TALL_CAP_START", "2")
     parts = _sharded(m.lengths, reads, mode, n_shards, known_rank=exchange != "tables")
     loci = np.concatenate([p[0].loci for p in parts])
     sigs = np.concatenate([p[1] for p in parts])
