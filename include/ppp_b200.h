@@ -237,6 +237,10 @@ PPP_API int ppp_host_bin_thresholds(float max_freq, float* thresholds /* 999 */)
  * for n floats >= 1. */
 PPP_API int ppp_emul_bin_thresholds(float max_freq, float* thresholds /* 999 */);
 PPP_API int ppp_emul_log10f(const float* x, size_t n, float* out);
+/* Test hook, host only: h0 + w[0] + w[1] + ... in single precision, left to right (pingpongpro.cpp:487), evaluated the
+ * way the device folds very long stacks: `piece` additions at a time as one composed integer map per binade
+ * (csrc/fadd_chain.h), real additions only where the sum changes binade.  *real_additions counts the latter. */
+PPP_API int ppp_emul_fadd_chain(float h0, const float* w, size_t n, uint32_t piece, float* out, uint64_t* real_additions);
 
 /* What the last pass found, once it is known to the host (waits for the pass): the tallest stack (rounded height), the
  * signatures and overlap-`pingpong` signatures of this context, the stacks in its compact store.  Each optional. */

@@ -106,11 +106,12 @@ def lib() -> C.CDLL:
     L.ppp_host_bin_thresholds.argtypes = [C.c_float, vp]
     L.ppp_emul_bin_thresholds.argtypes = [C.c_float, vp]
     L.ppp_emul_log10f.argtypes = [vp, C.c_size_t, vp]
+    L.ppp_emul_fadd_chain.argtypes = [C.c_float, vp, C.c_size_t, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     L.ppp_pass_info.argtypes = [vp, C.POINTER(C.c_uint32), u64p, u64p, u64p]
     for name in ("ppp_device_count", "ppp_warmup", "ppp_init", "ppp_reset", "ppp_set_allreduce", "ppp_set_rank", "ppp_nccl_unique_id", "ppp_nccl_attach", "ppp_pinned_alloc", "ppp_pinned_free", "ppp_reads_submit",
                  "ppp_reads_submit_device", "ppp_reads_submit_packed", "ppp_stacks_finish", "ppp_reads_foreign", "ppp_stacks_download", "ppp_height_hist", "ppp_scan", "ppp_score",
                  "ppp_pairs_download", "ppp_transposons", "ppp_timings_get", "ppp_timings_reset", "ppp_layout", "ppp_host_bin_thresholds", "ppp_emul_bin_thresholds",
-                 "ppp_emul_log10f", "ppp_pass_info"):
+                 "ppp_emul_log10f", "ppp_emul_fadd_chain", "ppp_pass_info"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -140,6 +141,15 @@ def emulated_log10f(x) -> np.ndarray:
     out = np.empty_like(x)
     _check(lib().ppp_emul_log10f(x.ctypes.data_as(C.c_void_p), len(x), out.ctypes.data_as(C.c_void_p)))
     return out
+
+
+def emulated_fadd_chain(h0: float, weights, piece: int):
+    """h0 + w0 + w1 + ... in float32, left to right, through the composed per-binade maps of csrc/fadd_chain.h (host).
+    Returns (sum, number of additions that were executed for real)."""
+    w = np.ascontiguousarray(weights, dtype=np.float32)
+    out, real = C.c_float(0), C.c_uint64(0)
+    _check(lib().ppp_emul_fadd_chain(C.c_float(h0), w.ctypes.data_as(C.c_void_p), len(w), piece, C.byref(out), C.byref(real)))
+    return np.float32(out.value), int(real.value)
 
 
 def device_count() -> int:

@@ -20,6 +20,7 @@
 #include "host_tables.h"
 #include "local_group.h"
 #include "log10f_emul.h"
+#include "fadd_chain.h"
 #include "nccl_loader.h"
 #include "ppp_b200.h"
 #include "transposons.cuh"
@@ -57,7 +58,15 @@ constexpr int kTile = kScanTile;
 struct Timer {
     cudaEvent_t a = nullptr, b = nullptr;
     bool used = false;
+    const char* what = nullptr;  // label in the PPP_K1_TIMELINE listing
 };
+
+// PPP_K1_TIMELINE=1: start and end of every copy, sort and fold of the stack builder on the device, relative to the first
+// one, printed by ppp_stacks_finish (how well the three streams overlap)
+bool k1Timeline() {
+    static const bool on = getenv("PPP_K1_TIMELINE") != nullptr;
+    return on;
+}
 
 struct PinnedScalars {
     // mirror of the tail of PassState (one copy): totals[2], maxCount, maxHeight, ticket, overflow, pad
@@ -356,6 +365,7 @@ int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n, c
     if ((rc = timerStart(c, t, c->sortStream))) return rc;
     CK(launch_stack_sort(dReads, n, c->G, slot, c->dCounters, c->sort[set], c->sortStream, &c->launches, &run));
     if ((rc = timerStop(c, t, c->sortStream))) return rc;
+    t.what = "sort";
     c->buildTimers.push_back(t);
     if (consumed) CK(cudaEventRecord(consumed, c->sortStream));
     CK(cudaEventRecord(c->evSorted[set], c->sortStream));
@@ -364,6 +374,7 @@ int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n, c
     if ((rc = timerStart(c, tf, fs))) return rc;
     CK(launch_stack_fold(run, c->H, c->G, c->occ, c->sort[set].capacity, fs, &c->launches));
     if ((rc = timerStop(c, tf, fs))) return rc;
+    tf.what = "fold";
     c->buildTimers.push_back(tf);
     CK(cudaEventRecord(c->evFolded[set], fs));
     c->sortUsed[set] = true;
@@ -372,8 +383,17 @@ int buildChunk(ppp_ctx* c, const Slot& slot, const ppp_read* dReads, size_t n, c
 }
 
 int foldBuildTimers(ppp_ctx* c) {
+    if (k1Timeline() && !c->buildTimers.empty()) {
+        cudaEvent_t t0 = c->buildTimers[0].a;
+        for (Timer& t : c->buildTimers) {
+            float a = 0.f, b = 0.f;
+            if (!t.used || cudaEventElapsedTime(&a, t0, t.a) != cudaSuccess || cudaEventElapsedTime(&b, t0, t.b) != cudaSuccess) continue;
+            fprintf(stderr, "[ppp_k1] %-6s %9.3f .. %9.3f ms  (%.3f)\n", t.what ? t.what : "?", a, b, b - a);
+        }
+        cudaGetLastError();
+    }
     for (Timer& t : c->buildTimers) {
-        c->buildMs += timerMs(t);
+        if (!(t.what && t.what[0] == 'c')) c->buildMs += timerMs(t);  // (the timeline's copy spans are not kernels)
         cudaEventDestroy(t.a);
         cudaEventDestroy(t.b);
     }
@@ -628,8 +648,13 @@ int ppp_reset(ppp_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->copyStream));
     for (int k = 0; k < kFoldStreams; ++k) CK(cudaStreamSynchronize(c->foldStream[k]));  // folds still in flight write H
-    CK(cudaMemsetAsync(c->H, 0, (2 * c->G + 64) * sizeof(uint32_t), c->stream));
-    CK(cudaMemsetAsync(c->occ, 0, c->occWords * sizeof(uint32_t), c->stream));
+    if (c->finished && ((uint64_t)c->nStacksP + c->nStacksM) * 8 < c->G) {
+        // a sparse store (the usual case: a few per cent of the positions hold a stack): only the occupied sectors
+        CK(launch_sparse_clear(c->H, c->occ, (size_t)(2 * c->G / 32), c->stream, &c->launches));
+    } else {
+        CK(cudaMemsetAsync(c->H, 0, (2 * c->G + 64) * sizeof(uint32_t), c->stream));
+        CK(cudaMemsetAsync(c->occ, 0, c->occWords * sizeof(uint32_t), c->stream));
+    }
     CK(cudaMemsetAsync(c->dCounters, 0, 2 * sizeof(unsigned long long), c->stream));
     CK(cudaEventRecord(c->evReset, c->stream));  // the sort stream's kernels count into dCounters
     CK(cudaStreamWaitEvent(c->sortStream, c->evReset, 0));
@@ -780,10 +805,13 @@ int ppp_reads_submit_packed(ppp_ctx* c, int32_t contig, const uint32_t* keys, co
         uint32_t* hTable = c->hNhTable + (size_t)s * PPP_PACKED_NH_CODES;
         memcpy(hTable, nhTable, PPP_PACKED_NH_CODES * sizeof(uint32_t));
         if (c->slotUsed[s]) CK(cudaStreamWaitEvent(c->copyStream, c->evConsumed[s], 0));  // kernels done with dStage[s]
+        Timer tc;
+        if (k1Timeline()) { int trc = timerStart(c, tc, c->copyStream); if (trc) return trc; }
         CK(cudaMemcpyAsync(dKeys, keys + o, k * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copyStream));
         CK(cudaMemcpyAsync(dMeta, meta + o, k, cudaMemcpyHostToDevice, c->copyStream));
         CK(cudaMemcpyAsync(dTable, hTable, PPP_PACKED_NH_CODES * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copyStream));
         CK(launch_unpack_reads(dKeys, dMeta, dTable, k, c->dStage[s], c->copyStream, &c->launches));
+        if (k1Timeline()) { int trc = timerStop(c, tc, c->copyStream); if (trc) return trc; tc.what = "copy"; c->buildTimers.push_back(tc); }
         CK(cudaEventRecord(c->evCopied[s], c->copyStream));
         int rc = buildChunk(c, slot, c->dStage[s], k, c->evCopied[s], c->evConsumed[s]);
         if (rc) return rc;
@@ -824,6 +852,7 @@ int ppp_stacks_finish(ppp_ctx* c) {
     }
     CK(launch_compact_write(c->H, c->occ, c->G, c->nTiles, c->dTileOffP, c->dTileOffM, c->dCmp, c->dCmp + c->nStacksP, c->stream, &c->launches));
     if ((rc = timerStop(c, t))) return rc;
+    t.what = "finish";
     c->buildTimers.push_back(t);
     CK(cudaStreamSynchronize(c->stream));
     foldBuildTimers(c);
@@ -1323,6 +1352,31 @@ int ppp_emul_bin_thresholds(float max_freq, float* thresholds) {
 int ppp_emul_log10f(const float* x, size_t n, float* out) {
     if (n && (!x || !out)) return fail(PPP_ERR_ARG, "null argument");
     for (size_t i = 0; i < n; ++i) out[i] = emul_log10f(x[i]);
+    return PPP_OK;
+}
+
+int ppp_emul_fadd_chain(float h0, const float* w, size_t n, uint32_t piece, float* out, uint64_t* realAdditions) {
+    if ((n && !w) || !out || piece == 0) return fail(PPP_ERR_ARG, "bad argument");
+    uint32_t bits;
+    memcpy(&bits, &h0, 4);
+    uint64_t real = 0;
+    for (size_t b = 0; b < n; b += piece) {
+        const size_t e = std::min(n, b + (size_t)piece);
+        AddMap m = {0u, 0u};
+        for (size_t i = b; i < e; ++i) {
+            uint32_t wb;
+            memcpy(&wb, &w[i], 4);
+            m = addmap_compose(m, addmap_of(bits >> 23, wb));
+        }
+        if (!addmap_crosses(bits, m)) { bits = addmap_apply(bits, m); continue; }
+        float h;
+        memcpy(&h, &bits, 4);
+        for (size_t i = b; i < e; ++i) { volatile float t = h + w[i]; h = t; }
+        memcpy(&bits, &h, 4);
+        real += e - b;
+    }
+    memcpy(out, &bits, 4);
+    if (realAdditions) *realAdditions = real;
     return PPP_OK;
 }
 

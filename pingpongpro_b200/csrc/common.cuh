@@ -165,6 +165,8 @@ cudaError_t launch_stack_fold(const SortedRun& r, uint32_t* H, uint64_t G, uint3
 
 // stacks_finish: dense accumulation arrays -> compact stack store (compact.cu)
 cudaError_t launch_tile_popc(const uint32_t* occ, uint64_t G, uint32_t nTiles, uint32_t* cntP, uint32_t* cntM, cudaStream_t s, int* launches);
+// zeroes the words of H whose occupancy bits are set, and the bitmaps (occWords: 32-bit words of both strands' bitmaps)
+cudaError_t launch_sparse_clear(uint32_t* H, uint32_t* occ, size_t occWords, cudaStream_t s, int* launches);
 cudaError_t launch_compact_write(const uint32_t* H, const uint32_t* occ, uint64_t G, uint32_t nTiles, const uint32_t* offP, const uint32_t* offM,
                                  uint32_t* cmpP, uint32_t* cmpM, cudaStream_t s, int* launches);
 

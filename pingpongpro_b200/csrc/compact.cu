@@ -96,7 +96,30 @@ __global__ void __launch_bounds__(kThreads) k_compact_write(const uint32_t* __re
     }
 }
 
+// ppp_reset of a sparse store: a word of H is non-zero only where its occupancy bit is set, so the bitmaps say which
+// 32-byte sectors (8 positions = one bitmap byte) have to be zeroed -- instead of a memset over both dense arrays.
+__global__ void __launch_bounds__(kThreads) k_sparse_clear(uint32_t* __restrict__ H, uint32_t* __restrict__ occ, size_t occWords) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t w = (size_t)blockIdx.x * kThreads + threadIdx.x; w < occWords; w += stride) {
+        const uint32_t m = occ[w];
+        if (m == 0u) continue;
+        occ[w] = 0u;
+        uint4* dst = reinterpret_cast<uint4*>(H + w * 32);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if ((m >> (8 * b)) & 0xffu) { dst[2 * b] = z; dst[2 * b + 1] = z; }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_sparse_clear(uint32_t* H, uint32_t* occ, size_t occWords, cudaStream_t s, int* launches) {
+    if (occWords == 0) return cudaSuccess;
+    k_sparse_clear<<<148 * 16, kThreads, 0, s>>>(H, occ, occWords);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_tile_popc(const uint32_t* occ, uint64_t G, uint32_t nTiles, uint32_t* cntP, uint32_t* cntM, cudaStream_t s, int* launches) {
     unsigned blocks = (nTiles + 7) / 8;

@@ -24,6 +24,7 @@
 // Bound: L2 atomic throughput / 32-byte sector read-modify-write traffic, not streaming bandwidth.
 // Algorithmic bytes: 8 N (records) + 8 N (word read+write) + 8 G (zero fill at init/reset).
 #include "common.cuh"
+#include "fadd_chain.h"
 
 namespace pppk {
 
@@ -109,59 +110,90 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t* __r
 }
 
 // offsets = exclusive scan of blockHist ([digit][block] flattened): the first output slot of (digit, block).
-__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+// The tile is first put in digit order in shared memory (stable: warp, round, lane = input order), then written out, so
+// that consecutive threads store to consecutive addresses wherever the tile holds several keys of one digit -- a direct
+// scatter costs one 32-byte sector write per 4-byte key and is bound by exactly that.
+__global__ void __launch_bounds__(kSortThreads, 3) k_radix_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                                                                  uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, size_t n, int shift,
                                                                  const uint32_t* __restrict__ offsets, uint32_t nBlocks) {
     __shared__ uint32_t cnt[kSortWarps][256];
+    __shared__ uint32_t sKey[kSortTile], sVal[kSortTile];
+    __shared__ uint32_t sBase[256];      // destination of the tile's first key of a digit, minus that key's place in the tile
+    __shared__ uint32_t sWarpSum[kSortWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = threadIdx.x; k < kSortWarps * 256; k += kSortThreads) (&cnt[0][0])[k] = 0;
     __syncthreads();
-    size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)warp * kSortPerWarp;
+    const size_t tileBase = (size_t)blockIdx.x * kSortTile;
+    const size_t wbase = tileBase + (size_t)warp * kSortPerWarp;
     uint32_t key[kSortRounds], val[kSortRounds];
-    // phase 1: per-warp digit counts (each warp owns a contiguous run of the tile, so order = warp, round, lane)
+    uint32_t rank[kSortRounds / 2];  // place among the warp's earlier keys of the same digit, two per register
+    // phase 1: per-warp digit counts and ranks (each warp owns a contiguous run of the tile, so order = warp, round, lane)
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
         size_t i = wbase + r * 32 + lane;
         bool ok = i < n;
         key[r] = ok ? keysIn[i] : 0xffffffffu;
         val[r] = ok ? valsIn[i] : 0;
-        unsigned act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            uint32_t d = (key[r] >> shift) & 255u;
-            unsigned peers = __match_any_sync(act, d);
-            if (lane == __ffs(peers) - 1) cnt[warp][d] += __popc(peers);
-        }
-        __syncwarp();
     }
-    __syncthreads();
-    // phase 2: first destination of (warp, digit)
-    {
-        uint32_t d = threadIdx.x;
-        uint32_t run = offsets[(size_t)d * nBlocks + blockIdx.x];
-#pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t c = cnt[w][d];
-            cnt[w][d] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-    // phase 3: stable placement
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
-        size_t i = wbase + r * 32 + lane;
-        bool ok = i < n;
-        unsigned act = __ballot_sync(0xffffffffu, ok);
+        const bool ok = wbase + r * 32 + lane < n;
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        uint32_t rk = 0;
         if (ok) {
-            uint32_t d = (key[r] >> shift) & 255u;
-            unsigned peers = __match_any_sync(act, d);
-            uint32_t dst = cnt[warp][d] + __popc(peers & ((1u << lane) - 1u));
-            keysOut[dst] = key[r];
-            valsOut[dst] = val[r];
+            const uint32_t d = (key[r] >> shift) & 255u;
+            const unsigned peers = __match_any_sync(act, d);
+            rk = cnt[warp][d] + __popc(peers & ((1u << lane) - 1u));
             __syncwarp(act);
             if (lane == __ffs(peers) - 1) cnt[warp][d] += __popc(peers);
         }
         __syncwarp();
+        if (r & 1) rank[r / 2] |= rk << 16; else rank[r / 2] = rk;
+    }
+    __syncthreads();
+    // phase 2: place of (warp, digit) inside the digit-ordered tile, and where the tile's keys of a digit go
+    {
+        const uint32_t d = threadIdx.x;
+        uint32_t c[kSortWarps], total = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) { c[w] = cnt[w][d]; total += c[w]; }
+        uint32_t inc = total;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, k);
+            if (lane >= k) inc += t;
+        }
+        if (lane == 31) sWarpSum[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w)
+            if (w < warp) before += sWarpSum[w];
+        uint32_t run = before + inc - total;  // keys of smaller digits in this tile
+        sBase[d] = offsets[(size_t)d * nBlocks + blockIdx.x] - run;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) { cnt[w][d] = run; run += c[w]; }
+    }
+    __syncthreads();
+    // phase 3: the tile in digit order
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        if (wbase + r * 32 + lane < n) {
+            const uint32_t d = (key[r] >> shift) & 255u;
+            const uint32_t j = cnt[warp][d] + ((r & 1) ? rank[r / 2] >> 16 : rank[r / 2] & 0xffffu);
+            sKey[j] = key[r];
+            sVal[j] = val[r];
+        }
+    }
+    __syncthreads();
+    // phase 4: out, in tile order
+    const uint32_t count = (uint32_t)(n - tileBase < (size_t)kSortTile ? n - tileBase : (size_t)kSortTile);
+#pragma unroll 4
+    for (uint32_t j = threadIdx.x; j < count; j += kSortThreads) {
+        const uint32_t k = sKey[j];
+        const uint32_t dst = sBase[(k >> shift) & 255u] + j;
+        keysOut[dst] = k;
+        valsOut[dst] = sVal[j];
     }
 }
 
@@ -175,6 +207,10 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t* 
 constexpr int kShortRun = 32;
 constexpr int kFoldBlock = 256;  // records per pipeline stage of k_fold_long
 constexpr int kWeightLut = 64;
+constexpr int kHugeRun = 4096;        // runs at least this long leave the serial chain of k_fold_long for k_fold_huge
+constexpr int kHugeThreads = 512;
+constexpr int kHugePerLane = 32;      // consecutive records per lane and trip of k_fold_huge
+constexpr int kHugeTrip = kHugeThreads * kHugePerLane;
 
 __device__ __forceinline__ float read_weight_weighted(uint32_t meta) {
     // readWeight = 1.0 / multiHits in double, narrowed to float (:449).  For multiHits < 2^24 the correctly rounded
@@ -262,7 +298,7 @@ __device__ __forceinline__ void pair_barrier(unsigned pair) { asm volatile("bar.
 __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t n,
                                                               uint32_t* __restrict__ H, uint64_t G, uint32_t* __restrict__ occ,
                                                               const unsigned long long* __restrict__ longRuns, const unsigned int* __restrict__ nLong,
-                                                              unsigned int longCap) {
+                                                              unsigned int longCap, unsigned long long* __restrict__ hugeRuns, unsigned int* __restrict__ nHuge) {
     constexpr int kPairs = kBuildThreads / 64;
     constexpr int kDepth = kFoldBlock / 32;
     __shared__ __align__(16) float stage[kPairs][2][2][kFoldBlock];  // [pair][buffer][strand][record]
@@ -283,7 +319,18 @@ __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __r
         const uint32_t pos = keys[i];
         if (producer) {
             const size_t end = warp_run_end(keys, i, n, pos, lane);
-            if (lane == 0) sEnd[pair] = end;
+            const bool huge = end - i >= (size_t)kHugeRun;  // a chain this long is folded by a whole block (k_fold_huge)
+            if (lane == 0) sEnd[pair] = huge ? ~0ull : end;
+            if (huge) {
+                if (lane == 0) {
+                    const unsigned int slot = atomicAdd(nHuge, 1u);
+                    hugeRuns[2 * (size_t)slot] = (unsigned long long)i;
+                    hugeRuns[2 * (size_t)slot + 1] = (unsigned long long)end;
+                }
+                pair_barrier(pair);  // the consumer reads the mark ...
+                pair_barrier(pair);  // ... before the next run overwrites it
+                continue;
+            }
             const size_t nBlocks = (end - i + kFoldBlock - 1) / kFoldBlock;
             uint32_t vq[kDepth];
             auto fetch = [&](size_t blk) {
@@ -348,6 +395,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __r
             float hp = __uint_as_float(wp & kValueMask), hm = __uint_as_float(wm & kValueMask);
             pair_barrier(pair);
             const size_t end = (size_t)sEnd[pair];
+            if (end == ~(size_t)0) { pair_barrier(pair); continue; }  // handed over to k_fold_huge
             const size_t nBlocks = (end - i + kFoldBlock - 1) / kFoldBlock;
             for (size_t blk = 0; blk < nBlocks; ++blk) {
                 const float4* qp = reinterpret_cast<const float4*>(stage[pair][blk & 1][0]);
@@ -387,6 +435,157 @@ __global__ void __launch_bounds__(kBuildThreads) k_fold_long(const uint32_t* __r
                 }
             }
             pair_barrier(pair);
+        }
+    }
+}
+
+// One BLOCK per run of at least kHugeRun records.  The additions of :487 stay in file order, but they are not executed one
+// after the other: inside the binade of the current height every addition is an integer map on the bit pattern of the
+// height (fadd_chain.h), and maps compose.  Per trip of kHugeTrip records every lane composes the maps of its 32
+// consecutive records (looked up per NH code in a table built for the current binade), a warp scan and a short serial
+// walk over the warp totals give the height after the trip.  When the height would leave its binade in a trip, the lane
+// in which that happens adds its 32 records for real and the next trip starts behind them, in the new binade (a height
+// changes binade some 40 times in its life).  Both strands' chains of the position are carried side by side.
+__global__ void __launch_bounds__(kHugeThreads) k_fold_huge(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t* __restrict__ H, uint64_t G,
+                                                             uint32_t* __restrict__ occ, const unsigned long long* __restrict__ hugeRuns,
+                                                             const unsigned int* __restrict__ nHuge) {
+    constexpr int kWarps = kHugeThreads / 32;
+    __shared__ float weightOf[kWeightLut];
+    __shared__ AddMap sTab[2][kWeightLut];   // [strand][NH code]: the addition of that weight in the binade sTabExp[strand]
+    __shared__ uint32_t sTabExp[2];
+    __shared__ AddMap sTotal[2][kWarps];     // [strand][warp]: the warp's 1024 records composed
+    __shared__ uint32_t sStart[2][kWarps];   // bit pattern of the height before the warp's records
+    __shared__ uint32_t sBits[2];            // the heights (plus, minus) before the current trip
+    __shared__ unsigned sFlags[2];
+    __shared__ int sCross;                   // warp in which a height leaves its binade during this trip, or -1
+    __shared__ unsigned long long sBase;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < kWeightLut) weightOf[tid] = read_weight_weighted((uint32_t)tid << PPP_READ_NH_SHIFT);
+    const unsigned int count = *nHuge;
+    for (unsigned int run = blockIdx.x; run < count; run += gridDim.x) {
+        const size_t i = (size_t)hugeRuns[2 * (size_t)run], end = (size_t)hugeRuns[2 * (size_t)run + 1];
+        const uint32_t pos = keys[i];
+        uint32_t wordP = 0, wordM = 0;
+        unsigned accP = 0, accM = 0;
+        __syncthreads();  // the previous run's shared state has been read
+        if (tid == 0) {
+            wordP = H[pos];
+            wordM = H[G + pos];
+            float hp = __uint_as_float(wordP & kValueMask), hm = __uint_as_float(wordM & kValueMask);
+            size_t b = i;
+            for (; (b & 3) != 0 && b < end; ++b) {  // up to three records in front of the first 16-byte boundary
+                const uint32_t meta = vals[b];
+                const float w = read_weight_weighted(meta);
+                if (meta & PPP_READ_MINUS) { hm = __fadd_rn(hm, w); accM |= meta | 0x80000000u; }
+                else { hp = __fadd_rn(hp, w); accP |= meta | 0x80000000u; }
+            }
+            sBits[0] = __float_as_uint(hp);
+            sBits[1] = __float_as_uint(hm);
+            sBase = b;
+            sTabExp[0] = sTabExp[1] = ~0u;
+            sFlags[0] = sFlags[1] = 0u;
+        }
+        __syncthreads();
+        for (;;) {
+            const size_t base = (size_t)sBase;
+            if (base >= end) break;
+            const uint32_t bitsP = sBits[0], bitsM = sBits[1];
+            const uint32_t expP = bitsP >> 23, expM = bitsM >> 23;
+            if (sTabExp[0] != expP || sTabExp[1] != expM) {  // (block-uniform) a new binade: the maps of the common weights
+                __syncthreads();
+                if (tid < kWeightLut) sTab[0][tid] = addmap_of(expP, __float_as_uint(weightOf[tid]));
+                else if (tid < 2 * kWeightLut) sTab[1][tid - kWeightLut] = addmap_of(expM, __float_as_uint(weightOf[tid - kWeightLut]));
+                if (tid == 0) { sTabExp[0] = expP; sTabExp[1] = expM; }
+                __syncthreads();
+            }
+            // ---- this lane's 32 consecutive records -> one map per strand
+            const size_t idx0 = base + (size_t)tid * kHugePerLane;
+            AddMap mp = {0u, 0u}, mm = {0u, 0u};
+            auto take = [&](uint32_t meta) {
+                const uint32_t nh = meta >> PPP_READ_NH_SHIFT;
+                const bool minus = (meta & PPP_READ_MINUS) != 0;
+                AddMap m;
+                if (nh < (uint32_t)kWeightLut) m = sTab[minus ? 1 : 0][nh];
+                else m = addmap_of(minus ? expM : expP, __float_as_uint(read_weight_weighted(meta)));
+                const AddMap id = {0u, 0u};
+                mp = addmap_compose(mp, minus ? id : m);
+                mm = addmap_compose(mm, minus ? m : id);
+                if (minus) accM |= meta | 0x80000000u; else accP |= meta | 0x80000000u;  // A10 flag: :471 / :483
+            };
+            if (idx0 + kHugePerLane <= end) {
+                const uint4* src = reinterpret_cast<const uint4*>(vals + idx0);
+                uint4 v[kHugePerLane / 4];
+#pragma unroll
+                for (int u = 0; u < kHugePerLane / 4; ++u) v[u] = __ldg(src + u);
+#pragma unroll
+                for (int u = 0; u < kHugePerLane / 4; ++u) { take(v[u].x); take(v[u].y); take(v[u].z); take(v[u].w); }
+            } else {
+                for (size_t j = idx0; j < end; ++j) take(vals[j]);
+            }
+            // ---- inclusive scan over the warp, warp totals, serial walk over the warps
+            AddMap ip = mp, im = mm;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                AddMap qp, qm;
+                qp.a0 = __shfl_up_sync(0xffffffffu, ip.a0, d); qp.a1 = __shfl_up_sync(0xffffffffu, ip.a1, d);
+                qm.a0 = __shfl_up_sync(0xffffffffu, im.a0, d); qm.a1 = __shfl_up_sync(0xffffffffu, im.a1, d);
+                if (lane >= (unsigned)d) { ip = addmap_compose(qp, ip); im = addmap_compose(qm, im); }
+            }
+            if (lane == 31) { sTotal[0][warp] = ip; sTotal[1][warp] = im; }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t bp = bitsP, bm = bitsM;
+                int cross = -1;
+                for (int w = 0; w < kWarps; ++w) {
+                    sStart[0][w] = bp;
+                    sStart[1][w] = bm;
+                    if (addmap_crosses(bp, sTotal[0][w]) || addmap_crosses(bm, sTotal[1][w])) { cross = w; break; }
+                    bp = addmap_apply(bp, sTotal[0][w]);
+                    bm = addmap_apply(bm, sTotal[1][w]);
+                }
+                sCross = cross;
+                if (cross < 0) { sBits[0] = bp; sBits[1] = bm; sBase = base + kHugeTrip; }
+            }
+            __syncthreads();
+            const int cross = sCross;
+            if (cross >= 0 && (int)warp == cross) {
+                const uint32_t bp = sStart[0][warp], bm = sStart[1][warp];
+                const unsigned first = __ballot_sync(0xffffffffu, addmap_crosses(bp, ip) || addmap_crosses(bm, im));  // (monotone: a suffix of the lanes)
+                const int lc = __ffs(first) - 1;
+                // the maps of the lanes in front of lane lc are valid: its starting heights
+                AddMap ep, em;
+                ep.a0 = __shfl_up_sync(0xffffffffu, ip.a0, 1); ep.a1 = __shfl_up_sync(0xffffffffu, ip.a1, 1);
+                em.a0 = __shfl_up_sync(0xffffffffu, im.a0, 1); em.a1 = __shfl_up_sync(0xffffffffu, im.a1, 1);
+                if ((int)lane == lc) {
+                    float hp = __uint_as_float(lane ? addmap_apply(bp, ep) : bp), hm = __uint_as_float(lane ? addmap_apply(bm, em) : bm);
+                    const size_t stop = idx0 + kHugePerLane < end ? idx0 + kHugePerLane : end;
+                    for (size_t j = idx0; j < stop; ++j) {  // real additions across the binade boundary
+                        const uint32_t meta = vals[j];
+                        const float w = read_weight_weighted(meta);
+                        if (meta & PPP_READ_MINUS) hm = __fadd_rn(hm, w); else hp = __fadd_rn(hp, w);
+                    }
+                    sBits[0] = __float_as_uint(hp);
+                    sBits[1] = __float_as_uint(hm);
+                    sBase = idx0 + kHugePerLane;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- the run's A10 flags, then the two words
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { accP |= __shfl_xor_sync(0xffffffffu, accP, d); accM |= __shfl_xor_sync(0xffffffffu, accM, d); }
+        if (lane == 0) { if (accP) atomicOr(&sFlags[0], accP); if (accM) atomicOr(&sFlags[1], accM); }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned flagsP = sFlags[0], flagsM = sFlags[1];
+            if (flagsP) {
+                H[pos] = (sBits[0] & kValueMask) | (wordP & kA10Bit) | ((flagsP & PPP_READ_A10) ? kA10Bit : 0u);
+                if (wordP == 0u) atomicOr(&occ[pos >> 5], 1u << (pos & 31u));
+            }
+            if (flagsM) {
+                H[G + pos] = (sBits[1] & kValueMask) | (wordM & kA10Bit) | ((flagsM & PPP_READ_A10) ? kA10Bit : 0u);
+                if (wordM == 0u) atomicOr(&occ[(G + pos) >> 5], 1u << (pos & 31u));
+            }
         }
     }
 }
@@ -531,11 +730,15 @@ cudaError_t launch_stack_fold(const SortedRun& r, uint32_t* H, uint64_t G, uint3
     unsigned long long* longRuns = reinterpret_cast<unsigned long long*>(r.spareA);
     unsigned int* nLong = reinterpret_cast<unsigned int*>(r.spareB);
     unsigned int longCap = (unsigned int)(capacity / 2);
-    cudaError_t e = cudaMemsetAsync(nLong, 0, sizeof(unsigned int), s);
+    // spareB[1] = number of huge runs, their (first, end) pairs behind it (at most n / kHugeRun of them)
+    unsigned int* nHuge = nLong + 1;
+    unsigned long long* hugeRuns = reinterpret_cast<unsigned long long*>(r.spareB + 2);
+    cudaError_t e = cudaMemsetAsync(nLong, 0, 2 * sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;
     k_fold_runs<<<blocks, kBuildThreads, 0, s>>>(r.keys, r.vals, r.n, H, G, occ, longRuns, nLong, longCap);
-    k_fold_long<<<148 * 2, kBuildThreads, 0, s>>>(r.keys, r.vals, r.n, H, G, occ, longRuns, nLong, longCap);
-    if (launches) *launches += 2;
+    k_fold_long<<<148 * 2, kBuildThreads, 0, s>>>(r.keys, r.vals, r.n, H, G, occ, longRuns, nLong, longCap, hugeRuns, nHuge);
+    k_fold_huge<<<64, kHugeThreads, 0, s>>>(r.keys, r.vals, H, G, occ, hugeRuns, nHuge);
+    if (launches) *launches += 3;
     return cudaGetLastError();
 }
 

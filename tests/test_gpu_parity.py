@@ -522,12 +522,14 @@ def _fold_f32(weights):
 
 @pytest.mark.parametrize("batches", [1, 3, 40])  # 40: batches below 4096 records take the single-launch path
 def test_tall_stacks_fold_in_file_order(batches):
-    """-m weighted on tall stacks (the warp-cooperative fold): run lengths around its 32-record and 256-record
+    """-m weighted on tall stacks (the warp-cooperative fold and, from 4096 records on, the block-wide fold through
+    composed per-binade addition maps): run lengths around the 32-record, 256-record, 4096-record and 16384-record
     boundaries, both strands interleaved at one position, multiplicities beyond the weight table and beyond 2^24,
     and sums continued across submissions.  Expected value: the literal single-precision loop."""
     rng = np.random.default_rng(7)
     nh_pool = np.array([1, 1, 1, 1, 2, 3, 5, 7, 10, 63, 64, 100, (1 << 24) - 1, (1 << 24) + 3, 1 << 29], dtype=np.uint32)
-    lengths_of_runs = [31, 32, 33, 34, 255, 256, 257, 511, 512, 513, 777, 5000, 40000]
+    lengths_of_runs = [31, 32, 33, 34, 255, 256, 257, 511, 512, 513, 777, 5000, 40000, 4095, 4096, 4097, 16389, 120001, 700003]
+    common = np.array([1, 1, 1, 2, 3, 4], dtype=np.uint32)  # the last two runs: heights that climb through many binades
     key, minus, a10, nh = [], [], [], []
     for i, n in enumerate(lengths_of_runs):
         pos = 100 + 50 * i
@@ -535,7 +537,7 @@ def test_tall_stacks_fold_in_file_order(batches):
         both = i % 3 != 0                      # every third position holds one strand only
         minus.append(rng.random(n) < 0.5 if both else np.full(n, i % 2 == 0))
         a10.append(rng.random(n) < 0.01)
-        nh.append(rng.choice(nh_pool, size=n))
+        nh.append(rng.choice(common if n > 100000 else nh_pool, size=n))
     key, minus, a10, nh = map(np.concatenate, (key, minus, a10, nh))
     order = rng.permutation(len(key))         # positions interleaved in the "file"; the order within a position is what matters
     key, minus, a10, nh = key[order], minus[order], a10[order], nh[order]
@@ -555,3 +557,48 @@ def test_tall_stacks_fold_in_file_order(batches):
                 assert bits(np.array([h[pos]]))[0] == bits(np.array([want]))[0], (strand, n, h[pos], want)
                 assert bool(a[pos]) == bool(a10[sel].any())
             assert np.count_nonzero(h) == sum(1 for i in range(len(lengths_of_runs)) if ((key == 100 + 50 * i) & (minus == bool(strand))).any())
+
+
+@pytest.mark.parametrize("mode", ["weighted", "unique"])
+def test_reset_leaves_no_trace_of_the_previous_run(mode):
+    """ppp_reset of a sparse store clears only the sectors whose occupancy bits are set (compact.cu: k_sparse_clear); a
+    reset in the middle of an upload falls back to the memset.  A context that is reused for another read set must give
+    what a fresh context gives: stacks, signatures, loci."""
+    a = host.SynthModel("tiny", n_reads=120_000, seed=21)
+    b = host.SynthModel("tiny", n_reads=90_000, seed=22)
+    ra, rb = a.generate(mode=mode), b.generate(mode=mode)
+    assert a.lengths == b.lengths
+    fresh = {id(r): run_gpu(a.lengths, r, mode) for r in (ra, rb)}
+    fresh_stacks = {id(r): gpu_stacks(a.lengths, r, mode) for r in (ra, rb)}
+
+    def run(ctx, reads):
+        for c, r in enumerate(reads):
+            if len(r):
+                ctx.count_reads(c, r)
+        ctx.finish()
+        rows = []
+        for strand in (0, 1):
+            for c, L in enumerate(a.lengths):
+                h, a10 = ctx.stacks(c, strand, 0, L + 64)
+                nz = np.flatnonzero(h)
+                rows.append((np.full(len(nz), strand, np.uint32), np.full(len(nz), c, np.uint32), nz.astype(np.uint32), h[nz], a10[nz].astype(np.uint32)))
+        stacks = [np.concatenate([r[i] for r in rows]) for i in range(5)]
+        ctx.map_heights_to_scores(False)
+        ctx.count_stacks_by_group(False)
+        return stacks, ctx.calculate_fdrs(0).loci.copy(), ctx.signatures().copy()
+
+    with api.Context(a.lengths, mode=mode) as ctx:
+        for reads in (ra, rb, ra):
+            stacks, loci, sigs = run(ctx, reads)
+            for got, want in zip(stacks, fresh_stacks[id(reads)]):
+                assert np.array_equal(bits(got) if got.dtype == np.float32 else got, bits(want) if want.dtype == np.float32 else want)
+            assert np.array_equal(loci, fresh[id(reads)]["score"].loci) and np.array_equal(sigs, fresh[id(reads)]["signatures"])
+            ctx.reset()                         # finished store: sparse clear
+        for c, r in enumerate(rb):              # half an upload, then a reset (dense memset), then another run
+            if len(r):
+                ctx.count_reads(c, r[: len(r) // 2])
+        ctx.reset()
+        stacks, loci, sigs = run(ctx, ra)
+        assert np.array_equal(loci, fresh[id(ra)]["score"].loci) and np.array_equal(sigs, fresh[id(ra)]["signatures"])
+        for got, want in zip(stacks, fresh_stacks[id(ra)]):
+            assert np.array_equal(bits(got) if got.dtype == np.float32 else got, bits(want) if want.dtype == np.float32 else want)

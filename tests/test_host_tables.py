@@ -104,3 +104,37 @@ def test_device_threshold_tables_equal_the_host_tables():
     for mf in freqs:
         a, b = api.bin_thresholds(mf), api.emulated_bin_thresholds(mf)
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), mf
+
+
+def _float_chain(h0, w):
+    h = np.float32(h0)
+    for v in w:
+        h = np.float32(h + v)
+    return h
+
+
+def test_composed_addition_maps_equal_the_float_additions():
+    """csrc/fadd_chain.h: a run of float additions as one integer map per binade (k_fold_huge folds stacks of 10^4..10^6
+    reads this way) against the additions themselves (pingpongpro.cpp:487): read weights 1/NH, ties (powers of two),
+    sums that start at zero, cross binades and saturate at 2^24."""
+    rng = np.random.default_rng(5)
+    real_total = n_total = 0
+    for trial in range(300):
+        n = int(rng.integers(1, 3000))
+        kind = trial % 4
+        nh = (rng.integers(1, 5, n) if kind == 0 else rng.integers(1, 65, n) if kind == 1 else rng.integers(1, 100000, n) if kind == 2
+              else 1 << rng.integers(0, 12, n))
+        w = (1.0 / nh.astype(np.float64)).astype(np.float32)
+        w[rng.random(n) < 0.15] = 0.0  # the other strand's records are staged as +0.0f
+        h0 = [0.0, 1.0, float(rng.integers(1, 1 << 24)), float(np.uint32(0x3f800000 + rng.integers(0, 24 << 23)).view(np.float32)), 16777215.0][trial % 5]
+        got, real = api.emulated_fadd_chain(h0, w, int(rng.integers(1, 65)))
+        assert np.float32(got).view(np.uint32) == _float_chain(h0, w).view(np.uint32), (trial, h0)
+        real_total += real
+        n_total += n
+    assert real_total < n_total // 10  # nearly everything went through the maps
+    # saturation: 2^24 + 1 = 2^24 (the tie rounds to the even mantissa), + 0.5 and + 1/3 do not move it either
+    got, real = api.emulated_fadd_chain(16777216.0, np.array([1.0, 0.5, 1.0 / 3, 1.0] * 100, np.float32), 32)
+    assert got == np.float32(16777216.0) and real == 0
+    # an infinite height (NH:i:0 through the C ABI) stays infinite
+    got, _ = api.emulated_fadd_chain(np.inf, np.ones(50, np.float32), 16)
+    assert np.isinf(got)
