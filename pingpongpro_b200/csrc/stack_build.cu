@@ -13,7 +13,9 @@
 // (own LSD sort, 8-bit digits: block histograms -> device scan -> stable scatter) and every run of equal
 // keys is folded sequentially with __fadd_rn, continuing from the word's current value so that
 // successive batches extend the same left-to-right sum: runs of up to 32 records by one thread each
-// (k_fold_runs), longer ones by a producer/consumer warp pair (k_fold_long), batches of up to 4096 records
+// (k_fold_runs), longer ones by a producer/consumer warp pair (k_fold_long), runs of 8192 records and more by a whole
+// block that composes the additions as integer maps per binade instead of executing them one by one (k_fold_huge,
+// fadd_chain.h), batches of up to 4096 records
 // in a single launch (k_small_batch).  The launchers are split into a sort half and a fold half so that the
 // caller (api.cu: buildChunk) can run the sort of the next batches beside the folds of earlier ones.
 //
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) k_radix_scatter(const uint32_
 constexpr int kShortRun = 32;
 constexpr int kFoldBlock = 256;  // records per pipeline stage of k_fold_long
 constexpr int kWeightLut = 64;
-constexpr int kHugeRun = 4096;        // runs at least this long leave the serial chain of k_fold_long for k_fold_huge
+constexpr int kHugeRun = 8192;        // runs at least this long leave the serial chain of k_fold_long for k_fold_huge
 constexpr int kHugeThreads = 512;
 constexpr int kHugePerLane = 32;      // consecutive records per lane and trip of k_fold_huge
 constexpr int kHugeTrip = kHugeThreads * kHugePerLane;
@@ -507,10 +509,9 @@ __global__ void __launch_bounds__(kHugeThreads) k_fold_huge(const uint32_t* __re
                 AddMap m;
                 if (nh < (uint32_t)kWeightLut) m = sTab[minus ? 1 : 0][nh];
                 else m = addmap_of(minus ? expM : expP, __float_as_uint(read_weight_weighted(meta)));
-                const AddMap id = {0u, 0u};
-                mp = addmap_compose(mp, minus ? id : m);
-                mm = addmap_compose(mm, minus ? m : id);
-                if (minus) accM |= meta | 0x80000000u; else accP |= meta | 0x80000000u;  // A10 flag: :471 / :483
+                // (a run is nearly always of one strand: the branch is warp-uniform then)
+                if (minus) { mm = addmap_compose(mm, m); accM |= meta | 0x80000000u; }   // A10 flag: :471
+                else { mp = addmap_compose(mp, m); accP |= meta | 0x80000000u; }        // :483
             };
             if (idx0 + kHugePerLane <= end) {
                 const uint4* src = reinterpret_cast<const uint4*>(vals + idx0);
@@ -737,7 +738,7 @@ cudaError_t launch_stack_fold(const SortedRun& r, uint32_t* H, uint64_t G, uint3
     if (e != cudaSuccess) return e;
     k_fold_runs<<<blocks, kBuildThreads, 0, s>>>(r.keys, r.vals, r.n, H, G, occ, longRuns, nLong, longCap);
     k_fold_long<<<148 * 2, kBuildThreads, 0, s>>>(r.keys, r.vals, r.n, H, G, occ, longRuns, nLong, longCap, hugeRuns, nHuge);
-    k_fold_huge<<<64, kHugeThreads, 0, s>>>(r.keys, r.vals, H, G, occ, hugeRuns, nHuge);
+    k_fold_huge<<<148 * 2, kHugeThreads, 0, s>>>(r.keys, r.vals, H, G, occ, hugeRuns, nHuge);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }

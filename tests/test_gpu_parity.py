@@ -522,13 +522,13 @@ def _fold_f32(weights):
 
 @pytest.mark.parametrize("batches", [1, 3, 40])  # 40: batches below 4096 records take the single-launch path
 def test_tall_stacks_fold_in_file_order(batches):
-    """-m weighted on tall stacks (the warp-cooperative fold and, from 4096 records on, the block-wide fold through
-    composed per-binade addition maps): run lengths around the 32-record, 256-record, 4096-record and 16384-record
+    """-m weighted on tall stacks (the warp-cooperative fold and, from 8192 records on, the block-wide fold through
+    composed per-binade addition maps): run lengths around the 32-record, 256-record, 8192-record and 16384-record
     boundaries, both strands interleaved at one position, multiplicities beyond the weight table and beyond 2^24,
     and sums continued across submissions.  Expected value: the literal single-precision loop."""
     rng = np.random.default_rng(7)
     nh_pool = np.array([1, 1, 1, 1, 2, 3, 5, 7, 10, 63, 64, 100, (1 << 24) - 1, (1 << 24) + 3, 1 << 29], dtype=np.uint32)
-    lengths_of_runs = [31, 32, 33, 34, 255, 256, 257, 511, 512, 513, 777, 5000, 40000, 4095, 4096, 4097, 16389, 120001, 700003]
+    lengths_of_runs = [31, 32, 33, 34, 255, 256, 257, 511, 512, 513, 777, 5000, 40000, 8191, 8192, 8193, 16389, 120001, 700003]
     common = np.array([1, 1, 1, 2, 3, 4], dtype=np.uint32)  # the last two runs: heights that climb through many binades
     key, minus, a10, nh = [], [], [], []
     for i, n in enumerate(lengths_of_runs):
