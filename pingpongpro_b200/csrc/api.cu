@@ -408,16 +408,24 @@ int hookReduce(ppp_ctx* c, void* buf, size_t count, int dtype, int op) {
     return PPP_OK;
 }
 
-// PPP_TRACE=1: host wall time between the phases of one call, to stderr (where a multi-GPU step waits)
+// PPP_TRACE=1: host wall time between the phases of one call, to stderr (where a multi-GPU step waits); `at` is the time
+// since the first traced call of the process, so the gaps BETWEEN calls (the caller's own time) can be read off as well
 struct Trace {
     bool on;
     const char* call;
     std::chrono::steady_clock::time_point t;
-    explicit Trace(const char* name) : on(getenv("PPP_TRACE") != nullptr), call(name), t(std::chrono::steady_clock::now()) {}
+    static std::chrono::steady_clock::time_point epoch() {
+        static const std::chrono::steady_clock::time_point e = std::chrono::steady_clock::now();
+        return e;
+    }
+    explicit Trace(const char* name) : on(getenv("PPP_TRACE") != nullptr), call(name), t(std::chrono::steady_clock::now()) {
+        if (on) (void)epoch();
+    }
     void mark(const char* what) {
         if (!on) return;
         auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[ppp_trace %s] %-28s +%.3f ms\n", call, what, std::chrono::duration<double, std::milli>(now - t).count());
+        fprintf(stderr, "[ppp_trace %s] %-28s +%.3f ms  (at %.3f)\n", call, what, std::chrono::duration<double, std::milli>(now - t).count(),
+                std::chrono::duration<double, std::milli>(now - epoch()).count());
         t = now;
     }
 };
@@ -907,6 +915,7 @@ namespace {
 int enqueueScanStage(ppp_ctx* c) {
     int rc;
     Trace tr("scan stage");
+    tr.mark("begin");
     if ((rc = timerStart(c, c->tPass))) return rc;
     c->tPass.used = false;
     CK(cudaMemsetAsync(c->dState, 0, c->passZeroBytes, c->stream));  // pass scalars, look-back states, grouped counts
@@ -1158,7 +1167,9 @@ int ppp_scan(ppp_ctx* c, uint64_t* grouped, uint64_t* nPairs) {
     CK(cudaSetDevice(c->device));
     int rc;
     const size_t tableWords = (size_t)c->W * kBins * 4;
+    Trace tr("scan");
     if ((rc = enqueueBinStage(c))) return rc;
+    tr.mark("bin stage enqueued");
     c->haveScan = true;
     c->viewValid = false;
     if (!grouped && !nPairs) return PPP_OK;
@@ -1182,6 +1193,7 @@ int ppp_score(ppp_ctx* c, uint32_t minStackHeight, uint32_t* nBins, uint16_t* bi
     int rc;
     Trace tr("score");
     if ((rc = enqueueScoreStage(c, minStackHeight))) return rc;
+    tr.mark("score stage enqueued");
     if ((rc = settle(c))) return rc;
     tr.mark("pass settled");
     size_t n = minStackHeight > 0 ? (size_t)c->hs->nLoci : (size_t)c->nPP;  // -s 0: every overlap-`pingpong` record is a locus
