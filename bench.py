@@ -386,8 +386,8 @@ def measure(args, genome, reads_n, seed, rank, world, local_rank, tdist, strong,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)  # (a step is 0.5-2 ms: short timed regions are at the mercy of one late rank)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--reads", type=int, default=500_000_000, help="reads of the data set (configs[3]: 500 M)")
     ap.add_argument("--genome", default="human")
