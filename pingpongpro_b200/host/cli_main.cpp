@@ -293,6 +293,35 @@ static int run(int argc, char const** argv) {
         if (!haveContexts) {
             names = reader.names();
             lengths = reader.lengths();
+            if (lengths.empty() && !reader.isBam()) {
+                // SAM text without @SQ lines: the reference (SeqAn) grows its name store while it reads and never needs a
+                // length (:1493-1517).  The dense stack arrays do, so such input is read twice: a first pass over every input
+                // file collects the names (in order of appearance) and the extent of the kept reads per contig.
+                const int scanThreads = options.threads > 0 ? options.threads : (int)std::thread::hardware_concurrency();
+                for (const std::string& p : options.inputFiles) {
+                    std::vector<std::string> nm;
+                    std::vector<uint64_t> ext;
+                    const int rc = scan_extents(p.c_str(), eo, nm, ext, scanThreads > 2 ? scanThreads - 2 : 1);
+                    if (rc == 1) {
+                        std::cerr << "Failed to open input file: " << p << std::endl;  // :1485
+                        return 1;
+                    }
+                    if (rc != 0) {
+                        std::cerr << "Failed to read record" << std::endl;  // :411
+                        return 1;
+                    }
+                    if (&p == &options.inputFiles.front()) {
+                        names = nm;
+                        lengths = ext;
+                    } else if (nm != names) {
+                        std::cerr << "@SQ header lines of '" << p << "' differ from those of previous input files" << std::endl;  // :1514
+                        return 1;
+                    } else {
+                        for (size_t c = 0; c < lengths.size(); ++c) lengths[c] = std::max(lengths[c], ext[c]);
+                    }
+                }
+                mark("headerless input scanned");
+            }
             if (lengths.empty()) lengths.push_back(0);
             mark("header read");
             // CUDA start-up (cuInit + context creation, 0.4-0.8 s on the measured boxes) is a fixed cost.  Letting the
@@ -368,8 +397,9 @@ static int run(int argc, char const** argv) {
             std::cerr << "Failed to read record" << std::endl;
             return 1;
         }
-        // A contig that has no @SQ line: the reference (SeqAn) appends such names while reading and works without lengths;
-        // the dense stack arrays need every length before the first record (documented divergence).
+        // A contig that the header lacks although it lists others: the reference (SeqAn) appends such names while reading and
+        // works without lengths; the dense stack arrays need every length before the first record.  (Input without any @SQ
+        // line is scanned first, see above; a partial header is a documented divergence)
         if (foreignContig) {
             std::cerr << "'" << path << "': a record names a contig that has no @SQ header line (contig lengths must be known before the first record)" << std::endl;
             return 1;

@@ -17,13 +17,33 @@ void extract_record_fn(void* user, const AlnView& v, std::vector<uint8_t>& out) 
     out.insert(out.end(), p, p + sizeof e);
 }
 
-int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int threads) {
+namespace {
+
+// One pass over a file.  `keep`: the reads are stored per contig (decode_file); otherwise only names and extents are
+// collected (scan_extents).  extents[c] = 1 + the largest 5'-end key among the kept reads of contig c.
+int walk_file(const char* path, const ExtractOptions& o, DecodedFile& out, std::vector<uint64_t>& extents, int threads, bool keep) {
     ExtractOptions opts = o;  // read by the reader's worker threads: declared before the reader, so that it outlives them on every return path
     AlnReader rd;
     if (!rd.open(path)) return 1;
     out.names = rd.names();
     out.lengths = rd.lengths();
     out.reads.assign(out.names.size(), std::vector<ppp_read>());
+    extents.assign(out.names.size(), 0);
+    auto take = [&](int32_t contig, const ppp_read& r, float w) -> bool {
+        if ((size_t)contig >= out.reads.size()) {  // contig that is missing from the header: the name store grew
+            out.names = rd.names();
+            out.lengths = rd.lengths();
+            out.reads.resize(out.names.size());
+            extents.resize(out.names.size(), 0);
+            if ((size_t)contig >= out.reads.size()) return false;
+        }
+        if (keep) out.reads[contig].push_back(r);
+        if ((uint64_t)r.key + 1 > extents[contig]) extents[contig] = (uint64_t)r.key + 1;
+        out.totalWeight += (double)w;  // :488, file order
+        ++out.nKept;
+        return true;
+    };
+    int rc = 0;
     if (threads > 1) {
         rd.startBatches(threads, extract_record_fn, &opts);
         const uint8_t* bytes;
@@ -33,42 +53,52 @@ int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int
         while (rd.nextBatch(bytes, nBytes, n, err)) {
             out.nRecords += n;
             const ExtractedRead* e = reinterpret_cast<const ExtractedRead*>(bytes);
-            for (size_t k = 0, m = nBytes / sizeof(ExtractedRead); k < m; ++k) {
-                if ((size_t)e[k].contig >= out.reads.size()) {  // contig that is missing from the header
-                    out.names = rd.names();
-                    out.lengths = rd.lengths();
-                    out.reads.resize(out.names.size());
-                    if ((size_t)e[k].contig >= out.reads.size()) return 2;
-                }
-                out.reads[e[k].contig].push_back(e[k].read);
-                out.totalWeight += (double)e[k].weight;  // :488, file order
-                ++out.nKept;
-            }
+            for (size_t k = 0, m = nBytes / sizeof(ExtractedRead); k < m; ++k)
+                if (!take(e[k].contig, e[k].read, e[k].weight)) return 2;
             if (err) return 2;
         }
         out.nRejectedGuesses = rd.rejectedBoundaryGuesses();
-        return rd.good() ? 0 : 2;
-    }
-    AlnView v;
-    while (!rd.atEnd()) {
-        if (rd.next(v) != 0) return 2;
-        ++out.nRecords;
-        ppp_read r;
-        int32_t contig;
-        float w;
-        if (!extract_read(v, o, r, contig, w)) continue;
-        if ((size_t)contig >= out.reads.size()) {  // contig that is missing from the header
-            out.names = rd.names();
-            out.lengths = rd.lengths();
-            out.reads.resize(out.names.size());
-            if ((size_t)contig >= out.reads.size()) return 2;
+        rc = rd.good() ? 0 : 2;
+    } else {
+        AlnView v;
+        while (!rd.atEnd()) {
+            if (rd.next(v) != 0) return 2;
+            ++out.nRecords;
+            ppp_read r;
+            int32_t contig;
+            float w;
+            if (!extract_read(v, o, r, contig, w)) continue;
+            if (!take(contig, r, w)) return 2;
         }
-        out.reads[contig].push_back(r);
-        out.totalWeight += (double)w;  // :488, file order
-        ++out.nKept;
+        if (!rd.good()) rc = 2;
     }
-    if (!rd.good()) return 2;
-    return 0;
+    // names that only filtered records carried (the name store grows for every record, like SeqAn's)
+    out.names = rd.names();
+    out.lengths = rd.lengths();
+    out.reads.resize(out.names.size());
+    extents.resize(out.names.size(), 0);
+    return rc;
+}
+
+}  // namespace
+
+int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int threads) {
+    std::vector<uint64_t> extents;
+    const int rc = walk_file(path, o, out, extents, threads, true);
+    // a contig without an @SQ length (headerless SAM, or a name the header lacks): the reference works without lengths
+    // (std::map per contig); the dense stack arrays get the extent of the reads instead
+    for (size_t c = 0; c < out.lengths.size() && c < extents.size(); ++c)
+        if (out.lengths[c] == 0) out.lengths[c] = extents[c];
+    return rc;
+}
+
+int scan_extents(const char* path, const ExtractOptions& o, std::vector<std::string>& names, std::vector<uint64_t>& extents, int threads) {
+    DecodedFile f;
+    const int rc = walk_file(path, o, f, extents, threads, false);
+    names = f.names;
+    for (size_t c = 0; c < extents.size() && c < f.lengths.size(); ++c)
+        if (f.lengths[c] > extents[c]) extents[c] = f.lengths[c];  // (a length the header does give wins)
+    return rc;
 }
 
 }  // namespace ppp

@@ -85,6 +85,13 @@ struct DecodedFile {
 // 0 = ok, 1 = cannot open, 2 = malformed record.
 // threads <= 1: the sequential record walk; otherwise inflate / line parsing, record decoding and extraction all run on
 // `threads` workers and this thread only appends the kept reads in file order.
+// A contig whose length the header does not give (headerless SAM; a name the @SQ lines lack) gets the extent of its kept
+// reads (largest 5'-end key + 1) as its length.
 int decode_file(const char* path, const ExtractOptions& o, DecodedFile& out, int threads = 1);
+
+// The same pass without keeping the reads: the name store after the whole file (names the header lacks appended in order
+// of appearance, like SeqAn's) and per contig 1 + the largest 5'-end key of the kept reads.  The command line runs it
+// over headerless SAM input before it sizes the stack arrays.  Return codes of decode_file.
+int scan_extents(const char* path, const ExtractOptions& o, std::vector<std::string>& names, std::vector<uint64_t>& extents, int threads = 1);
 
 }  // namespace ppp

@@ -400,3 +400,33 @@ def test_corrupted_bam_sequential_and_batch_modes_agree(tmp_path):
             _decoded_equal(results[0], results[1])
         outcomes["ok" if results[0] is not None else "error"] += 1
     assert outcomes["ok"] >= 5 and outcomes["error"] >= 5  # both behaviours were exercised
+
+
+def test_headerless_sam_gets_names_by_appearance_and_lengths_from_the_reads(tmp_path):
+    """SAM text without @SQ lines (`samtools view` without -h, bowtie --sam-nohead): the reference works on it -- SeqAn's
+    name store grows in order of appearance and pingpongpro.cpp never needs a length (:1493-1517).  Here the reads come
+    out as from the same file with its header (contig by contig, in file order), the contigs are numbered in order of
+    appearance and each gets the extent of its kept reads (largest 5'-end key + 1) as its length -- what the dense
+    stack arrays are sized from."""
+    tool = os.path.join(_build.BIN, "ppp_synth")
+    full = tmp_path / "with.sam"
+    subprocess.check_call([tool, "--genome", "tiny", "--reads", "20000", "--seed", "9", "--out", str(full)], stdout=subprocess.DEVNULL)
+    lines = full.read_text().splitlines(keepends=True)
+    body = [l for l in lines if not l.startswith("@")]
+    # a different order of appearance than the header's: the records of the last contig first
+    last = [l for l in body if l.split("\t")[2] == "ctgC"]
+    rest = [l for l in body if l.split("\t")[2] != "ctgC"]
+    bare = tmp_path / "without.sam"
+    bare.write_text("".join(last[:50] + rest + last[50:]))
+    want_file = tmp_path / "reordered.sam"
+    want_file.write_text("".join([l for l in lines if l.startswith("@")] + last[:50] + rest + last[50:]))
+    want = host.decode_file(str(want_file), mode="weighted")
+    for threads in (1, 4):
+        got = host.decode_file(str(bare), mode="weighted", threads=threads)
+        assert got.names[0] == "ctgC" and sorted(got.names) == sorted(want.names)
+        assert got.n_records == want.n_records and got.n_kept == want.n_kept and got.total_weight == want.total_weight
+        for i, name in enumerate(got.names):
+            j = want.names.index(name)
+            assert np.array_equal(got.reads[i], want.reads[j])
+            assert got.lengths[i] == (int(got.reads[i]["key"].max()) + 1 if len(got.reads[i]) else 0)
+            assert got.lengths[i] <= want.lengths[j] + 1
